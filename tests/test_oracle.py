@@ -1,0 +1,142 @@
+"""The oracle restatement against (a) committed outputs of the unmodified reference
+(tests/golden, made by oracle/gen_golden.py) and (b) the reference itself when
+/root/reference is mounted (build container)."""
+import numpy as np
+import pytest
+
+from oracle import statistics_oracle as so
+from oracle import mining_oracle as mo
+
+
+def test_pairwise_golden(golden_dir):
+    g = np.load(golden_dir / 'pairwise.npz')
+    xa, xb = g['xa'], g['xb']
+    for metric in (0, 1):
+        got = so.pairwise_similarities(xa.copy(), metric=metric)
+        assert got.dtype == np.float32 and got.shape == (37 * 36 // 2,)
+        np.testing.assert_array_equal(got, g['self_m%d' % metric])
+        got = so.pairwise_similarities(xa.copy(), xb.copy(), metric=metric)
+        assert got.shape == (37, 21)
+        np.testing.assert_array_equal(got, g['cross_m%d' % metric])
+
+
+def test_pairwise_errors_and_empty():
+    x = np.eye(4, 8, dtype=np.float32)
+    with pytest.raises(ValueError, match='Undefined similarity metric 2'):
+        so.pairwise_similarities(x, metric=2)
+    with pytest.raises(ValueError, match='embeddings must be normalized to 1'):
+        so.pairwise_similarities(2 * x, x)
+    e = so.pairwise_similarities(x[:1])
+    assert e.size == 0
+
+
+def test_confidence_literal_and_vectorised_golden(golden_dir):
+    g = np.load(golden_dir / 'confidence.npz')
+    x, labels = g['embeddings'], g['labels']
+    for metric in (0, 1):
+        thr = so.default_thresholds(metric)
+        lit = so.ConfidenceMatrix(so.SimilarityCalculator(x, labels, metric), thr)
+        for name in ('tp', 'tn', 'fp', 'fn', 'accuracy', 'precision', 'tp_rates', 'tn_rates'):
+            np.testing.assert_array_equal(getattr(lit, name), g['%s_m%d' % (name, metric)], err_msg=name)
+        counts, sizes = so.class_pair_counts(x, labels, thr, metric)
+        ref_counts = g['counts_m%d' % metric]
+        # whole-Gram vs per-block sgemm may differ in the last ulp for a pair sitting on a threshold
+        assert np.abs(counts - ref_counts).sum() <= 2
+        vec = so.confidence_matrix_exact_order(x, labels, thr, metric)
+        wgt = so.confidence_matrix_weighted(x, labels, thr, metric)
+        for name in ('tp', 'tn', 'fp', 'fn'):
+            ref = g['%s_m%d' % (name, metric)]
+            if np.array_equal(counts, ref_counts):
+                np.testing.assert_array_equal(getattr(vec, name), ref, err_msg=name)
+            np.testing.assert_allclose(getattr(vec, name), ref, rtol=0, atol=1e-3)
+            np.testing.assert_allclose(getattr(wgt, name), getattr(vec, name), rtol=0, atol=1e-13)
+        one = so.confidence_matrix_exact_order(x, labels, np.array(thr[31] + 0.0123), metric)
+        np.testing.assert_allclose([one.tp[0], one.tn[0], one.fp[0], one.fn[0]], g['single_m%d' % metric],
+                                   rtol=0, atol=1e-3)
+
+
+def test_pair_histogram_consistency():
+    x, labels = so.synthetic_embeddings([5, 1, 9, 30, 2, 2, 17], dim=64, sigma=1.0, seed=2)
+    thr = so.default_thresholds(0)
+    h = so.pair_histogram(x, labels, thr, 0, block=16)
+    n = x.shape[0]
+    assert h['n_same'] + h['n_diff'] == n * (n - 1) // 2
+    d = so.pairwise_similarities(x.copy())
+    iu = np.triu_indices(n, 1)
+    same = labels[iu[0]] == labels[iu[1]]
+    for t_i in (0, 17, 50, 99):
+        assert abs(h['same'][t_i] - np.count_nonzero(d[same] < thr[t_i])) <= 1
+        assert abs(h['diff'][t_i] - np.count_nonzero(d[~same] < thr[t_i])) <= 1
+    assert np.all(np.diff(h['same']) >= 0) and np.all(np.diff(h['diff']) >= 0)
+    assert h['same'][0] == 0 and h['diff'][0] == 0          # nothing is < 0
+
+
+def test_thresholds_f32_up_equivalence():
+    rng = np.random.default_rng(0)
+    thr = so.default_thresholds(0)
+    t32 = so.thresholds_f32_up(thr)
+    near = np.concatenate([np.nextafter(t32, np.float32(-np.inf)), t32, np.nextafter(t32, np.float32(np.inf)),
+                           rng.uniform(0, 4, 1000).astype(np.float32)])
+    for t, tu in zip(thr, t32):
+        np.testing.assert_array_equal(near < t, near < tu)
+
+
+def test_kfold_matches_sklearn():
+    from sklearn.model_selection import KFold
+    for n, k in ((330, 10), (103, 10), (50, 3)):
+        ref = list(KFold(n_splits=k, shuffle=True, random_state=0).split(np.arange(n)))
+        got = list(so.kfold_split(n, k))
+        assert len(ref) == len(got)
+        for (a, b), (c, d) in zip(ref, got):
+            np.testing.assert_array_equal(a, c)
+            np.testing.assert_array_equal(b, d)
+
+
+def test_validation_golden(golden_dir):
+    g = np.load(golden_dir / 'validation.npz')
+    x, labels = g['embeddings'], g['labels']
+    for metric in (0, 1):
+        for conf in (so.confidence_matrix_exact_order, so.confidence_matrix_weighted):
+            out = so.face_to_face_validation(x, labels, metric, 10, 1.e-3, confidence=conf)
+            for tag, key in (('acc', 'MaximumAccuracy'), ('far', 'FalseAlarmRate(FAR = 0.001)')):
+                keys = [str(k) for k in g['%s_keys_m%d' % (tag, metric)]]
+                vals = g['%s_vals_m%d' % (tag, metric)]
+                assert sorted(out[key].keys()) == keys
+                got = np.array([float(out[key][k]) for k in keys])
+                np.testing.assert_allclose(got, vals, rtol=0, atol=2e-3, err_msg='%s m%d' % (key, metric))
+            np.testing.assert_array_equal(out['_thresholds'][:, 0], g['acc_thr_m%d' % metric])
+            np.testing.assert_allclose(out['_thresholds'][:, 1], g['far_thr_m%d' % metric], rtol=0, atol=2e-3)
+
+
+@pytest.mark.reference
+def test_restatement_equals_live_reference():
+    """Build container only: the unmodified reference on a fresh ragged input."""
+    from oracle.reference_loader import load_reference_statistics
+    st = load_reference_statistics()
+    x, labels = so.synthetic_embeddings([3, 1, 6, 2, 11, 1, 4], dim=32, sigma=1.5, seed=9)
+    for metric in (0, 1):
+        thr = so.default_thresholds(metric)
+        ref = st.ConfidenceMatrix(st.SimilarityCalculator(x, labels, metric=metric), thr)
+        lit = so.ConfidenceMatrix(so.SimilarityCalculator(x, labels, metric), thr)
+        for name in ('tp', 'tn', 'fp', 'fn'):
+            np.testing.assert_array_equal(getattr(lit, name), getattr(ref, name))
+        np.testing.assert_array_equal(st.pairwise_similarities(x.copy(), metric=metric),
+                                      so.pairwise_similarities(x.copy(), metric=metric))
+
+
+def test_mining_oracle_small():
+    x, labels = so.synthetic_embeddings([4, 4, 4], dim=32, sigma=1.0, seed=1, shuffle=False)
+    out = mo.mine(x, labels, alpha=0.2)
+    d = mo.distance_matrix(x)
+    for a in range(12):
+        p = out['hardest_pos'][a]
+        n = out['hardest_neg'][a]
+        assert labels[p] == labels[a] and p != a and labels[n] != labels[a]
+        assert d[a, p] == max(d[a, q] for q in range(12) if labels[q] == labels[a] and q != a)
+        assert d[a, n] == min(d[a, q] for q in range(12) if labels[q] != labels[a])
+        for j in range(3):
+            p = out['pos_index'][a, j]
+            s = out['semi_hard'][a, j]
+            if s >= 0:
+                assert labels[s] != labels[a] and d[a, s] > d[a, p] and np.float32(d[a, s] - d[a, p]) < np.float32(0.2)
+    assert out['pos_index'].shape == (12, 3)
