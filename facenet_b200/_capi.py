@@ -1,0 +1,374 @@
+"""ctypes binding of the C ABI in include/facenet_b200.h.
+
+Arrays cross the boundary as DLPack tensors: any object with ``__dlpack__`` (NumPy,
+PyTorch, TensorFlow) is exported to a capsule and the ``DLTensor`` inside is BORROWED for
+the duration of the call (the capsule keeps ownership, nothing is copied on this side).
+NumPy arrays arrive as kDLCPU and are staged to the GPU by the library; GPU tensors
+(kDLCUDA) are used in place.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present
+the import / handle creation raises.
+"""
+import ctypes
+import threading
+from pathlib import Path
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / '_lib' / 'libfacenet_b200.so'
+
+FNB_OK, FNB_ERR_INVALID, FNB_ERR_NOT_NORMALIZED, FNB_ERR_BAD_METRIC, FNB_ERR_CUDA, FNB_ERR_UNSUPPORTED = range(6)
+MODES = {'fp16x3': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3, 'fp16': 4}
+MAX_THRESHOLDS = 127
+
+EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info',
+           'fnb_pairwise', 'fnb_pair_histogram_bins', 'fnb_counts_from_bins', 'fnb_pair_histogram',
+           'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine')
+
+
+class DLDevice(ctypes.Structure):
+    _fields_ = [('device_type', ctypes.c_int32), ('device_id', ctypes.c_int32)]
+
+
+class DLDataType(ctypes.Structure):
+    _fields_ = [('code', ctypes.c_uint8), ('bits', ctypes.c_uint8), ('lanes', ctypes.c_uint16)]
+
+
+class DLTensor(ctypes.Structure):
+    _fields_ = [('data', ctypes.c_void_p), ('device', DLDevice), ('ndim', ctypes.c_int32), ('dtype', DLDataType),
+                ('shape', ctypes.POINTER(ctypes.c_int64)), ('strides', ctypes.POINTER(ctypes.c_int64)),
+                ('byte_offset', ctypes.c_uint64)]
+
+
+class Options(ctypes.Structure):
+    _fields_ = [('mode', ctypes.c_int32), ('metric', ctypes.c_int32), ('atol', ctypes.c_float), ('eps', ctypes.c_float),
+                ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('cta_group', ctypes.c_int32),
+                ('region_rows', ctypes.c_int32), ('cuts', ctypes.POINTER(ctypes.c_float)),
+                ('max_ctas', ctypes.c_int32), ('reserved', ctypes.c_int32 * 7)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [('n_pairs', ctypes.c_uint64), ('eps_window', ctypes.c_uint64), ('smin', ctypes.c_float),
+                ('smax', ctypes.c_float), ('max_abs', ctypes.c_float), ('kernel_ms', ctypes.c_float),
+                ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
+                ('reserved', ctypes.c_uint32 * 4)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
+
+
+class Region(ctypes.Structure):
+    _fields_ = [('row_begin', ctypes.c_int32), ('row_end', ctypes.c_int32), ('col_begin', ctypes.c_int32),
+                ('col_end', ctypes.c_int32), ('tri', ctypes.c_int32), ('key', ctypes.c_int32)]
+
+
+REGION_DTYPE = np.dtype([('row_begin', '<i4'), ('row_end', '<i4'), ('col_begin', '<i4'), ('col_end', '<i4'),
+                         ('tri', '<i4'), ('key', '<i4')])
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load libfacenet_b200.so (built by ``python -m facenet_b200.build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not _LIB_PATH.exists():
+            raise ImportError('%s is missing: run `python -m facenet_b200.build` (needs nvcc). '
+                              'facenet_b200 has no CPU fallback.' % _LIB_PATH)
+        lib = ctypes.CDLL(str(_LIB_PATH))
+        c = ctypes
+        P = c.POINTER
+        lib.fnb_version.restype = c.c_int
+        lib.fnb_default_options.argtypes = [P(Options)]
+        lib.fnb_default_options.restype = None
+        lib.fnb_create.argtypes = [c.c_int, P(c.c_void_p)]
+        lib.fnb_destroy.argtypes = [c.c_void_p]
+        lib.fnb_destroy.restype = None
+        lib.fnb_last_error.argtypes = [c.c_void_p]
+        lib.fnb_last_error.restype = c.c_char_p
+        lib.fnb_device_info.argtypes = [c.c_void_p, P(c.c_int), P(c.c_int), P(c.c_int), P(c.c_uint64)]
+        lib.fnb_pairwise.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(Options), P(DLTensor), P(c.c_float)]
+        lib.fnb_pair_histogram_bins.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(c.c_double), c.c_int, P(Options),
+                                                P(DLTensor), P(Stats)]
+        lib.fnb_counts_from_bins.argtypes = [P(c.c_double), c.c_int, P(Options), P(c.c_uint64), P(c.c_uint64),
+                                             P(c.c_uint64), P(c.c_uint64), P(c.c_uint64)]
+        lib.fnb_pair_histogram.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(c.c_double), c.c_int, P(Options),
+                                           P(c.c_uint64), P(c.c_uint64), P(c.c_uint64), P(c.c_uint64), P(Stats)]
+        lib.fnb_region_histogram_bins.argtypes = [c.c_void_p, P(DLTensor), P(c.c_int64), P(c.c_int32), P(Region), c.c_int,
+                                                  c.c_int, P(c.c_double), c.c_int, P(Options), P(c.c_uint64), P(Stats)]
+        lib.fnb_confidence_from_last_bins.argtypes = [c.c_void_p, c.c_int, P(c.c_double), P(c.c_double), P(c.c_double),
+                                                      c.c_int, P(Options), c.c_double, P(c.c_double), P(c.c_double),
+                                                      P(c.c_double), P(c.c_double), P(c.c_int32), P(c.c_double)]
+        lib.fnb_mine.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), c.c_float, P(Options), P(c.c_int32), P(c.c_int32),
+                                 c.c_int, P(c.c_int32), P(c.c_int32), P(c.c_int32), P(Stats)]
+        for name in EXPORTS:
+            fn = getattr(lib, name)
+            if fn.restype is c.c_int and name not in ('fnb_version',):
+                fn.restype = c.c_int
+        _lib = lib
+        return lib
+
+
+# ----------------------------------------------------------------------------------------
+# DLPack ingestion
+
+_pyapi = ctypes.pythonapi
+_pyapi.PyCapsule_GetPointer.restype = ctypes.c_void_p
+_pyapi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+_pyapi.PyCapsule_IsValid.restype = ctypes.c_int
+_pyapi.PyCapsule_IsValid.argtypes = [ctypes.py_object, ctypes.c_char_p]
+
+_NP_CODES = {'i': 0, 'u': 1, 'f': 2}
+
+
+class Borrowed:
+    """A DLTensor borrowed from ``obj``; keeps whatever owns the memory alive."""
+
+    def __init__(self, obj):
+        self.keep = [obj]
+        self.ptr = None
+        capsule = None
+        if hasattr(obj, '__dlpack__') and not (isinstance(obj, np.ndarray) and not obj.flags.writeable):
+            try:
+                capsule = obj.__dlpack__()
+            except Exception:
+                if not isinstance(obj, np.ndarray):
+                    raise
+        if capsule is not None:
+            if not _pyapi.PyCapsule_IsValid(capsule, b'dltensor'):
+                raise ValueError('object did not produce a "dltensor" capsule')
+            addr = _pyapi.PyCapsule_GetPointer(capsule, b'dltensor')      # DLManagedTensor*, dl_tensor at offset 0
+            self.keep.append(capsule)          # capsule stays un-consumed: its destructor calls the deleter
+            self.ptr = ctypes.cast(addr, ctypes.POINTER(DLTensor))
+        else:
+            arr = np.asarray(obj)
+            if not arr.flags.c_contiguous:
+                raise ValueError('array must be C-contiguous')
+            shape = (ctypes.c_int64 * max(arr.ndim, 1))(*arr.shape)
+            t = DLTensor()
+            t.data = arr.ctypes.data
+            t.device = DLDevice(1, 0)
+            t.ndim = arr.ndim
+            t.dtype = DLDataType(_NP_CODES[arr.dtype.kind], arr.dtype.itemsize * 8, 1)
+            t.shape = shape
+            t.strides = None
+            t.byte_offset = 0
+            self.keep += [arr, shape, t]
+            self.ptr = ctypes.pointer(t)
+
+
+def _as_f32_matrix(x, name):
+    """float32 C-contiguous [N, D]; NumPy inputs are converted if needed, GPU tensors must already comply."""
+    if isinstance(x, np.ndarray) or not hasattr(x, '__dlpack__'):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2:
+            raise ValueError('%s must be 2-D' % name)
+    return x
+
+
+def _as_labels(x):
+    if isinstance(x, np.ndarray) or not hasattr(x, '__dlpack__'):
+        x = np.asarray(x)
+        if x.dtype.kind not in 'iu' or x.dtype.itemsize not in (4, 8) or x.dtype.kind == 'u':
+            x = x.astype(np.int64)
+        x = np.ascontiguousarray(x)
+    return x
+
+
+class FnbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+def numpy_cuts(thresholds, metric):
+    """Per threshold, the smallest float32 similarity s in [-1, 1] with
+    ``dist(s) < threshold`` (float64 compare of the float32 distance, statistics.py:131), +inf if
+    none -- evaluated with NumPy's own float32 arithmetic (``2 * (1 - s)`` / ``np.arccos``), so the
+    kernel's similarity-domain bins reproduce NumPy's distance-domain comparison exactly."""
+    thr = np.atleast_1d(np.asarray(thresholds, dtype=np.float64))
+
+    def dist(s):
+        s = np.clip(s, np.float32(-1), np.float32(1))
+        return (2 * (1 - s)) if metric == 0 else np.arccos(s)
+
+    def to_ord(f):
+        u = np.asarray(f, dtype=np.float32).view(np.uint32).astype(np.int64)
+        return np.where(u & 0x80000000, 0xFFFFFFFF - u, u | 0x80000000)
+
+    def from_ord(o):
+        o = np.asarray(o, dtype=np.int64)
+        u = np.where(o & 0x80000000, o & 0x7FFFFFFF, 0xFFFFFFFF - o)
+        return u.astype(np.uint32).view(np.float32)
+
+    def pred(s):
+        return dist(s.astype(np.float32)).astype(np.float64) < thr
+
+    n = thr.size
+    lo = np.full(n, to_ord(np.float32(-1)), dtype=np.int64)
+    hi = np.full(n, to_ord(np.float32(1)), dtype=np.int64)
+    none = ~pred(np.full(n, 1, dtype=np.float32))
+    allp = pred(np.full(n, -1, dtype=np.float32))
+    while np.any(hi - lo > 1):
+        mid = lo + (hi - lo) // 2
+        ok = pred(from_ord(mid))
+        hi = np.where(ok, mid, hi)
+        lo = np.where(ok, lo, mid)
+    cuts = from_ord(hi).astype(np.float32)
+    cuts[allp] = -1
+    cuts[none] = np.inf
+    return cuts
+
+
+class Handle:
+    """One library context (one GPU, one stream).  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.fnb_create(int(device), ctypes.byref(h))
+        if rc != FNB_OK:
+            raise FnbError(rc, 'fnb_create(%d) failed: %s' % (device, self.lib.fnb_last_error(None).decode()))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.fnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _raise(self, rc):
+        raise FnbError(rc, self.lib.fnb_last_error(self.h).decode())
+
+    def device_info(self):
+        sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_uint64()
+        self.lib.fnb_device_info(self.h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(mem))
+        return {'sm_count': sm.value, 'cc': (ma.value, mi.value), 'total_mem': mem.value}
+
+    def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
+                cuts=None, max_ctas=0):
+        o = Options()
+        self.lib.fnb_default_options(ctypes.byref(o))
+        o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        o.metric = int(metric)
+        o.atol = float(atol)
+        o.eps = float(eps)
+        o.rank, o.world = int(rank), int(world)
+        o.cta_group = int(cta_group)
+        o.region_rows = int(region_rows)
+        o.max_ctas = int(max_ctas)
+        keep = None
+        if cuts is not None:
+            keep = np.ascontiguousarray(cuts, dtype=np.float32)
+            o.cuts = keep.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        return o, keep
+
+    # ---- pairwise_similarities (statistics.py:22-57)
+    def pairwise(self, xa, xb=None, metric=0, atol=1.e-5, mode='fp16x3', cta_group=0, out=None):
+        xa = _as_f32_matrix(xa, 'xa')
+        na = xa.shape[0]
+        if xb is not None:
+            xb = _as_f32_matrix(xb, 'xb')
+            shape = (na, xb.shape[0])
+        else:
+            shape = (na * (na - 1) // 2,)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        o, keep = self.options(mode=mode, metric=metric, atol=atol, cta_group=cta_group)
+        rng = (ctypes.c_float * 2)()
+        ba, bo = Borrowed(xa), Borrowed(out)
+        bb = Borrowed(xb) if xb is not None else None
+        rc = self.lib.fnb_pairwise(self.h, ba.ptr, bb.ptr if bb else None, ctypes.byref(o), bo.ptr, rng)
+        self.last_range = (rng[0], rng[1])
+        if rc != FNB_OK:
+            self._raise(rc)
+        return out
+
+    # ---- whole-set verification histogram
+    def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
+                            rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy'):
+        embeddings = _as_f32_matrix(embeddings, 'embeddings')
+        labels = _as_labels(labels)
+        thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
+        if cuts == 'numpy':
+            cuts = numpy_cuts(thr, metric)
+        o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
+                               region_rows=region_rows, cuts=cuts, max_ctas=max_ctas)
+        if bins_out is None:
+            bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
+        st = Stats()
+        be, bl, bb = Borrowed(embeddings), Borrowed(labels), Borrowed(bins_out)
+        rc = self.lib.fnb_pair_histogram_bins(self.h, be.ptr, bl.ptr, thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                              thr.size, ctypes.byref(o), bb.ptr, ctypes.byref(st))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return bins_out, st.as_dict()
+
+    def counts_from_bins(self, bins, thresholds, metric=0, eps=1.e-5, cuts='numpy'):
+        thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
+        if cuts == 'numpy':
+            cuts = numpy_cuts(thr, metric)
+        o, keep = self.options(metric=metric, eps=eps, cuts=cuts)
+        bins = np.ascontiguousarray(bins, dtype=np.uint64)
+        same = np.zeros(thr.size, dtype=np.uint64)
+        diff = np.zeros(thr.size, dtype=np.uint64)
+        ns, nd = ctypes.c_uint64(), ctypes.c_uint64()
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        rc = self.lib.fnb_counts_from_bins(thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), thr.size, ctypes.byref(o),
+                                           bins.ctypes.data_as(u64p), same.ctypes.data_as(u64p), diff.ctypes.data_as(u64p),
+                                           ctypes.byref(ns), ctypes.byref(nd))
+        if rc != FNB_OK:
+            raise FnbError(rc, 'fnb_counts_from_bins failed (%d)' % rc)
+        return {'same': same.astype(np.int64), 'diff': diff.astype(np.int64), 'n_same': ns.value, 'n_diff': nd.value}
+
+    def pair_histogram(self, embeddings, labels, thresholds, metric=0, **kw):
+        eps = kw.get('eps', 1.e-5)
+        bins, st = self.pair_histogram_bins(embeddings, labels, thresholds, metric=metric, **kw)
+        out = self.counts_from_bins(bins, thresholds, metric=metric, eps=eps)
+        out['stats'] = st
+        out['bins'] = bins
+        return out
+
+    # ---- keyed histogram over rectangles
+    def region_histogram_bins(self, embeddings, perm, cls, regions, nkeys, thresholds, metric=0, atol=1.e-5, eps=1.e-5,
+                              mode='fp16x3', cta_group=0, cuts='numpy', rank=0, world=1):
+        embeddings = _as_f32_matrix(embeddings, 'embeddings')
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        cls = np.ascontiguousarray(cls, dtype=np.int32)
+        regions = np.ascontiguousarray(regions, dtype=REGION_DTYPE)
+        thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
+        if cuts == 'numpy':
+            cuts = numpy_cuts(thr, metric)
+        o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, cta_group=cta_group, cuts=cuts, rank=rank, world=world)
+        bins = np.zeros((int(nkeys), 2, thr.size + 1), dtype=np.uint64)
+        st = Stats()
+        be = Borrowed(embeddings)
+        rc = self.lib.fnb_region_histogram_bins(
+            self.h, be.ptr, perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), cls.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            regions.ctypes.data_as(ctypes.POINTER(Region)), regions.size, int(nkeys),
+            thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), thr.size, ctypes.byref(o),
+            bins.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), ctypes.byref(st))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return bins, st.as_dict()
+
+
+_default_handles = {}
+
+
+def default_handle(device=0):
+    """Process-wide handle per device (created on first use)."""
+    h = _default_handles.get(device)
+    if h is None or h.h is None:
+        h = Handle(device)
+        _default_handles[device] = h
+    return h

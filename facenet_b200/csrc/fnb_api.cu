@@ -1,0 +1,711 @@
+// facenet_b200 -- C-ABI entry points (include/facenet_b200.h): argument checking, DLPack
+// ingestion, workspace management, similarity-cut tables, region schedules and kernel launches.
+#include "fnb_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+using namespace fnb;
+
+static thread_local std::string g_create_error;
+
+int fnb_context::fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return h->fail(FNB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+// ---------------------------------------------------------------------------------------
+// modes
+
+namespace fnb {
+
+int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, float* prescale) {
+    switch (mode) {
+        case FNB_MODE_FP16X3: *num_pass = 3; *tf32 = false; *fmt = kFmtF16;  *elem_bytes = 2; *prescale = 256.f; return 0;
+        case FNB_MODE_TF32X3: *num_pass = 3; *tf32 = true;  *fmt = kFmtTF32; *elem_bytes = 4; *prescale = 1.f;   return 0;
+        case FNB_MODE_TF32:   *num_pass = 1; *tf32 = true;  *fmt = kFmtTF32; *elem_bytes = 4; *prescale = 1.f;   return 0;
+        case FNB_MODE_BF16:   *num_pass = 1; *tf32 = false; *fmt = kFmtBF16; *elem_bytes = 2; *prescale = 1.f;   return 0;
+        case FNB_MODE_FP16:   *num_pass = 1; *tf32 = false; *fmt = kFmtF16;  *elem_bytes = 2; *prescale = 1.f;   return 0;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------
+// similarity cuts.  dist32() restates statistics.py:45-53 on one fp32 value.
+
+static inline float dist32(float s, int metric) {
+    if (s < -1.f) s = -1.f;
+    if (s > 1.f) s = 1.f;
+    if (metric == 0) { volatile float one_minus = 1.0f - s; return 2.0f * one_minus; }
+    return acosf(s);
+}
+
+// smallest fp32 similarity in [-1, 1] whose distance is < t (float64 compare, statistics.py:131); +inf if none
+static float cut_for_threshold(double t, int metric) {
+    auto pred = [&](float s) { return (double)dist32(s, metric) < t; };
+    if (!pred(1.0f)) return std::numeric_limits<float>::infinity();
+    if (pred(-1.0f)) return -1.0f;
+    uint32_t lo = float_to_ordered(-1.0f), hi = float_to_ordered(1.0f);   // pred(lo) false, pred(hi) true
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (pred(ordered_to_float(mid))) hi = mid; else lo = mid;
+    }
+    return ordered_to_float(hi);
+}
+
+int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out) {
+    if (T < 1 || T >= kMaxBins) return -1;
+    CutTables& c = *out;
+    c.T = T;
+    std::vector<float> cut(T);
+    for (int n = 0; n < T; ++n) cut[n] = cuts_override ? cuts_override[n] : cut_for_threshold(thresholds[n], metric);
+    for (int n = 0; n < T; ++n) c.order[n] = n;
+    std::stable_sort(c.order, c.order + T, [&](int a, int b) { return cut[a] < cut[b]; });
+    const float inf = std::numeric_limits<float>::infinity();
+    for (int j = 0; j < kMaxBins; ++j) c.cuts[j] = inf;
+    for (int j = 0; j < kMaxBins + 4; ++j) { c.wlo[j] = inf; c.whi[j] = -inf; }
+    c.T_fin = 0;
+    for (int j = 0; j < T; ++j) {
+        const int n = c.order[j];
+        c.cuts[j] = cut[n];
+        if (std::isfinite(cut[n])) c.T_fin = j + 1;
+        const double t = thresholds[n];
+        double lo_s, hi_s;
+        if (metric == 0) { lo_s = 1.0 - (t + eps) / 2.0; hi_s = 1.0 - (t - eps) / 2.0; }
+        else { lo_s = std::cos(std::min(t + eps, M_PI)); hi_s = std::cos(std::max(t - eps, 0.0)); if (t - eps > M_PI) hi_s = -2.0; if (t + eps < 0) lo_s = 2.0; }
+        c.wlo[j] = (float)lo_s;
+        c.whi[j + 1] = (float)hi_s;
+    }
+    for (int n = 0; n < T; ++n)
+        c.pos[n] = (int)(std::upper_bound(c.cuts, c.cuts + T, cut[n]) - c.cuts);
+    // arithmetic-progression fit of the finite cuts (true for np.linspace thresholds with metric 0)
+    c.uniform = 0;
+    if (c.T_fin >= 2) {
+        c.e0 = c.cuts[0];
+        c.h = ((double)c.cuts[c.T_fin - 1] - (double)c.cuts[0]) / (c.T_fin - 1);
+        double dev = 0;
+        for (int j = 0; j < c.T_fin; ++j) dev = std::max(dev, std::fabs((double)c.cuts[j] - (c.e0 + j * c.h)));
+        c.dev = dev;
+        if (c.h > 1e-4 && dev / c.h < 2e-4) c.uniform = 1;
+    }
+    return 0;
+}
+
+}  // namespace fnb
+
+// ---------------------------------------------------------------------------------------
+// tensors
+
+struct TensorView {
+    void* data = nullptr;
+    bool on_device = false;
+    long long rows = 0, cols = 1;
+    int bits = 0, code = 0;
+};
+
+static int view_tensor(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_min, int want_ndim_max, TensorView* v) {
+    if (!t) return h->fail(FNB_ERR_INVALID, "%s: NULL tensor", name);
+    if (t->ndim < want_ndim_min || t->ndim > want_ndim_max) return h->fail(FNB_ERR_INVALID, "%s: ndim %d not supported", name, t->ndim);
+    if (t->dtype.lanes != 1) return h->fail(FNB_ERR_INVALID, "%s: vector dtypes not supported", name);
+    long long expect = 1;
+    for (int i = t->ndim - 1; i >= 0; --i) {
+        if (t->strides && t->shape[i] > 1 && t->strides[i] != expect) return h->fail(FNB_ERR_INVALID, "%s: must be C-contiguous", name);
+        expect *= t->shape[i];
+    }
+    v->rows = t->ndim >= 1 ? t->shape[0] : 1;
+    v->cols = t->ndim >= 2 ? t->shape[1] : 1;
+    v->bits = t->dtype.bits;
+    v->code = t->dtype.code;
+    v->data = (char*)t->data + t->byte_offset;
+    if (t->device.device_type == kDLCUDA) {
+        if (t->device.device_id != h->device) return h->fail(FNB_ERR_INVALID, "%s: tensor on cuda:%d, handle on cuda:%d", name, t->device.device_id, h->device);
+        v->on_device = true;
+    } else if (t->device.device_type == kDLCPU || t->device.device_type == kDLCUDAHost) {
+        v->on_device = false;
+    } else {
+        return h->fail(FNB_ERR_INVALID, "%s: unsupported DLPack device type %d", name, t->device.device_type);
+    }
+    return FNB_OK;
+}
+
+// device pointer to the tensor's bytes (staged through `stage` when the tensor lives on the host)
+static int to_device(fnb_context* h, const TensorView& v, size_t bytes, DevBuf& stage, const void** out) {
+    if (v.on_device || bytes == 0) { *out = v.data; return FNB_OK; }
+    CK(stage.ensure(bytes));
+    CK(cudaMemcpyAsync(stage.p, v.data, bytes, cudaMemcpyHostToDevice, h->stream));
+    *out = stage.p;
+    return FNB_OK;
+}
+
+static int make_tmap(fnb_context* h, CUtensorMap* m, void* base, int fmt, long long rows, int d) {
+    CUtensorMapDataType dt = fmt == kFmtTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const int eb = fmt == kFmtTF32 ? 4 : 2;
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)d * eb};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)kRowsPerCta};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(m, dt, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return h->fail(FNB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld d=%d", (int)r, rows, d);
+    return FNB_OK;
+}
+
+static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
+
+// ---------------------------------------------------------------------------------------
+// regions
+
+static void finish_regions(std::vector<RegionDev>& regs, int tile) {
+    long long t = 0;
+    for (auto& r : regs) {
+        r.nrb = (r.row_end - r.row_begin + tile - 1) / tile;
+        r.ncb = (r.col_end - r.col_begin + tile - 1) / tile;
+        r.tile_begin = t;
+        t += (long long)r.nrb * r.ncb;
+    }
+    RegionDev sentinel = {};
+    sentinel.tile_begin = t;
+    regs.push_back(sentinel);
+}
+
+// strict upper triangle of an n x n pair matrix as super-rows of `rr` rows: one diagonal square
+// (tri) plus one rectangle to its right per super-row -> L2-friendly tile order
+static void triangle_regions(long long n, int rr, int key, std::vector<RegionDev>& regs) {
+    for (long long r0 = 0; r0 < n; r0 += rr) {
+        const long long r1 = std::min<long long>(n, r0 + rr);
+        RegionDev d = {};
+        d.row_begin = (int)r0; d.row_end = (int)r1; d.col_begin = (int)r0; d.col_end = (int)r1; d.tri = 1; d.key = key;
+        regs.push_back(d);
+        if (r1 < n) {
+            RegionDev f = {};
+            f.row_begin = (int)r0; f.row_end = (int)r1; f.col_begin = (int)r1; f.col_end = (int)n; f.tri = 0; f.key = key;
+            regs.push_back(f);
+        }
+    }
+}
+
+static int pick_cta_group(const fnb_options* o) { return (o->cta_group == 1 || o->cta_group == 2) ? o->cta_group : 2; }
+
+static int pick_region_rows(const fnb_options* o, int tile) {
+    int rr = o->region_rows > 0 ? o->region_rows : 2048;
+    rr = std::max(tile, (rr / tile) * tile);
+    return rr;
+}
+
+// ---------------------------------------------------------------------------------------
+// lifecycle
+
+extern "C" int fnb_version(void) { return 100; }
+
+extern "C" void fnb_default_options(fnb_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->mode = FNB_MODE_FP16X3;
+    o->metric = 0;
+    o->atol = 1.e-5f;
+    o->eps = 1.e-5f;
+    o->rank = 0;
+    o->world = 1;
+}
+
+extern "C" int fnb_create(int device, fnb_handle* out) {
+    if (!out) { g_create_error = "fnb_create: NULL out"; return FNB_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (facenet_b200 has no CPU fallback)";
+        return FNB_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "fnb_create: bad device index"; return FNB_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice/GetDeviceProperties: ") + cudaGetErrorString(e);
+        return FNB_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "device %d is sm_%d%d; facenet_b200 kernels are built for sm_100a only", device, prop.major, prop.minor);
+        g_create_error = buf;
+        return FNB_ERR_UNSUPPORTED;
+    }
+    fnb_context* h = new fnb_context();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->cc_major = prop.major; h->cc_minor = prop.minor;
+    h->total_mem = prop.totalGlobalMem;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) { g_create_error = "cuTensorMapEncodeTiled entry point not found"; delete h; return FNB_ERR_CUDA; }
+    h->encode = (PFN_tmapEncodeTiled)fn;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return FNB_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+    *out = h;
+    return FNB_OK;
+}
+
+extern "C" void fnb_destroy(fnb_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->perm, &h->cls,
+                      &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
+                      &h->counters, &h->out, &h->strip, &h->mine_out};
+    for (DevBuf* b : bufs) b->release();
+    h->pinned.release();
+    for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* fnb_last_error(fnb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem) {
+    if (!h) return FNB_ERR_INVALID;
+    if (sm_count) *sm_count = h->sm_count;
+    if (cc_major) *cc_major = h->cc_major;
+    if (cc_minor) *cc_minor = h->cc_minor;
+    if (total_mem) *total_mem = h->total_mem;
+    return FNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// shared launch plumbing
+
+struct Operands {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int num_pass = 3; bool tf32 = false; int fmt = 0; int elem_bytes = 2; float prescale = 1.f;
+};
+
+// split/convert `x` ([n, d] fp32 on the device, optionally gathered through perm) into hi/lo arrays + TMA maps
+static int prepare_side(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
+                        DevBuf& hi, DevBuf& lo, Operands& op, CUtensorMap* m_hi, CUtensorMap* m_lo) {
+    const long long n_pad = pad_rows(n);
+    const size_t bytes = (size_t)n_pad * d * op.elem_bytes;
+    CK(hi.ensure(bytes));
+    if (op.num_pass == 3) CK(lo.ensure(bytes));
+    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass == 3 ? lo.p : nullptr, h->stream));
+    int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d);
+    if (rc) return rc;
+    if (op.num_pass == 3) rc = make_tmap(h, m_lo, lo.p, op.fmt, n_pad, d);
+    else *m_lo = *m_hi;
+    return rc;
+}
+
+static int check_embeddings(fnb_context* h, const TensorView& v, const char* name) {
+    if (v.code != kDLFloat || v.bits != 32) return h->fail(FNB_ERR_INVALID, "%s: embeddings must be float32", name);
+    if (v.cols < 64 || v.cols > 4096 || (v.cols % 64) != 0)
+        return h->fail(FNB_ERR_INVALID, "%s: embedding dimension %lld not supported (multiple of 64 in [64, 4096])", name, v.cols);
+    if (v.rows > (1LL << 30)) return h->fail(FNB_ERR_INVALID, "%s: too many rows", name);
+    return FNB_OK;
+}
+
+struct DeviceScalars {      // layout of h->counters
+    unsigned long long counters[2];
+    unsigned int range_ord[4];
+};
+
+static int reset_scalars(fnb_context* h) {
+    CK(h->counters.ensure(sizeof(DeviceScalars)));
+    DeviceScalars init;
+    init.counters[0] = init.counters[1] = 0;
+    init.range_ord[0] = 0xFFFFFFFFu;                    // min
+    init.range_ord[1] = 0;                              // max
+    init.range_ord[2] = float_to_ordered(0.f);          // max |s|
+    init.range_ord[3] = 0;
+    CK(h->pinned.ensure(4096));
+    memcpy(h->pinned.p, &init, sizeof(init));
+    CK(cudaMemcpyAsync(h->counters.p, h->pinned.p, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    return FNB_OK;
+}
+
+static int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs) {
+    CK(h->regions.ensure(regs.size() * sizeof(RegionDev)));
+    CK(cudaMemcpyAsync(h->regions.p, regs.data(), regs.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, h->stream));
+    return FNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// fnb_pairwise
+
+extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb, const fnb_options* opt_in,
+                            DLTensor* out, float* range)
+{
+    if (!h) return FNB_ERR_INVALID;
+    fnb_options opt; if (opt_in) opt = *opt_in; else fnb_default_options(&opt);
+    if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
+    CK(cudaSetDevice(h->device));
+    Operands op;
+    if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
+    TensorView va, vb, vo;
+    int rc = view_tensor(h, xa, "xa", 2, 2, &va); if (rc) return rc;
+    if ((rc = check_embeddings(h, va, "xa"))) return rc;
+    const bool self = (xb == nullptr);
+    if (!self) {
+        if ((rc = view_tensor(h, xb, "xb", 2, 2, &vb))) return rc;
+        if ((rc = check_embeddings(h, vb, "xb"))) return rc;
+        if (vb.cols != va.cols) return h->fail(FNB_ERR_INVALID, "xa and xb have different dimensions");
+    }
+    if ((rc = view_tensor(h, out, "out", 1, 2, &vo))) return rc;
+    if (vo.code != kDLFloat || vo.bits != 32) return h->fail(FNB_ERR_INVALID, "out must be float32");
+    const long long na = va.rows, nb = self ? va.rows : vb.rows;
+    const int d = (int)va.cols;
+    const long long out_elems = self ? na * (na - 1) / 2 : na * nb;
+    const long long have = vo.rows * vo.cols;
+    if (have != out_elems) return h->fail(FNB_ERR_INVALID, "out has %lld elements, expected %lld", have, out_elems);
+    if (range) { range[0] = INFINITY; range[1] = -INFINITY; }
+    if (out_elems == 0) return FNB_OK;                   // statistics.py:38: empty in -> empty out
+
+    const void* da = nullptr; const void* db = nullptr;
+    if ((rc = to_device(h, va, (size_t)na * d * 4, h->stage_a, &da))) return rc;
+    if (!self && (rc = to_device(h, vb, (size_t)nb * d * 4, h->stage_b, &db))) return rc;
+    if ((rc = prepare_side(h, opt.mode, (const float*)da, nullptr, na, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
+    if (self) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; }
+    else if ((rc = prepare_side(h, opt.mode, (const float*)db, nullptr, nb, d, h->b_hi, h->b_lo, op, &op.b_hi, &op.b_lo))) return rc;
+
+    const int cg = pick_cta_group(&opt);
+    const int tile = kRowsPerCta * cg;
+    std::vector<RegionDev> regs;
+    if (self) triangle_regions(na, pick_region_rows(&opt, tile), 0, regs);
+    else {
+        RegionDev r = {}; r.row_end = (int)na; r.col_end = (int)nb; regs.push_back(r);
+    }
+    finish_regions(regs, tile);
+    if ((rc = upload_regions(h, regs))) return rc;
+    if ((rc = reset_scalars(h))) return rc;
+
+    float* dout = nullptr;
+    if (vo.on_device) dout = (float*)vo.data;
+    else { CK(h->out.ensure((size_t)out_elems * 4)); dout = h->out.as<float>(); }
+
+    GramParams p = {};
+    p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
+    p.rank = 0; p.world = 1;
+    p.kblocks = d / (128 / op.elem_bytes);
+    p.acc_scale = 1.0f / (op.prescale * op.prescale);
+    p.operand_fmt = op.fmt;
+    DeviceScalars* sc = h->counters.as<DeviceScalars>();
+    p.counters = sc->counters; p.range_ord = sc->range_ord;
+    p.out = dout; p.out_ld = nb; p.tri_packed = self ? 1 : 0; p.metric = opt.metric;
+    p.n_rows = (int)na; p.n_cols = (int)nb;
+    if ((rc = launch_gram(h, cg, op.num_pass, op.tf32, EPI_PAIRWISE, opt.max_ctas, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p, 0))) return rc;
+
+    DeviceScalars hs;
+    CK(cudaMemcpyAsync(h->pinned.p, h->counters.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+    if (!vo.on_device) CK(cudaMemcpyAsync(vo.data, dout, (size_t)out_elems * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(&hs, h->pinned.p, sizeof(hs));
+    const float smin = ordered_to_float(hs.range_ord[0]), smax = ordered_to_float(hs.range_ord[1]);
+    if (range) { range[0] = smin; range[1] = smax; }
+    const double lim = 1.0 + (double)opt.atol;
+    if ((double)smin < -lim || (double)smax > lim || smin != smin || smax != smax)
+        return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
+    return FNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// histograms
+
+struct HistLaunch {
+    CutTables ct;
+    int nkeys = 1;
+    int stride = kMaxBins + 1;
+};
+
+// uploads tables, zeroes bins, launches the HIST kernel over `regs`; leaves bins on the device
+static int run_hist(fnb_context* h, const fnb_options& opt, Operands& op, const std::vector<RegionDev>& regs, int cg,
+                    int d, const int32_t* cls_dev, const double* thresholds, int T, HistLaunch& hl, int force_slow)
+{
+    if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &hl.ct))
+        return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
+    int rc;
+    if ((rc = upload_regions(h, regs))) return rc;
+    if ((rc = reset_scalars(h))) return rc;
+    const size_t tab_floats = kMaxBins + 2 * (kMaxBins + 4);
+    CK(h->tables.ensure(tab_floats * 4));
+    float* htab = h->pinned.as<float>() + 256;           // past the scalars staging area
+    memcpy(htab, hl.ct.cuts, kMaxBins * 4);
+    memcpy(htab + kMaxBins, hl.ct.wlo, (kMaxBins + 4) * 4);
+    memcpy(htab + kMaxBins + kMaxBins + 4, hl.ct.whi, (kMaxBins + 4) * 4);
+    CK(cudaMemcpyAsync(h->tables.p, htab, tab_floats * 4, cudaMemcpyHostToDevice, h->stream));
+    const size_t bins_bytes = (size_t)hl.nkeys * 2 * hl.stride * 8;
+    CK(h->bins.ensure(bins_bytes));
+    CK(cudaMemsetAsync(h->bins.p, 0, bins_bytes, h->stream));
+
+    GramParams p = {};
+    p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
+    p.rank = opt.rank; p.world = opt.world;
+    p.kblocks = d / (128 / op.elem_bytes);
+    p.acc_scale = 1.0f / (op.prescale * op.prescale);
+    p.operand_fmt = op.fmt;
+    p.force_slow = force_slow;
+    p.row_cls = cls_dev; p.col_cls = cls_dev;
+    p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
+    p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
+    if (hl.ct.uniform) {
+        // u = (s - e0) / h computed from the raw accumulator; guard band covers the eps window, the fp32
+        // rounding of u (< 2e-5 for <= 127 bins) and the deviation of the true cuts from the progression
+        const double eps_s = (opt.metric == 0) ? opt.eps / 2.0 : opt.eps;
+        p.u_scale = (float)((double)p.acc_scale / hl.ct.h);
+        p.u_bias = (float)(-hl.ct.e0 / hl.ct.h);
+        p.u_guard = (float)(eps_s / hl.ct.h + 2.0 * hl.ct.dev / hl.ct.h + 1.0e-4);
+    }
+    p.bins = h->bins.as<unsigned long long>(); p.bins_stride = hl.stride;
+    DeviceScalars* sc = h->counters.as<DeviceScalars>();
+    p.counters = sc->counters; p.range_ord = sc->range_ord;
+    p.metric = opt.metric;
+    const size_t hist_bytes = (size_t)(T + 1) * kEpiThreads * 2;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if ((rc = launch_gram(h, cg, op.num_pass, op.tf32, EPI_HIST, opt.max_ctas, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p, hist_bytes))) return rc;
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    h->last_nkeys = hl.nkeys; h->last_T = T;
+    return FNB_OK;
+}
+
+static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats, float* smin_out, float* smax_out, bool* violated) {
+    DeviceScalars hs;
+    CK(cudaMemcpyAsync(h->pinned.p, h->counters.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(&hs, h->pinned.p, sizeof(hs));
+    // checked tiles track min/max exactly; fast tiles (every pair valid) only track max |s|
+    const bool have_checked = hs.range_ord[0] != 0xFFFFFFFFu;
+    const float smin = have_checked ? ordered_to_float(hs.range_ord[0]) : NAN;
+    const float smax = have_checked ? ordered_to_float(hs.range_ord[1]) : NAN;
+    const float amax = ordered_to_float(hs.range_ord[2]);
+    const double lim = 1.0 + (double)opt.atol;
+    *violated = (have_checked && !((double)smin >= -lim && (double)smax <= lim)) || !((double)amax <= lim);
+    *smin_out = smin;
+    *smax_out = smax;
+    if (stats) {
+        float ms = 0.f, pm = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&pm, h->ev[0], h->ev[1]);
+        stats->kernel_ms = ms;
+        stats->prepare_ms = pm;
+        stats->eps_window = hs.counters[0];
+        stats->tiles = hs.counters[1];
+        stats->smin = smin;
+        stats->smax = smax;
+        stats->max_abs = amax;
+        stats->kernel_launches += 1;
+    }
+    return FNB_OK;
+}
+
+static uint64_t sum_bins(const uint64_t* b, int n) { uint64_t s = 0; for (int i = 0; i < n; ++i) s += b[i]; return s; }
+
+extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const DLTensor* labels,
+                                       const double* thresholds, int T, const fnb_options* opt_in,
+                                       DLTensor* bins_out, fnb_stats* stats)
+{
+    if (!h) return FNB_ERR_INVALID;
+    fnb_options opt; if (opt_in) opt = *opt_in; else fnb_default_options(&opt);
+    if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
+    if (!thresholds || T < 1 || T >= kMaxBins) return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
+    if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) return h->fail(FNB_ERR_INVALID, "bad rank/world %d/%d", opt.rank, opt.world);
+    CK(cudaSetDevice(h->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    Operands op;
+    if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
+    TensorView ve, vl, vb;
+    int rc = view_tensor(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
+    if ((rc = check_embeddings(h, ve, "embeddings"))) return rc;
+    if ((rc = view_tensor(h, labels, "labels", 1, 1, &vl))) return rc;
+    if (vl.code != kDLInt || (vl.bits != 32 && vl.bits != 64)) return h->fail(FNB_ERR_INVALID, "labels must be int32 or int64");
+    if (vl.rows != ve.rows) return h->fail(FNB_ERR_INVALID, "len(labels) != embeddings.shape[0]");
+    if ((rc = view_tensor(h, bins_out, "bins_out", 2, 2, &vb))) return rc;
+    if (vb.bits != 64 || vb.rows != 2 || vb.cols != T + 1) return h->fail(FNB_ERR_INVALID, "bins_out must be a 64-bit integer [2, T+1] tensor");
+    const long long n = ve.rows;
+    const int d = (int)ve.cols;
+
+    const size_t row_bytes = (size_t)(T + 1) * 8;
+    auto write_bins = [&](const unsigned long long* dev_bins, int stride) -> int {
+        for (int r = 0; r < 2; ++r) {
+            CK(cudaMemcpyAsync((char*)vb.data + r * row_bytes, dev_bins + (size_t)r * stride, row_bytes,
+                               vb.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return FNB_OK;
+    };
+    if (n < 2) {
+        CK(h->bins.ensure(2 * (kMaxBins + 1) * 8));
+        CK(cudaMemsetAsync(h->bins.p, 0, 2 * (kMaxBins + 1) * 8, h->stream));
+        return write_bins(h->bins.as<unsigned long long>(), kMaxBins + 1);
+    }
+
+    const void* de = nullptr; const void* dl = nullptr;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    if ((rc = to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
+    if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
+    if ((rc = prepare_side(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
+    op.b_hi = op.a_hi; op.b_lo = op.a_lo;
+
+    const int cg = pick_cta_group(&opt);
+    const int tile = kRowsPerCta * cg;
+    std::vector<RegionDev> regs;
+    triangle_regions(n, pick_region_rows(&opt, tile), 0, regs);
+    finish_regions(regs, tile);
+
+    HistLaunch hl;
+    if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
+    float smin, smax; bool violated = false;
+    if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
+    if (violated) {
+        // re-run with every tile on the checked path to report the exact similarity range
+        if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 1))) return rc;
+        if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
+        return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
+    }
+    if ((rc = write_bins(h->bins.as<unsigned long long>(), hl.stride))) return rc;
+    if (stats) {
+        if (!vb.on_device) stats->n_pairs = sum_bins((const uint64_t*)vb.data, T + 1);
+        else {
+            uint64_t tmp[kMaxBins + 1];
+            CK(cudaMemcpy(tmp, h->bins.p, row_bytes, cudaMemcpyDeviceToHost));
+            stats->n_pairs = sum_bins(tmp, T + 1);
+        }
+    }
+    return FNB_OK;
+}
+
+extern "C" int fnb_counts_from_bins(const double* thresholds, int T, const fnb_options* opt_in, const uint64_t* bins,
+                                    uint64_t* same_lt, uint64_t* diff_lt, uint64_t* n_same, uint64_t* n_diff)
+{
+    fnb_options opt; if (opt_in) opt = *opt_in; else fnb_default_options(&opt);
+    if (!thresholds || !bins || T < 1 || T >= kMaxBins) return FNB_ERR_INVALID;
+    if (opt.metric != 0 && opt.metric != 1) return FNB_ERR_BAD_METRIC;
+    CutTables ct;
+    if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &ct)) return FNB_ERR_INVALID;
+    const uint64_t* all = bins; const uint64_t* same = bins + (T + 1);
+    // suffix sums: pairs whose similarity is >= the pos-th smallest cut
+    uint64_t suf_all[kMaxBins + 2], suf_same[kMaxBins + 2];
+    suf_all[T + 1] = suf_same[T + 1] = 0;
+    for (int k = T; k >= 0; --k) { suf_all[k] = suf_all[k + 1] + all[k]; suf_same[k] = suf_same[k + 1] + same[k]; }
+    for (int n = 0; n < T; ++n) {
+        const int pos = ct.pos[n];
+        const uint64_t a = pos <= T ? suf_all[pos] : 0, s = pos <= T ? suf_same[pos] : 0;
+        if (same_lt) same_lt[n] = s;
+        if (diff_lt) diff_lt[n] = a - s;
+    }
+    if (n_same) *n_same = suf_same[0];
+    if (n_diff) *n_diff = suf_all[0] - suf_same[0];
+    return FNB_OK;
+}
+
+extern "C" int fnb_pair_histogram(fnb_handle h, const DLTensor* emb, const DLTensor* labels, const double* thresholds, int T,
+                                  const fnb_options* opt, uint64_t* same_lt, uint64_t* diff_lt, uint64_t* n_same,
+                                  uint64_t* n_diff, fnb_stats* stats)
+{
+    if (!h) return FNB_ERR_INVALID;
+    if (T < 1 || T >= kMaxBins) return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
+    std::vector<uint64_t> bins(2 * (size_t)(T + 1));
+    int64_t shape[2] = {2, T + 1};
+    DLTensor t = {};
+    t.data = bins.data(); t.device.device_type = kDLCPU; t.ndim = 2; t.dtype.code = kDLUInt; t.dtype.bits = 64; t.dtype.lanes = 1;
+    t.shape = shape;
+    int rc = fnb_pair_histogram_bins(h, emb, labels, thresholds, T, opt, &t, stats);
+    if (rc) return rc;
+    rc = fnb_counts_from_bins(thresholds, T, opt, bins.data(), same_lt, diff_lt, n_same, n_diff);
+    if (rc) return h->fail(rc, "fnb_counts_from_bins failed");
+    return FNB_OK;
+}
+
+extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, const int64_t* perm, const int32_t* cls,
+                                         const fnb_region* regions, int nregions, int nkeys,
+                                         const double* thresholds, int T, const fnb_options* opt_in,
+                                         uint64_t* bins_host, fnb_stats* stats)
+{
+    if (!h) return FNB_ERR_INVALID;
+    fnb_options opt; if (opt_in) opt = *opt_in; else fnb_default_options(&opt);
+    if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
+    if (!thresholds || T < 1 || T >= kMaxBins) return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
+    if (!perm || !cls || !regions || nregions < 0 || nkeys < 1 || !bins_host) return h->fail(FNB_ERR_INVALID, "NULL / empty argument");
+    if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) return h->fail(FNB_ERR_INVALID, "bad rank/world");
+    CK(cudaSetDevice(h->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    Operands op;
+    if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
+    TensorView ve;
+    int rc = view_tensor(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
+    if ((rc = check_embeddings(h, ve, "embeddings"))) return rc;
+    const long long n = ve.rows;
+    const int d = (int)ve.cols;
+    const size_t out_bytes = (size_t)nkeys * 2 * (T + 1) * 8;
+    memset(bins_host, 0, out_bytes);
+    const int cg = pick_cta_group(&opt);
+    const int tile = kRowsPerCta * cg;
+    std::vector<RegionDev> regs;
+    for (int i = 0; i < nregions; ++i) {
+        const fnb_region& r = regions[i];
+        if (r.row_begin < 0 || r.row_end > n || r.col_begin < 0 || r.col_end > n || r.key < 0 || r.key >= nkeys)
+            return h->fail(FNB_ERR_INVALID, "region %d out of range", i);
+        if (r.row_end <= r.row_begin || r.col_end <= r.col_begin) continue;
+        if (r.tri && (r.row_begin != r.col_begin || r.row_end != r.col_end)) return h->fail(FNB_ERR_INVALID, "region %d: tri needs row range == col range", i);
+        RegionDev rd = {};
+        rd.row_begin = r.row_begin; rd.row_end = r.row_end; rd.col_begin = r.col_begin; rd.col_end = r.col_end;
+        rd.tri = r.tri ? 1 : 0; rd.key = r.key;
+        regs.push_back(rd);
+    }
+    finish_regions(regs, tile);
+    if (regs.back().tile_begin == 0 || n < 1) { h->last_nkeys = 0; return FNB_OK; }
+
+    const void* de = nullptr;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    CK(h->perm.ensure(n * 8));
+    CK(h->cls.ensure(n * 4));
+    CK(cudaMemcpyAsync(h->perm.p, perm, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->cls.p, cls, n * 4, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = prepare_side(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
+    op.b_hi = op.a_hi; op.b_lo = op.a_lo;
+
+    HistLaunch hl; hl.nkeys = nkeys;
+    if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
+    float smin, smax; bool violated = false;
+    if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
+    if (violated) {
+        if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 1))) return rc;
+        if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
+        return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
+    }
+    // compact [nkeys][2][stride] -> [nkeys][2][T+1]
+    CK(h->pinned.ensure((size_t)nkeys * 2 * hl.stride * 8 + 8192));
+    uint64_t* stage = (uint64_t*)((char*)h->pinned.p + 8192);
+    CK(cudaMemcpyAsync(stage, h->bins.p, (size_t)nkeys * 2 * hl.stride * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    uint64_t total = 0;
+    for (int k = 0; k < nkeys * 2; ++k) {
+        memcpy(bins_host + (size_t)k * (T + 1), stage + (size_t)k * hl.stride, (size_t)(T + 1) * 8);
+        if ((k & 1) == 0) total += sum_bins(stage + (size_t)k * hl.stride, T + 1);
+    }
+    if (stats) stats->n_pairs = total;
+    return FNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// TEMPORARY stubs (replaced by fnb_select.cu / fnb_mine.cu)
+extern "C" int fnb_confidence_from_last_bins(fnb_handle h, int, const double*, const double*, const double*, int,
+                                             const fnb_options*, double, double*, double*, double*, double*, int32_t*, double*) {
+    return h ? h->fail(FNB_ERR_UNSUPPORTED, "not implemented yet") : FNB_ERR_INVALID;
+}
+extern "C" int fnb_mine(fnb_handle h, const DLTensor*, const DLTensor*, float, const fnb_options*, int32_t*, int32_t*, int,
+                        int32_t*, int32_t*, int32_t*, fnb_stats*) {
+    return h ? h->fail(FNB_ERR_UNSUPPORTED, "not implemented yet") : FNB_ERR_INVALID;
+}

@@ -1,0 +1,266 @@
+// facenet_b200 -- sm_100a device primitives (inline PTX) shared by the kernels.
+//
+// Everything here is a thin wrapper over one PTX instruction: mbarrier, TMA
+// (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / fences), cluster
+// helpers.  No CUTLASS/CuTe: descriptors are built by hand (layouts documented at
+// make_smem_desc / make_idesc).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace fnb {
+
+// ---------------------------------------------------------------------------------------
+// misc
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
+    return out;
+}
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// mbarrier
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// arrive on the copy of `bar` that lives in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    uint32_t a = mapa_u32(smem_u32(bar), rank);
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(a) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// same, acquiring at cluster scope (barrier completed by another CTA's arrive / async proxy)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+#ifndef FNB_SPIN_LIMIT
+#define FNB_SPIN_LIMIT (1u << 24)   // try_wait suspends ~us each; a stuck pipeline traps instead of hanging
+#endif
+
+template <bool kCluster>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0;; ++spins) {
+        bool ok = kCluster ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity);
+        if (ok) return;
+        if (spins > FNB_SPIN_LIMIT) __trap();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA (bulk tensor copy global -> shared, completion on an mbarrier)
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+// 1-CTA form: data and barrier both in the executing CTA
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// CTA-pair form: data lands in the executing CTA, bytes are signalled on the barrier at
+// cluster address `bar_cluster_addr` (the leader CTA's copy)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// tcgen05: tensor memory + 5th-gen tensor core
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int kCtaGroup>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+
+template <int kCtaGroup>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+    } else {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+    }
+}
+
+// Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes
+// with the 128-byte swizzle (exactly what a TMA box {128 B, rows} with
+// CU_TENSOR_MAP_SWIZZLE_128B writes): 8-row groups are 1024 B apart (SBO), the tile base
+// is 1024-B aligned.  Bit layout (PTX "matrix descriptor", sm_100):
+//   [ 0,14) start address >> 4      [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 [46,48) version = 1            [61,64) layout: 2 = SWIZZLE_128B
+// Advancing along K inside the 128-B span = adding the byte offset (>>4) to the start address.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(1) << 16;                       // LBO = 16 B (ignored)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO = 1024 B
+    d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+// Instruction descriptor (32 bit) for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major:
+//   [4,6) D format: 1 = f32      [7,10) A format   [10,13) B format  (0 = f16, 1 = bf16, 2 = tf32)
+//   [15] A major (0 = K)         [16] B major (0 = K)
+//   [17,23) N >> 3               [24,29) M >> 4
+enum : uint32_t { kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2 };
+
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t m, uint32_t n) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
+template <int kCtaGroup, bool kTf32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kCtaGroup == 1 && !kTf32) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else if constexpr (kCtaGroup == 1 && kTf32) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else if constexpr (kCtaGroup == 2 && !kTf32) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                     :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+
+// mbarrier arrive when all previously issued MMAs of this thread have completed.
+// CTA-pair form arrives on the same barrier offset in both CTAs (mask 0b11).
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     :: "r"(smem_u32(bar)) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     :: "r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+    }
+}
+
+// TMEM -> registers: 32 lanes (this warp's quadrant) x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------
+// ordered-uint encoding of floats (for atomicMin/atomicMax on float values)
+
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+}  // namespace fnb

@@ -1,0 +1,74 @@
+// facenet_b200 -- instantiations and launcher of the Gram kernel (see fnb_gram.cuh).
+#include "fnb_host.h"
+
+namespace fnb {
+
+static constexpr size_t kSmemLimit = 232448;   // 227 KB per CTA on sm_100
+
+size_t gram_smem_bytes(int num_slots, size_t hist_bytes) {
+    return 1024 + (size_t)num_slots * kSlotBytes + sizeof(GramSmemMisc) + hist_bytes;
+}
+
+int gram_pick_slots(size_t hist_bytes) {
+    int s = kMaxSlots;
+    while (s > 2 && gram_smem_bytes(s, hist_bytes) > kSmemLimit) --s;
+    return s;
+}
+
+template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi>
+static int launch_one(fnb_context* h, int max_ctas, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                      const CUtensorMap& b_hi, const CUtensorMap& b_lo, const GramParams& p, size_t smem)
+{
+    auto kern = gram_kernel<kCtaGroup, kNumPass, kTf32, kEpi>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    int ctas = h->sm_count;
+    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+    ctas -= ctas % kCtaGroup;
+    if (ctas < kCtaGroup) ctas = kCtaGroup;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kGramThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, p);
+    if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "gram kernel launch: %s", cudaGetErrorString(e));
+    return FNB_OK;
+}
+
+template <int kCtaGroup, int kEpi>
+static int launch_mode(fnb_context* h, int num_pass, bool tf32, int max_ctas, const CUtensorMap& a_hi,
+                       const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const GramParams& p, size_t smem)
+{
+    if (num_pass == 3 && !tf32) return launch_one<kCtaGroup, 3, false, kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    if (num_pass == 3 && tf32)  return launch_one<kCtaGroup, 3, true,  kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    if (num_pass == 1 && !tf32) return launch_one<kCtaGroup, 1, false, kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    return launch_one<kCtaGroup, 1, true, kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+}
+
+int launch_gram(fnb_context* h, int cta_group, int num_pass, bool tf32, int epi, int max_ctas,
+                const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                GramParams& p, size_t hist_bytes)
+{
+    p.num_slots = gram_pick_slots(hist_bytes);
+    const size_t smem = gram_smem_bytes(p.num_slots, hist_bytes);
+    if (smem > kSmemLimit) return h->fail(FNB_ERR_UNSUPPORTED, "shared memory budget exceeded (%zu bytes)", smem);
+    if (cta_group == 2) {
+        if (epi == EPI_HIST)     return launch_mode<2, EPI_HIST>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+        if (epi == EPI_PAIRWISE) return launch_mode<2, EPI_PAIRWISE>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+        return launch_mode<2, EPI_ROWSTRIP>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    }
+    if (epi == EPI_HIST)     return launch_mode<1, EPI_HIST>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    if (epi == EPI_PAIRWISE) return launch_mode<1, EPI_PAIRWISE>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    return launch_mode<1, EPI_ROWSTRIP>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+}
+
+}  // namespace fnb

@@ -1,0 +1,503 @@
+// facenet_b200 -- the Gram-matrix kernel: S = Xa * Xb^T on tcgen05 tensor cores with the
+// consumer fused into the epilogue, so the N x N similarity matrix never reaches HBM.
+//
+// Replaces (reference, /root/reference/facenet/statistics.py):
+//   :33,:36   xa @ xb.T                         -> TMA-fed tcgen05.mma, fp32 accumulators in TMEM
+//   :40-46    range check + clamp               -> epilogue (max |s| / min,max; clamp)
+//   :50,:53   2*(1-s) | arccos(s)               -> epilogue (PAIRWISE) or folded into similarity cuts (HIST)
+//   :130-131  count_nonzero(sims < threshold)   -> epilogue per-thread histogram over similarity bins
+//   :124-126  per-class-pair blocking           -> rows sorted by class, rectangles ("regions") with a key
+//
+// Structure (one CTA per SM, or one CTA PAIR per two SMs with cta_group::2):
+//   warp 0   TMA producer   : 128-row x 128-byte operand boxes (SWIZZLE_128B) into a ring of 32 KB slots
+//   warp 1   MMA issuer     : one thread issues tcgen05.mma (leader CTA only in pair mode)
+//   warp 2   TMEM allocator
+//   warps 4-11 epilogue     : tcgen05.ld the finished accumulator (double buffered in TMEM) and
+//                             consume it while the next tile's MMAs run
+// Tile = 128x128 (cta_group 1) or 256x256 per CTA pair (each CTA owns 128 rows x 256 columns).
+#pragma once
+
+#include "fnb_common.cuh"
+
+namespace fnb {
+
+constexpr int kMaxBins      = 128;                 // bins k in [0, T], T <= 127
+constexpr int kEpiWarps     = 8;
+constexpr int kEpiThreads   = kEpiWarps * 32;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kGramThreads  = (kFirstEpiWarp + kEpiWarps) * 32;   // 384
+constexpr int kRowsPerCta   = 128;                 // MMA M per CTA, and B rows loaded per CTA
+constexpr int kBoxBytes     = kRowsPerCta * 128;   // one operand box: 128 rows x 128 B = 16 KB
+constexpr int kSlotBytes    = 2 * kBoxBytes;       // {A part, B part}
+constexpr int kMaxSlots     = 8;
+
+enum EpiKind : int { EPI_HIST = 0, EPI_PAIRWISE = 1, EPI_ROWSTRIP = 2 };
+
+struct RegionDev {
+    int32_t row_begin, row_end, col_begin, col_end;
+    int32_t tri, key;
+    int32_t nrb, ncb;          // tile grid of the region (row blocks fastest)
+    long long tile_begin;      // first global tile index of the region
+};
+
+struct GramParams {
+    // schedule
+    const RegionDev* regions;  // [nregions + 1], last entry is a sentinel with tile_begin = total_tiles
+    int nregions;
+    long long total_tiles;
+    int rank, world;
+    int kblocks;               // D / (elements per 128 B)
+    int num_slots;
+    float acc_scale;           // similarity = accumulator * acc_scale
+    int operand_fmt;           // kFmtF16 / kFmtBF16 / kFmtTF32 (must agree with the kTf32 template flag)
+    int force_slow;            // take the fully-checked epilogue path for every tile
+    // HIST epilogue
+    const int32_t* row_cls;    // class id per (permuted) row, non-decreasing
+    const int32_t* col_cls;
+    const float* cuts;         // [kMaxBins] ascending similarity cuts, padded with +inf
+    const float* wlo;          // [kMaxBins + 1] wlo[k]: lower edge of the eps window of cut k (+inf padded)
+    const float* whi;          // [kMaxBins + 1] whi[k]: upper edge of the eps window of cut k-1 (whi[0] = -inf)
+    int T;                     // number of cuts (bins 0..T)
+    int T_fin;                 // number of finite cuts (the +inf ones sort last)
+    int uniform;               // cuts are (numerically) an arithmetic progression -> arithmetic binning
+    float u_scale, u_bias, u_guard;
+    unsigned long long* bins;  // [nkeys][2][bins_stride]  (0: all pairs, 1: same-identity pairs)
+    int bins_stride;
+    unsigned long long* counters;  // [0] eps-window pairs, [1] tiles processed
+    unsigned int* range_ord;   // [0] min(s) [1] max(s) as ordered uints (checked tiles) [2] max|s| (fast tiles)
+    // PAIRWISE / ROWSTRIP epilogue
+    float* out;                // PAIRWISE: packed triangle or [na, nb]; ROWSTRIP: [n_rows, out_ld] distances
+    long long out_ld;
+    int tri_packed;
+    int metric;
+    int n_rows, n_cols;
+};
+
+struct TileInfo {
+    int row0, col0, row_end, col_end, tri, key;
+};
+
+template <int kCtaGroup>
+struct TileScheduler {
+    static constexpr int kTile = kRowsPerCta * kCtaGroup;
+    const RegionDev* regions;
+    long long pos, stride, total;
+    int cur;
+
+    __device__ TileScheduler(const GramParams& p, int cluster_id, int num_clusters)
+        : regions(p.regions), pos((long long)cluster_id * p.world + p.rank),
+          stride((long long)num_clusters * p.world), total(p.total_tiles), cur(0) {}
+
+    __device__ bool next(TileInfo& t) {
+        while (pos < total) {
+            while (pos >= regions[cur + 1].tile_begin) ++cur;
+            const RegionDev r = regions[cur];
+            const int li = (int)(pos - r.tile_begin);
+            const int cb = li / r.nrb;
+            const int rb = li - cb * r.nrb;
+            pos += stride;
+            t.row0 = r.row_begin + rb * kTile;
+            t.col0 = r.col_begin + cb * kTile;
+            t.row_end = r.row_end;
+            t.col_end = r.col_end;
+            t.tri = r.tri;
+            t.key = r.key;
+            if (r.tri && t.col0 + kTile - 1 <= t.row0) continue;   // tile entirely on/below the diagonal
+            return true;
+        }
+        return false;
+    }
+};
+
+struct __align__(16) GramSmemMisc {
+    uint64_t full[kMaxSlots];
+    uint64_t empty[kMaxSlots];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+    float cuts[kMaxBins];
+    float wlo[kMaxBins + 4];
+    float whi[kMaxBins + 4];
+    uint32_t same[kMaxBins + 4];
+    int32_t col_cls[2][256];
+};
+
+__device__ __forceinline__ int exact_bin(float s, const float* cuts_s) {
+    // k = #{j : cuts[j] <= s}, cuts ascending, padded with +inf up to kMaxBins
+    int k = 0;
+#pragma unroll
+    for (int step = kMaxBins / 2; step >= 1; step >>= 1) {
+        if (cuts_s[k + step - 1] <= s) k += step;
+    }
+    return k;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+
+template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi>
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+            const GramParams p)
+{
+    constexpr int kTile   = kRowsPerCta * kCtaGroup;       // tile rows == tile cols
+    constexpr int kUmmaN  = kTile;                         // accumulator columns per stage
+    constexpr int kParts  = (kNumPass == 3) ? 2 : 1;       // slots per k-block: {hi} or {hi, lo}
+    constexpr int kColsPerWarp = kUmmaN / 2;               // two epilogue warps per TMEM lane quadrant
+    constexpr uint32_t kTmemCols = 2 * kUmmaN;             // double-buffered accumulator
+    constexpr int kElemsPerBox = kTf32 ? 32 : 64;          // K elements per 128-byte row
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* slots = smem;
+    GramSmemMisc* misc = reinterpret_cast<GramSmemMisc*>(smem + (size_t)p.num_slots * kSlotBytes);
+    uint16_t* hist_priv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(misc) + sizeof(GramSmemMisc));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+    const int cluster_id = blockIdx.x / kCtaGroup;
+    const int num_clusters = gridDim.x / kCtaGroup;
+    const int num_slots = p.num_slots;
+    // fp16 vs bf16 is a runtime choice (same instruction kind, one descriptor field)
+    const uint32_t idesc = make_idesc((uint32_t)p.operand_fmt, kTile, kUmmaN);
+
+    // ---- one-time setup
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < num_slots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&misc->tfull[i], 1); mbar_init(&misc->tempty[i], kEpiWarps * kCtaGroup); }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
+        if (kNumPass == 3) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
+    }
+    if (warp == 2) tmem_alloc<kCtaGroup>(&misc->tmem_base, kTmemCols);
+    if (kEpi == EPI_HIST && warp >= kFirstEpiWarp) {
+        const int te = threadIdx.x - kFirstEpiWarp * 32;
+        for (int i = te; i < kMaxBins; i += kEpiThreads) misc->cuts[i] = p.cuts[i];
+        for (int i = te; i < kMaxBins + 1; i += kEpiThreads) { misc->wlo[i] = p.wlo[i]; misc->whi[i] = p.whi[i]; misc->same[i] = 0; }
+        for (int i = te; i < (p.T + 1) * kEpiThreads; i += kEpiThreads) hist_priv[i] = 0;
+    }
+    __syncwarp();
+    tc_fence_before();
+    if (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = misc->tmem_base;
+
+    // =====================================================================================
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------------
+        if (lane == 0) {
+            TileScheduler<kCtaGroup> sched(p, cluster_id, num_clusters);
+            TileInfo t;
+            int slot = 0; uint32_t phase = 0;
+            while (sched.next(t)) {
+                const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
+                const int brow = t.col0 + (int)cta_rank * kRowsPerCta;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+#pragma unroll
+                    for (int part = 0; part < kParts; ++part) {
+                        mbar_wait<kCtaGroup == 2>(&misc->empty[slot], phase ^ 1u);
+                        uint8_t* dst = slots + (size_t)slot * kSlotBytes;
+                        const CUtensorMap* ma = part ? &tm_a_lo : &tm_a_hi;
+                        const CUtensorMap* mb = part ? &tm_b_lo : &tm_b_hi;
+                        if (kCtaGroup == 1) {
+                            mbar_arrive_expect_tx(&misc->full[slot], kSlotBytes);
+                            tma_load_2d(dst, ma, &misc->full[slot], kb * kElemsPerBox, arow);
+                            tma_load_2d(dst + kBoxBytes, mb, &misc->full[slot], kb * kElemsPerBox, brow);
+                        } else {
+                            if (is_leader) mbar_arrive_expect_tx(&misc->full[slot], 2 * kSlotBytes);
+                            const uint32_t bar = mapa_u32(smem_u32(&misc->full[slot]), 0);
+                            tma_load_2d_pair(dst, ma, bar, kb * kElemsPerBox, arow);
+                            tma_load_2d_pair(dst + kBoxBytes, mb, bar, kb * kElemsPerBox, brow);
+                        }
+                        if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer --------------------------------------
+        if (lane == 0 && is_leader) {
+            TileScheduler<kCtaGroup> sched(p, cluster_id, num_clusters);
+            TileInfo t;
+            int slot = 0; uint32_t phase = 0;
+            uint32_t it = 0;
+            while (sched.next(t)) {
+                const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+                mbar_wait<kCtaGroup == 2>(&misc->tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kUmmaN;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    const int slot_hi = slot;
+                    mbar_wait<kCtaGroup == 2>(&misc->full[slot_hi], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(slots + (size_t)slot_hi * kSlotBytes);
+                    const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + kBoxBytes);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                    if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                    if (kNumPass == 3) {
+                        const int slot_lo = slot;
+                        mbar_wait<kCtaGroup == 2>(&misc->full[slot_lo], phase);
+                        tc_fence_after();
+                        const uint32_t sl = smem_u32(slots + (size_t)slot_lo * kSlotBytes);
+                        const uint64_t a_lo = make_smem_desc(sl), b_lo = make_smem_desc(sl + kBoxBytes);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1u);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma<kCtaGroup, kTf32>(d_tmem, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
+                        umma_commit<kCtaGroup>(&misc->empty[slot_hi]);
+                        umma_commit<kCtaGroup>(&misc->empty[slot_lo]);
+                        if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                    } else {
+                        umma_commit<kCtaGroup>(&misc->empty[slot_hi]);
+                    }
+                }
+                umma_commit<kCtaGroup>(&misc->tfull[acc]);
+                ++it;
+            }
+        }
+    } else if (warp >= kFirstEpiWarp) {
+        // ------------------------------ epilogue ----------------------------------------
+        const int e = warp - kFirstEpiWarp;          // 0..7
+        const int q = e & 3;                         // TMEM lane quadrant (== warp % 4)
+        const int half = e >> 2;                     // column half
+        const int te = e * 32 + lane;                // epilogue thread id 0..255
+        const int row_in_tile = (int)cta_rank * kRowsPerCta + q * 32 + lane;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float scale = p.acc_scale;
+
+        TileScheduler<kCtaGroup> sched(p, cluster_id, num_clusters);
+        TileInfo t;
+        uint32_t it = 0;
+
+        float smin = INFINITY, smax = -INFINITY, amax = 0.f;
+        uint32_t eps_cnt = 0, tiles_done = 0;
+        int cur_key = -1;
+        uint32_t since_flush = 0;
+        constexpr uint32_t kFlushEvery = 65535u / (uint32_t)kColsPerWarp;
+
+        auto flush = [&](int key) {
+            named_bar_sync(1, kEpiThreads);
+            if (key >= 0) {
+                unsigned long long* dst_all = p.bins + ((size_t)key * 2 + 0) * p.bins_stride;
+                unsigned long long* dst_same = p.bins + ((size_t)key * 2 + 1) * p.bins_stride;
+                for (int b = e; b <= p.T; b += kEpiWarps) {
+                    uint32_t sum = 0;
+#pragma unroll
+                    for (int j = 0; j < kEpiThreads / 32; ++j) {
+                        const int idx = b * kEpiThreads + j * 32 + lane;
+                        sum += hist_priv[idx];
+                        hist_priv[idx] = 0;
+                    }
+                    sum = warp_sum(sum);
+                    if (lane == 0) {
+                        if (sum) atomicAdd(dst_all + b, (unsigned long long)sum);
+                        const uint32_t sm = misc->same[b];
+                        if (sm) { atomicAdd(dst_same + b, (unsigned long long)sm); misc->same[b] = 0; }
+                    }
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+        };
+
+        while (sched.next(t)) {
+            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const int row = t.row0 + row_in_tile;
+            const int colw = t.col0 + half * kColsPerWarp;       // first column of this warp
+            const uint32_t taddr0 = tmem_lane + acc * kUmmaN + half * kColsPerWarp;
+
+            if constexpr (kEpi == EPI_HIST) {
+                if (t.key != cur_key || since_flush >= kFlushEvery) {
+                    if (cur_key >= 0) flush(cur_key);
+                    cur_key = t.key; since_flush = 0;
+                }
+                ++since_flush;
+                // classify the tile (identical in every epilogue thread of the CTA pair)
+                const bool edge = (t.row0 + kTile > t.row_end) || (t.col0 + kTile > t.col_end) ||
+                                  (t.tri && t.col0 <= t.row0 + kTile - 1);
+                const int rlast = min(t.row0 + kTile, t.row_end) - 1;
+                const int clast = min(t.col0 + kTile, t.col_end) - 1;
+                const bool lab = (__ldg(p.row_cls + t.row0) <= __ldg(p.col_cls + clast)) &&
+                                 (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + rlast));
+                const bool slow = edge || lab || !p.uniform || p.force_slow;
+
+                mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                tc_fence_after();
+
+                int my_cls = -1;
+                if (slow) {
+                    // stage this tile's column classes (kTile <= 256 columns).  Safe after the tfull wait:
+                    // every epilogue warp has released the tile that last used col_cls[acc].
+                    if (te < kTile) {
+                        const int c = t.col0 + te;
+                        misc->col_cls[acc][te] = (c < t.col_end) ? __ldg(p.col_cls + c) : -2;
+                    }
+                    if (row < t.row_end) my_cls = __ldg(p.row_cls + row);
+                    named_bar_sync(2, kEpiThreads);
+                }
+
+                uint16_t* hp = hist_priv + te;
+                if (!slow) {
+                    const float a_floor = -1.0f / scale;
+                    const float us = p.u_scale, ub = p.u_bias, guard = p.u_guard;
+                    const float u_hi = (float)p.T_fin - 0.5f;
+#pragma unroll 1
+                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr0 + c * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            int k[4]; bool near_any = false;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float a = __uint_as_float(r[j + i]);
+                                amax = fmaxf(amax, fabsf(a));
+                                float u = fmaf(fmaxf(a, a_floor), us, ub);
+                                u = fminf(fmaxf(u, -1.0f), u_hi);
+                                const float v = u + 12582912.0f;
+                                const float d = u - (v - 12582912.0f);
+                                k[i] = (__float_as_int(v) - 0x4B400000) + (d >= 0.0f ? 1 : 0);
+                                near_any |= (fabsf(d) <= guard);
+                            }
+                            if (near_any) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float s = fmaxf(__uint_as_float(r[j + i]) * scale, -1.0f);
+                                    const int ke = exact_bin(s, misc->cuts);
+                                    k[i] = ke;
+                                    if (s <= misc->whi[ke] || s >= misc->wlo[ke]) ++eps_cnt;
+                                }
+                            }
+                            // grouped read-modify-write of the thread-private counters
+                            uint32_t cnt[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) cnt[i] = hp[k[i] * kEpiThreads];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint32_t m = 0;
+#pragma unroll
+                                for (int i2 = 0; i2 < 4; ++i2) m += (k[i2] == k[i]) ? 1u : 0u;
+                                cnt[i] += m;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) hp[k[i] * kEpiThreads] = (uint16_t)cnt[i];
+                        }
+                    }
+                } else {
+                    const bool row_ok = row < t.row_end;
+#pragma unroll 1
+                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr0 + c * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = colw + c * 32 + j;
+                            const bool ok = row_ok && (col < t.col_end) && (!t.tri || col > row);
+                            if (ok) {
+                                float s = __uint_as_float(r[j]) * scale;
+                                smin = fminf(smin, s); smax = fmaxf(smax, s);
+                                s = fminf(fmaxf(s, -1.0f), 1.0f);
+                                const int ke = exact_bin(s, misc->cuts);
+                                if (s <= misc->whi[ke] || s >= misc->wlo[ke]) ++eps_cnt;
+                                hp[ke * kEpiThreads] = (uint16_t)(hp[ke * kEpiThreads] + 1);
+                                if (misc->col_cls[acc][col - t.col0] == my_cls) atomicAdd(&misc->same[ke], 1u);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // ------------------- PAIRWISE / ROWSTRIP: materialise distances --------------
+                mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                tc_fence_after();
+                const bool row_ok = row < t.row_end;
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr0 + c * 32, r);
+                    tmem_ld_wait();
+                    if (row_ok) {
+                        long long base;
+                        if (p.tri_packed) base = (long long)row * p.n_rows - ((long long)row * (row + 1)) / 2 - row - 1;
+                        else base = (long long)row * p.out_ld;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = colw + c * 32 + j;
+                            const bool ok = (col < t.col_end) && (!t.tri || col > row);
+                            if (ok) {
+                                float s = __uint_as_float(r[j]) * scale;
+                                if (kEpi == EPI_PAIRWISE || col != row) { smin = fminf(smin, s); smax = fmaxf(smax, s); }
+                                s = fminf(fmaxf(s, -1.0f), 1.0f);
+                                float d;
+                                if (p.metric == 0) d = __fmul_rn(2.0f, __fsub_rn(1.0f, s));
+                                else d = acosf(s);
+                                p.out[base + col] = d;
+                            }
+                        }
+                    }
+                }
+            }
+
+            // release this accumulator stage to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (kCtaGroup == 2) mbar_arrive_remote(&misc->tempty[acc], 0);
+                else mbar_arrive(&misc->tempty[acc]);
+            }
+            ++it; ++tiles_done;
+        }
+
+        if constexpr (kEpi == EPI_HIST) {
+            flush(cur_key);
+            eps_cnt = warp_sum(eps_cnt);
+            amax = warp_max(amax) * scale;
+            if (lane == 0) {
+                if (eps_cnt) atomicAdd(p.counters + 0, (unsigned long long)eps_cnt);
+                atomicMax(p.range_ord + 2, float_to_ordered(amax));
+            }
+        }
+        smin = warp_min(smin); smax = warp_max(smax);
+        if (lane == 0) {
+            if (smin <= smax) {
+                atomicMin(p.range_ord + 0, float_to_ordered(smin));
+                atomicMax(p.range_ord + 1, float_to_ordered(smax));
+            }
+            if (e == 0 && is_leader) atomicAdd(p.counters + 1, (unsigned long long)tiles_done);
+        }
+    }
+
+    // ---- teardown (reconverge each warp first: the barriers below are .aligned)
+    __syncwarp();
+    tc_fence_before();
+    if (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols); }
+}
+
+}  // namespace fnb

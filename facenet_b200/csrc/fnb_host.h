@@ -1,0 +1,102 @@
+// facenet_b200 -- host-side internals shared by the C-ABI translation units.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+
+#include "../../include/facenet_b200.h"
+#include "fnb_gram.cuh"
+
+namespace fnb {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {   // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// similarity cuts derived from the distance thresholds (host)
+struct CutTables {
+    int T = 0, T_fin = 0;
+    float cuts[kMaxBins];          // ascending, +inf padded
+    float wlo[kMaxBins + 4];
+    float whi[kMaxBins + 4];
+    int order[kMaxBins];           // sorted position j -> threshold index
+    int pos[kMaxBins];             // threshold n -> number of sorted cuts <= cut_n
+    int uniform = 0;
+    double e0 = 0, h = 0, dev = 0; // arithmetic-progression fit of the finite cuts
+};
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace fnb
+
+struct fnb_context {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    fnb::PFN_tmapEncodeTiled encode = nullptr;
+    std::string err;
+
+    fnb::DevBuf stage_a, stage_b, stage_lab;          // H2D staging of kDLCPU inputs
+    fnb::DevBuf a_hi, a_lo, b_hi, b_lo;               // split / converted operands
+    fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
+    fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out;
+    fnb::HostBuf pinned;
+    int last_nkeys = 0, last_T = 0;
+
+    int fail(int code, const char* fmt, ...);
+};
+
+namespace fnb {
+
+// fnb_api.cu
+int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, float* prescale);
+int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out);
+
+// fnb_prepare.cu
+cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
+                              void* hi, void* lo, cudaStream_t s);
+int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
+
+// fnb_gram.cu
+int launch_gram(fnb_context* h, int cta_group, int num_pass, bool tf32, int epi, int max_ctas,
+                const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                GramParams& p, size_t hist_bytes);
+size_t gram_smem_bytes(int num_slots, size_t hist_bytes);
+int gram_pick_slots(size_t hist_bytes);
+
+}  // namespace fnb

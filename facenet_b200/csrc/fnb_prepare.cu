@@ -1,0 +1,136 @@
+// facenet_b200 -- operand preparation: class ranking of labels (replaces np.unique(labels) /
+// split_embeddings, facenet/statistics.py:68-79) and the row gather + precision split that turns
+// fp32 embeddings into the tensor-core operand arrays.  HBM-bound streaming kernels.
+#include "fnb_host.h"
+#include <cub/cub.cuh>
+
+namespace fnb {
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// One thread converts 8 consecutive elements of one row.  Rows [n, n_pad) are written as zeros.
+template <int kMode>
+__global__ void split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ perm,
+                                  long long n, long long n_pad, int d, void* __restrict__ hi, void* __restrict__ lo)
+{
+    const int vec_per_row = d >> 3;
+    const long long total = n_pad * vec_per_row;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+        const long long row = v / vec_per_row;
+        const int c8 = (int)(v - row * vec_per_row);
+        float f[8];
+        if (row < n) {
+            const long long src = perm ? perm[row] : row;
+            const float4* s4 = reinterpret_cast<const float4*>(x + src * d + (long long)c8 * 8);
+            const float4 p0 = __ldg(s4), p1 = __ldg(s4 + 1);
+            f[0] = p0.x; f[1] = p0.y; f[2] = p0.z; f[3] = p0.w; f[4] = p1.x; f[5] = p1.y; f[6] = p1.z; f[7] = p1.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = 0.f;
+        }
+        const long long o = row * d + (long long)c8 * 8;
+        if (kMode == FNB_MODE_FP16X3 || kMode == FNB_MODE_FP16) {
+            const float pre = (kMode == FNB_MODE_FP16X3) ? 256.0f : 1.0f;
+            __half hh[8], ll[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float xs = f[i] * pre;
+                hh[i] = __float2half_rn(xs);
+                ll[i] = __float2half_rn(xs - __half2float(hh[i]));
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(hi) + o) = *reinterpret_cast<uint4*>(hh);
+            if (kMode == FNB_MODE_FP16X3)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(lo) + o) = *reinterpret_cast<uint4*>(ll);
+        } else if (kMode == FNB_MODE_BF16) {
+            __nv_bfloat16 hh[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hh[i] = __float2bfloat16_rn(f[i]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(hi) + o) = *reinterpret_cast<uint4*>(hh);
+        } else {
+            float hh[8], ll[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { hh[i] = tf32_rn(f[i]); ll[i] = tf32_rn(f[i] - hh[i]); }
+            float4* dh = reinterpret_cast<float4*>(reinterpret_cast<float*>(hi) + o);
+            dh[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            dh[1] = make_float4(hh[4], hh[5], hh[6], hh[7]);
+            if (kMode == FNB_MODE_TF32X3) {
+                float4* dl = reinterpret_cast<float4*>(reinterpret_cast<float*>(lo) + o);
+                dl[0] = make_float4(ll[0], ll[1], ll[2], ll[3]);
+                dl[1] = make_float4(ll[4], ll[5], ll[6], ll[7]);
+            }
+        }
+    }
+}
+
+cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
+                              void* hi, void* lo, cudaStream_t s)
+{
+    const long long total = n_pad * (d >> 3);
+    if (total == 0) return cudaSuccess;
+    const int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    switch (mode) {
+        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
+        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
+        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
+        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
+        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// labels -> (perm, cls): rows ordered by label value; cls = rank of the label value
+
+template <typename L>
+__global__ void labels_to_keys_kernel(const L* __restrict__ labels, long long n, long long* keys, long long* idx) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        keys[i] = (long long)labels[i];
+        idx[i] = i;
+    }
+}
+
+__global__ void boundary_flags_kernel(const long long* __restrict__ sorted_keys, long long n, int* flags) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        flags[i] = (i > 0 && sorted_keys[i] != sorted_keys[i - 1]) ? 1 : 0;
+}
+
+int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n)
+{
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return h->fail(FNB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+    CKS(h->keys_in.ensure(n * 8));
+    CKS(h->keys_out.ensure(n * 8));
+    CKS(h->vals_in.ensure(n * 8));
+    CKS(h->perm.ensure(n * 8));
+    CKS(h->flags.ensure(n * 4));
+    CKS(h->cls.ensure(n * 4));
+    const int threads = 256;
+    unsigned blocks = (unsigned)std::min<long long>((n + threads - 1) / threads, 148LL * 16);
+    if (label_bits == 64)
+        labels_to_keys_kernel<long long><<<blocks, threads, 0, h->stream>>>((const long long*)labels_dev, n, h->keys_in.as<long long>(), h->vals_in.as<long long>());
+    else
+        labels_to_keys_kernel<int><<<blocks, threads, 0, h->stream>>>((const int*)labels_dev, n, h->keys_in.as<long long>(), h->vals_in.as<long long>());
+    CKS(cudaGetLastError());
+    size_t tmp1 = 0, tmp2 = 0;
+    CKS(cub::DeviceRadixSort::SortPairs(nullptr, tmp1, h->keys_in.as<long long>(), h->keys_out.as<long long>(),
+                                        h->vals_in.as<long long>(), h->perm.as<long long>(), (int)n, 0, 64, h->stream));
+    CKS(cub::DeviceScan::InclusiveSum(nullptr, tmp2, h->flags.as<int>(), h->cls.as<int>(), (int)n, h->stream));
+    CKS(h->cub_tmp.ensure(std::max(tmp1, tmp2)));
+    size_t cap = h->cub_tmp.cap;
+    CKS(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, cap, h->keys_in.as<long long>(), h->keys_out.as<long long>(),
+                                        h->vals_in.as<long long>(), h->perm.as<long long>(), (int)n, 0, 64, h->stream));
+    boundary_flags_kernel<<<blocks, threads, 0, h->stream>>>(h->keys_out.as<long long>(), n, h->flags.as<int>());
+    CKS(cudaGetLastError());
+    cap = h->cub_tmp.cap;
+    CKS(cub::DeviceScan::InclusiveSum(h->cub_tmp.p, cap, h->flags.as<int>(), h->cls.as<int>(), (int)n, h->stream));
+#undef CKS
+    return FNB_OK;
+}
+
+}  // namespace fnb

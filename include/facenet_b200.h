@@ -1,0 +1,174 @@
+/* facenet_b200 -- C ABI of the B200-native embedding-evaluation hot path.
+ *
+ * The reference (sMedX/FaceNet) has no FFI layer: the path is pure Python/NumPy in
+ * facenet/statistics.py.  Every entry point below therefore names the reference
+ * FUNCTION it replaces (file:line into /root/reference); the Python binding a
+ * maintainer would add is shown in INTEGRATION.md and shipped as
+ * facenet_b200/statistics.py (ctypes).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes and DLPack tensor structs only (no torch / numpy types);
+ *  - tensors are BORROWED `DLTensor*` (the struct inside a DLPack capsule): kDLCPU data is
+ *    staged through pinned memory, kDLCUDA data on the handle's device is used in place;
+ *  - embeddings: float32, C-contiguous [N, D], D a multiple of 64, 64 <= D <= 4096;
+ *    labels: int32 or int64 [N];
+ *  - every function returns FNB_OK (0) or an FNB_ERR_* code; fnb_last_error() gives the text;
+ *  - a handle is not thread-safe; use one handle per thread / per GPU.  ctypes releases the
+ *    GIL around each call.
+ *  - there is NO CPU fallback: without a CUDA device fnb_create fails.
+ */
+#ifndef FACENET_B200_H
+#define FACENET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- DLPack (ABI-compatible restatement of dlpack.h v0.8 structs) ------------------- */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3, kDLCUDAManaged = 13 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef enum { kDLInt = 0, kDLUInt = 1, kDLFloat = 2, kDLBfloat = 4 } DLDataTypeCode;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+    void* data;
+    DLDevice device;
+    int32_t ndim;
+    DLDataType dtype;
+    int64_t* shape;
+    int64_t* strides;      /* NULL = compact row-major */
+    uint64_t byte_offset;
+} DLTensor;
+#endif
+
+typedef struct fnb_context* fnb_handle;
+
+enum {
+    FNB_OK = 0,
+    FNB_ERR_INVALID = 1,         /* bad argument (shape, dtype, contiguity, NULL) */
+    FNB_ERR_NOT_NORMALIZED = 2,  /* statistics.py:40-42 -> ValueError('embeddings must be normalized to 1 ...') */
+    FNB_ERR_BAD_METRIC = 3,      /* statistics.py:55,260 -> ValueError('Undefined similarity metric ...') */
+    FNB_ERR_CUDA = 4,
+    FNB_ERR_UNSUPPORTED = 5
+};
+
+/* Arithmetic of the Gram contraction (all accumulate in fp32 in tensor memory):
+ *   FP16X3  x = hi + lo with hi, lo fp16 (pre-scaled by 2^8): hi*hi + hi*lo + lo*hi, three
+ *           kind::f16 MMAs per k-step -- fp32-equivalent (|ds| ~ 1e-7); the DEFAULT, and the only
+ *           modes that meet the reference tolerance (|dd| <= 1e-5) are the two X3 modes;
+ *   TF32X3  same split with tf32 operands, kind::tf32;
+ *   TF32    single kind::tf32 pass on RN-rounded operands (|dd| ~ 3.5e-5 rms);
+ *   BF16    single kind::f16 pass on bf16 operands;  FP16: single pass on fp16 operands. */
+enum { FNB_MODE_FP16X3 = 0, FNB_MODE_TF32X3 = 1, FNB_MODE_TF32 = 2, FNB_MODE_BF16 = 3, FNB_MODE_FP16 = 4 };
+
+typedef struct {
+    int32_t mode;          /* FNB_MODE_*                                        default FP16X3 */
+    int32_t metric;        /* 0: 2*(1-s)   1: arccos(s)   (statistics.py:48-55)  default 0     */
+    float   atol;          /* normalisation tolerance (statistics.py:22,40)      default 1e-5  */
+    float   eps;           /* |d - threshold| <= eps pairs are counted            default 1e-5  */
+    int32_t rank, world;   /* this process computes tiles t with t % world == rank  default 0,1 */
+    int32_t cta_group;     /* 0 auto, 1: 128x128 tiles per CTA, 2: 256x256 per CTA pair           */
+    int32_t region_rows;   /* rows per L2 super-row, 0 = auto                                     */
+    const float* cuts;     /* optional [T]: per threshold the smallest fp32 similarity whose distance is
+                              < threshold (+inf if none); NULL = computed here with libm (metric 1:
+                              acosf).  The Python host passes NumPy's so that results are bit-exact
+                              with NumPy's arccos. */
+    int32_t max_ctas;      /* 0 = all SMs (debug / profiling knob) */
+    int32_t reserved[7];
+} fnb_options;
+
+typedef struct {
+    uint64_t n_pairs;      /* pairs binned by this rank                                         */
+    uint64_t eps_window;   /* of those, pairs within eps of some threshold                      */
+    float    smin, smax;   /* exact range of raw similarities over the tiles that took the checked path
+                              (diagonal / edge / same-identity tiles; NaN if none)                */
+    float    max_abs;      /* max |similarity| over the remaining (interior) tiles               */
+    float    kernel_ms;    /* device time of the Gram kernel (CUDA events)                      */
+    float    prepare_ms;   /* device time of sort/split/convert                                 */
+    uint64_t tiles;        /* tiles processed by this rank                                      */
+    uint32_t kernel_launches;
+    uint32_t reserved[4];
+} fnb_stats;
+
+/* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:
+ * row range == col range and only pairs col > row are counted. */
+typedef struct {
+    int32_t row_begin, row_end, col_begin, col_end;
+    int32_t tri;
+    int32_t key;           /* histogram slot the rectangle accumulates into */
+} fnb_region;
+
+int  fnb_version(void);
+void fnb_default_options(fnb_options* o);
+int  fnb_create(int device, fnb_handle* out);
+void fnb_destroy(fnb_handle h);
+const char* fnb_last_error(fnb_handle h);          /* h may be NULL: error of the last failed fnb_create */
+int  fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+
+/* Replaces pairwise_similarities(xa, xb=None, metric, atol)  (facenet/statistics.py:22-57).
+ *   xb == NULL: out = float32 [n(n-1)/2], strict upper triangle in row-major triu_indices(n,1) order;
+ *   else      : out = float32 [na, nb].
+ * out may be kDLCPU or kDLCUDA.  range[0..1] (host) receive min/max raw similarity.
+ * FNB_ERR_NOT_NORMALIZED when a similarity is outside [-(1+atol), 1+atol] (range still filled). */
+int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb, const fnb_options* opt,
+                 DLTensor* out, float* range);
+
+/* Whole-set verification histogram: for every unordered pair {a,b}, a != b, of emb [N,D], bin the
+ * similarity against the T thresholds.  This is the inner statement of ConfidenceMatrix
+ * (count_nonzero(sims < threshold), facenet/statistics.py:130-131) applied to the whole set with
+ * same/different identity decided by labels (statistics.py:68-79,124-126).
+ *   bins_out: uint64 [2, T+1] (kDLCPU or kDLCUDA): row 0 all pairs, row 1 same-identity pairs;
+ *             bin k = pairs with exactly k of the ascending similarity cuts <= s.
+ * Integer results: identical for any (world) split after summing ranks' bins. */
+int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const DLTensor* labels,
+                            const double* thresholds, int T, const fnb_options* opt,
+                            DLTensor* bins_out, fnb_stats* stats);
+
+/* Host-side conversion of (summed) bins into per-threshold counts:
+ *   same_lt[n] = #{same-identity pairs with d < thresholds[n]}, diff_lt[n] likewise (strict <,
+ *   float64 compare against the fp32 distance, statistics.py:131). */
+int fnb_counts_from_bins(const double* thresholds, int T, const fnb_options* opt,
+                         const uint64_t* bins /* host [2][T+1] */,
+                         uint64_t* same_lt, uint64_t* diff_lt, uint64_t* n_same, uint64_t* n_diff);
+
+/* Convenience, one GPU: bins + counts. */
+int fnb_pair_histogram(fnb_handle h, const DLTensor* emb, const DLTensor* labels,
+                       const double* thresholds, int T, const fnb_options* opt,
+                       uint64_t* same_lt, uint64_t* diff_lt, uint64_t* n_same, uint64_t* n_diff,
+                       fnb_stats* stats);
+
+/* Keyed histogram over caller-defined rectangles of the pair matrix -- the building block of the
+ * class-balanced ConfidenceMatrix (facenet/statistics.py:111-138) and of k-fold validation
+ * (statistics.py:277-311).  perm [N] (host): row r of the permuted order is emb[perm[r]];
+ * cls [N] (host): class id of permuted row r, NON-DECREASING in r.
+ *   bins_host: uint64 [nkeys][2][T+1]. */
+int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, const int64_t* perm, const int32_t* cls,
+                              const fnb_region* regions, int nregions, int nkeys,
+                              const double* thresholds, int T, const fnb_options* opt,
+                              uint64_t* bins_host, fnb_stats* stats);
+
+/* Class-balanced confidence matrix from keyed bins, on the device (prefix scan over bins, fp64):
+ *   tp[n] = sum_key w_same[key] * #{same pairs of key with d < thr[n]},  fn[n] = total_same - tp[n],
+ *   fp/tn likewise with w_diff (statistics.py:133-138), then accuracy argmax (first maximum,
+ *   statistics.py:296) and the FAR threshold by piecewise-linear interpolation of thresholds over
+ *   fp_rates at far_target (statistics.py:299-302; 0 when max(fp_rates) < far_target).
+ * Uses the bins left on the device by the last fnb_region_histogram_bins call on this handle. */
+int fnb_confidence_from_last_bins(fnb_handle h, int nkeys, const double* w_same, const double* w_diff,
+                                  const double* thresholds, int T, const fnb_options* opt, double far_target,
+                                  double* tp, double* tn, double* fp, double* fn,
+                                  int32_t* argmax_accuracy, double* far_threshold);
+
+/* Triplet mining on one batch (NOT in the reference fork -- semantics defined in
+ * oracle/mining_oracle.py; batch layout facenet/facenet.py:89-123).  Distances are metric 0.
+ *   hardest_pos, hardest_neg: int32 [B];  kmax >= max class size - 1;
+ *   pos_index, semi_hard, eligible: int32 [B, kmax] (host). */
+int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* labels, float alpha, const fnb_options* opt,
+             int32_t* hardest_pos, int32_t* hardest_neg,
+             int kmax, int32_t* pos_index, int32_t* semi_hard, int32_t* eligible, fnb_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACENET_B200_H */
