@@ -165,8 +165,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     constexpr uint32_t kTmemCols = 2 * kUmmaN;             // double-buffered accumulator
     constexpr int kElemsPerBox = kTf32 ? 32 : 64;          // K elements per 128-byte row
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the shared array itself, so the
+    // compiler keeps every derived pointer in the shared address space (LDS/STS, not generic LD/ST)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* slots = smem;
     GramSmemMisc* misc = reinterpret_cast<GramSmemMisc*>(smem + (size_t)p.num_slots * kSlotBytes);
     uint16_t* hist_priv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(misc) + sizeof(GramSmemMisc));
