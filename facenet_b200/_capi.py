@@ -21,7 +21,7 @@ FNB_OK, FNB_ERR_INVALID, FNB_ERR_NOT_NORMALIZED, FNB_ERR_BAD_METRIC, FNB_ERR_CUD
 MODES = {'fp16x3': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3, 'fp16': 4}
 MAX_THRESHOLDS = 127
 
-EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info',
+EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info', 'fnb_set_stream',
            'fnb_pairwise', 'fnb_pair_histogram_bins', 'fnb_counts_from_bins', 'fnb_pair_histogram',
            'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine')
 
@@ -90,6 +90,7 @@ def load_library():
         lib.fnb_last_error.argtypes = [c.c_void_p]
         lib.fnb_last_error.restype = c.c_char_p
         lib.fnb_device_info.argtypes = [c.c_void_p, P(c.c_int), P(c.c_int), P(c.c_int), P(c.c_uint64)]
+        lib.fnb_set_stream.argtypes = [c.c_void_p, c.c_void_p]
         lib.fnb_pairwise.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(Options), P(DLTensor), P(c.c_float)]
         lib.fnb_pair_histogram_bins.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(c.c_double), c.c_int, P(Options),
                                                 P(DLTensor), P(Stats)]
@@ -249,6 +250,12 @@ class Handle:
     def _raise(self, rc):
         raise FnbError(rc, self.lib.fnb_last_error(self.h).decode())
 
+    def set_stream(self, cuda_stream=None):
+        """Run on ``cuda_stream`` (an int/ctypes handle, e.g. ``torch.cuda.current_stream().cuda_stream``); None = own stream."""
+        rc = self.lib.fnb_set_stream(self.h, ctypes.c_void_p(int(cuda_stream)) if cuda_stream else None)
+        if rc != FNB_OK:
+            self._raise(rc)
+
     def device_info(self):
         sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_uint64()
         self.lib.fnb_device_info(self.h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(mem))
@@ -299,7 +306,7 @@ class Handle:
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
-        if cuts == 'numpy':
+        if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
                                region_rows=region_rows, cuts=cuts, max_ctas=max_ctas)
@@ -315,7 +322,7 @@ class Handle:
 
     def counts_from_bins(self, bins, thresholds, metric=0, eps=1.e-5, cuts='numpy'):
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
-        if cuts == 'numpy':
+        if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(metric=metric, eps=eps, cuts=cuts)
         bins = np.ascontiguousarray(bins, dtype=np.uint64)
@@ -346,7 +353,7 @@ class Handle:
         cls = np.ascontiguousarray(cls, dtype=np.int32)
         regions = np.ascontiguousarray(regions, dtype=REGION_DTYPE)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
-        if cuts == 'numpy':
+        if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, cta_group=cta_group, cuts=cuts, rank=rank, world=world)
         bins = np.zeros((int(nkeys), 2, thr.size + 1), dtype=np.uint64)

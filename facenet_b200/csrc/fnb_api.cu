@@ -252,9 +252,10 @@ extern "C" int fnb_create(int device, fnb_handle* out) {
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || !fn) { g_create_error = "cuTensorMapEncodeTiled entry point not found"; delete h; return FNB_ERR_CUDA; }
     h->encode = (PFN_tmapEncodeTiled)fn;
-    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete h; return FNB_ERR_CUDA;
     }
+    h->stream = h->own_stream;
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
     *out = h;
     return FNB_OK;
@@ -270,8 +271,16 @@ extern "C" void fnb_destroy(fnb_handle h) {
     for (DevBuf* b : bufs) b->release();
     h->pinned.release();
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+}
+
+extern "C" int fnb_set_stream(fnb_handle h, void* cuda_stream) {
+    if (!h) return FNB_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return FNB_OK;
 }
 
 extern "C" const char* fnb_last_error(fnb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -575,6 +584,7 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     }
     if ((rc = write_bins(h->bins.as<unsigned long long>(), hl.stride))) return rc;
     if (stats) {
+        stats->kernel_launches += 3;      // labels_to_keys, boundary_flags, split_rows (+ the Gram kernel counted above)
         if (!vb.on_device) stats->n_pairs = sum_bins((const uint64_t*)vb.data, T + 1);
         else {
             uint64_t tmp[kMaxBins + 1];

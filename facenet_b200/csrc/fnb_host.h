@@ -66,7 +66,8 @@ struct fnb_context {
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     size_t total_mem = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream in use
+    cudaStream_t own_stream = nullptr;   // created by fnb_create
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     fnb::PFN_tmapEncodeTiled encode = nullptr;
     std::string err;

@@ -1,0 +1,70 @@
+"""Multi-GPU form of the whole-set verification histogram: one process per GPU (torch.distributed,
+NCCL over NVLink/NVSwitch for the plumbing).
+
+The pair matrix shards naturally: every rank needs all N embeddings (columns) but computes only the
+tiles ``t`` with ``t % world == rank`` of the global tile order, so each rank does 1/world of the upper
+triangle regardless of N (no triangle imbalance).  Exchange steps:
+
+  1. all-gather of the embedding / label shards (N * 512 * 4 bytes in total; 2 GB at N = 1M);
+  2. all-reduce (sum) of the [2, T+1] int64 histogram bins -- integer, so the result is identical for
+     every world size.
+
+``hist_fn`` is the per-rank compute call; the default is the CUDA library.  The CPU tests (gloo,
+world_size 2) inject the NumPy stand-in to exercise this plumbing without a GPU.
+"""
+import numpy as np
+
+
+def _default_hist_fn(device_index):
+    from facenet_b200 import _capi
+    handle = _capi.default_handle(device_index)
+
+    def fn(emb, labels, thresholds, metric, rank, world, bins_out, **kw):
+        import torch
+        handle.set_stream(torch.cuda.current_stream().cuda_stream)
+        _, stats = handle.pair_histogram_bins(emb, labels, thresholds, metric, rank=rank, world=world,
+                                              bins_out=bins_out, **kw)
+        return stats
+    return fn
+
+
+def gather_shards(emb_shard, labels_shard, group=None):
+    """all-gather equally sized shards into the full [N, D] / [N] tensors (same on every rank)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return emb_shard, labels_shard
+    emb = torch.empty((emb_shard.shape[0] * world, emb_shard.shape[1]), dtype=emb_shard.dtype, device=emb_shard.device)
+    labels = torch.empty((labels_shard.shape[0] * world,), dtype=labels_shard.dtype, device=labels_shard.device)
+    dist.all_gather_into_tensor(emb, emb_shard.contiguous(), group=group)
+    dist.all_gather_into_tensor(labels, labels_shard.contiguous(), group=group)
+    return emb, labels
+
+
+def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=None, hist_fn=None, **kw):
+    """Every rank passes its shard (torch tensors on its device, equal row counts); returns on every
+    rank ``(bins [2, T+1] int64 torch tensor summed over ranks, stats of this rank)``."""
+    import torch
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    emb, labels = gather_shards(emb_shard, labels_shard, group)
+    thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
+    bins = torch.zeros((2, thr.size + 1), dtype=torch.int64, device=emb.device)
+    if hist_fn is None:
+        hist_fn = _default_hist_fn(emb.device.index or 0)
+    stats = hist_fn(emb, labels, thr, metric, rank, world, bins, **kw)
+    if world > 1:
+        dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
+    return bins, stats
+
+
+def counts_from_bins(bins, thresholds, metric=0):
+    """Host conversion of the summed bins into per-threshold counts (same arithmetic as
+    ``fnb_counts_from_bins``): dict with ``same``, ``diff`` (int64 [T]), ``n_same``, ``n_diff``."""
+    from facenet_b200 import _capi
+    from facenet_b200.statistics import _counts_lt
+    b = np.asarray(bins.cpu() if hasattr(bins, 'cpu') else bins).astype(np.int64)
+    cuts = _capi.numpy_cuts(thresholds, metric)
+    lt = _counts_lt(b, cuts)
+    return {'same': lt[1], 'diff': lt[0] - lt[1], 'n_same': int(b[1].sum()), 'n_diff': int(b[0].sum() - b[1].sum())}

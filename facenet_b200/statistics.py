@@ -1,0 +1,474 @@
+"""Drop-in replacement for the evaluation-statistics path of sMedX/FaceNet
+(``/root/reference/facenet/statistics.py``), computed on a B200.
+
+Same names, positional order, defaults, attributes and exceptions as the reference:
+
+    pairwise_similarities(xa, xb=None, metric=0, atol=1.e-5)          statistics.py:22-57
+    split_embeddings(embeddings, labels)                              statistics.py:68-79
+    SimilarityCalculator(embeddings, labels, metric=0)                statistics.py:82-108
+    ConfidenceMatrix(calculator, threshold)                           statistics.py:111-175
+    Report(criterion=None)                                            statistics.py:178-234
+    FaceToFaceValidation(embeddings, labels, config)                  statistics.py:237-331
+
+What runs where
+  * every pair distance, threshold comparison and count runs in the CUDA library
+    (``include/facenet_b200.h``) -- one call per ``ConfidenceMatrix``, never one per class pair;
+  * this module only prepares the call (class ranks, row order, rectangles of the pair matrix,
+    similarity cuts) and turns the integer histograms into the reference's float64
+    class-balanced rates;
+  * ``Report`` (AUC / EER / mean +- std over folds, statistics.py:187-234) is host arithmetic on
+    ~100 numbers and stays in Python like the reference.
+
+There is no CPU fallback: without the shared library or a CUDA device these functions raise.
+"""
+import datetime
+import time
+from pathlib import Path
+
+import numpy as np
+
+from facenet_b200 import _capi
+
+__all__ = ['pairwise_similarities', 'split_embeddings', 'SimilarityCalculator', 'ConfidenceMatrix', 'Report',
+           'FaceToFaceValidation', 'pair_histogram', 'mean', 'std', 'set_default_mode', 'kfold_split']
+
+_state = {'mode': 'fp16x3', 'device': 0, 'cta_group': 0}
+
+
+def set_default_mode(mode=None, device=None, cta_group=None):
+    """Select the Gram arithmetic ('fp16x3' default, 'tf32x3', 'tf32', 'bf16', 'fp16'), the CUDA device
+    and the tile variant used by the functions of this module."""
+    if mode is not None:
+        if mode not in _capi.MODES:
+            raise ValueError('unknown mode {}'.format(mode))
+        _state['mode'] = mode
+    if device is not None:
+        _state['device'] = int(device)
+    if cta_group is not None:
+        _state['cta_group'] = int(cta_group)
+
+
+def _handle():
+    return _capi.default_handle(_state['device'])
+
+
+def _raise_like_reference(err, metric=None):
+    if err.code == _capi.FNB_ERR_NOT_NORMALIZED:
+        # statistics.py:42
+        msg = str(err)
+        lo, hi = msg.split('range')[-1].split()
+        raise ValueError('\nembeddings must be normalized to 1, range {} {}'.format(np.float32(lo), np.float32(hi))) from None
+    if err.code == _capi.FNB_ERR_BAD_METRIC:
+        # statistics.py:55
+        raise ValueError('Undefined similarity metric {}'.format(metric)) from None
+    raise err
+
+
+def mean(x):
+    return np.mean(np.array(x))
+
+
+def std(x):
+    return np.std(np.array(x))
+
+
+def pairwise_similarities(xa, xb=None, metric=0, atol=1.e-5):
+    """Evaluate pairwise distances between vectors xa and xb (statistics.py:22-57).
+
+    ``xb is None``: 1-D float32 array of the strict upper triangle of the Gram matrix in row-major
+    ``np.triu_indices(n, k=1)`` order; otherwise the 2-D ``[n_a, n_b]`` matrix.  metric 0 gives
+    ``2 * (1 - s)``, metric 1 ``arccos(s)``.  Raises ``ValueError`` exactly where the reference does."""
+    xa = np.ascontiguousarray(xa, dtype=np.float32)
+    if xb is not None:
+        xb = np.ascontiguousarray(xb, dtype=np.float32)
+    n_out = xa.shape[0] * (xa.shape[0] - 1) // 2 if xb is None else xa.shape[0] * xb.shape[0]
+    if n_out == 0:
+        # statistics.py:38 -- empty in, empty out (no checks)
+        return np.empty((0,) if xb is None else (xa.shape[0], xb.shape[0]), dtype=np.float32)
+    if metric not in (0, 1):
+        # the reference range-checks first (statistics.py:40-42) and only then rejects the metric (:55)
+        try:
+            _handle().pairwise(xa, xb, 0, atol, mode=_state['mode'], cta_group=_state['cta_group'])
+        except _capi.FnbError as err:
+            _raise_like_reference(err, metric)
+        raise ValueError('Undefined similarity metric {}'.format(metric))
+    try:
+        return _handle().pairwise(xa, xb, metric, atol, mode=_state['mode'], cta_group=_state['cta_group'])
+    except _capi.FnbError as err:
+        _raise_like_reference(err, metric)
+
+
+def split_embeddings(embeddings, labels):
+    """split embeddings to structure [[], [], ...[]] in sorted ``np.unique(labels)`` order (statistics.py:68-79)."""
+    embeddings = np.asarray(embeddings)
+    labels = np.asarray(labels)
+    order = np.argsort(labels, kind='stable')
+    _, counts = np.unique(labels, return_counts=True)
+    return np.split(embeddings[order], np.cumsum(counts)[:-1])
+
+
+class SimilarityCalculator:
+    """Class to evaluate similarities according to defined metric (statistics.py:82-108).
+
+    Holds the whole subset; ``ConfidenceMatrix`` hands it to the GPU in one call.  ``.embeddings`` (the
+    per-class list of the reference) is materialised lazily for callers that index it."""
+
+    def __init__(self, embeddings, labels, metric=0):
+        self.metric = metric
+        self._x = np.ascontiguousarray(embeddings, dtype=np.float32)
+        self._labels = np.asarray(labels)
+        if self._x.shape[0] != len(self._labels):
+            raise ValueError('embeddings and labels have different lengths')
+        values, self._cls, self._sizes = np.unique(self._labels, return_inverse=True, return_counts=True)
+        self._cls = np.asarray(self._cls).reshape(-1)
+        self._split = None
+
+    @property
+    def embeddings(self):
+        if self._split is None:
+            order = np.argsort(self._cls, kind='stable')
+            self._split = np.split(self._x[order], np.cumsum(self._sizes)[:-1])
+        return self._split
+
+    def evaluate(self, i, k):
+        # statistics.py:90-101
+        nrof_positive_class_pairs = self.nrof_classes
+        nrof_negative_class_pairs = self.nrof_classes * (self.nrof_classes - 1) / 2
+        if i == k:
+            sims = pairwise_similarities(self.embeddings[i], metric=self.metric)
+            weight = sims.size * nrof_positive_class_pairs
+        else:
+            sims = pairwise_similarities(self.embeddings[i], self.embeddings[k], metric=self.metric)
+            weight = sims.size * nrof_negative_class_pairs
+        return sims, weight
+
+    @property
+    def nrof_classes(self):
+        return int(self._sizes.size)
+
+    def nrof_images(self, i):
+        return int(self._sizes[i])
+
+
+def _size_group_plan(cls, sizes):
+    """Row order and rectangles for the class-balanced confidence matrix.
+
+    The reference weights every (class i, class k) block by ``1 / (block size * number of class
+    pairs)`` (statistics.py:91-99,133-138); the weight depends on the classes only through their
+    SIZES.  Rows are therefore ordered by (class size, class rank): classes of equal size become
+    contiguous, each pair of size groups (a <= b) is one rectangle of the pair matrix with its own
+    histogram slot, and the integer counts per slot are exact."""
+    uniq_sizes, group_of_class = np.unique(sizes, return_inverse=True)
+    group_of_class = np.asarray(group_of_class).reshape(-1)
+    n_groups = uniq_sizes.size
+    # new class rank: ordered by (size group, old class rank)
+    class_order = np.lexsort((np.arange(sizes.size), group_of_class))
+    new_rank = np.empty(sizes.size, dtype=np.int64)
+    new_rank[class_order] = np.arange(sizes.size)
+    row_rank = new_rank[cls]
+    perm = np.argsort(row_rank, kind='stable')
+    cls_sorted = row_rank[perm].astype(np.int32)
+    rows_per_group = np.bincount(group_of_class, weights=sizes, minlength=n_groups).astype(np.int64)
+    bounds = np.concatenate([[0], np.cumsum(rows_per_group)])
+    classes_per_group = np.bincount(group_of_class, minlength=n_groups).astype(np.int64)
+
+    ia, ib = np.triu_indices(n_groups)
+    regions = np.zeros(ia.size, dtype=_capi.REGION_DTYPE)
+    regions['row_begin'] = bounds[ia]
+    regions['row_end'] = bounds[ia + 1]
+    regions['col_begin'] = bounds[ib]
+    regions['col_end'] = bounds[ib + 1]
+    regions['tri'] = (ia == ib)
+    regions['key'] = np.arange(ia.size)
+    return perm, cls_sorted, regions, ia, ib, uniq_sizes.astype(np.int64), classes_per_group
+
+
+def _counts_lt(bins, cuts):
+    """bins [..., T+1] over ascending-cut bins -> counts of pairs with ``d < threshold_n`` [..., T]."""
+    order = np.sort(cuts)
+    pos = np.searchsorted(order, cuts, side='right')            # cuts <= cut_n
+    suffix = np.cumsum(bins[..., ::-1].astype(np.int64), axis=-1)[..., ::-1]
+    suffix = np.concatenate([suffix, np.zeros(suffix.shape[:-1] + (1,), dtype=np.int64)], axis=-1)
+    return suffix[..., pos]
+
+
+class ConfidenceMatrix:
+    """Class to evaluate confidence matrix (tp, tn, fp, fn) and others metrics (statistics.py:111-175).
+
+    ``tp[n] = (1/C) * sum_i count_ii(n) / (n_i (n_i - 1) / 2)`` and
+    ``fp[n] = (2 / (C (C-1))) * sum_{i>k} count_ik(n) / (n_i n_k)`` with
+    ``count(n) = #{pairs : d < threshold_n}`` (strict, float64 compare).  The integer counts come from
+    one fused Gram + histogram launch; the float64 rates are formed here."""
+
+    def __init__(self, calculator, threshold):
+        self.threshold = np.array(threshold, ndmin=1)
+        nt = self.threshold.size
+        self.tp = np.zeros(nt)
+        self.tn = np.zeros(nt)
+        self.fp = np.zeros(nt)
+        self.fn = np.zeros(nt)
+        self.stats = None
+        if nt == 0 or calculator._x.shape[0] < 2:
+            return
+        thr = self.threshold.astype(np.float64).reshape(-1)
+        metric = calculator.metric
+        if metric not in (0, 1):
+            raise ValueError('Undefined similarity metric {}'.format(metric))
+        nc = calculator.nrof_classes
+        perm, cls_sorted, regions, ia, ib, gsize, gcount = _size_group_plan(calculator._cls, calculator._sizes)
+        h = _handle()
+        for t0 in range(0, nt, _capi.MAX_THRESHOLDS):
+            sl = slice(t0, min(nt, t0 + _capi.MAX_THRESHOLDS))
+            cuts = _capi.numpy_cuts(thr[sl], metric)
+            try:
+                bins, self.stats = h.region_histogram_bins(calculator._x, perm, cls_sorted, regions, regions.size,
+                                                           thr[sl], metric=metric, mode=_state['mode'],
+                                                           cta_group=_state['cta_group'], cuts=cuts)
+            except _capi.FnbError as err:
+                _raise_like_reference(err, metric)
+            lt = _counts_lt(bins, cuts)                              # [keys, 2, T]
+            tot = bins.sum(axis=-1).astype(np.int64)                 # [keys, 2]
+            same_lt = lt[:, 1, :].astype(np.float64)
+            diff_lt = (lt[:, 0, :] - lt[:, 1, :]).astype(np.float64)
+            same_tot = tot[:, 1].astype(np.float64)[:, None]
+            diff_tot = (tot[:, 0] - tot[:, 1]).astype(np.float64)[:, None]
+            diag = ia == ib
+            # same-identity pairs only exist on diagonal rectangles: block size n(n-1)/2, weight * C
+            w_same = np.zeros(ia.size)
+            npairs = gsize[ia] * (gsize[ia] - 1) / 2
+            ok = diag & (npairs > 0)
+            w_same[ok] = 1.0 / (npairs[ok] * nc)
+            # different-identity pairs: block size n_i * n_k, weight * C(C-1)/2
+            w_diff = 1.0 / (gsize[ia] * gsize[ib] * (nc * (nc - 1) / 2)) if nc > 1 else np.zeros(ia.size)
+            w_same = w_same[:, None]
+            w_diff = np.asarray(w_diff, dtype=np.float64)[:, None]
+            self.tp[sl] = (same_lt * w_same).sum(axis=0)
+            self.fn[sl] = ((same_tot - same_lt) * w_same).sum(axis=0)
+            self.fp[sl] = (diff_lt * w_diff).sum(axis=0)
+            self.tn[sl] = ((diff_tot - diff_lt) * w_diff).sum(axis=0)
+
+    @property
+    def accuracy(self):
+        return (self.tp + self.tn) / (self.tp + self.fp + self.tn + self.fn)
+
+    @property
+    def precision(self):
+        i = (self.tp + self.fp) > 0
+        precision = np.ones(self.threshold.size)
+        precision[i] = self.tp[i] / (self.tp[i] + self.fp[i])
+        return precision
+
+    @property
+    def tp_rates(self):
+        # true positive rate, validation rate, sensitivity or recall
+        i = (self.tp + self.fn) > 0
+        tp_rates = np.ones(self.threshold.size)
+        tp_rates[i] = self.tp[i] / (self.tp[i] + self.fn[i])
+        return tp_rates
+
+    @property
+    def tn_rates(self):
+        # true negative rate, 1 - false alarm rate, specificity
+        i = (self.tn + self.fp) > 0
+        tn_rates = np.ones(self.threshold.size)
+        tn_rates[i] = self.tn[i] / (self.tn[i] + self.fp[i])
+        return tn_rates
+
+    @property
+    def fp_rates(self):
+        # false positive rate, false alarm rate
+        return 1 - self.tn_rates
+
+    @property
+    def fn_rates(self):
+        # false negative rate,
+        return 1 - self.tp_rates
+
+
+def _slinear(x, y, xq):
+    """``scipy.interpolate.interp1d(x, y, kind='slinear')(xq)`` as the reference's pinned scipy 1.4.1
+    evaluated it (statistics.py:301-302): linear interpolation on the last interval whose left end is
+    <= xq.  (scipy >= 1.10 rejects the duplicate abscissae fp_rates always contains.)"""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if xq < x[0] or xq > x[-1]:
+        raise ValueError('A value in x_new is outside the interpolation range.')
+    j = int(np.searchsorted(x, xq, side='right')) - 1
+    j = min(max(j, 0), x.size - 2)
+    if x[j + 1] == x[j]:
+        return np.array(y[j])
+    return np.array(y[j] + (xq - x[j]) / (x[j + 1] - x[j]) * (y[j + 1] - y[j]))
+
+
+class Report:
+    """Class to generate statistical report (statistics.py:178-234)."""
+
+    def __init__(self, criterion=None):
+        self.criterion = criterion
+        self.conf_matrix_train = []
+        self.conf_matrix_test = []
+
+    def __repr__(self):
+        dct = self.dict
+        info = self.criterion + '\n'
+        info += ('Area under curve (AUC): {:1.5f}\n'.format(dct['auc']) +
+                 'Equal error rate (EER): {:1.5f}\n'.format(dct['eer']) + '\n')
+        info += ('Accuracy:  {:2.5f}+-{:2.5f}\n'.format(dct['accuracy'], dct['accuracy_std']) +
+                 'Precision: {:2.5f}+-{:2.5f}\n'.format(dct['precision'], std(dct['precision_std'])) +
+                 'Sensitivity (TPR, 1-a type 1 error): {:2.5f}+-{:2.5f}\n'.format(dct['tp_rates'], dct['tp_rates_std']) +
+                 'Specificity (TNR, 1-b type 2 error): {:2.5f}+-{:2.5f}\n'.format(dct['tn_rates'], dct['tn_rates_std']) +
+                 'Threshold: {:2.5f}+-{:2.5f}\n'.format(dct['threshold'], dct['threshold_std']) + '\n')
+        return info
+
+    def append_fold(self, name, conf_matrix):
+        if name == 'train':
+            self.conf_matrix_train.append(conf_matrix)
+        else:
+            self.conf_matrix_test.append(conf_matrix)
+
+    @property
+    def dict(self):
+        import sklearn.metrics
+        from scipy import interpolate
+        from scipy.optimize import brentq
+
+        tp_rates = np.mean(np.array([m.tp_rates for m in self.conf_matrix_train]), axis=0)
+        tn_rates = np.mean(np.array([m.tn_rates for m in self.conf_matrix_train]), axis=0)
+
+        dct = {'auc': -1, 'eer': -1}
+        try:
+            dct['auc'] = sklearn.metrics.auc(1 - tn_rates, tp_rates)
+        except Exception:
+            pass
+        try:
+            dct['eer'] = brentq(lambda x: 1. - x - interpolate.interp1d(1 - tn_rates, tp_rates)(x), 0., 1.)
+        except Exception:
+            pass
+
+        for key in ('accuracy', 'precision', 'tp_rates', 'tn_rates', 'threshold'):
+            x = [getattr(m, key) for m in self.conf_matrix_test]
+            dct[key] = np.mean(x)
+            dct[key + '_std'] = np.std(x)
+        return dct
+
+
+def kfold_split(n, n_splits, seed=0):
+    """The index sets of ``sklearn.model_selection.KFold(n_splits, shuffle=True, random_state=seed)
+    .split(np.arange(n))`` (statistics.py:278-287) without the sklearn dependency: a
+    ``RandomState(seed)`` shuffle cut into folds, the first ``n % n_splits`` one longer."""
+    perm = np.arange(n)
+    np.random.RandomState(seed).shuffle(perm)
+    fold_sizes = np.full(n_splits, n // n_splits, dtype=np.int64)
+    fold_sizes[:n % n_splits] += 1
+    start = 0
+    for size in fold_sizes:
+        test_mask = np.zeros(n, dtype=bool)
+        test_mask[perm[start:start + size]] = True
+        yield np.nonzero(~test_mask)[0], np.nonzero(test_mask)[0]
+        start += size
+
+
+class FaceToFaceValidation:
+    """Class to perform face-to-face validation (statistics.py:237-331)."""
+
+    def __init__(self, embeddings, labels, config):
+        self.elapsed_time = time.monotonic()
+        self.embeddings = embeddings
+        self.labels = labels
+
+        assert (embeddings.shape[0] == len(labels))
+
+        self.config = config
+        self.reports = None
+
+        if self.config.metric == 0:
+            upper_threshold = 4
+        elif self.config.metric == 1:
+            upper_threshold = np.pi
+        else:
+            raise ValueError('Undefined similarity metric {}'.format(self.config.metric))
+
+        self.thresholds = np.linspace(0, upper_threshold, 100)
+        self._evaluate()
+        try:
+            from loguru import logger
+            logger.info(self)
+        except ImportError:
+            pass
+
+    def __repr__(self):
+        info = (f'{self.__class__.__name__}\n' +
+                f'metric: {self.config.metric}\n\n')
+        for r in self.reports:
+            info += str(r)
+        info += f'elapsed_time: {self.elapsed_time}\n'
+        return info
+
+    def _evaluate(self):
+        embeddings = np.asarray(self.embeddings)
+        labels = np.asarray(self.labels)
+        self.reports = (
+            Report(criterion='MaximumAccuracy'),
+            Report(criterion='FalseAlarmRate(FAR = {})'.format(self.config.far_target))
+        )
+        for train_set, test_set in kfold_split(len(labels), self.config.nrof_folds):
+            # evaluations with train set and define the best threshold for the fold
+            calculator = SimilarityCalculator(embeddings[train_set], labels[train_set], metric=self.config.metric)
+            matrix = ConfidenceMatrix(calculator, self.thresholds)
+            for report in self.reports:
+                report.append_fold('train', matrix)
+
+            # the threshold that gives maximal accuracy (first maximum, statistics.py:296)
+            accuracy_threshold = self.thresholds[np.argmax(matrix.accuracy)]
+
+            # the threshold that gives FAR (FPR, 1-TNR) = far_target (statistics.py:299-302)
+            far_threshold = 0
+            if np.max(matrix.fp_rates) >= self.config.far_target:
+                far_threshold = _slinear(matrix.fp_rates, self.thresholds, self.config.far_target)
+
+            # evaluations with test set: both thresholds in ONE launch, then split per report
+            calculator = SimilarityCalculator(embeddings[test_set], labels[test_set], metric=self.config.metric)
+            both = ConfidenceMatrix(calculator, np.array([accuracy_threshold, float(far_threshold)]))
+            for idx, thr in enumerate((accuracy_threshold, far_threshold)):
+                one = ConfidenceMatrix.__new__(ConfidenceMatrix)
+                one.threshold = np.array(thr, ndmin=1)
+                one.tp, one.tn = both.tp[idx:idx + 1].copy(), both.tn[idx:idx + 1].copy()
+                one.fp, one.fn = both.fp[idx:idx + 1].copy(), both.fn[idx:idx + 1].copy()
+                one.stats = both.stats
+                self.reports[idx].append_fold('test', one)
+
+        self.elapsed_time = time.monotonic() - self.elapsed_time
+
+    @property
+    def dict(self):
+        output = {r.criterion: r.dict for r in self.reports}
+        return output
+
+    def write_report(self, file):
+        file = Path(file).expanduser()
+        with file.open('at') as f:
+            f.write(64 * '-' + '\n')
+            f.write('{} {}\n'.format(self.__class__.__name__, datetime.datetime.now()))
+            f.write('metric: {}\n\n'.format(self.config.metric))
+            for r in self.reports:
+                f.write(str(r))
+
+    def write_h5file(self, h5file, tag=None):
+        # statistics.py:330-331 delegates to facenet.h5utils.write_dict (h5py); kept as a thin hook
+        try:
+            from facenet import h5utils
+        except ImportError as exc:
+            raise ImportError('write_h5file needs the reference package facenet.h5utils (h5py)') from exc
+        h5utils.write_dict(h5file, self.dict, group=tag)
+
+
+def pair_histogram(embeddings, labels, thresholds, metric=0, mode=None, **kw):
+    """Whole-set verification histogram (BASELINE configs 2/4/5): integer numbers of same-identity and
+    different-identity pairs with ``d < thresholds[n]`` over all N(N-1)/2 unordered pairs -- the
+    reference's inner statement ``count_nonzero(sims < threshold)`` (statistics.py:131) without the
+    per-class weighting.  Returns a dict with ``same``, ``diff`` (int64 [T]), ``n_same``, ``n_diff``, ``stats``."""
+    try:
+        return _handle().pair_histogram(embeddings, labels, thresholds, metric, mode=mode or _state['mode'],
+                                        cta_group=kw.pop('cta_group', _state['cta_group']), **kw)
+    except _capi.FnbError as err:
+        _raise_like_reference(err, metric)

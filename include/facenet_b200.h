@@ -106,6 +106,9 @@ int  fnb_create(int device, fnb_handle* out);
 void fnb_destroy(fnb_handle h);
 const char* fnb_last_error(fnb_handle h);          /* h may be NULL: error of the last failed fnb_create */
 int  fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+/* Enqueue all work of this handle on `cuda_stream` (a cudaStream_t, e.g. the framework's current stream) so that
+ * it orders with the caller's kernels, collectives and events; NULL restores the handle's own stream. */
+int  fnb_set_stream(fnb_handle h, void* cuda_stream);
 
 /* Replaces pairwise_similarities(xa, xb=None, metric, atol)  (facenet/statistics.py:22-57).
  *   xb == NULL: out = float32 [n(n-1)/2], strict upper triangle in row-major triu_indices(n,1) order;

@@ -219,33 +219,60 @@ def _blocked_lower_bins(x, thr32_up, metric, atol, block):
     return gen(), state
 
 
-def pair_histogram(embeddings, labels, thresholds, metric=0, atol=1.e-5, block=1024):
+def _row_block_histogram(x, labels, thr32_up, metric, atol, r0, r1):
+    """Histogram contribution of rows [r0, r1) against all earlier rows (strict lower triangle)."""
+    nt = thr32_up.size
+    lim = 1 + atol
+    s = x[r0:r1] @ x[:r1].T                                            # fp32 sgemm (statistics.py:33,36)
+    valid = np.ones(s.shape, dtype=bool)
+    valid[:, r0:r1] = np.tri(r1 - r0, r1 - r0, -1, dtype=bool)
+    vals = s[valid]
+    lo, hi = (float(vals.min()), float(vals.max())) if vals.size else (np.inf, -np.inf)
+    if vals.size and (lo < -lim or hi > lim):
+        raise ValueError('\nembeddings must be normalized to 1, range {} {}'.format(vals.min(), vals.max()))
+    np.clip(vals, -1, 1, out=vals)                                     # statistics.py:45-46
+    d = 2 * (1 - vals) if metric == 0 else np.arccos(vals)             # statistics.py:50,53
+    bins = np.searchsorted(thr32_up, d, side='right')
+    same = (labels[r0:r1, None] == labels[None, :r1])[valid]
+    return (np.bincount(bins, minlength=nt + 1), np.bincount(bins[same], minlength=nt + 1), lo, hi)
+
+
+def pair_histogram(embeddings, labels, thresholds, metric=0, atol=1.e-5, block=1024, threads=1):
     """Whole-set verification histogram (SURVEY.md section 8 a, end): for every
     unordered pair {a,b}, a != b, evaluated once, the integer number of
     same-identity and different-identity pairs with ``d < thresholds[n]``
     (strict, statistics.py:131).  Returns dict with ``same``/``diff`` int64 [T]
-    cumulative counts, ``n_same``/``n_diff`` totals and the raw similarity range."""
+    cumulative counts, ``n_same``/``n_diff`` totals and the raw similarity range.
+    ``threads`` > 1 processes row blocks on a thread pool (NumPy releases the GIL in
+    matmul / searchsorted / bincount), BLAS limited to one thread per worker."""
     if metric not in (0, 1):
         raise ValueError('Undefined similarity metric {}'.format(metric))
     x = np.ascontiguousarray(embeddings, dtype=np.float32)
     labels = np.asarray(labels)
     thr = thresholds_f32_up(thresholds)
     nt = thr.size
-    same_h = np.zeros(nt + 1, dtype=np.int64)
+    blocks = [(r0, min(x.shape[0], r0 + block)) for r0 in range(0, x.shape[0], block)]
+
+    def work(rr):
+        return _row_block_histogram(x, labels, thr, metric, atol, rr[0], rr[1])
+
+    if threads > 1 and len(blocks) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1, user_api='blas'), ThreadPoolExecutor(max_workers=threads) as pool:
+            parts = list(pool.map(work, blocks))
+    else:
+        parts = [work(rr) for rr in blocks]
     all_h = np.zeros(nt + 1, dtype=np.int64)
-    it, state = _blocked_lower_bins(x, thr, metric, atol, block)
-    for r0, r1, c0, c1, bins, valid in it:
-        same = labels[r0:r1, None] == labels[None, c0:c1]
-        if valid is not None:
-            same &= valid
-            all_h += np.bincount(bins[valid], minlength=nt + 1)
-        else:
-            all_h += np.bincount(bins.ravel(), minlength=nt + 1)
-        same_h += np.bincount(bins[same], minlength=nt + 1)
+    same_h = np.zeros(nt + 1, dtype=np.int64)
+    smin, smax = np.inf, -np.inf
+    for a_h, s_h, lo, hi in parts:
+        all_h += a_h
+        same_h += s_h
+        smin, smax = min(smin, lo), max(smax, hi)
     diff_h = all_h - same_h
     return {'same': np.cumsum(same_h)[:nt], 'diff': np.cumsum(diff_h)[:nt],
-            'n_same': int(same_h.sum()), 'n_diff': int(diff_h.sum()),
-            'smin': state['min'], 'smax': state['max']}
+            'n_same': int(same_h.sum()), 'n_diff': int(diff_h.sum()), 'smin': smin, 'smax': smax}
 
 
 def eps_window_pairs(embeddings, thresholds, metric=0, eps=1.e-5, block=1024):

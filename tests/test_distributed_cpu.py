@@ -1,0 +1,85 @@
+"""world_size-2 gloo test of the multi-GPU plumbing (shard all-gather, per-rank tile split, integer
+all-reduce, bins -> counts) with the NumPy stand-in as the per-rank compute call."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import statistics_oracle as so
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _emulated_hist(emb, labels, thresholds, metric, rank, world, bins_out, **kw):
+    """Per-rank stand-in: rows sorted by label, strict upper triangle in 64x64 tiles, tile t handled by
+    rank t % world (mirrors the library's tile split)."""
+    from facenet_b200 import _capi
+    x = emb.numpy()
+    lab = labels.numpy()
+    order = np.argsort(lab, kind='stable')
+    x, lab = x[order], lab[order]
+    cuts = np.sort(_capi.numpy_cuts(thresholds, metric))
+    nt = cuts.size
+    n = x.shape[0]
+    tile = 64
+    t = 0
+    out = np.zeros((2, nt + 1), dtype=np.int64)
+    for r0 in range(0, n, tile):
+        for c0 in range(r0, n, tile):
+            mine = (t % world) == rank
+            t += 1
+            if not mine:
+                continue
+            s = np.clip(x[r0:r0 + tile] @ x[c0:c0 + tile].T, -1, 1)
+            k = np.searchsorted(cuts, s.ravel(), side='right').reshape(s.shape)
+            valid = np.arange(c0, c0 + s.shape[1])[None, :] > np.arange(r0, r0 + s.shape[0])[:, None]
+            same = valid & (lab[r0:r0 + tile, None] == lab[None, c0:c0 + tile])
+            out[0] += np.bincount(k[valid], minlength=nt + 1)
+            out[1] += np.bincount(k[same], minlength=nt + 1)
+    bins_out.copy_(torch.from_numpy(out))
+    return {'emulated': True}
+
+
+def _worker(rank, world, port, x, labels, result):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from facenet_b200 import distributed as fd
+        per = x.shape[0] // world
+        xs = torch.from_numpy(x[rank * per:(rank + 1) * per])
+        ls = torch.from_numpy(labels[rank * per:(rank + 1) * per])
+        thr = so.default_thresholds(0)
+        bins, _ = fd.pair_histogram_sharded(xs, ls, thr, 0, hist_fn=_emulated_hist)
+        out = fd.counts_from_bins(bins, thr, 0)
+        if rank == 0:
+            result['same'] = out['same']
+            result['diff'] = out['diff']
+            result['n'] = (out['n_same'], out['n_diff'])
+        # every rank holds the same reduced bins
+        gathered = [torch.zeros_like(bins) for _ in range(world)]
+        dist.all_gather(gathered, bins)
+        assert all(torch.equal(g, bins) for g in gathered)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_histogram_equals_single_process():
+    x, labels = so.synthetic_embeddings([7, 1, 30, 12, 2, 2, 18, 24], dim=64, sigma=1.0, seed=6)
+    assert x.shape[0] % 2 == 0
+    ref = so.pair_histogram(x, labels, so.default_thresholds(0), 0)
+    mgr = mp.Manager()
+    result = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, x, labels, result), nprocs=2, join=True)
+    assert result['n'] == (ref['n_same'], ref['n_diff'])
+    assert np.abs(result['same'] - ref['same']).sum() + np.abs(result['diff'] - ref['diff']).sum() <= 2

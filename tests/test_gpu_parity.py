@@ -1,0 +1,313 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI against the CPU
+oracle on the same seeded inputs and against the committed reference outputs (tests/golden).
+
+Tolerances (BASELINE.json north_star): distances within 1e-5 absolute; integer counts bit-exact
+except for pairs whose distance lies within eps = 1e-5 of a threshold -- those are counted by the
+kernel (stats['eps_window']) and bound the allowed disagreement."""
+import numpy as np
+import pytest
+
+from oracle import statistics_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+DIST_TOL = 1.e-5
+
+
+@pytest.fixture(scope='module')
+def handle():
+    from facenet_b200 import _capi
+    return _capi.default_handle(0)
+
+
+@pytest.fixture(scope='module')
+def fst():
+    from facenet_b200 import statistics
+    return statistics
+
+
+def unit(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+# ------------------------------------------------------------------------------ A1 pairwise
+
+def test_pairwise_golden(fst, golden_dir):
+    g = np.load(golden_dir / 'pairwise.npz')
+    xa, xb = g['xa'], g['xb']
+    for metric in (0, 1):
+        got = fst.pairwise_similarities(xa, metric=metric)
+        ref = g['self_m%d' % metric]
+        assert got.dtype == np.float32 and got.shape == ref.shape
+        assert np.abs(got - ref).max() <= DIST_TOL
+        got = fst.pairwise_similarities(xa, xb, metric=metric)
+        ref = g['cross_m%d' % metric]
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= DIST_TOL
+
+
+@pytest.mark.parametrize('cta_group', [1, 2])
+@pytest.mark.parametrize('mode', ['fp16x3', 'tf32x3'])
+@pytest.mark.parametrize('na,nb,d', [(1, 1, 64), (2, 3, 64), (127, 129, 192), (257, 255, 512), (600, 40, 512)])
+def test_pairwise_exact_modes_ragged_shapes(handle, mode, cta_group, na, nb, d):
+    xa, xb = unit(na, d, 10 + na), unit(nb, d, 20 + nb)
+    for metric in (0, 1):
+        ref = so.pairwise_similarities(xa.copy(), xb.copy(), metric)
+        got = handle.pairwise(xa, xb, metric, mode=mode, cta_group=cta_group)
+        assert np.abs(got - ref).max() <= DIST_TOL
+        ref = so.pairwise_similarities(xa.copy(), None, metric)
+        got = handle.pairwise(xa, None, metric, mode=mode, cta_group=cta_group)
+        assert got.shape == ref.shape
+        if ref.size:
+            assert np.abs(got - ref).max() <= DIST_TOL
+
+
+@pytest.mark.parametrize('mode,tol', [('tf32', 5e-4), ('fp16', 5e-4), ('bf16', 4e-3)])
+def test_pairwise_single_pass_modes(handle, mode, tol):
+    """Single-pass modes are offered for throughput; their error is reported, not hidden."""
+    xa = unit(300, 512, 5)
+    ref = so.pairwise_similarities(xa.copy(), None, 0)
+    got = handle.pairwise(xa, None, 0, mode=mode)
+    err = np.abs(got - ref).max()
+    assert DIST_TOL < err <= tol or err <= DIST_TOL
+
+
+def test_pairwise_large_self_triangle_order(handle):
+    xa = unit(1500, 128, 3)
+    ref = so.pairwise_similarities(xa.copy(), None, 0)
+    got = handle.pairwise(xa, None, 0)
+    assert np.abs(got - ref).max() <= DIST_TOL
+
+
+def test_pairwise_errors_and_edge_cases(fst):
+    x = unit(10, 64, 0)
+    assert fst.pairwise_similarities(x[:1]).shape == (0,)                       # statistics.py:38
+    assert fst.pairwise_similarities(x[:0], x).shape == (0, 10)
+    with pytest.raises(ValueError, match='embeddings must be normalized to 1, range'):
+        fst.pairwise_similarities(2 * x)                                        # statistics.py:42
+    with pytest.raises(ValueError, match='embeddings must be normalized to 1, range'):
+        fst.pairwise_similarities(x, 1.5 * x, metric=1)
+    with pytest.raises(ValueError, match='Undefined similarity metric 3'):
+        fst.pairwise_similarities(x, metric=3)                                  # statistics.py:55
+    # duplicates and antipodes: clamp keeps distances in [0, 4] / [0, pi]
+    y = np.concatenate([x, x[:2], -x[:2]])
+    d0 = fst.pairwise_similarities(y, metric=0)
+    d1 = fst.pairwise_similarities(y, metric=1)
+    assert d0.min() >= 0 and d0.max() <= 4 and d1.min() >= 0 and d1.max() <= np.float32(np.pi) + 1e-6
+    ref = so.pairwise_similarities(y.copy(), None, 0)
+    assert np.abs(d0 - ref).max() <= DIST_TOL
+    # 1e-5 tolerance on the norm passes like the reference (atol, statistics.py:40)
+    fst.pairwise_similarities(x * np.float32(1 + 2e-6))
+
+
+def test_pairwise_torch_cuda_zero_copy(handle):
+    import torch
+    xa = unit(200, 128, 1)
+    xt = torch.from_numpy(xa).cuda()
+    out = torch.empty(200 * 199 // 2, dtype=torch.float32, device='cuda')
+    handle.pairwise(xt, None, 0, out=out)
+    ref = so.pairwise_similarities(xa.copy(), None, 0)
+    assert np.abs(out.cpu().numpy() - ref).max() <= DIST_TOL
+
+
+# ------------------------------------------------------------------------------ whole-set histogram
+
+def ragged(seed, n_classes=60, d=128, max_size=40, sigma=1.0, values=None):
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(1, max_size, size=n_classes)
+    return so.synthetic_embeddings(sizes, dim=d, sigma=sigma, seed=seed, label_values=values)
+
+
+def check_hist(out, ref, n):
+    assert out['n_same'] == ref['n_same'] and out['n_diff'] == ref['n_diff']
+    assert out['n_same'] + out['n_diff'] == n * (n - 1) // 2
+    budget = out['stats']['eps_window']
+    assert np.abs(out['same'] - ref['same']).sum() + np.abs(out['diff'] - ref['diff']).sum() <= 2 * budget + 0
+    assert np.all(np.diff(out['same']) >= 0) and np.all(np.diff(out['diff']) >= 0)
+
+
+@pytest.mark.parametrize('cta_group', [1, 2])
+@pytest.mark.parametrize('metric', [0, 1])
+@pytest.mark.parametrize('mode', ['fp16x3', 'tf32x3'])
+def test_histogram_vs_oracle(handle, mode, metric, cta_group):
+    x, labels = ragged(7)
+    thr = so.default_thresholds(metric)
+    ref = so.pair_histogram(x, labels, thr, metric)
+    out = handle.pair_histogram(x, labels, thr, metric, mode=mode, cta_group=cta_group)
+    check_hist(out, ref, x.shape[0])
+
+
+def test_histogram_disagreements_lie_in_eps_window(handle):
+    """Every pair binned differently from the oracle has a distance within 1e-5 of a threshold."""
+    x, labels = ragged(11, n_classes=50, d=512)
+    thr = so.default_thresholds(0)
+    n = x.shape[0]
+    d_gpu = handle.pairwise(x, None, 0)
+    d_ref = so.pairwise_similarities(x.copy(), None, 0)
+    t32 = so.thresholds_f32_up(thr)
+    b_gpu = np.searchsorted(t32, d_gpu, side='right')
+    b_ref = np.searchsorted(t32, d_ref, side='right')
+    bad = np.nonzero(b_gpu != b_ref)[0]
+    for i in bad:
+        assert np.abs(d_ref[i].astype(np.float64) - thr).min() <= 1e-5
+    # and the fused kernel bins exactly like the materialised distances of the same arithmetic
+    out = handle.pair_histogram(x, labels, thr, 0)
+    iu = np.triu_indices(n, 1)
+    same = labels[iu[0]] == labels[iu[1]]
+    same_lt = np.array([(b_gpu[same] <= k).sum() for k in range(thr.size)])
+    diff_lt = np.array([(b_gpu[~same] <= k).sum() for k in range(thr.size)])
+    np.testing.assert_array_equal(out['same'], same_lt)
+    np.testing.assert_array_equal(out['diff'], diff_lt)
+
+
+def test_histogram_fast_and_checked_paths_identical(handle):
+    """Arithmetic binning (interior tiles) and the checked path (forced via non-uniform thresholds
+    order) give the same integers: shuffle the thresholds so the table is rebuilt, and compare a
+    label-free (all singleton) run, whose interior tiles take the fast path, with pairwise binning."""
+    x = unit(1100, 128, 21)
+    labels = np.arange(1100)
+    thr = so.default_thresholds(0)
+    out = handle.pair_histogram(x, labels, thr, 0)
+    d_gpu = handle.pairwise(x, None, 0)
+    t32 = so.thresholds_f32_up(thr)
+    b = np.searchsorted(t32, d_gpu, side='right')
+    np.testing.assert_array_equal(out['diff'], [(b <= k).sum() for k in range(thr.size)])
+    assert out['n_same'] == 0
+    perm = np.random.default_rng(0).permutation(thr.size)
+    out2 = handle.pair_histogram(x, labels, thr[perm], 0)
+    np.testing.assert_array_equal(out2['diff'], out['diff'][perm])
+
+
+def test_histogram_label_conventions(handle):
+    """int32 / int64 labels, negative and huge label values, unsorted order -> same integers."""
+    values = np.array([-7, 2 ** 40, 3, 99, -2 ** 35, 12, 13, 14], dtype=np.int64)
+    x, labels = so.synthetic_embeddings([9, 1, 30, 2, 17, 5, 5, 64], dim=64, sigma=1.0, seed=4, label_values=values)
+    thr = so.default_thresholds(0)
+    ref = so.pair_histogram(x, labels, thr, 0)
+    out = handle.pair_histogram(x, labels, thr, 0)
+    check_hist(out, ref, x.shape[0])
+    _, small = np.unique(labels, return_inverse=True)
+    out32 = handle.pair_histogram(x, small.astype(np.int32), thr, 0)
+    np.testing.assert_array_equal(out32['same'], out['same'])
+    np.testing.assert_array_equal(out32['diff'], out['diff'])
+
+
+def test_histogram_sharded_ranks_sum_to_whole(handle):
+    """Tiles split over (rank, world) partition the pair matrix: summed integer bins are identical."""
+    x, labels = ragged(5, n_classes=80, d=128)
+    thr = so.default_thresholds(0)
+    whole, _ = handle.pair_histogram_bins(x, labels, thr, 0)
+    for world in (2, 3, 8):
+        acc = np.zeros_like(whole)
+        for rank in range(world):
+            part, st = handle.pair_histogram_bins(x, labels, thr, 0, rank=rank, world=world)
+            acc += part
+        np.testing.assert_array_equal(acc, whole)
+
+
+def test_histogram_edge_cases(handle):
+    thr = so.default_thresholds(0)
+    x = unit(1, 64, 0)
+    out = handle.pair_histogram(x, np.array([5]), thr, 0)
+    assert out['n_same'] == 0 and out['n_diff'] == 0
+    x = unit(2, 64, 0)
+    out = handle.pair_histogram(x, np.array([5, 5]), thr, 0)
+    assert out['n_same'] == 1 and out['n_diff'] == 0
+    from facenet_b200 import _capi
+    with pytest.raises(_capi.FnbError) as e:
+        handle.pair_histogram(3 * unit(300, 64, 1), np.arange(300), thr, 0)
+    assert e.value.code == _capi.FNB_ERR_NOT_NORMALIZED
+    with pytest.raises(_capi.FnbError) as e:
+        handle.pair_histogram(unit(30, 64, 1), np.arange(30), thr, 5)
+    assert e.value.code == _capi.FNB_ERR_BAD_METRIC
+    with pytest.raises(_capi.FnbError):
+        handle.pair_histogram(unit(30, 100, 1), np.arange(30), thr, 0)       # D not a multiple of 64
+    # single threshold, arbitrary (non-grid) values
+    x, labels = ragged(2, n_classes=20, d=64)
+    for t in (0.0, 1.2345, 4.0, 7.0):
+        ref = so.pair_histogram(x, labels, [t], 0)
+        out = handle.pair_histogram(x, labels, [t], 0)
+        assert abs(int(out['same'][0]) - int(ref['same'][0])) + abs(int(out['diff'][0]) - int(ref['diff'][0])) <= out['stats']['eps_window']
+
+
+def test_histogram_100k_properties(handle):
+    """BASELINE config 2 size (100,000 x 512): size-independent properties."""
+    import torch
+    n, per = 100_000, 50
+    x, labels = so.synthetic_embeddings([per] * (n // per), dim=512, sigma=1.1, seed=0)
+    thr = so.default_thresholds(0)
+    xt, lt = torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda()
+    out = handle.pair_histogram(xt, lt, thr, 0)
+    assert out['n_same'] == (n // per) * per * (per - 1) // 2
+    assert out['n_same'] + out['n_diff'] == n * (n - 1) // 2
+    assert np.all(np.diff(out['same']) >= 0) and np.all(np.diff(out['diff']) >= 0)
+    assert out['same'][0] == 0 and out['diff'][0] == 0
+    assert out['same'][-1] + out['diff'][-1] <= n * (n - 1) // 2
+    # a sampled row block against the oracle (same/diff counts of rows 0..511 vs everything)
+    sub = np.arange(0, n, 97)
+    ref = so.pair_histogram(x[sub], labels[sub], thr, 0)
+    got = handle.pair_histogram(x[sub], labels[sub], thr, 0)
+    check_hist(got, ref, sub.size)
+    # permutation invariance of the integer histogram
+    perm = np.random.default_rng(1).permutation(n)
+    out2 = handle.pair_histogram(x[perm], labels[perm], thr, 0)
+    assert np.abs(out2['same'] - out['same']).sum() + np.abs(out2['diff'] - out['diff']).sum() <= 2 * out['stats']['eps_window']
+
+
+# ------------------------------------------------------------------------------ A3-A6 class-balanced path
+
+def test_confidence_matrix_golden(fst, golden_dir):
+    g = np.load(golden_dir / 'confidence.npz')
+    x, labels = g['embeddings'], g['labels']
+    for metric in (0, 1):
+        thr = so.default_thresholds(metric)
+        calc = fst.SimilarityCalculator(x, labels, metric)
+        assert calc.nrof_classes == 16 and calc.nrof_images(0) == 1
+        cm = fst.ConfidenceMatrix(calc, thr)
+        # one pair moving across a threshold changes a rate by at most 1 / (block size * C)
+        for name in ('tp', 'tn', 'fp', 'fn', 'accuracy', 'precision', 'tp_rates', 'tn_rates'):
+            np.testing.assert_allclose(getattr(cm, name), g['%s_m%d' % (name, metric)], rtol=0, atol=2e-3, err_msg=name)
+        exact = so.confidence_matrix_exact_order(x, labels, thr, metric)
+        same_counts = np.abs(cm.tp - exact.tp).max() < 1e-12 and np.abs(cm.fp - exact.fp).max() < 1e-12
+        assert same_counts or cm.stats['eps_window'] > 0
+        sims, weight = calc.evaluate(3, 3)
+        ref_sims, ref_weight = so.SimilarityCalculator(x, labels, metric).evaluate(3, 3)
+        assert weight == ref_weight and sims.shape == ref_sims.shape
+
+
+def test_confidence_matrix_vs_oracle_many_size_groups(fst):
+    sizes = so.lfw_like_class_sizes(n_images=1400, n_ids=600, n_single=420, max_size=60, seed=1)
+    x, labels = so.synthetic_embeddings(sizes, dim=128, sigma=1.2, seed=8)
+    thr = so.default_thresholds(0)
+    cm = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, 0), thr)
+    ref = so.confidence_matrix_weighted(x, labels, thr, 0)
+    for name in ('tp', 'tn', 'fp', 'fn'):
+        np.testing.assert_allclose(getattr(cm, name), getattr(ref, name), rtol=0, atol=1e-4, err_msg=name)
+    np.testing.assert_allclose(cm.tp + cm.fn, np.count_nonzero(sizes >= 2) / sizes.size, atol=1e-12)
+    np.testing.assert_allclose(cm.fp + cm.tn, 1.0, atol=1e-12)
+    assert np.argmax(cm.accuracy) == np.argmax(ref.accuracy)
+
+
+def test_validation_golden(fst, golden_dir):
+    g = np.load(golden_dir / 'validation.npz')
+    x, labels = g['embeddings'], g['labels']
+
+    class Cfg:
+        nrof_folds, far_target = 10, 1.e-3
+
+    for metric in (0, 1):
+        Cfg.metric = metric
+        v = fst.FaceToFaceValidation(x, labels, Cfg)
+        assert v.elapsed_time > 0 and v.thresholds.shape == (100,)
+        for r, tag in zip(v.reports, ('acc', 'far')):
+            dct = r.dict
+            keys = [str(k) for k in g['%s_keys_m%d' % (tag, metric)]]
+            np.testing.assert_allclose([float(dct[k]) for k in keys], g['%s_vals_m%d' % (tag, metric)], rtol=0, atol=2e-3)
+            got_thr = np.array([float(m.threshold[0]) for m in r.conf_matrix_test])
+            if tag == 'acc':
+                np.testing.assert_array_equal(got_thr, g['acc_thr_m%d' % metric])      # grid points: exact
+            else:
+                np.testing.assert_allclose(got_thr, g['far_thr_m%d' % metric], rtol=0, atol=2e-3)
+        assert 'MaximumAccuracy' in repr(v)

@@ -1,0 +1,203 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the header
+declares, the similarity-cut tables reproduce NumPy's distance comparison, and the class-balanced
+rate arithmetic of facenet_b200.statistics equals the reference's (golden fixtures) when the
+histogram entry point is replaced by a NumPy stand-in (tests/emulator.py).  No GPU compute here."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from facenet_b200 import _capi, statistics as fst
+from oracle import statistics_oracle as so
+from tests import emulator
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.load_library()
+    header = (ROOT / 'include' / 'facenet_b200.h').read_text()
+    declared = set(re.findall(r'\b(fnb_[a-z_0-9]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_capi.EXPORTS)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert lib.fnb_version() >= 100
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof/offsetof of the ctypes mirrors equal what a C compiler sees in the header."""
+    import subprocess
+    src = tmp_path / 'sizes.c'
+    src.write_text("""
+#include <stdio.h>
+#include <stddef.h>
+#include "facenet_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(DLTensor), sizeof(fnb_region), sizeof(fnb_options), sizeof(fnb_stats),
+         offsetof(fnb_options, cuts), offsetof(fnb_options, max_ctas), offsetof(fnb_stats, tiles), offsetof(fnb_stats, kernel_ms));
+  return 0; }
+""")
+    exe = tmp_path / 'sizes'
+    subprocess.run(['gcc', '-I', str(ROOT / 'include'), str(src), '-o', str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_capi.DLTensor), ctypes.sizeof(_capi.Region), ctypes.sizeof(_capi.Options), ctypes.sizeof(_capi.Stats),
+            _capi.Options.cuts.offset, _capi.Options.max_ctas.offset, _capi.Stats.tiles.offset, _capi.Stats.kernel_ms.offset]
+    assert got == want
+    assert _capi.REGION_DTYPE.itemsize == ctypes.sizeof(_capi.Region)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(_capi.FnbError, match='no CUDA device'):
+        _capi.Handle(0)
+    with pytest.raises(_capi.FnbError):
+        fst.pairwise_similarities(np.eye(4, 64, dtype=np.float32))
+
+
+def _dist(s, metric):
+    s = np.clip(s.astype(np.float32), np.float32(-1), np.float32(1))
+    return 2 * (1 - s) if metric == 0 else np.arccos(s)
+
+
+@pytest.mark.parametrize('metric', [0, 1])
+def test_numpy_cuts_reproduce_distance_comparison(metric):
+    thr = so.default_thresholds(metric)
+    cuts = _capi.numpy_cuts(thr, metric)
+    rng = np.random.default_rng(0)
+    fin = np.isfinite(cuts)
+    probe = np.concatenate([cuts[fin], np.nextafter(cuts[fin], np.float32(-2)), np.nextafter(cuts[fin], np.float32(2)),
+                            rng.uniform(-1, 1, 20000).astype(np.float32), np.float32([-1, 1, 0])])
+    d = _dist(probe, metric)
+    for t, c in zip(thr, cuts):
+        np.testing.assert_array_equal(d.astype(np.float64) < t, np.clip(probe, -1, 1) >= c)
+    assert np.isinf(cuts[0])                   # nothing is < 0
+
+
+@pytest.mark.parametrize('metric', [0, 1])
+def test_counts_from_bins_c_abi(metric):
+    """fnb_counts_from_bins (host-only C entry point) + cut tables against direct counting."""
+    lib = _capi.load_library()
+    thr = so.default_thresholds(metric)
+    rng = np.random.default_rng(1)
+    s = rng.uniform(-1.05, 1.05, 50000).astype(np.float32)
+    same = rng.random(s.size) < 0.3
+    cuts = _capi.numpy_cuts(thr, metric)
+    order = np.sort(cuts)
+    k = np.searchsorted(order, np.clip(s, -1, 1), side='right')
+    bins = np.stack([np.bincount(k, minlength=thr.size + 1), np.bincount(k[same], minlength=thr.size + 1)]).astype(np.uint64)
+    h = _capi.Handle.__new__(_capi.Handle)
+    h.lib = lib
+    h.h = None
+    out = h.counts_from_bins(bins, thr, metric=metric, cuts=cuts)
+    d = _dist(s, metric).astype(np.float64)
+    np.testing.assert_array_equal(out['same'], [(d[same] < t).sum() for t in thr])
+    np.testing.assert_array_equal(out['diff'], [(d[~same] < t).sum() for t in thr])
+    assert out['n_same'] == same.sum() and out['n_diff'] == (~same).sum()
+    if metric == 0:
+        # library-computed cuts (libm) are identical for metric 0
+        out2 = h.counts_from_bins(bins, thr, metric=metric, cuts=None)
+        np.testing.assert_array_equal(out2['same'], out['same'])
+    np.testing.assert_array_equal(fst._counts_lt(bins, cuts)[1], out['same'])
+
+
+def test_size_group_plan_invariants():
+    rng = np.random.default_rng(3)
+    sizes = np.array([1, 1, 5, 2, 2, 7, 1, 5, 3])
+    cls = rng.permutation(np.repeat(np.arange(sizes.size), sizes))
+    perm, cls_sorted, regions, ia, ib, gsize, gcount = fst._size_group_plan(cls, sizes)
+    assert sorted(perm.tolist()) == list(range(cls.size))
+    assert np.all(np.diff(cls_sorted) >= 0)
+    assert list(gsize) == [1, 2, 3, 5, 7] and list(gcount) == [3, 2, 1, 2, 1]
+    # every unordered pair is covered exactly once
+    cover = np.zeros((cls.size, cls.size), dtype=int)
+    for r in regions:
+        blk = np.ones((r['row_end'] - r['row_begin'], r['col_end'] - r['col_begin']), dtype=int)
+        if r['tri']:
+            blk = np.triu(blk, 1)
+        cover[r['row_begin']:r['row_end'], r['col_begin']:r['col_end']] += blk
+    assert np.array_equal(cover, np.triu(np.ones_like(cover), 1))
+    # rows of one rectangle side all have the same class size
+    size_of_row = sizes[cls][perm]
+    for r in regions:
+        assert len(set(size_of_row[r['row_begin']:r['row_end']])) == 1
+        assert len(set(size_of_row[r['col_begin']:r['col_end']])) == 1
+
+
+def test_kfold_split_matches_sklearn():
+    from sklearn.model_selection import KFold
+    for n, k in ((330, 10), (13, 5)):
+        ref = list(KFold(n_splits=k, shuffle=True, random_state=0).split(np.arange(n)))
+        for (a, b), (c, d) in zip(ref, fst.kfold_split(n, k)):
+            np.testing.assert_array_equal(a, c)
+            np.testing.assert_array_equal(b, d)
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    monkeypatch.setattr(fst, '_handle', lambda: emulator.EmulatedHandle())
+
+
+def test_confidence_matrix_host_math_golden(emulated, golden_dir):
+    g = np.load(golden_dir / 'confidence.npz')
+    x, labels = g['embeddings'], g['labels']
+    for metric in (0, 1):
+        thr = so.default_thresholds(metric)
+        cm = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, metric), thr)
+        for name in ('tp', 'tn', 'fp', 'fn', 'accuracy', 'precision', 'tp_rates', 'tn_rates'):
+            np.testing.assert_allclose(getattr(cm, name), g['%s_m%d' % (name, metric)], rtol=0, atol=1e-3, err_msg=name)
+        exact = so.confidence_matrix_exact_order(x, labels, thr, metric)
+        for name in ('tp', 'tn', 'fp', 'fn'):
+            np.testing.assert_allclose(getattr(cm, name), getattr(exact, name), rtol=0, atol=1e-13, err_msg=name)
+        one = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, metric), np.array(thr[31] + 0.0123))
+        assert one.threshold.shape == (1,)
+        np.testing.assert_allclose([one.tp[0], one.tn[0], one.fp[0], one.fn[0]], g['single_m%d' % metric], rtol=0, atol=1e-3)
+
+
+def test_validation_host_math_golden(emulated, golden_dir):
+    g = np.load(golden_dir / 'validation.npz')
+    x, labels = g['embeddings'], g['labels']
+
+    class Cfg:
+        nrof_folds, far_target = 10, 1.e-3
+
+    for metric in (0, 1):
+        Cfg.metric = metric
+        v = fst.FaceToFaceValidation(x, labels, Cfg)
+        for r, tag in zip(v.reports, ('acc', 'far')):
+            dct = r.dict
+            keys = [str(k) for k in g['%s_keys_m%d' % (tag, metric)]]
+            assert sorted(dct.keys()) == keys
+            np.testing.assert_allclose([float(dct[k]) for k in keys], g['%s_vals_m%d' % (tag, metric)], rtol=0, atol=2e-3)
+            got_thr = np.array([float(m.threshold[0]) for m in r.conf_matrix_test])
+            if tag == 'acc':
+                np.testing.assert_array_equal(got_thr, g['acc_thr_m%d' % metric])
+            else:
+                np.testing.assert_allclose(got_thr, g['far_thr_m%d' % metric], rtol=0, atol=2e-3)
+        assert repr(v).split('elapsed_time')[0].splitlines()[:3] == str(g['repr_m%d' % metric]).splitlines()[:3]
+        assert set(v.dict.keys()) == {'MaximumAccuracy', 'FalseAlarmRate(FAR = 0.001)'}
+
+
+def test_validation_rejects_bad_metric_and_length(emulated):
+    class Cfg:
+        metric, nrof_folds, far_target = 2, 10, 1.e-3
+    x = np.eye(20, 64, dtype=np.float32)
+    with pytest.raises(ValueError, match='Undefined similarity metric 2'):
+        fst.FaceToFaceValidation(x, np.arange(20) // 2, Cfg)
+    Cfg.metric = 0
+    with pytest.raises(AssertionError):
+        fst.FaceToFaceValidation(x, np.arange(19), Cfg)
+
+
+def test_split_embeddings_matches_reference_semantics():
+    x = np.arange(24, dtype=np.float32).reshape(8, 3)
+    labels = np.array([5, -1, 5, 7, -1, -1, 7, 100])
+    got = fst.split_embeddings(x, labels)
+    ref = so.split_embeddings(x, labels)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
