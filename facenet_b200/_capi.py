@@ -369,7 +369,58 @@ class Handle:
         return bins, st.as_dict()
 
 
+    # ---- class-balanced confidence matrix + threshold selection from the bins left on the device
+    def confidence_from_last_bins(self, nkeys, w_same, w_diff, thresholds, metric=0, far_target=0.0, cuts='numpy', eps=1.e-5):
+        """tp, tn, fp, fn (float64 [T]), index of the first accuracy maximum and the FAR threshold
+        (statistics.py:130-138,296,299-302) from the keyed bins of the last ``region_histogram_bins`` call."""
+        thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
+        if isinstance(cuts, str) and cuts == 'numpy':
+            cuts = numpy_cuts(thr, metric)
+        o, keep = self.options(metric=metric, eps=eps, cuts=cuts)
+        ws = np.ascontiguousarray(w_same, dtype=np.float64).reshape(-1)
+        wd = np.ascontiguousarray(w_diff, dtype=np.float64).reshape(-1)
+        if ws.size != nkeys or wd.size != nkeys:
+            raise ValueError('w_same / w_diff must have nkeys entries')
+        out = np.zeros((4, thr.size), dtype=np.float64)
+        amax = ctypes.c_int32(-1)
+        far = ctypes.c_double(0.0)
+        dp = ctypes.POINTER(ctypes.c_double)
+        rc = self.lib.fnb_confidence_from_last_bins(
+            self.h, int(nkeys), ws.ctypes.data_as(dp), wd.ctypes.data_as(dp), thr.ctypes.data_as(dp), thr.size,
+            ctypes.byref(o), float(far_target), out[0].ctypes.data_as(dp), out[1].ctypes.data_as(dp),
+            out[2].ctypes.data_as(dp), out[3].ctypes.data_as(dp), ctypes.byref(amax), ctypes.byref(far))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return {'tp': out[0], 'tn': out[1], 'fp': out[2], 'fn': out[3], 'argmax_accuracy': int(amax.value),
+                'far_threshold': float(far.value)}
+
+    # ---- triplet mining (semantics: oracle/mining_oracle.py; not in the reference fork)
+    def mine(self, embeddings, labels, alpha=0.2, kmax=None, mode='fp16x3', atol=1.e-5):
+        embeddings = _as_f32_matrix(embeddings, 'embeddings')
+        labels = _as_labels(labels)
+        b = int(embeddings.shape[0])
+        if kmax is None:
+            lab_np = labels if isinstance(labels, np.ndarray) else np.asarray(labels.cpu())
+            kmax = int(np.unique(lab_np, return_counts=True)[1].max()) - 1 if b else 0
+        kmax = int(kmax)
+        hp = np.full(b, -1, dtype=np.int32)
+        hn = np.full(b, -1, dtype=np.int32)
+        pi = np.full((b, kmax), -1, dtype=np.int32)
+        sh = np.full((b, kmax), -1, dtype=np.int32)
+        el = np.zeros((b, kmax), dtype=np.int32)
+        o, keep = self.options(mode=mode, metric=0, atol=atol)
+        st = Stats()
+        be, bl = Borrowed(embeddings), Borrowed(labels)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        rc = self.lib.fnb_mine(self.h, be.ptr, bl.ptr, float(alpha), ctypes.byref(o), hp.ctypes.data_as(ip), hn.ctypes.data_as(ip),
+                               kmax, pi.ctypes.data_as(ip), sh.ctypes.data_as(ip), el.ctypes.data_as(ip), ctypes.byref(st))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return {'hardest_pos': hp, 'hardest_neg': hn, 'pos_index': pi, 'semi_hard': sh, 'eligible': el, 'stats': st.as_dict()}
+
+
 _default_handles = {}
+
 
 
 def default_handle(device=0):

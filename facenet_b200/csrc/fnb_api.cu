@@ -107,14 +107,7 @@ int build_cut_tables(const double* thresholds, int T, int metric, double eps, co
 // ---------------------------------------------------------------------------------------
 // tensors
 
-struct TensorView {
-    void* data = nullptr;
-    bool on_device = false;
-    long long rows = 0, cols = 1;
-    int bits = 0, code = 0;
-};
-
-static int view_tensor(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_min, int want_ndim_max, TensorView* v) {
+int fnb::dl_view(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_min, int want_ndim_max, DLView* v) {
     if (!t) return h->fail(FNB_ERR_INVALID, "%s: NULL tensor", name);
     if (t->ndim < want_ndim_min || t->ndim > want_ndim_max) return h->fail(FNB_ERR_INVALID, "%s: ndim %d not supported", name, t->ndim);
     if (t->dtype.lanes != 1) return h->fail(FNB_ERR_INVALID, "%s: vector dtypes not supported", name);
@@ -140,7 +133,7 @@ static int view_tensor(fnb_context* h, const DLTensor* t, const char* name, int 
 }
 
 // device pointer to the tensor's bytes (staged through `stage` when the tensor lives on the host)
-static int to_device(fnb_context* h, const TensorView& v, size_t bytes, DevBuf& stage, const void** out) {
+int fnb::dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, const void** out) {
     if (v.on_device || bytes == 0) { *out = v.data; return FNB_OK; }
     CK(stage.ensure(bytes));
     CK(cudaMemcpyAsync(stage.p, v.data, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -167,7 +160,7 @@ static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 // ---------------------------------------------------------------------------------------
 // regions
 
-static void finish_regions(std::vector<RegionDev>& regs, int tile) {
+void fnb::finish_regions(std::vector<RegionDev>& regs, int tile) {
     long long t = 0;
     for (auto& r : regs) {
         r.nrb = (r.row_end - r.row_begin + tile - 1) / tile;
@@ -267,7 +260,7 @@ extern "C" void fnb_destroy(fnb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
-                      &h->counters, &h->out, &h->strip, &h->mine_out};
+                      &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io};
     for (DevBuf* b : bufs) b->release();
     h->pinned.release();
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -297,14 +290,9 @@ extern "C" int fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* 
 // ---------------------------------------------------------------------------------------
 // shared launch plumbing
 
-struct Operands {
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    int num_pass = 3; bool tf32 = false; int fmt = 0; int elem_bytes = 2; float prescale = 1.f;
-};
-
 // split/convert `x` ([n, d] fp32 on the device, optionally gathered through perm) into hi/lo arrays + TMA maps
-static int prepare_side(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
-                        DevBuf& hi, DevBuf& lo, Operands& op, CUtensorMap* m_hi, CUtensorMap* m_lo) {
+int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
+                        DevBuf& hi, DevBuf& lo, GramOperands& op, CUtensorMap* m_hi, CUtensorMap* m_lo) {
     const long long n_pad = pad_rows(n);
     const size_t bytes = (size_t)n_pad * d * op.elem_bytes;
     CK(hi.ensure(bytes));
@@ -317,7 +305,7 @@ static int prepare_side(fnb_context* h, int mode, const float* x, const long lon
     return rc;
 }
 
-static int check_embeddings(fnb_context* h, const TensorView& v, const char* name) {
+int fnb::dl_check_embeddings(fnb_context* h, const DLView& v, const char* name) {
     if (v.code != kDLFloat || v.bits != 32) return h->fail(FNB_ERR_INVALID, "%s: embeddings must be float32", name);
     if (v.cols < 64 || v.cols > 4096 || (v.cols % 64) != 0)
         return h->fail(FNB_ERR_INVALID, "%s: embedding dimension %lld not supported (multiple of 64 in [64, 4096])", name, v.cols);
@@ -325,12 +313,7 @@ static int check_embeddings(fnb_context* h, const TensorView& v, const char* nam
     return FNB_OK;
 }
 
-struct DeviceScalars {      // layout of h->counters
-    unsigned long long counters[2];
-    unsigned int range_ord[4];
-};
-
-static int reset_scalars(fnb_context* h) {
+int fnb::reset_scalars(fnb_context* h) {
     CK(h->counters.ensure(sizeof(DeviceScalars)));
     DeviceScalars init;
     init.counters[0] = init.counters[1] = 0;
@@ -344,7 +327,7 @@ static int reset_scalars(fnb_context* h) {
     return FNB_OK;
 }
 
-static int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs) {
+int fnb::upload_regions(fnb_context* h, const std::vector<RegionDev>& regs) {
     CK(h->regions.ensure(regs.size() * sizeof(RegionDev)));
     CK(cudaMemcpyAsync(h->regions.p, regs.data(), regs.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, h->stream));
     return FNB_OK;
@@ -360,18 +343,18 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     fnb_options opt; if (opt_in) opt = *opt_in; else fnb_default_options(&opt);
     if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
     CK(cudaSetDevice(h->device));
-    Operands op;
+    GramOperands op;
     if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
-    TensorView va, vb, vo;
-    int rc = view_tensor(h, xa, "xa", 2, 2, &va); if (rc) return rc;
-    if ((rc = check_embeddings(h, va, "xa"))) return rc;
+    DLView va, vb, vo;
+    int rc = dl_view(h, xa, "xa", 2, 2, &va); if (rc) return rc;
+    if ((rc = dl_check_embeddings(h, va, "xa"))) return rc;
     const bool self = (xb == nullptr);
     if (!self) {
-        if ((rc = view_tensor(h, xb, "xb", 2, 2, &vb))) return rc;
-        if ((rc = check_embeddings(h, vb, "xb"))) return rc;
+        if ((rc = dl_view(h, xb, "xb", 2, 2, &vb))) return rc;
+        if ((rc = dl_check_embeddings(h, vb, "xb"))) return rc;
         if (vb.cols != va.cols) return h->fail(FNB_ERR_INVALID, "xa and xb have different dimensions");
     }
-    if ((rc = view_tensor(h, out, "out", 1, 2, &vo))) return rc;
+    if ((rc = dl_view(h, out, "out", 1, 2, &vo))) return rc;
     if (vo.code != kDLFloat || vo.bits != 32) return h->fail(FNB_ERR_INVALID, "out must be float32");
     const long long na = va.rows, nb = self ? va.rows : vb.rows;
     const int d = (int)va.cols;
@@ -382,11 +365,11 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     if (out_elems == 0) return FNB_OK;                   // statistics.py:38: empty in -> empty out
 
     const void* da = nullptr; const void* db = nullptr;
-    if ((rc = to_device(h, va, (size_t)na * d * 4, h->stage_a, &da))) return rc;
-    if (!self && (rc = to_device(h, vb, (size_t)nb * d * 4, h->stage_b, &db))) return rc;
-    if ((rc = prepare_side(h, opt.mode, (const float*)da, nullptr, na, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
+    if ((rc = dl_to_device(h, va, (size_t)na * d * 4, h->stage_a, &da))) return rc;
+    if (!self && (rc = dl_to_device(h, vb, (size_t)nb * d * 4, h->stage_b, &db))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)da, nullptr, na, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
     if (self) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; }
-    else if ((rc = prepare_side(h, opt.mode, (const float*)db, nullptr, nb, d, h->b_hi, h->b_lo, op, &op.b_hi, &op.b_lo))) return rc;
+    else if ((rc = prepare_operand(h, opt.mode, (const float*)db, nullptr, nb, d, h->b_hi, h->b_lo, op, &op.b_hi, &op.b_lo))) return rc;
 
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
@@ -438,7 +421,7 @@ struct HistLaunch {
 };
 
 // uploads tables, zeroes bins, launches the HIST kernel over `regs`; leaves bins on the device
-static int run_hist(fnb_context* h, const fnb_options& opt, Operands& op, const std::vector<RegionDev>& regs, int cg,
+static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, const std::vector<RegionDev>& regs, int cg,
                     int d, const int32_t* cls_dev, const double* thresholds, int T, HistLaunch& hl, int force_slow)
 {
     if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &hl.ct))
@@ -530,15 +513,15 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) return h->fail(FNB_ERR_INVALID, "bad rank/world %d/%d", opt.rank, opt.world);
     CK(cudaSetDevice(h->device));
     if (stats) memset(stats, 0, sizeof(*stats));
-    Operands op;
+    GramOperands op;
     if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
-    TensorView ve, vl, vb;
-    int rc = view_tensor(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
-    if ((rc = check_embeddings(h, ve, "embeddings"))) return rc;
-    if ((rc = view_tensor(h, labels, "labels", 1, 1, &vl))) return rc;
+    DLView ve, vl, vb;
+    int rc = dl_view(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
+    if ((rc = dl_check_embeddings(h, ve, "embeddings"))) return rc;
+    if ((rc = dl_view(h, labels, "labels", 1, 1, &vl))) return rc;
     if (vl.code != kDLInt || (vl.bits != 32 && vl.bits != 64)) return h->fail(FNB_ERR_INVALID, "labels must be int32 or int64");
     if (vl.rows != ve.rows) return h->fail(FNB_ERR_INVALID, "len(labels) != embeddings.shape[0]");
-    if ((rc = view_tensor(h, bins_out, "bins_out", 2, 2, &vb))) return rc;
+    if ((rc = dl_view(h, bins_out, "bins_out", 2, 2, &vb))) return rc;
     if (vb.bits != 64 || vb.rows != 2 || vb.cols != T + 1) return h->fail(FNB_ERR_INVALID, "bins_out must be a 64-bit integer [2, T+1] tensor");
     const long long n = ve.rows;
     const int d = (int)ve.cols;
@@ -560,10 +543,10 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
 
     const void* de = nullptr; const void* dl = nullptr;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if ((rc = to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
-    if ((rc = to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
+    if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    if ((rc = dl_to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
-    if ((rc = prepare_side(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
     op.b_hi = op.a_hi; op.b_lo = op.a_lo;
 
     const int cg = pick_cta_group(&opt);
@@ -650,11 +633,11 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) return h->fail(FNB_ERR_INVALID, "bad rank/world");
     CK(cudaSetDevice(h->device));
     if (stats) memset(stats, 0, sizeof(*stats));
-    Operands op;
+    GramOperands op;
     if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
-    TensorView ve;
-    int rc = view_tensor(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
-    if ((rc = check_embeddings(h, ve, "embeddings"))) return rc;
+    DLView ve;
+    int rc = dl_view(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
+    if ((rc = dl_check_embeddings(h, ve, "embeddings"))) return rc;
     const long long n = ve.rows;
     const int d = (int)ve.cols;
     const size_t out_bytes = (size_t)nkeys * 2 * (T + 1) * 8;
@@ -678,12 +661,12 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
 
     const void* de = nullptr;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if ((rc = to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
     CK(h->perm.ensure(n * 8));
     CK(h->cls.ensure(n * 4));
     CK(cudaMemcpyAsync(h->perm.p, perm, n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->cls.p, cls, n * 4, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = prepare_side(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
     op.b_hi = op.a_hi; op.b_lo = op.a_lo;
 
     HistLaunch hl; hl.nkeys = nkeys;
@@ -709,13 +692,3 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     return FNB_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// TEMPORARY stubs (replaced by fnb_select.cu / fnb_mine.cu)
-extern "C" int fnb_confidence_from_last_bins(fnb_handle h, int, const double*, const double*, const double*, int,
-                                             const fnb_options*, double, double*, double*, double*, double*, int32_t*, double*) {
-    return h ? h->fail(FNB_ERR_UNSUPPORTED, "not implemented yet") : FNB_ERR_INVALID;
-}
-extern "C" int fnb_mine(fnb_handle h, const DLTensor*, const DLTensor*, float, const fnb_options*, int32_t*, int32_t*, int,
-                        int32_t*, int32_t*, int32_t*, fnb_stats*) {
-    return h ? h->fail(FNB_ERR_UNSUPPORTED, "not implemented yet") : FNB_ERR_INVALID;
-}

@@ -75,7 +75,7 @@ struct fnb_context {
     fnb::DevBuf stage_a, stage_b, stage_lab;          // H2D staging of kDLCPU inputs
     fnb::DevBuf a_hi, a_lo, b_hi, b_lo;               // split / converted operands
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
-    fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out;
+    fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
     int last_nkeys = 0, last_T = 0;
 
@@ -84,7 +84,34 @@ struct fnb_context {
 
 namespace fnb {
 
+// tensors crossing the C ABI (fnb_api.cu)
+struct DLView {
+    void* data = nullptr;
+    bool on_device = false;
+    long long rows = 0, cols = 1;
+    int bits = 0, code = 0;
+};
+
+// operand arrays of one Gram launch: TMA maps over the split / converted embeddings
+struct GramOperands {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int num_pass = 3; bool tf32 = false; int fmt = 0; int elem_bytes = 2; float prescale = 1.f;
+};
+
+struct DeviceScalars {      // layout of fnb_context::counters
+    unsigned long long counters[2];
+    unsigned int range_ord[4];
+};
+
 // fnb_api.cu
+int dl_view(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_min, int want_ndim_max, DLView* v);
+int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, const void** out);
+int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
+int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
+                    DevBuf& hi, DevBuf& lo, GramOperands& op, CUtensorMap* m_hi, CUtensorMap* m_lo);
+void finish_regions(std::vector<RegionDev>& regs, int tile);
+int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
+int reset_scalars(fnb_context* h);
 int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, float* prescale);
 int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out);
 

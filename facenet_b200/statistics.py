@@ -200,7 +200,7 @@ class ConfidenceMatrix:
     ``count(n) = #{pairs : d < threshold_n}`` (strict, float64 compare).  The integer counts come from
     one fused Gram + histogram launch; the float64 rates are formed here."""
 
-    def __init__(self, calculator, threshold):
+    def __init__(self, calculator, threshold, _far_target=None):
         self.threshold = np.array(threshold, ndmin=1)
         nt = self.threshold.size
         self.tp = np.zeros(nt)
@@ -208,6 +208,9 @@ class ConfidenceMatrix:
         self.fp = np.zeros(nt)
         self.fn = np.zeros(nt)
         self.stats = None
+        # filled by the device selection kernel when the whole threshold grid went through one launch
+        self._argmax_accuracy = None
+        self._far_threshold = None
         if nt == 0 or calculator._x.shape[0] < 2:
             return
         thr = self.threshold.astype(np.float64).reshape(-1)
@@ -216,6 +219,15 @@ class ConfidenceMatrix:
             raise ValueError('Undefined similarity metric {}'.format(metric))
         nc = calculator.nrof_classes
         perm, cls_sorted, regions, ia, ib, gsize, gcount = _size_group_plan(calculator._cls, calculator._sizes)
+        # weight of one pair of the rectangle (size group a, size group b): statistics.py:91-99,133-138
+        #   same identity (diagonal rectangles only): 1 / (n (n - 1) / 2 * C)
+        #   different identity:                       1 / (n_a * n_b * C (C - 1) / 2)
+        npairs = gsize[ia] * (gsize[ia] - 1) / 2
+        w_same = np.zeros(ia.size)
+        ok = (ia == ib) & (npairs > 0)
+        w_same[ok] = 1.0 / (npairs[ok] * nc)
+        w_diff = 1.0 / (gsize[ia] * gsize[ib] * (nc * (nc - 1) / 2)) if nc > 1 else np.zeros(ia.size)
+        w_diff = np.asarray(w_diff, dtype=np.float64)
         h = _handle()
         for t0 in range(0, nt, _capi.MAX_THRESHOLDS):
             sl = slice(t0, min(nt, t0 + _capi.MAX_THRESHOLDS))
@@ -224,28 +236,15 @@ class ConfidenceMatrix:
                 bins, self.stats = h.region_histogram_bins(calculator._x, perm, cls_sorted, regions, regions.size,
                                                            thr[sl], metric=metric, mode=_state['mode'],
                                                            cta_group=_state['cta_group'], cuts=cuts)
+                sel = h.confidence_from_last_bins(regions.size, w_same, w_diff, thr[sl], metric=metric, cuts=cuts,
+                                                  far_target=0.0 if _far_target is None else float(_far_target))
             except _capi.FnbError as err:
                 _raise_like_reference(err, metric)
-            lt = _counts_lt(bins, cuts)                              # [keys, 2, T]
-            tot = bins.sum(axis=-1).astype(np.int64)                 # [keys, 2]
-            same_lt = lt[:, 1, :].astype(np.float64)
-            diff_lt = (lt[:, 0, :] - lt[:, 1, :]).astype(np.float64)
-            same_tot = tot[:, 1].astype(np.float64)[:, None]
-            diff_tot = (tot[:, 0] - tot[:, 1]).astype(np.float64)[:, None]
-            diag = ia == ib
-            # same-identity pairs only exist on diagonal rectangles: block size n(n-1)/2, weight * C
-            w_same = np.zeros(ia.size)
-            npairs = gsize[ia] * (gsize[ia] - 1) / 2
-            ok = diag & (npairs > 0)
-            w_same[ok] = 1.0 / (npairs[ok] * nc)
-            # different-identity pairs: block size n_i * n_k, weight * C(C-1)/2
-            w_diff = 1.0 / (gsize[ia] * gsize[ib] * (nc * (nc - 1) / 2)) if nc > 1 else np.zeros(ia.size)
-            w_same = w_same[:, None]
-            w_diff = np.asarray(w_diff, dtype=np.float64)[:, None]
-            self.tp[sl] = (same_lt * w_same).sum(axis=0)
-            self.fn[sl] = ((same_tot - same_lt) * w_same).sum(axis=0)
-            self.fp[sl] = (diff_lt * w_diff).sum(axis=0)
-            self.tn[sl] = ((diff_tot - diff_lt) * w_diff).sum(axis=0)
+            self.tp[sl], self.tn[sl], self.fp[sl], self.fn[sl] = sel['tp'], sel['tn'], sel['fp'], sel['fn']
+            if nt <= _capi.MAX_THRESHOLDS:
+                self._argmax_accuracy = sel['argmax_accuracy']
+                if _far_target is not None:
+                    self._far_threshold = sel['far_threshold']
 
     @property
     def accuracy(self):
@@ -414,17 +413,27 @@ class FaceToFaceValidation:
         for train_set, test_set in kfold_split(len(labels), self.config.nrof_folds):
             # evaluations with train set and define the best threshold for the fold
             calculator = SimilarityCalculator(embeddings[train_set], labels[train_set], metric=self.config.metric)
-            matrix = ConfidenceMatrix(calculator, self.thresholds)
+            matrix = ConfidenceMatrix(calculator, self.thresholds, _far_target=self.config.far_target)
             for report in self.reports:
                 report.append_fold('train', matrix)
 
-            # the threshold that gives maximal accuracy (first maximum, statistics.py:296)
-            accuracy_threshold = self.thresholds[np.argmax(matrix.accuracy)]
-
-            # the threshold that gives FAR (FPR, 1-TNR) = far_target (statistics.py:299-302)
-            far_threshold = 0
-            if np.max(matrix.fp_rates) >= self.config.far_target:
-                far_threshold = _slinear(matrix.fp_rates, self.thresholds, self.config.far_target)
+            if matrix._argmax_accuracy is not None:
+                # selected on the device (fnb_confidence_from_last_bins): first accuracy maximum (statistics.py:296)
+                # and the FAR threshold by linear interpolation over fp_rates (statistics.py:299-302)
+                accuracy_threshold = self.thresholds[matrix._argmax_accuracy]
+                far_threshold = matrix._far_threshold
+                if far_threshold != far_threshold:
+                    raise ValueError('A value in x_new is outside the interpolation range.')
+                if far_threshold != 0:
+                    far_threshold = np.array(far_threshold)
+                else:
+                    far_threshold = 0
+            else:
+                # degenerate fold (fewer than two embeddings): nothing was launched
+                accuracy_threshold = self.thresholds[np.argmax(matrix.accuracy)]
+                far_threshold = 0
+                if np.max(matrix.fp_rates) >= self.config.far_target:
+                    far_threshold = _slinear(matrix.fp_rates, self.thresholds, self.config.far_target)
 
             # evaluations with test set: both thresholds in ONE launch, then split per report
             calculator = SimilarityCalculator(embeddings[test_set], labels[test_set], metric=self.config.metric)

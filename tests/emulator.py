@@ -27,8 +27,44 @@ def region_histogram_bins(embeddings, perm, cls, regions, nkeys, thresholds, met
     return bins, {'emulated': True}
 
 
+def confidence_from_bins(bins, w_same, w_diff, thresholds, cuts, far_target):
+    """NumPy statement of fnb_confidence_from_last_bins (include/facenet_b200.h)."""
+    thr = np.asarray(thresholds, dtype=np.float64)
+    order = np.sort(np.asarray(cuts, dtype=np.float32))
+    pos = np.searchsorted(order, cuts, side='right')
+    b = bins.astype(np.int64)
+    suffix = np.concatenate([np.cumsum(b[..., ::-1], axis=-1)[..., ::-1], np.zeros(b.shape[:-1] + (1,), dtype=np.int64)], axis=-1)
+    lt = suffix[..., pos]                                            # [keys, 2, T]
+    tot = suffix[..., 0]
+    ws = np.asarray(w_same, dtype=np.float64)[:, None]
+    wd = np.asarray(w_diff, dtype=np.float64)[:, None]
+    same_lt, diff_lt = lt[:, 1], lt[:, 0] - lt[:, 1]
+    same_tot, diff_tot = tot[:, 1][:, None], (tot[:, 0] - tot[:, 1])[:, None]
+    tp = (same_lt * ws).sum(axis=0)
+    fn = ((same_tot - same_lt) * ws).sum(axis=0)
+    fp = (diff_lt * wd).sum(axis=0)
+    tn = ((diff_tot - diff_lt) * wd).sum(axis=0)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        acc = (tp + tn) / (tp + fp + tn + fn)
+        tnr = np.where((tn + fp) > 0, tn / np.where((tn + fp) > 0, tn + fp, 1), 1.0)
+    fpr = 1 - tnr
+    far = 0.0
+    if fpr.max() >= far_target:
+        if thr.size < 2 or far_target < fpr[0] or far_target > fpr[-1]:
+            far = float('nan')
+        else:
+            j = min(max(int(np.searchsorted(fpr, far_target, side='right')) - 1, 0), thr.size - 2)
+            far = thr[j] if fpr[j + 1] == fpr[j] else thr[j] + (far_target - fpr[j]) / (fpr[j + 1] - fpr[j]) * (thr[j + 1] - thr[j])
+    return {'tp': tp, 'tn': tn, 'fp': fp, 'fn': fn, 'argmax_accuracy': int(np.argmax(acc)), 'far_threshold': float(far)}
+
+
 class EmulatedHandle:
     def region_histogram_bins(self, *a, **kw):
         kw.pop('mode', None)
         kw.pop('cta_group', None)
-        return region_histogram_bins(*a, **kw)
+        self.last_bins, st = region_histogram_bins(*a, **kw)
+        return self.last_bins, st
+
+    def confidence_from_last_bins(self, nkeys, w_same, w_diff, thresholds, metric=0, far_target=0.0, cuts=None, **_):
+        assert self.last_bins.shape[0] == nkeys
+        return confidence_from_bins(self.last_bins, w_same, w_diff, thresholds, cuts, far_target)

@@ -311,3 +311,132 @@ def test_validation_golden(fst, golden_dir):
             else:
                 np.testing.assert_allclose(got_thr, g['far_thr_m%d' % metric], rtol=0, atol=2e-3)
         assert 'MaximumAccuracy' in repr(v)
+
+
+# ------------------------------------------------------------------------------ threshold selection on the device
+
+def test_confidence_selection_kernels_vs_numpy_statement(handle, fst):
+    """fnb_confidence_from_last_bins (suffix scan + fp64 rates + argmax + FAR interpolation) against the NumPy
+    statement of the same contract applied to the SAME integer bins: rates to 1e-15, selections identical."""
+    from tests import emulator
+    from facenet_b200 import _capi
+    sizes = so.lfw_like_class_sizes(n_images=900, n_ids=300, n_single=150, max_size=40, seed=3)
+    x, labels = so.synthetic_embeddings(sizes, dim=128, sigma=1.15, seed=4)
+    for metric in (0, 1):
+        thr = so.default_thresholds(metric)
+        calc = fst.SimilarityCalculator(x, labels, metric)
+        perm, cls_sorted, regions, ia, ib, gsize, gcount = fst._size_group_plan(calc._cls, calc._sizes)
+        nc = calc.nrof_classes
+        rng = np.random.default_rng(0)
+        w_same = np.where(ia == ib, rng.uniform(0.1, 1.0, ia.size), 0.0) / nc
+        w_diff = rng.uniform(0.1, 1.0, ia.size) / (nc * (nc - 1) / 2)
+        cuts = _capi.numpy_cuts(thr, metric)
+        bins, _ = handle.region_histogram_bins(x, perm, cls_sorted, regions, regions.size, thr, metric=metric, cuts=cuts)
+        for far_target in (1e-3, 0.05, 0.5, 2.0):
+            got = handle.confidence_from_last_bins(regions.size, w_same, w_diff, thr, metric=metric, cuts=cuts, far_target=far_target)
+            ref = emulator.confidence_from_bins(bins, w_same, w_diff, thr, cuts, far_target)
+            for name in ('tp', 'tn', 'fp', 'fn'):
+                np.testing.assert_allclose(got[name], ref[name], rtol=1e-14, atol=1e-300, err_msg=name)
+            assert got['argmax_accuracy'] == ref['argmax_accuracy']
+            if np.isnan(ref['far_threshold']):
+                assert np.isnan(got['far_threshold'])
+            else:
+                assert abs(got['far_threshold'] - ref['far_threshold']) <= 1e-12 * max(1.0, abs(ref['far_threshold']))
+    with pytest.raises(_capi.FnbError):
+        handle.confidence_from_last_bins(regions.size + 1, np.zeros(regions.size + 1), np.zeros(regions.size + 1), thr)
+
+
+def test_validation_uses_device_selection(fst, golden_dir):
+    g = np.load(golden_dir / 'validation.npz')
+    x, labels = g['embeddings'], g['labels']
+    thr = so.default_thresholds(0)
+    cm = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, 0), thr, _far_target=1e-3)
+    assert cm._argmax_accuracy == int(np.argmax(cm.accuracy))
+    far = 0.0
+    if np.max(cm.fp_rates) >= 1e-3:
+        far = float(fst._slinear(cm.fp_rates, thr, 1e-3))
+    assert abs(cm._far_threshold - far) <= 1e-12
+
+
+# ------------------------------------------------------------------------------ A8 triplet mining
+
+def _near_tie(d, a, i, j, tol=2.e-5):
+    return i >= 0 and j >= 0 and abs(float(d[a, i]) - float(d[a, j])) <= tol
+
+
+def check_mining(got, x, labels, alpha, handle, mode='fp16x3'):
+    from oracle import mining_oracle as mo
+    b = x.shape[0]
+    ref = mo.mine(x, labels, alpha)
+    d = mo.distance_matrix(x)
+    assert got['pos_index'].shape == ref['pos_index'].shape
+    np.testing.assert_array_equal(got['pos_index'], ref['pos_index'])          # integer bookkeeping: exact
+    # index results: identical, or the two candidates are a near-tie in the oracle's own distances
+    for name in ('hardest_pos', 'hardest_neg'):
+        bad = np.nonzero(got[name] != ref[name])[0]
+        for a in bad:
+            assert _near_tie(d, a, got[name][a], ref[name][a]), (name, a)
+    alpha32 = np.float32(alpha)
+    neg_mask = labels[:, None] != labels[None, :]
+    n_window = 0
+    for a, j in zip(*np.nonzero(got['semi_hard'] != ref['semi_hard'])):
+        p = ref['pos_index'][a, j]
+        g_, r_ = got['semi_hard'][a, j], ref['semi_hard'][a, j]
+        cands = [c for c in (g_, r_) if c >= 0]
+        # a disagreement must involve a candidate within eps of one of the two decision boundaries, or a near-tie
+        near = any(abs(float(d[a, c]) - float(d[a, p])) <= 2e-5 or abs(float(d[a, c]) - float(d[a, p]) - float(alpha32)) <= 2e-5 for c in cands)
+        assert near or _near_tie(d, a, g_, r_), (a, j, g_, r_)
+        n_window += 1
+    diff = np.abs(got['eligible'].astype(np.int64) - ref['eligible'])
+    for a, j in zip(*np.nonzero(diff)):
+        p = ref['pos_index'][a, j]
+        margin = d[a][neg_mask[a]].astype(np.float64) - float(d[a, p]) - float(alpha32)
+        assert diff[a, j] <= np.count_nonzero(np.abs(margin) <= 2e-5), (a, j)
+    # exact equality when the oracle's selection runs on the library's own distances
+    dist_gpu = handle.pairwise(x, x, 0, mode=mode, cta_group=1)
+    ref2 = mo.mine(x, labels, alpha, dist=dist_gpu)
+    exact = all(np.array_equal(got[k], ref2[k]) for k in ('hardest_pos', 'hardest_neg', 'pos_index', 'semi_hard', 'eligible'))
+    return exact, n_window
+
+
+@pytest.mark.parametrize('sizes,d,alpha,shuffle', [
+    ([40] * 45, 512, 0.2, False),                 # BASELINE config 3: 45 identities x 40 images
+    ([5] * 20, 128, 0.2, False),                  # facenet/dataset.py:46-101 variant (20 classes x 5)
+    ([1, 7, 3, 1, 12, 2, 30, 1, 5], 64, 0.5, True),   # ragged, singletons, shuffled rows
+    ([9], 64, 0.2, False),                        # one class: no negatives at all
+    ([1] * 33, 64, 0.2, False),                   # all singletons: no positives at all
+])
+def test_mining_vs_oracle(handle, sizes, d, alpha, shuffle):
+    x, labels = so.synthetic_embeddings(sizes, dim=d, sigma=1.0, seed=11, shuffle=shuffle)
+    labels = labels.astype(np.int64) * 7 - 3          # label VALUES are arbitrary
+    got = handle.mine(x, labels, alpha=alpha)
+    exact, _ = check_mining(got, x, labels, alpha, handle)
+    assert exact
+    assert got['stats']['kernel_launches'] == 3
+    got32 = handle.mine(x, labels.astype(np.int32), alpha=alpha)
+    for k in ('hardest_pos', 'hardest_neg', 'pos_index', 'semi_hard', 'eligible'):
+        np.testing.assert_array_equal(got[k], got32[k])
+
+
+def test_mining_python_surface_and_errors(handle):
+    from facenet_b200 import facenet as ff, _capi
+    x, labels = so.synthetic_embeddings([6] * 10, dim=64, sigma=1.0, seed=2, shuffle=False)
+    out = ff.mine(x, labels, alpha=0.3)
+    trip = ff.semi_hard_triplets(x, labels, alpha=0.3)
+    assert trip.shape[1] == 3 and np.all(labels[trip[:, 0]] == labels[trip[:, 1]]) and np.all(labels[trip[:, 0]] != labels[trip[:, 2]])
+    assert np.all(trip[:, 1] > trip[:, 0])
+    hard = ff.hardest_triplets(x, labels)
+    assert hard.shape == (60, 3)
+    np.testing.assert_array_equal(hard[:, 1], out['hardest_pos'])
+    t2, elig = ff.select_triplets(x, [6] * 10, alpha=0.3)
+    np.testing.assert_array_equal(t2, trip)
+    assert elig.shape[0] == 10 * 15
+    with pytest.raises(ValueError, match='embeddings must be normalized'):
+        ff.mine(x * 3.0, labels)
+    with pytest.raises(_capi.FnbError):
+        handle.mine(x, labels, kmax=2)                  # smaller than the largest class - 1
+    import torch
+    xt, lt = torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda()
+    out_t = handle.mine(xt, lt, alpha=0.3, kmax=5)
+    for k in ('hardest_pos', 'hardest_neg', 'pos_index', 'semi_hard', 'eligible'):
+        np.testing.assert_array_equal(out[k], out_t[k])

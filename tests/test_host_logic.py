@@ -139,7 +139,8 @@ def test_kfold_split_matches_sklearn():
 
 @pytest.fixture
 def emulated(monkeypatch):
-    monkeypatch.setattr(fst, '_handle', lambda: emulator.EmulatedHandle())
+    handle = emulator.EmulatedHandle()
+    monkeypatch.setattr(fst, '_handle', lambda: handle)
 
 
 def test_confidence_matrix_host_math_golden(emulated, golden_dir):
