@@ -44,14 +44,14 @@ class Options(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('metric', ctypes.c_int32), ('atol', ctypes.c_float), ('eps', ctypes.c_float),
                 ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('cta_group', ctypes.c_int32),
                 ('region_rows', ctypes.c_int32), ('cuts', ctypes.POINTER(ctypes.c_float)),
-                ('max_ctas', ctypes.c_int32), ('reserved', ctypes.c_int32 * 7)]
+                ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('reserved', ctypes.c_int32 * 6)]
 
 
 class Stats(ctypes.Structure):
     _fields_ = [('n_pairs', ctypes.c_uint64), ('eps_window', ctypes.c_uint64), ('smin', ctypes.c_float),
                 ('smax', ctypes.c_float), ('max_abs', ctypes.c_float), ('kernel_ms', ctypes.c_float),
                 ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
-                ('reserved', ctypes.c_uint32 * 4)]
+                ('eps_counted', ctypes.c_float), ('reserved', ctypes.c_uint32 * 3)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
@@ -262,7 +262,7 @@ class Handle:
         return {'sm_count': sm.value, 'cc': (ma.value, mi.value), 'total_mem': mem.value}
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
-                cuts=None, max_ctas=0):
+                cuts=None, max_ctas=0, force_checked=False):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -273,6 +273,7 @@ class Handle:
         o.cta_group = int(cta_group)
         o.region_rows = int(region_rows)
         o.max_ctas = int(max_ctas)
+        o.force_checked = 1 if force_checked else 0
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -302,14 +303,15 @@ class Handle:
 
     # ---- whole-set verification histogram
     def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
-                            rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy'):
+                            rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy',
+                            force_checked=False):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
         if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
-                               region_rows=region_rows, cuts=cuts, max_ctas=max_ctas)
+                               region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked)
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -297,7 +298,10 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     const size_t bytes = (size_t)n_pad * d * op.elem_bytes;
     CK(hi.ensure(bytes));
     if (op.num_pass == 3) CK(lo.ensure(bytes));
-    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass == 3 ? lo.p : nullptr, h->stream));
+    CK(h->counters.ensure(sizeof(DeviceScalars)));
+    unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;
+    CK(cudaMemsetAsync(norm, 0, 4, h->stream));
+    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass == 3 ? lo.p : nullptr, norm, h->stream));
     int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d);
     if (rc) return rc;
     if (op.num_pass == 3) rc = make_tmap(h, m_lo, lo.p, op.fmt, n_pad, d);
@@ -315,7 +319,7 @@ int fnb::dl_check_embeddings(fnb_context* h, const DLView& v, const char* name) 
 
 int fnb::reset_scalars(fnb_context* h) {
     CK(h->counters.ensure(sizeof(DeviceScalars)));
-    DeviceScalars init;
+    DeviceScalars init = {};
     init.counters[0] = init.counters[1] = 0;
     init.range_ord[0] = 0xFFFFFFFFu;                    // min
     init.range_ord[1] = 0;                              // max
@@ -323,7 +327,8 @@ int fnb::reset_scalars(fnb_context* h) {
     init.range_ord[3] = 0;
     CK(h->pinned.ensure(4096));
     memcpy(h->pinned.p, &init, sizeof(init));
-    CK(cudaMemcpyAsync(h->counters.p, h->pinned.p, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    // the row-norm word behind the first 32 bytes is written by the split kernel and survives the reset
+    CK(cudaMemcpyAsync(h->counters.p, h->pinned.p, offsetof(DeviceScalars, norm_max_ord), cudaMemcpyHostToDevice, h->stream));
     return FNB_OK;
 }
 
@@ -446,23 +451,48 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
-    p.force_slow = force_slow;
+    p.force_slow = force_slow || opt.force_checked;
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
+    p.nb8 = hl.ct.T_fin + 3;
+    p.frac_bits = 12;                                    // keeps hb well-defined on the checked-only path
     if (hl.ct.uniform) {
-        // u = (s - e0) / h computed from the raw accumulator; guard band covers the eps window, the fp32
-        // rounding of u (< 2e-5 for <= 127 bins) and the deviation of the true cuts from the progression
+        // Arithmetic binning of interior tiles (see GramParams): with u = (s - cut_0) / h and Q = T_fin + 2,
+        //   v = sat((u + 0.5) / Q),  kw = v * Q * R + R/2 = (u + 1) R,  bin = kw >> F,  R = 2^F.
+        // A pair is flagged "near a threshold" when kw is within `half` units of a multiple of R; `half` covers
+        // the eps window, the deviation of the true cuts from the progression and the fp32 rounding (< 1.5 units).
         const double eps_s = (opt.metric == 0) ? opt.eps / 2.0 : opt.eps;
-        p.u_scale = (float)((double)p.acc_scale / hl.ct.h);
-        p.u_bias = (float)(-hl.ct.e0 / hl.ct.h);
-        p.u_guard = (float)(eps_s / hl.ct.h + 2.0 * hl.ct.dev / hl.ct.h + 1.0e-4);
+        const int Q = hl.ct.T_fin + 2;
+        int F = 16;
+        while (F > 4 && (double)(Q + 1) * (double)(1u << F) > 4194304.0) --F;
+        const double R = (double)(1u << F);
+        const double need = (eps_s / hl.ct.h + 2.0 * hl.ct.dev / hl.ct.h) * R + 1.5;
+        int W = 1;
+        while ((double)(1u << (W - 1)) < need && W < 30) ++W;
+        if (W > F - 2) {
+            p.uniform = 0;                               // thresholds too dense for the eps window: checked path
+        } else {
+            const double half = (double)(1u << (W - 1));
+            p.f_s1 = (float)((double)p.acc_scale / (hl.ct.h * Q));
+            p.f_b1 = (float)((-hl.ct.e0 / hl.ct.h + 0.5) / Q);
+            p.f_k2 = (float)(Q * R);
+            p.f_magic_k = (float)(12582912.0 + 0.5 * R);
+            p.f_magic_n = (float)(12582912.0 + 0.5 * R + half);
+            p.frac_bits = (unsigned)F;
+            p.near_mask = ((1u << F) - 1u) & ~((1u << W) - 1u);
+            h->last_eps_counted = (opt.metric == 0 ? 2.0 : 1.0) * half / R * hl.ct.h;
+        }
     }
+    // interior tiles skip the per-pair range check when every row norm proves |s| <= 1 + atol (Cauchy-Schwarz);
+    // the 3-pass modes reproduce fp32 to ~2e-7, single-pass modes get the checked path only on real violations
+    p.norm_max_ord = &h->counters.as<DeviceScalars>()->norm_max_ord;
+    p.norm_limit_ord = float_to_ordered((float)(1.0 + (double)opt.atol - 2.0e-6));
     p.bins = h->bins.as<unsigned long long>(); p.bins_stride = hl.stride;
     DeviceScalars* sc = h->counters.as<DeviceScalars>();
     p.counters = sc->counters; p.range_ord = sc->range_ord;
     p.metric = opt.metric;
-    const size_t hist_bytes = (size_t)(T + 1) * kEpiThreads * 2;
+    const size_t hist_bytes = (size_t)p.nb8 * kHist8Row;
     CK(cudaEventRecord(h->ev[1], h->stream));
     if ((rc = launch_gram(h, cg, op.num_pass, op.tf32, EPI_HIST, opt.max_ctas, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p, hist_bytes))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
@@ -470,18 +500,20 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     return FNB_OK;
 }
 
+static double mode_slack(int mode);
 static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats, float* smin_out, float* smax_out, bool* violated) {
     DeviceScalars hs;
     CK(cudaMemcpyAsync(h->pinned.p, h->counters.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     memcpy(&hs, h->pinned.p, sizeof(hs));
-    // checked tiles track min/max exactly; fast tiles (every pair valid) only track max |s|
+    // checked tiles track min/max exactly; interior tiles are covered by the row-norm bound (max squared norm)
     const bool have_checked = hs.range_ord[0] != 0xFFFFFFFFu;
     const float smin = have_checked ? ordered_to_float(hs.range_ord[0]) : NAN;
     const float smax = have_checked ? ordered_to_float(hs.range_ord[1]) : NAN;
-    const float amax = ordered_to_float(hs.range_ord[2]);
-    const double lim = 1.0 + (double)opt.atol;
-    *violated = (have_checked && !((double)smin >= -lim && (double)smax <= lim)) || !((double)amax <= lim);
+    const unsigned int norm_ord = hs.norm_max_ord;
+    const float amax = norm_ord ? ordered_to_float(norm_ord) : NAN;
+    const double lim = 1.0 + (double)opt.atol + mode_slack(opt.mode);
+    *violated = have_checked && !((double)smin >= -lim && (double)smax <= lim);
     *smin_out = smin;
     *smax_out = smax;
     if (stats) {
@@ -495,9 +527,20 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         stats->smin = smin;
         stats->smax = smax;
         stats->max_abs = amax;
+        stats->eps_counted = (float)h->last_eps_counted;
         stats->kernel_launches += 1;
     }
     return FNB_OK;
+}
+
+// absolute error of a similarity computed in a single low-precision pass: the range check must not reject
+// normalised inputs because of the arithmetic mode (the 3-pass modes are fp32-equivalent: no slack)
+static double mode_slack(int mode) {
+    switch (mode) {
+        case FNB_MODE_BF16: return 1.6e-2;
+        case FNB_MODE_TF32: case FNB_MODE_FP16: return 2.0e-3;
+        default: return 0.0;
+    }
 }
 
 static uint64_t sum_bins(const uint64_t* b, int n) { uint64_t s = 0; for (int i = 0; i < n; ++i) s += b[i]; return s; }

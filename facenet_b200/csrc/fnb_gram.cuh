@@ -22,14 +22,16 @@
 namespace fnb {
 
 constexpr int kMaxBins      = 128;                 // bins k in [0, T], T <= 127
-constexpr int kEpiWarps     = 8;
+constexpr int kEpiWarps     = 16;                  // four per TMEM lane quadrant: 4 warps per SM sub-partition hide LDS / LDTM latency
 constexpr int kEpiThreads   = kEpiWarps * 32;
+constexpr int kColSplit     = kEpiWarps / 4;       // accumulator columns are split four ways
 constexpr int kFirstEpiWarp = 4;
-constexpr int kGramThreads  = (kFirstEpiWarp + kEpiWarps) * 32;   // 384
+constexpr int kGramThreads  = (kFirstEpiWarp + kEpiWarps) * 32;   // 640
 constexpr int kRowsPerCta   = 128;                 // MMA M per CTA, and B rows loaded per CTA
 constexpr int kBoxBytes     = kRowsPerCta * 128;   // one operand box: 128 rows x 128 B = 16 KB
 constexpr int kSlotBytes    = 2 * kBoxBytes;       // {A part, B part}
 constexpr int kMaxSlots     = 8;
+constexpr int kHist8Row     = kEpiThreads;         // bytes per bin of the thread-private u8 counters
 
 enum EpiKind : int { EPI_HIST = 0, EPI_PAIRWISE = 1, EPI_ROWSTRIP = 2 };
 
@@ -51,6 +53,8 @@ struct GramParams {
     float acc_scale;           // similarity = accumulator * acc_scale
     int operand_fmt;           // kFmtF16 / kFmtBF16 / kFmtTF32 (must agree with the kTf32 template flag)
     int force_slow;            // take the fully-checked epilogue path for every tile
+    const unsigned int* norm_max_ord;   // ordered-uint max squared row norm (written by the split kernel), may be NULL
+    unsigned int norm_limit_ord;        // above this the interior tiles cannot be proven in range -> checked path
     // HIST epilogue
     const int32_t* row_cls;    // class id per (permuted) row, non-decreasing
     const int32_t* col_cls;
@@ -60,11 +64,16 @@ struct GramParams {
     int T;                     // number of cuts (bins 0..T)
     int T_fin;                 // number of finite cuts (the +inf ones sort last)
     int uniform;               // cuts are (numerically) an arithmetic progression -> arithmetic binning
-    float u_scale, u_bias, u_guard;
+    // arithmetic binning of the interior tiles (uniform != 0), see fast_bin():
+    //   v  = sat(acc * f_s1 + f_b1)                      in [0, 1]  <->  (u + 0.5) / Q,  u = (s - cut_0) / h
+    //   kw = v * f_k2 + 0.5 R  (R = 2^frac_bits)         = (u + 1) R  -> bin = kw >> frac_bits, clipped to T_fin
+    float f_s1, f_b1, f_k2, f_magic_k, f_magic_n;
+    unsigned int frac_bits, near_mask;
+    int nb8;                   // bins of the u8 counters (T_fin + 3)
     unsigned long long* bins;  // [nkeys][2][bins_stride]  (0: all pairs, 1: same-identity pairs)
     int bins_stride;
     unsigned long long* counters;  // [0] eps-window pairs, [1] tiles processed
-    unsigned int* range_ord;   // [0] min(s) [1] max(s) as ordered uints (checked tiles) [2] max|s| (fast tiles)
+    unsigned int* range_ord;   // [0] min(s) [1] max(s) as ordered uints (checked tiles)
     // PAIRWISE / ROWSTRIP epilogue
     float* out;                // PAIRWISE: packed triangle or [na, nb]; ROWSTRIP: [n_rows, out_ld] distances
     long long out_ld;
@@ -119,7 +128,8 @@ struct __align__(16) GramSmemMisc {
     float cuts[kMaxBins];
     float wlo[kMaxBins + 4];
     float whi[kMaxBins + 4];
-    uint32_t same[kMaxBins + 4];
+    uint32_t cta_all[kMaxBins + 4];     // CTA-level counters (all pairs / same-identity pairs) of the current key
+    uint32_t cta_same[kMaxBins + 4];
     int32_t col_cls[2][256];
 };
 
@@ -149,6 +159,22 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     return v;
 }
 
+// thread-private byte counters live in shared memory and are touched only through these (32-bit shared
+// addresses, program order preserved among them by `volatile`)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v));
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------
 // the kernel
 
@@ -161,7 +187,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     constexpr int kTile   = kRowsPerCta * kCtaGroup;       // tile rows == tile cols
     constexpr int kUmmaN  = kTile;                         // accumulator columns per stage
     constexpr int kParts  = (kNumPass == 3) ? 2 : 1;       // slots per k-block: {hi} or {hi, lo}
-    constexpr int kColsPerWarp = kUmmaN / 2;               // two epilogue warps per TMEM lane quadrant
+    constexpr int kColsPerWarp = kUmmaN / kColSplit;       // four epilogue warps per TMEM lane quadrant
     constexpr uint32_t kTmemCols = 2 * kUmmaN;             // double-buffered accumulator
     constexpr int kElemsPerBox = kTf32 ? 32 : 64;          // K elements per 128-byte row
 
@@ -171,7 +197,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* slots = smem;
     GramSmemMisc* misc = reinterpret_cast<GramSmemMisc*>(smem + (size_t)p.num_slots * kSlotBytes);
-    uint16_t* hist_priv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(misc) + sizeof(GramSmemMisc));
+    uint8_t* hist8 = reinterpret_cast<uint8_t*>(misc) + sizeof(GramSmemMisc);   // [nb8][kHist8Row] thread-private u8 counters
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -197,8 +223,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (kEpi == EPI_HIST && warp >= kFirstEpiWarp) {
         const int te = threadIdx.x - kFirstEpiWarp * 32;
         for (int i = te; i < kMaxBins; i += kEpiThreads) misc->cuts[i] = p.cuts[i];
-        for (int i = te; i < kMaxBins + 1; i += kEpiThreads) { misc->wlo[i] = p.wlo[i]; misc->whi[i] = p.whi[i]; misc->same[i] = 0; }
-        for (int i = te; i < (p.T + 1) * kEpiThreads; i += kEpiThreads) hist_priv[i] = 0;
+        for (int i = te; i < kMaxBins + 1; i += kEpiThreads) { misc->wlo[i] = p.wlo[i]; misc->whi[i] = p.whi[i]; }
+        for (int i = te; i < kMaxBins + 4; i += kEpiThreads) { misc->cta_all[i] = 0; misc->cta_same[i] = 0; }
+        uint32_t* h32 = reinterpret_cast<uint32_t*>(hist8);
+        for (int i = te; i < p.nb8 * (kHist8Row / 4); i += kEpiThreads) h32[i] = 0;
     }
     __syncwarp();
     tc_fence_before();
@@ -285,10 +313,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
     } else if (warp >= kFirstEpiWarp) {
         // ------------------------------ epilogue ----------------------------------------
-        const int e = warp - kFirstEpiWarp;          // 0..7
+        const int e = warp - kFirstEpiWarp;          // 0..15
         const int q = e & 3;                         // TMEM lane quadrant (== warp % 4)
-        const int half = e >> 2;                     // column half
-        const int te = e * 32 + lane;                // epilogue thread id 0..255
+        const int colq = e >> 2;                     // column quarter
+        const int te = e * 32 + lane;                // epilogue thread id 0..511
         const int row_in_tile = (int)cta_rank * kRowsPerCta + q * 32 + lane;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float scale = p.acc_scale;
@@ -297,48 +325,65 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         TileInfo t;
         uint32_t it = 0;
 
-        float smin = INFINITY, smax = -INFINITY, amax = 0.f;
+        float smin = INFINITY, smax = -INFINITY;
         uint32_t eps_cnt = 0, tiles_done = 0;
         int cur_key = -1;
-        uint32_t since_flush = 0;
-        constexpr uint32_t kFlushEvery = 65535u / (uint32_t)kColsPerWarp;
+        uint32_t fast_since_flush = 0, tiles_since_global = 0;
+        // u8 counters hold <= 255: one fast tile adds at most kColsPerWarp (+1 for the pair rule) per counter
+        constexpr uint32_t kFlushEvery = 254u / (uint32_t)kColsPerWarp;
+        const bool all_slow = p.force_slow || !p.uniform ||
+                              (p.norm_max_ord != nullptr && __ldg(p.norm_max_ord) > p.norm_limit_ord);
 
-        auto flush = [&](int key) {
+        // thread-private byte counters: bin b of thread (colq, q, lane) lives at byte b * 512 + (colq * 32 + lane) * 4 + q,
+        // i.e. a warp always touches 32 different banks.  hb folds in the exponent bits of the magic-number trick.
+        const uint32_t fbits = p.frac_bits;
+        const uint32_t hb = smem_u32(hist8) + (uint32_t)((colq * 32 + lane) * 4 + q) - ((0x4B400000u >> fbits) * (uint32_t)kHist8Row);
+
+        // fold the u8 counters into the CTA-level u32 counters (every epilogue thread takes part)
+        auto flush_u8 = [&]() {
             named_bar_sync(1, kEpiThreads);
+            for (int b = e; b < p.nb8; b += kEpiWarps) {
+                uint4* w = reinterpret_cast<uint4*>(hist8 + (size_t)b * kHist8Row) + lane;
+                const uint4 v = *w;
+                *w = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t sum = __dp4a(v.x, 0x01010101u, 0u);
+                sum = __dp4a(v.y, 0x01010101u, sum);
+                sum = __dp4a(v.z, 0x01010101u, sum);
+                sum = __dp4a(v.w, 0x01010101u, sum);
+                sum = __reduce_add_sync(0xffffffffu, sum);
+                if (lane == 0 && sum) atomicAdd(&misc->cta_all[min(b, p.T_fin)], sum);
+            }
+            named_bar_sync(1, kEpiThreads);
+            fast_since_flush = 0;
+        };
+        // CTA-level counters -> global 64-bit bins of `key`
+        auto flush_cta = [&](int key) {
+            if (fast_since_flush) flush_u8(); else named_bar_sync(1, kEpiThreads);
             if (key >= 0) {
                 unsigned long long* dst_all = p.bins + ((size_t)key * 2 + 0) * p.bins_stride;
                 unsigned long long* dst_same = p.bins + ((size_t)key * 2 + 1) * p.bins_stride;
-                for (int b = e; b <= p.T; b += kEpiWarps) {
-                    uint32_t sum = 0;
-#pragma unroll
-                    for (int j = 0; j < kEpiThreads / 32; ++j) {
-                        const int idx = b * kEpiThreads + j * 32 + lane;
-                        sum += hist_priv[idx];
-                        hist_priv[idx] = 0;
-                    }
-                    sum = warp_sum(sum);
-                    if (lane == 0) {
-                        if (sum) atomicAdd(dst_all + b, (unsigned long long)sum);
-                        const uint32_t sm = misc->same[b];
-                        if (sm) { atomicAdd(dst_same + b, (unsigned long long)sm); misc->same[b] = 0; }
-                    }
+                for (int b = te; b <= p.T; b += kEpiThreads) {
+                    const uint32_t a = misc->cta_all[b], sm = misc->cta_same[b];
+                    if (a) { atomicAdd(dst_all + b, (unsigned long long)a); misc->cta_all[b] = 0; }
+                    if (sm) { atomicAdd(dst_same + b, (unsigned long long)sm); misc->cta_same[b] = 0; }
                 }
             }
             named_bar_sync(1, kEpiThreads);
+            tiles_since_global = 0;
         };
 
         while (sched.next(t)) {
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
             const int row = t.row0 + row_in_tile;
-            const int colw = t.col0 + half * kColsPerWarp;       // first column of this warp
-            const uint32_t taddr0 = tmem_lane + acc * kUmmaN + half * kColsPerWarp;
+            const int colw = t.col0 + colq * kColsPerWarp;       // first column of this warp
+            const uint32_t taddr0 = tmem_lane + acc * kUmmaN + colq * kColsPerWarp;
 
             if constexpr (kEpi == EPI_HIST) {
-                if (t.key != cur_key || since_flush >= kFlushEvery) {
-                    if (cur_key >= 0) flush(cur_key);
-                    cur_key = t.key; since_flush = 0;
+                if (t.key != cur_key || tiles_since_global >= 65536u) {
+                    if (cur_key >= 0) flush_cta(cur_key);
+                    cur_key = t.key;
                 }
-                ++since_flush;
+                ++tiles_since_global;
                 // classify the tile (identical in every epilogue thread of the CTA pair)
                 const bool edge = (t.row0 + kTile > t.row_end) || (t.col0 + kTile > t.col_end) ||
                                   (t.tri && t.col0 <= t.row0 + kTile - 1);
@@ -346,81 +391,57 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const int clast = min(t.col0 + kTile, t.col_end) - 1;
                 const bool lab = (__ldg(p.row_cls + t.row0) <= __ldg(p.col_cls + clast)) &&
                                  (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + rlast));
-                const bool slow = edge || lab || !p.uniform || p.force_slow;
+                const bool slow = all_slow || edge || lab;
 
-                mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
-                tc_fence_after();
-
-                int my_cls = -1;
-                if (slow) {
+                if (!slow) {
+                    // ---------------- interior tile: every element valid, no same-identity pair -------------
+                    if (fast_since_flush >= kFlushEvery) flush_u8();
+                    ++fast_since_flush;
+                    mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                    tc_fence_after();
+                    const float s1 = p.f_s1, b1 = p.f_b1, k2 = p.f_k2, mk = p.f_magic_k, mn = p.f_magic_n;
+                    const uint32_t nmask = p.near_mask;
+#pragma unroll 1
+                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr0 + c * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float v0 = fma_sat(__uint_as_float(r[j]), s1, b1);
+                            const float v1 = fma_sat(__uint_as_float(r[j + 1]), s1, b1);
+                            const uint32_t a0 = (__float_as_uint(fmaf(v0, k2, mk)) >> fbits) * (uint32_t)kHist8Row + hb;
+                            const uint32_t a1 = (__float_as_uint(fmaf(v1, k2, mk)) >> fbits) * (uint32_t)kHist8Row + hb;
+                            eps_cnt += ((__float_as_uint(fmaf(v0, k2, mn)) & nmask) == 0u) ? 1u : 0u;
+                            eps_cnt += ((__float_as_uint(fmaf(v1, k2, mn)) & nmask) == 0u) ? 1u : 0u;
+                            const uint32_t c0 = lds_u8(a0);
+                            const uint32_t c1 = lds_u8(a1);
+                            const uint32_t inc = (a0 == a1) ? 2u : 1u;
+                            sts_u8(a0, c0 + inc);
+                            sts_u8(a1, c1 + inc);
+                        }
+                    }
+                } else {
+                    // ---------------- checked tile: edges, diagonal, same-identity pairs, general cuts --------
+                    mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                    tc_fence_after();
                     // stage this tile's column classes (kTile <= 256 columns).  Safe after the tfull wait:
                     // every epilogue warp has released the tile that last used col_cls[acc].
                     if (te < kTile) {
                         const int c = t.col0 + te;
                         misc->col_cls[acc][te] = (c < t.col_end) ? __ldg(p.col_cls + c) : -2;
                     }
-                    if (row < t.row_end) my_cls = __ldg(p.row_cls + row);
+                    const int my_cls = (row < t.row_end) ? __ldg(p.row_cls + row) : -1;
                     named_bar_sync(2, kEpiThreads);
-                }
-
-                uint16_t* hp = hist_priv + te;
-                if (!slow) {
-                    const float a_floor = -1.0f / scale;
-                    const float us = p.u_scale, ub = p.u_bias, guard = p.u_guard;
-                    const float u_hi = (float)p.T_fin - 0.5f;
-#pragma unroll 1
-                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
-                        uint32_t r[32];
-                        tmem_ld32(taddr0 + c * 32, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            int k[4]; bool near_any = false;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float a = __uint_as_float(r[j + i]);
-                                amax = fmaxf(amax, fabsf(a));
-                                float u = fmaf(fmaxf(a, a_floor), us, ub);
-                                u = fminf(fmaxf(u, -1.0f), u_hi);
-                                const float v = u + 12582912.0f;
-                                const float d = u - (v - 12582912.0f);
-                                k[i] = (__float_as_int(v) - 0x4B400000) + (d >= 0.0f ? 1 : 0);
-                                near_any |= (fabsf(d) <= guard);
-                            }
-                            if (near_any) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float s = fmaxf(__uint_as_float(r[j + i]) * scale, -1.0f);
-                                    const int ke = exact_bin(s, misc->cuts);
-                                    k[i] = ke;
-                                    if (s <= misc->whi[ke] || s >= misc->wlo[ke]) ++eps_cnt;
-                                }
-                            }
-                            // grouped read-modify-write of the thread-private counters
-                            uint32_t cnt[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) cnt[i] = hp[k[i] * kEpiThreads];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                uint32_t m = 0;
-#pragma unroll
-                                for (int i2 = 0; i2 < 4; ++i2) m += (k[i2] == k[i]) ? 1u : 0u;
-                                cnt[i] += m;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) hp[k[i] * kEpiThreads] = (uint16_t)cnt[i];
-                        }
-                    }
-                } else {
                     const bool row_ok = row < t.row_end;
 #pragma unroll 1
-                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
-                        uint32_t r[32];
-                        tmem_ld32(taddr0 + c * 32, r);
+                    for (int c = 0; c < kColsPerWarp; c += 4) {
+                        uint32_t r[4];
+                        tmem_ld4(taddr0 + c, r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = colw + c * 32 + j;
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = colw + c + j;
                             const bool ok = row_ok && (col < t.col_end) && (!t.tri || col > row);
                             if (ok) {
                                 float s = __uint_as_float(r[j]) * scale;
@@ -428,8 +449,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                 s = fminf(fmaxf(s, -1.0f), 1.0f);
                                 const int ke = exact_bin(s, misc->cuts);
                                 if (s <= misc->whi[ke] || s >= misc->wlo[ke]) ++eps_cnt;
-                                hp[ke * kEpiThreads] = (uint16_t)(hp[ke * kEpiThreads] + 1);
-                                if (misc->col_cls[acc][col - t.col0] == my_cls) atomicAdd(&misc->same[ke], 1u);
+                                atomicAdd(&misc->cta_all[ke], 1u);
+                                if (misc->col_cls[acc][col - t.col0] == my_cls) atomicAdd(&misc->cta_same[ke], 1u);
                             }
                         }
                     }
@@ -477,13 +498,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
 
         if constexpr (kEpi == EPI_HIST) {
-            flush(cur_key);
+            flush_cta(cur_key);
             eps_cnt = warp_sum(eps_cnt);
-            amax = warp_max(amax) * scale;
-            if (lane == 0) {
-                if (eps_cnt) atomicAdd(p.counters + 0, (unsigned long long)eps_cnt);
-                atomicMax(p.range_ord + 2, float_to_ordered(amax));
-            }
+            if (lane == 0 && eps_cnt) atomicAdd(p.counters + 0, (unsigned long long)eps_cnt);
         }
         smin = warp_min(smin); smax = warp_max(smax);
         if (lane == 0) {

@@ -78,6 +78,7 @@ struct fnb_context {
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
     int last_nkeys = 0, last_T = 0;
+    double last_eps_counted = 0;         // distance half-width of the near-threshold window counted by interior tiles
 
     int fail(int code, const char* fmt, ...);
 };
@@ -101,6 +102,8 @@ struct GramOperands {
 struct DeviceScalars {      // layout of fnb_context::counters
     unsigned long long counters[2];
     unsigned int range_ord[4];
+    unsigned int norm_max_ord;      // ordered-uint max squared row norm of the last prepared operand (not reset per launch)
+    unsigned int pad[7];
 };
 
 // fnb_api.cu
@@ -117,7 +120,7 @@ int build_cut_tables(const double* thresholds, int T, int metric, double eps, co
 
 // fnb_prepare.cu
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
-                              void* hi, void* lo, cudaStream_t s);
+                              void* hi, void* lo, unsigned int* norm_max_ord, cudaStream_t s);
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
 
 // fnb_gram.cu

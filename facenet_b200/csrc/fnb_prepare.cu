@@ -12,74 +12,90 @@ __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float(u);
 }
 
-// One thread converts 8 consecutive elements of one row.  Rows [n, n_pad) are written as zeros.
+// One warp converts one row (lanes stride over 8-element groups); rows [n, n_pad) are written as zeros.
+// The warp also forms the squared norm of the row; the maximum over rows (ordered-uint atomicMax) lets the
+// Gram kernel skip the per-pair range check of statistics.py:40-42 on interior tiles (|s_ab| <= |a| |b|).
 template <int kMode>
-__global__ void split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ perm,
-                                  long long n, long long n_pad, int d, void* __restrict__ hi, void* __restrict__ lo)
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ perm, long long n, long long n_pad, int d,
+                  void* __restrict__ hi, void* __restrict__ lo, unsigned int* __restrict__ norm_max_ord)
 {
     const int vec_per_row = d >> 3;
-    const long long total = n_pad * vec_per_row;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
-        const long long row = v / vec_per_row;
-        const int c8 = (int)(v - row * vec_per_row);
-        float f[8];
-        if (row < n) {
-            const long long src = perm ? perm[row] : row;
-            const float4* s4 = reinterpret_cast<const float4*>(x + src * d + (long long)c8 * 8);
-            const float4 p0 = __ldg(s4), p1 = __ldg(s4 + 1);
-            f[0] = p0.x; f[1] = p0.y; f[2] = p0.z; f[3] = p0.w; f[4] = p1.x; f[5] = p1.y; f[6] = p1.z; f[7] = p1.w;
-        } else {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float norm_max = 0.f;
+    for (long long row = warp0; row < n_pad; row += nwarps) {
+        const long long src = (row < n) ? (perm ? perm[row] : row) : 0;
+        float nrm = 0.f;
+        for (int c8 = lane; c8 < vec_per_row; c8 += 32) {
+            float f[8];
+            if (row < n) {
+                const float4* s4 = reinterpret_cast<const float4*>(x + src * d + (long long)c8 * 8);
+                const float4 p0 = __ldg(s4), p1 = __ldg(s4 + 1);
+                f[0] = p0.x; f[1] = p0.y; f[2] = p0.z; f[3] = p0.w; f[4] = p1.x; f[5] = p1.y; f[6] = p1.z; f[7] = p1.w;
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = 0.f;
-        }
-        const long long o = row * d + (long long)c8 * 8;
-        if (kMode == FNB_MODE_FP16X3 || kMode == FNB_MODE_FP16) {
-            const float pre = (kMode == FNB_MODE_FP16X3) ? 256.0f : 1.0f;
-            __half hh[8], ll[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xs = f[i] * pre;
-                hh[i] = __float2half_rn(xs);
-                ll[i] = __float2half_rn(xs - __half2float(hh[i]));
+                for (int i = 0; i < 8; ++i) f[i] = 0.f;
             }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(hi) + o) = *reinterpret_cast<uint4*>(hh);
-            if (kMode == FNB_MODE_FP16X3)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(lo) + o) = *reinterpret_cast<uint4*>(ll);
-        } else if (kMode == FNB_MODE_BF16) {
-            __nv_bfloat16 hh[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) hh[i] = __float2bfloat16_rn(f[i]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(hi) + o) = *reinterpret_cast<uint4*>(hh);
-        } else {
-            float hh[8], ll[8];
+            for (int i = 0; i < 8; ++i) nrm = fmaf(f[i], f[i], nrm);
+            const long long o = row * d + (long long)c8 * 8;
+            if (kMode == FNB_MODE_FP16X3 || kMode == FNB_MODE_FP16) {
+                const float pre = (kMode == FNB_MODE_FP16X3) ? 256.0f : 1.0f;
+                __half hh[8], ll[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { hh[i] = tf32_rn(f[i]); ll[i] = tf32_rn(f[i] - hh[i]); }
-            float4* dh = reinterpret_cast<float4*>(reinterpret_cast<float*>(hi) + o);
-            dh[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
-            dh[1] = make_float4(hh[4], hh[5], hh[6], hh[7]);
-            if (kMode == FNB_MODE_TF32X3) {
-                float4* dl = reinterpret_cast<float4*>(reinterpret_cast<float*>(lo) + o);
-                dl[0] = make_float4(ll[0], ll[1], ll[2], ll[3]);
-                dl[1] = make_float4(ll[4], ll[5], ll[6], ll[7]);
+                for (int i = 0; i < 8; ++i) {
+                    const float xs = f[i] * pre;
+                    hh[i] = __float2half_rn(xs);
+                    ll[i] = __float2half_rn(xs - __half2float(hh[i]));
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(hi) + o) = *reinterpret_cast<uint4*>(hh);
+                if (kMode == FNB_MODE_FP16X3)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(lo) + o) = *reinterpret_cast<uint4*>(ll);
+            } else if (kMode == FNB_MODE_BF16) {
+                __nv_bfloat16 hh[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hh[i] = __float2bfloat16_rn(f[i]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(hi) + o) = *reinterpret_cast<uint4*>(hh);
+            } else {
+                float hh[8], ll[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { hh[i] = tf32_rn(f[i]); ll[i] = tf32_rn(f[i] - hh[i]); }
+                float4* dh = reinterpret_cast<float4*>(reinterpret_cast<float*>(hi) + o);
+                dh[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                dh[1] = make_float4(hh[4], hh[5], hh[6], hh[7]);
+                if (kMode == FNB_MODE_TF32X3) {
+                    float4* dl = reinterpret_cast<float4*>(reinterpret_cast<float*>(lo) + o);
+                    dl[0] = make_float4(ll[0], ll[1], ll[2], ll[3]);
+                    dl[1] = make_float4(ll[4], ll[5], ll[6], ll[7]);
+                }
             }
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        // NaN rows must not hide: an unordered compare keeps them as "too large"
+        norm_max = (nrm <= norm_max) ? norm_max : nrm;
+    }
+    if (norm_max_ord && lane == 0) {
+        const float v = (norm_max == norm_max) ? norm_max : INFINITY;
+        if (v > 0.f) atomicMax(norm_max_ord, float_to_ordered(v));
     }
 }
 
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
-                              void* hi, void* lo, cudaStream_t s)
+                              void* hi, void* lo, unsigned int* norm_max_ord, cudaStream_t s)
 {
-    const long long total = n_pad * (d >> 3);
-    if (total == 0) return cudaSuccess;
+    if (n_pad == 0) return cudaSuccess;
     const int threads = 256;
-    long long blocks = (total + threads - 1) / threads;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    long long blocks = (n_pad + 7) / 8;                  // 8 warps (rows) per block
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
     switch (mode) {
-        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
-        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
-        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
-        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
-        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo); break;
+        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, norm_max_ord); break;
+        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, norm_max_ord); break;
+        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, norm_max_ord); break;
+        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, norm_max_ord); break;
+        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, norm_max_ord); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

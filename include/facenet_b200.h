@@ -76,20 +76,25 @@ typedef struct {
                               acosf).  The Python host passes NumPy's so that results are bit-exact
                               with NumPy's arccos. */
     int32_t max_ctas;      /* 0 = all SMs (debug / profiling knob) */
-    int32_t reserved[7];
+    int32_t force_checked; /* != 0: every tile takes the fully checked epilogue path (exact cut comparison, exact
+                              eps window, per-pair range check) -- the reference the arithmetic path is tested against */
+    int32_t reserved[6];
 } fnb_options;
 
 typedef struct {
     uint64_t n_pairs;      /* pairs binned by this rank                                         */
-    uint64_t eps_window;   /* of those, pairs within eps of some threshold                      */
+    uint64_t eps_window;   /* of those, pairs within eps of some threshold: exact on checked tiles; interior tiles
+                              count pairs within eps_counted (eps <= eps_counted < 2.5 eps), an upper bound     */
     float    smin, smax;   /* exact range of raw similarities over the tiles that took the checked path
                               (diagonal / edge / same-identity tiles; NaN if none)                */
-    float    max_abs;      /* max |similarity| over the remaining (interior) tiles               */
+    float    max_abs;      /* bound on |similarity| over the remaining (interior) tiles: the largest squared row
+                              norm (Cauchy-Schwarz); above 1 + atol every tile takes the checked path           */
     float    kernel_ms;    /* device time of the Gram kernel (CUDA events)                      */
     float    prepare_ms;   /* device time of sort/split/convert                                 */
     uint64_t tiles;        /* tiles processed by this rank                                      */
     uint32_t kernel_launches;
-    uint32_t reserved[4];
+    float    eps_counted;  /* distance half-width actually counted by interior tiles (see eps_window)           */
+    uint32_t reserved[3];
 } fnb_stats;
 
 /* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:

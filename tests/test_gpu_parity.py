@@ -158,26 +158,53 @@ def test_histogram_disagreements_lie_in_eps_window(handle):
     same = labels[iu[0]] == labels[iu[1]]
     same_lt = np.array([(b_gpu[same] <= k).sum() for k in range(thr.size)])
     diff_lt = np.array([(b_gpu[~same] <= k).sum() for k in range(thr.size)])
-    np.testing.assert_array_equal(out['same'], same_lt)
-    np.testing.assert_array_equal(out['diff'], diff_lt)
+    for kw in ({'force_checked': True}, {}):
+        out = handle.pair_histogram(x, labels, thr, 0, **kw)
+        if kw:                                           # checked path: exact cut comparison
+            np.testing.assert_array_equal(out['same'], same_lt)
+            np.testing.assert_array_equal(out['diff'], diff_lt)
+        else:                                            # arithmetic binning may move pairs inside the eps window only
+            assert np.abs(out['same'] - same_lt).sum() + np.abs(out['diff'] - diff_lt).sum() <= 2 * out['stats']['eps_window']
 
 
-def test_histogram_fast_and_checked_paths_identical(handle):
-    """Arithmetic binning (interior tiles) and the checked path (forced via non-uniform thresholds
-    order) give the same integers: shuffle the thresholds so the table is rebuilt, and compare a
-    label-free (all singleton) run, whose interior tiles take the fast path, with pairwise binning."""
-    x = unit(1100, 128, 21)
-    labels = np.arange(1100)
+def test_histogram_arithmetic_vs_checked_path(handle):
+    """Interior tiles bin arithmetically (two FMAs, no table); the checked path compares against the exact
+    similarity cuts.  Both see the same accumulators, so they may differ only for pairs closer to a cut than
+    the fp32 rounding of the arithmetic (<< eps): the mismatch is bounded by the counted eps-window pairs, the
+    checked path reproduces the materialised distances exactly, and both count every pair once."""
     thr = so.default_thresholds(0)
-    out = handle.pair_histogram(x, labels, thr, 0)
-    d_gpu = handle.pairwise(x, None, 0)
     t32 = so.thresholds_f32_up(thr)
-    b = np.searchsorted(t32, d_gpu, side='right')
-    np.testing.assert_array_equal(out['diff'], [(b <= k).sum() for k in range(thr.size)])
-    assert out['n_same'] == 0
-    perm = np.random.default_rng(0).permutation(thr.size)
-    out2 = handle.pair_histogram(x, labels, thr[perm], 0)
-    np.testing.assert_array_equal(out2['diff'], out['diff'][perm])
+    for n, d, cg in ((1100, 128, 2), (1500, 512, 1), (2300, 64, 2)):
+        x = unit(n, d, 21 + n)
+        labels = np.arange(n)                            # all singletons: every full tile off the diagonal is interior
+        fast = handle.pair_histogram(x, labels, thr, 0, cta_group=cg)
+        chk = handle.pair_histogram(x, labels, thr, 0, cta_group=cg, force_checked=True)
+        d_gpu = handle.pairwise(x, None, 0, cta_group=cg)
+        b = np.searchsorted(t32, d_gpu, side='right')
+        np.testing.assert_array_equal(chk['diff'], [(b <= k).sum() for k in range(thr.size)])
+        assert fast['n_same'] == 0 and fast['n_diff'] == n * (n - 1) // 2
+        mism = int(np.abs(fast['diff'] - chk['diff']).sum())
+        assert mism <= chk['stats']['eps_window'], (mism, chk['stats'])
+        # the arithmetic path counts a window at least as wide as eps (an upper bound on the exact count)
+        assert fast['stats']['eps_window'] >= chk['stats']['eps_window']
+        assert 1e-5 <= fast['stats']['eps_counted'] < 2.5e-5
+        perm = np.random.default_rng(0).permutation(thr.size)
+        out2 = handle.pair_histogram(x, labels, thr[perm], 0, cta_group=cg)
+        np.testing.assert_array_equal(out2['diff'], fast['diff'][perm])
+    # un-normalised rows: the row-norm bound fails, every tile is range-checked and the call raises
+    from facenet_b200 import _capi
+    x = unit(1100, 128, 3)
+    x[700] *= 1.01
+    x[701] = x[700]                                  # a pair with similarity 1.02
+    with pytest.raises(_capi.FnbError) as e:
+        handle.pair_histogram(x, np.arange(1100), thr, 0)
+    assert e.value.code == _capi.FNB_ERR_NOT_NORMALIZED
+    # a row slightly too long that violates nothing (no pair exceeds 1 + atol): no error, same counts as checked
+    x = unit(600, 128, 5)
+    x[10] *= 1.00002
+    a = handle.pair_histogram(x, np.arange(600), thr, 0)
+    b_ = handle.pair_histogram(x, np.arange(600), thr, 0, force_checked=True)
+    np.testing.assert_array_equal(a['diff'], b_['diff'])
 
 
 def test_histogram_label_conventions(handle):
