@@ -18,7 +18,7 @@ import numpy as np
 _LIB_PATH = Path(__file__).resolve().parent / '_lib' / 'libfacenet_b200.so'
 
 FNB_OK, FNB_ERR_INVALID, FNB_ERR_NOT_NORMALIZED, FNB_ERR_BAD_METRIC, FNB_ERR_CUDA, FNB_ERR_UNSUPPORTED = range(6)
-MODES = {'fp16x3': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3, 'fp16': 4}
+MODES = {'fp16x3': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3, 'fp16': 4, 'fp16f8': 5}
 MAX_THRESHOLDS = 127
 
 EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info', 'fnb_set_stream',

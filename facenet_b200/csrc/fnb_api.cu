@@ -38,6 +38,7 @@ int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, fl
         case FNB_MODE_TF32:   *num_pass = 1; *tf32 = true;  *fmt = kFmtTF32; *elem_bytes = 4; *prescale = 1.f;   return 0;
         case FNB_MODE_BF16:   *num_pass = 1; *tf32 = false; *fmt = kFmtBF16; *elem_bytes = 2; *prescale = 1.f;   return 0;
         case FNB_MODE_FP16:   *num_pass = 1; *tf32 = false; *fmt = kFmtF16;  *elem_bytes = 2; *prescale = 1.f;   return 0;
+        case FNB_MODE_FP16F8: *num_pass = 2; *tf32 = false; *fmt = kFmtF16;  *elem_bytes = 2; *prescale = 4096.f; return 0;
     }
     return -1;
 }
@@ -142,10 +143,13 @@ int fnb::dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& sta
     return FNB_OK;
 }
 
+constexpr int kFmtU8 = 100;          // byte arrays (e4m3 operands): 128 elements per 128-byte box row
+
 static int make_tmap(fnb_context* h, CUtensorMap* m, void* base, int fmt, long long rows, int d) {
     CUtensorMapDataType dt = fmt == kFmtTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                           : fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    const int eb = fmt == kFmtTF32 ? 4 : 2;
+                           : fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                           : fmt == kFmtU8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const int eb = fmt == kFmtTF32 ? 4 : fmt == kFmtU8 ? 1 : 2;
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)d * eb};
     cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)kRowsPerCta};
@@ -259,7 +263,7 @@ extern "C" void fnb_destroy(fnb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->perm, &h->cls,
+    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
                       &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io};
     for (DevBuf* b : bufs) b->release();
@@ -291,21 +295,32 @@ extern "C" int fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* 
 // ---------------------------------------------------------------------------------------
 // shared launch plumbing
 
-// split/convert `x` ([n, d] fp32 on the device, optionally gathered through perm) into hi/lo arrays + TMA maps
+// split/convert `x` ([n, d] fp32 on the device, optionally gathered through perm) into the operand arrays of one
+// side of the Gram product and encode their TMA maps into `op`
 int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
-                        DevBuf& hi, DevBuf& lo, GramOperands& op, CUtensorMap* m_hi, CUtensorMap* m_lo) {
+                         bool side_b, GramOperands& op) {
+    DevBuf& hi = side_b ? h->b_hi : h->a_hi;
+    DevBuf& lo = side_b ? h->b_lo : h->a_lo;
+    DevBuf& h8 = side_b ? h->b_h8 : h->a_h8;
+    CUtensorMap* m_hi = side_b ? &op.b_hi : &op.a_hi;
+    CUtensorMap* m_lo = side_b ? &op.b_lo : &op.a_lo;
+    CUtensorMap* m_h8 = side_b ? &op.b_h8 : &op.a_h8;
+    const bool f8 = (op.num_pass == 2);
     const long long n_pad = pad_rows(n);
     const size_t bytes = (size_t)n_pad * d * op.elem_bytes;
     CK(hi.ensure(bytes));
     if (op.num_pass == 3) CK(lo.ensure(bytes));
+    if (f8) { CK(lo.ensure((size_t)n_pad * d)); CK(h8.ensure((size_t)n_pad * d)); }
     CK(h->counters.ensure(sizeof(DeviceScalars)));
     unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;
     CK(cudaMemsetAsync(norm, 0, 4, h->stream));
-    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass == 3 ? lo.p : nullptr, norm, h->stream));
+    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream));
     int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d);
     if (rc) return rc;
     if (op.num_pass == 3) rc = make_tmap(h, m_lo, lo.p, op.fmt, n_pad, d);
+    else if (f8) { rc = make_tmap(h, m_lo, lo.p, kFmtU8, n_pad, d); if (!rc) rc = make_tmap(h, m_h8, h8.p, kFmtU8, n_pad, d); }
     else *m_lo = *m_hi;
+    if (!f8) *m_h8 = *m_hi;
     return rc;
 }
 
@@ -372,9 +387,9 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     const void* da = nullptr; const void* db = nullptr;
     if ((rc = dl_to_device(h, va, (size_t)na * d * 4, h->stage_a, &da))) return rc;
     if (!self && (rc = dl_to_device(h, vb, (size_t)nb * d * 4, h->stage_b, &db))) return rc;
-    if ((rc = prepare_operand(h, opt.mode, (const float*)da, nullptr, na, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
-    if (self) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; }
-    else if ((rc = prepare_operand(h, opt.mode, (const float*)db, nullptr, nb, d, h->b_hi, h->b_lo, op, &op.b_hi, &op.b_lo))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)da, nullptr, na, d, false, op))) return rc;
+    if (self) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; }
+    else if ((rc = prepare_operand(h, opt.mode, (const float*)db, nullptr, nb, d, true, op))) return rc;
 
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
@@ -401,7 +416,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     p.counters = sc->counters; p.range_ord = sc->range_ord;
     p.out = dout; p.out_ld = nb; p.tri_packed = self ? 1 : 0; p.metric = opt.metric;
     p.n_rows = (int)na; p.n_cols = (int)nb;
-    if ((rc = launch_gram(h, cg, op.num_pass, op.tf32, EPI_PAIRWISE, opt.max_ctas, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p, 0))) return rc;
+    if ((rc = launch_gram(h, cg, EPI_PAIRWISE, opt.max_ctas, op, p, 0))) return rc;
 
     DeviceScalars hs;
     CK(cudaMemcpyAsync(h->pinned.p, h->counters.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
@@ -494,7 +509,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.metric = opt.metric;
     const size_t hist_bytes = (size_t)p.nb8 * kHist8Row;
     CK(cudaEventRecord(h->ev[1], h->stream));
-    if ((rc = launch_gram(h, cg, op.num_pass, op.tf32, EPI_HIST, opt.max_ctas, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p, hist_bytes))) return rc;
+    if ((rc = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, p, hist_bytes))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
     h->last_nkeys = hl.nkeys; h->last_T = T;
     return FNB_OK;
@@ -539,6 +554,7 @@ static double mode_slack(int mode) {
     switch (mode) {
         case FNB_MODE_BF16: return 1.6e-2;
         case FNB_MODE_TF32: case FNB_MODE_FP16: return 2.0e-3;
+        case FNB_MODE_FP16F8: return 2.0e-5;
         default: return 0.0;
     }
 }
@@ -589,8 +605,8 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
     if ((rc = dl_to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
-    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
-    op.b_hi = op.a_hi; op.b_lo = op.a_lo;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
+    op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8;
 
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
@@ -709,8 +725,8 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     CK(h->cls.ensure(n * 4));
     CK(cudaMemcpyAsync(h->perm.p, perm, n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->cls.p, cls, n * 4, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
-    op.b_hi = op.a_hi; op.b_lo = op.a_lo;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
+    op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8;
 
     HistLaunch hl; hl.nkeys = nkeys;
     if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;

@@ -16,8 +16,7 @@ int gram_pick_slots(size_t hist_bytes) {
 }
 
 template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi>
-static int launch_one(fnb_context* h, int max_ctas, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
-                      const CUtensorMap& b_hi, const CUtensorMap& b_lo, const GramParams& p, size_t smem)
+static int launch_one(fnb_context* h, int max_ctas, const GramOperands& op, const GramParams& p, size_t smem)
 {
     auto kern = gram_kernel<kCtaGroup, kNumPass, kTf32, kEpi>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -38,37 +37,36 @@ static int launch_one(fnb_context* h, int max_ctas, const CUtensorMap& a_hi, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, p);
+    e = cudaLaunchKernelEx(&cfg, kern, op.a_hi, op.a_lo, op.b_hi, op.b_lo, op.a_h8, op.b_h8, p);
     if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "gram kernel launch: %s", cudaGetErrorString(e));
     return FNB_OK;
 }
 
 template <int kCtaGroup, int kEpi>
-static int launch_mode(fnb_context* h, int num_pass, bool tf32, int max_ctas, const CUtensorMap& a_hi,
-                       const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                       const GramParams& p, size_t smem)
+static int launch_mode(fnb_context* h, int max_ctas, const GramOperands& op, const GramParams& p, size_t smem)
 {
-    if (num_pass == 3 && !tf32) return launch_one<kCtaGroup, 3, false, kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
-    if (num_pass == 3 && tf32)  return launch_one<kCtaGroup, 3, true,  kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
-    if (num_pass == 1 && !tf32) return launch_one<kCtaGroup, 1, false, kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
-    return launch_one<kCtaGroup, 1, true, kEpi>(h, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    if (op.num_pass == 2 && !op.tf32) return launch_one<kCtaGroup, 2, false, kEpi>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 3 && !op.tf32) return launch_one<kCtaGroup, 3, false, kEpi>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 3 && op.tf32)  return launch_one<kCtaGroup, 3, true,  kEpi>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 1 && !op.tf32) return launch_one<kCtaGroup, 1, false, kEpi>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 1 && op.tf32)  return launch_one<kCtaGroup, 1, true, kEpi>(h, max_ctas, op, p, smem);
+    return h->fail(FNB_ERR_INVALID, "no kernel for num_pass=%d tf32=%d", op.num_pass, (int)op.tf32);
 }
 
-int launch_gram(fnb_context* h, int cta_group, int num_pass, bool tf32, int epi, int max_ctas,
-                const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                GramParams& p, size_t hist_bytes)
+int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const GramOperands& op, GramParams& p, size_t hist_bytes)
 {
     p.num_slots = gram_pick_slots(hist_bytes);
     const size_t smem = gram_smem_bytes(p.num_slots, hist_bytes);
     if (smem > kSmemLimit) return h->fail(FNB_ERR_UNSUPPORTED, "shared memory budget exceeded (%zu bytes)", smem);
+    if (op.num_pass == 2 && (p.kblocks & 1)) return h->fail(FNB_ERR_UNSUPPORTED, "fp16f8 mode needs an embedding dimension that is a multiple of 128");
     if (cta_group == 2) {
-        if (epi == EPI_HIST)     return launch_mode<2, EPI_HIST>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
-        if (epi == EPI_PAIRWISE) return launch_mode<2, EPI_PAIRWISE>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
-        return launch_mode<2, EPI_ROWSTRIP>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+        if (epi == EPI_HIST)     return launch_mode<2, EPI_HIST>(h, max_ctas, op, p, smem);
+        if (epi == EPI_PAIRWISE) return launch_mode<2, EPI_PAIRWISE>(h, max_ctas, op, p, smem);
+        return launch_mode<2, EPI_ROWSTRIP>(h, max_ctas, op, p, smem);
     }
-    if (epi == EPI_HIST)     return launch_mode<1, EPI_HIST>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
-    if (epi == EPI_PAIRWISE) return launch_mode<1, EPI_PAIRWISE>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
-    return launch_mode<1, EPI_ROWSTRIP>(h, num_pass, tf32, max_ctas, a_hi, a_lo, b_hi, b_lo, p, smem);
+    if (epi == EPI_HIST)     return launch_mode<1, EPI_HIST>(h, max_ctas, op, p, smem);
+    if (epi == EPI_PAIRWISE) return launch_mode<1, EPI_PAIRWISE>(h, max_ctas, op, p, smem);
+    return launch_mode<1, EPI_ROWSTRIP>(h, max_ctas, op, p, smem);
 }
 
 }  // namespace fnb

@@ -182,10 +182,14 @@ template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi>
 __global__ void __launch_bounds__(kGramThreads, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+            const __grid_constant__ CUtensorMap tm_a_h8, const __grid_constant__ CUtensorMap tm_b_h8,
             const GramParams p)
 {
     constexpr int kTile   = kRowsPerCta * kCtaGroup;       // tile rows == tile cols
     constexpr int kUmmaN  = kTile;                         // accumulator columns per stage
+    // kNumPass: 1 = one MMA per k-step; 3 = split operands x = hi + lo, hi*hi + hi*lo + lo*hi in the operand type;
+    //           2 = hi*hi in fp16 plus the two cross terms in fp8 (e4m3) at twice the MMA rate (kSchemeF8)
+    constexpr bool kF8    = (kNumPass == 2);
     constexpr int kParts  = (kNumPass == 3) ? 2 : 1;       // slots per k-block: {hi} or {hi, lo}
     constexpr int kColsPerWarp = kUmmaN / kColSplit;       // four epilogue warps per TMEM lane quadrant
     constexpr uint32_t kTmemCols = 2 * kUmmaN;             // double-buffered accumulator
@@ -208,6 +212,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const int num_slots = p.num_slots;
     // fp16 vs bf16 is a runtime choice (same instruction kind, one descriptor field)
     const uint32_t idesc = make_idesc((uint32_t)p.operand_fmt, kTile, kUmmaN);
+    const uint32_t idesc_f8 = make_idesc(kFmtE4M3, kTile, kUmmaN);
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
@@ -217,7 +222,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
-        if (kNumPass == 3) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
+        if (kNumPass != 1) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
+        if (kF8) { tma_prefetch_desc(&tm_a_h8); tma_prefetch_desc(&tm_b_h8); }
     }
     if (warp == 2) tmem_alloc<kCtaGroup>(&misc->tmem_base, kTmemCols);
     if (kEpi == EPI_HIST && warp >= kFirstEpiWarp) {
@@ -244,24 +250,33 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             while (sched.next(t)) {
                 const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
                 const int brow = t.col0 + (int)cta_rank * kRowsPerCta;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-#pragma unroll
-                    for (int part = 0; part < kParts; ++part) {
-                        mbar_wait<kCtaGroup == 2>(&misc->empty[slot], phase ^ 1u);
-                        uint8_t* dst = slots + (size_t)slot * kSlotBytes;
-                        const CUtensorMap* ma = part ? &tm_a_lo : &tm_a_hi;
-                        const CUtensorMap* mb = part ? &tm_b_lo : &tm_b_hi;
-                        if (kCtaGroup == 1) {
-                            mbar_arrive_expect_tx(&misc->full[slot], kSlotBytes);
-                            tma_load_2d(dst, ma, &misc->full[slot], kb * kElemsPerBox, arow);
-                            tma_load_2d(dst + kBoxBytes, mb, &misc->full[slot], kb * kElemsPerBox, brow);
-                        } else {
-                            if (is_leader) mbar_arrive_expect_tx(&misc->full[slot], 2 * kSlotBytes);
-                            const uint32_t bar = mapa_u32(smem_u32(&misc->full[slot]), 0);
-                            tma_load_2d_pair(dst, ma, bar, kb * kElemsPerBox, arow);
-                            tma_load_2d_pair(dst + kBoxBytes, mb, bar, kb * kElemsPerBox, brow);
-                        }
-                        if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
+                    mbar_wait<kCtaGroup == 2>(&misc->empty[slot], phase ^ 1u);
+                    uint8_t* dst = slots + (size_t)slot * kSlotBytes;
+                    if (kCtaGroup == 1) {
+                        mbar_arrive_expect_tx(&misc->full[slot], kSlotBytes);
+                        tma_load_2d(dst, ma, &misc->full[slot], kcol, arow);
+                        tma_load_2d(dst + kBoxBytes, mb, &misc->full[slot], kcol, brow);
+                    } else {
+                        if (is_leader) mbar_arrive_expect_tx(&misc->full[slot], 2 * kSlotBytes);
+                        const uint32_t bar = mapa_u32(smem_u32(&misc->full[slot]), 0);
+                        tma_load_2d_pair(dst, ma, bar, kcol, arow);
+                        tma_load_2d_pair(dst + kBoxBytes, mb, bar, kcol, brow);
+                    }
+                    if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                };
+                if constexpr (kF8) {
+                    // per 128 K-elements: two fp16 {hi, hi} slots, then {A e4m3(x), B e4m3(lo)} and {A e4m3(lo), B e4m3(x)}
+                    for (int ks = 0; ks < p.kblocks / 2; ++ks) {
+                        load_slot(&tm_a_hi, &tm_b_hi, (2 * ks) * 64);
+                        load_slot(&tm_a_hi, &tm_b_hi, (2 * ks + 1) * 64);
+                        load_slot(&tm_a_h8, &tm_b_lo, ks * 128);
+                        load_slot(&tm_a_lo, &tm_b_h8, ks * 128);
+                    }
+                } else {
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        load_slot(&tm_a_hi, &tm_b_hi, kb * kElemsPerBox);
+                        if (kParts == 2) load_slot(&tm_a_lo, &tm_b_lo, kb * kElemsPerBox);
                     }
                 }
             }
@@ -278,6 +293,24 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 mbar_wait<kCtaGroup == 2>(&misc->tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kUmmaN;
+                if constexpr (kF8) {
+                    for (int ks = 0; ks < p.kblocks / 2; ++ks) {
+#pragma unroll
+                        for (int part = 0; part < 4; ++part) {
+                            mbar_wait<kCtaGroup == 2>(&misc->full[slot], phase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_u32(slots + (size_t)slot * kSlotBytes);
+                            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kBoxBytes);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                if (part < 2) umma<kCtaGroup, false>(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (ks | part | k4) != 0 ? 1u : 0u);
+                                else umma_f8<kCtaGroup>(d_tmem, da + 2 * k4, db + 2 * k4, idesc_f8, 1u);
+                            }
+                            umma_commit<kCtaGroup>(&misc->empty[slot]);
+                            if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                        }
+                    }
+                } else
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     const int slot_hi = slot;
                     mbar_wait<kCtaGroup == 2>(&misc->full[slot_hi], phase);

@@ -73,7 +73,7 @@ struct fnb_context {
     std::string err;
 
     fnb::DevBuf stage_a, stage_b, stage_lab;          // H2D staging of kDLCPU inputs
-    fnb::DevBuf a_hi, a_lo, b_hi, b_lo;               // split / converted operands
+    fnb::DevBuf a_hi, a_lo, b_hi, b_lo, a_h8, b_h8;   // split / converted operands
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
@@ -96,6 +96,7 @@ struct DLView {
 // operand arrays of one Gram launch: TMA maps over the split / converted embeddings
 struct GramOperands {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap a_h8, b_h8;        // fp16f8 mode only: e4m3(x) arrays (a_lo / b_lo then hold e4m3(lo))
     int num_pass = 3; bool tf32 = false; int fmt = 0; int elem_bytes = 2; float prescale = 1.f;
 };
 
@@ -111,7 +112,7 @@ int dl_view(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_m
 int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, const void** out);
 int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
-                    DevBuf& hi, DevBuf& lo, GramOperands& op, CUtensorMap* m_hi, CUtensorMap* m_lo);
+                    bool side_b, GramOperands& op);
 void finish_regions(std::vector<RegionDev>& regs, int tile);
 int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
 int reset_scalars(fnb_context* h);
@@ -120,13 +121,11 @@ int build_cut_tables(const double* thresholds, int T, int metric, double eps, co
 
 // fnb_prepare.cu
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
-                              void* hi, void* lo, unsigned int* norm_max_ord, cudaStream_t s);
+                              void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s);
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
 
 // fnb_gram.cu
-int launch_gram(fnb_context* h, int cta_group, int num_pass, bool tf32, int epi, int max_ctas,
-                const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                GramParams& p, size_t hist_bytes);
+int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const GramOperands& op, GramParams& p, size_t hist_bytes);
 size_t gram_smem_bytes(int num_slots, size_t hist_bytes);
 int gram_pick_slots(size_t hist_bytes);
 

@@ -164,8 +164,8 @@ extern "C" int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* label
     CK(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = dl_to_device(h, ve, (size_t)b * d * 4, h->stage_a, &de))) return rc;
     if ((rc = dl_to_device(h, vl, (size_t)b * (vl.bits / 8), h->stage_lab, &dl))) return rc;
-    if ((rc = prepare_operand(h, opt.mode, (const float*)de, nullptr, b, d, h->a_hi, h->a_lo, op, &op.a_hi, &op.a_lo))) return rc;
-    op.b_hi = op.a_hi; op.b_lo = op.a_lo;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, nullptr, b, d, false, op))) return rc;
+    op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8;
 
     // stage 1: B x B distances (every ordered pair, diagonal included)
     const int cg = 1;                                   // 128 x 128 tiles: 225 tiles at B = 1800 fill the 148 SMs better than 64 pair-tiles
@@ -188,7 +188,7 @@ extern "C" int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* label
     p.out = h->strip.as<float>(); p.out_ld = ld; p.tri_packed = 0; p.metric = 0;
     p.n_rows = (int)b; p.n_cols = (int)b;
     CK(cudaEventRecord(h->ev[1], h->stream));
-    if ((rc = launch_gram(h, cg, op.num_pass, op.tf32, EPI_ROWSTRIP, opt.max_ctas, op.a_hi, op.a_lo, op.b_hi, op.b_lo, p, 0))) return rc;
+    if ((rc = launch_gram(h, cg, EPI_ROWSTRIP, opt.max_ctas, op, p, 0))) return rc;
 
     // stage 2: per-anchor selection
     const size_t n_out = (size_t)b * 2 + (size_t)b * kmax * 3 + 1;

@@ -60,8 +60,12 @@ enum {
  *           modes that meet the reference tolerance (|dd| <= 1e-5) are the two X3 modes;
  *   TF32X3  same split with tf32 operands, kind::tf32;
  *   TF32    single kind::tf32 pass on RN-rounded operands (|dd| ~ 3.5e-5 rms);
- *   BF16    single kind::f16 pass on bf16 operands;  FP16: single pass on fp16 operands. */
-enum { FNB_MODE_FP16X3 = 0, FNB_MODE_TF32X3 = 1, FNB_MODE_TF32 = 2, FNB_MODE_BF16 = 3, FNB_MODE_FP16 = 4 };
+ *   BF16    single kind::f16 pass on bf16 operands;  FP16: single pass on fp16 operands;
+ *   FP16F8  x = hi + lo, hi fp16 (pre-scaled by 2^12): hi*hi in kind::f16 plus the cross terms
+ *           e4m3(x)*e4m3(lo) + e4m3(lo)*e4m3(x) in kind::f8f6f4 at twice the MMA rate -- two fp16-pass
+ *           equivalents instead of three.  Error is statistical: |dd| ~ 1e-6 rms, < 1e-5 for dense
+ *           embeddings (every element small against the norm); needs D % 128 == 0. */
+enum { FNB_MODE_FP16X3 = 0, FNB_MODE_TF32X3 = 1, FNB_MODE_TF32 = 2, FNB_MODE_BF16 = 3, FNB_MODE_FP16 = 4, FNB_MODE_FP16F8 = 5 };
 
 typedef struct {
     int32_t mode;          /* FNB_MODE_*                                        default FP16X3 */

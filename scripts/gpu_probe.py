@@ -76,6 +76,26 @@ def case_bench(mode, cg, n=20000, d=512, reps=3):
                  pairs * 1024 / st['kernel_ms'] / 1e9, st['n_pairs']))
 
 
+def case_accuracy(mode, n=3000, d=512):
+    """Error of a mode's distances against float64 on random, clustered and tight-cluster embeddings."""
+    h = _capi.Handle(0)
+    rng = np.random.default_rng(0)
+    sets = {'random': unit(n, d, 1)}
+    x, _ = so.synthetic_embeddings([50] * (n // 50), dim=d, sigma=1.1, seed=0)
+    sets['clustered sigma=1.1'] = x
+    x, _ = so.synthetic_embeddings([50] * (n // 50), dim=d, sigma=0.3, seed=0)
+    sets['tight sigma=0.3'] = x
+    for name, x in sets.items():
+        x64 = x.astype(np.float64)
+        iu = np.triu_indices(n, 1)
+        exact = 2 * (1 - np.clip((x64 @ x64.T)[iu], -1, 1))
+        ref32 = so.pairwise_similarities(x.copy(), None, 0)
+        got = h.pairwise(x, None, 0, mode=mode)
+        e = np.abs(got - exact)
+        print('accuracy mode=%s %-20s n=%d: max|dd|=%.3e rms=%.3e  vs oracle(fp32 sgemm): max=%.3e   [oracle vs f64: max=%.3e]'
+              % (mode, name, n, e.max(), np.sqrt((e ** 2).mean()), np.abs(got - ref32).max(), np.abs(ref32 - exact).max()))
+
+
 if __name__ == '__main__':
     case = sys.argv[1]
     args = sys.argv[2:]
