@@ -52,7 +52,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='1m', choices=sorted(WORKLOADS))
-    ap.add_argument('--mode', default='fp16x3', choices=['fp16x3', 'tf32x3', 'tf32', 'bf16', 'fp16'])
+    ap.add_argument('--mode', default='fp16x3', choices=['fp16x3', 'fp16f8', 'tf32x3', 'tf32', 'bf16', 'fp16'])
     ap.add_argument('--cta-group', type=int, default=0)
     ap.add_argument('--cpu-sample-rows', type=int, default=16384)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -319,7 +319,7 @@ def main():
             traffic = json.loads(tf.read_text()).get('%s/%s' % (args.workload, args.mode))
         except ValueError:
             traffic = None
-    passes = 3 if args.mode.endswith('x3') else 1
+    passes = 3 if args.mode.endswith('x3') else 2 if args.mode == 'fp16f8' else 1
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
                 'traffic': traffic, 'kernel': 'gram_kernel<HIST>', 'kernel_ms': k_ms,
                 'peak_source': peak_src + ': bf16_tflops_sustained / 2 (TF32 rate = half the bf16 rate); of measured',
@@ -336,7 +336,8 @@ def main():
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': {'fp16x3': 'f16x3 split, f32 accumulate (fp32-equivalent)', 'tf32x3': 'tf32x3 split, f32 accumulate',
-                      'tf32': 'tf32', 'bf16': 'bf16', 'fp16': 'f16'}[args.mode],
+                      'tf32': 'tf32', 'bf16': 'bf16', 'fp16': 'f16',
+                      'fp16f8': 'f16 hi*hi + e4m3 cross terms, f32 accumulate'}[args.mode],
             'data': 'synthetic',
             'config': {'workload': wl['name'], 'mode': args.mode, 'parallelism': 'row-block tiles t %% %d == rank' % world,
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),

@@ -10,6 +10,7 @@ There is no CPU fallback: if the shared library is missing or no CUDA device is 
 the import / handle creation raises.
 """
 import ctypes
+import os
 import threading
 from pathlib import Path
 
@@ -44,7 +45,8 @@ class Options(ctypes.Structure):
     _fields_ = [('mode', ctypes.c_int32), ('metric', ctypes.c_int32), ('atol', ctypes.c_float), ('eps', ctypes.c_float),
                 ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('cta_group', ctypes.c_int32),
                 ('region_rows', ctypes.c_int32), ('cuts', ctypes.POINTER(ctypes.c_float)),
-                ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('reserved', ctypes.c_int32 * 6)]
+                ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('debug', ctypes.c_int32),
+                ('reserved', ctypes.c_int32 * 5)]
 
 
 class Stats(ctypes.Structure):
@@ -274,6 +276,7 @@ class Handle:
         o.region_rows = int(region_rows)
         o.max_ctas = int(max_ctas)
         o.force_checked = 1 if force_checked else 0
+        o.debug = int(os.environ.get('FNB_DEBUG', '0'))     # profiling knob (see fnb_options.debug)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)

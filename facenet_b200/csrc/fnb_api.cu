@@ -467,6 +467,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
     p.force_slow = force_slow || opt.force_checked;
+    p.debug = opt.debug;
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;

@@ -53,6 +53,7 @@ struct GramParams {
     float acc_scale;           // similarity = accumulator * acc_scale
     int operand_fmt;           // kFmtF16 / kFmtBF16 / kFmtTF32 (must agree with the kTf32 template flag)
     int force_slow;            // take the fully-checked epilogue path for every tile
+    int debug;                 // profiling knob (fnb_options.debug): bit 0 no epilogue work, bit 1 no operand loads
     const unsigned int* norm_max_ord;   // ordered-uint max squared row norm (written by the split kernel), may be NULL
     unsigned int norm_limit_ord;        // above this the interior tiles cannot be proven in range -> checked path
     // HIST epilogue
@@ -253,7 +254,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
                     mbar_wait<kCtaGroup == 2>(&misc->empty[slot], phase ^ 1u);
                     uint8_t* dst = slots + (size_t)slot * kSlotBytes;
-                    if (kCtaGroup == 1) {
+                    if (p.debug & 2) {
+                        if (is_leader) mbar_arrive(&misc->full[slot]);
+                    } else if (kCtaGroup == 1) {
                         mbar_arrive_expect_tx(&misc->full[slot], kSlotBytes);
                         tma_load_2d(dst, ma, &misc->full[slot], kcol, arow);
                         tma_load_2d(dst + kBoxBytes, mb, &misc->full[slot], kcol, brow);
@@ -426,7 +429,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                  (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + rlast));
                 const bool slow = all_slow || edge || lab;
 
-                if (!slow) {
+                if (p.debug & 1) {
+                    mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                    tc_fence_after();
+                } else if (!slow) {
                     // ---------------- interior tile: every element valid, no same-identity pair -------------
                     if (fast_since_flush >= kFlushEvery) flush_u8();
                     ++fast_since_flush;

@@ -82,7 +82,9 @@ typedef struct {
     int32_t max_ctas;      /* 0 = all SMs (debug / profiling knob) */
     int32_t force_checked; /* != 0: every tile takes the fully checked epilogue path (exact cut comparison, exact
                               eps window, per-pair range check) -- the reference the arithmetic path is tested against */
-    int32_t reserved[6];
+    int32_t debug;         /* profiling knob, results are MEANINGLESS when != 0: bit 0 skips the epilogue work,
+                              bit 1 skips the operand loads (MMA on whatever shared memory holds) */
+    int32_t reserved[5];
 } fnb_options;
 
 typedef struct {
