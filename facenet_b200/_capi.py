@@ -46,14 +46,14 @@ class Options(ctypes.Structure):
                 ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('cta_group', ctypes.c_int32),
                 ('region_rows', ctypes.c_int32), ('cuts', ctypes.POINTER(ctypes.c_float)),
                 ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('debug', ctypes.c_int32),
-                ('reserved', ctypes.c_int32 * 5)]
+                ('cluster_pairs', ctypes.c_int32), ('reserved', ctypes.c_int32 * 4)]
 
 
 class Stats(ctypes.Structure):
     _fields_ = [('n_pairs', ctypes.c_uint64), ('eps_window', ctypes.c_uint64), ('smin', ctypes.c_float),
                 ('smax', ctypes.c_float), ('max_abs', ctypes.c_float), ('kernel_ms', ctypes.c_float),
                 ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
-                ('eps_counted', ctypes.c_float), ('reserved', ctypes.c_uint32 * 3)]
+                ('eps_counted', ctypes.c_float), ('grid_ctas', ctypes.c_uint32), ('reserved', ctypes.c_uint32 * 2)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
@@ -264,7 +264,7 @@ class Handle:
         return {'sm_count': sm.value, 'cc': (ma.value, mi.value), 'total_mem': mem.value}
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
-                cuts=None, max_ctas=0, force_checked=False):
+                cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -277,6 +277,7 @@ class Handle:
         o.max_ctas = int(max_ctas)
         o.force_checked = 1 if force_checked else 0
         o.debug = int(os.environ.get('FNB_DEBUG', '0'))     # profiling knob (see fnb_options.debug)
+        o.cluster_pairs = int(cluster_pairs)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -307,14 +308,15 @@ class Handle:
     # ---- whole-set verification histogram
     def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
                             rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy',
-                            force_checked=False):
+                            force_checked=False, cluster_pairs=0):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
         if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
-                               region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked)
+                               region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked,
+                               cluster_pairs=cluster_pairs)
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()
@@ -352,7 +354,7 @@ class Handle:
 
     # ---- keyed histogram over rectangles
     def region_histogram_bins(self, embeddings, perm, cls, regions, nkeys, thresholds, metric=0, atol=1.e-5, eps=1.e-5,
-                              mode='fp16x3', cta_group=0, cuts='numpy', rank=0, world=1):
+                              mode='fp16x3', cta_group=0, cuts='numpy', rank=0, world=1, cluster_pairs=0):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         perm = np.ascontiguousarray(perm, dtype=np.int64)
         cls = np.ascontiguousarray(cls, dtype=np.int32)
@@ -360,7 +362,8 @@ class Handle:
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
         if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
-        o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, cta_group=cta_group, cuts=cuts, rank=rank, world=world)
+        o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, cta_group=cta_group, cuts=cuts, rank=rank, world=world,
+                               cluster_pairs=cluster_pairs)
         bins = np.zeros((int(nkeys), 2, thr.size + 1), dtype=np.uint64)
         st = Stats()
         be = Borrowed(embeddings)

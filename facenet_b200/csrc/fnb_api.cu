@@ -145,14 +145,14 @@ int fnb::dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& sta
 
 constexpr int kFmtU8 = 100;          // byte arrays (e4m3 operands): 128 elements per 128-byte box row
 
-static int make_tmap(fnb_context* h, CUtensorMap* m, void* base, int fmt, long long rows, int d) {
+static int make_tmap(fnb_context* h, CUtensorMap* m, void* base, int fmt, long long rows, int d, int box_rows = kRowsPerCta) {
     CUtensorMapDataType dt = fmt == kFmtTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                            : fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                            : fmt == kFmtU8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const int eb = fmt == kFmtTF32 ? 4 : fmt == kFmtU8 ? 1 : 2;
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)d * eb};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)kRowsPerCta};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = h->encode(m, dt, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -165,11 +165,13 @@ static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 // ---------------------------------------------------------------------------------------
 // regions
 
-void fnb::finish_regions(std::vector<RegionDev>& regs, int tile) {
+// tile grid of every region: `tile` rows x (`tile` * pairs) columns per scheduler step (see TileScheduler)
+void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs) {
     long long t = 0;
+    const int super_cols = tile * pairs;
     for (auto& r : regs) {
         r.nrb = (r.row_end - r.row_begin + tile - 1) / tile;
-        r.ncb = (r.col_end - r.col_begin + tile - 1) / tile;
+        r.ncb = (r.col_end - r.col_begin + super_cols - 1) / super_cols;
         r.tile_begin = t;
         t += (long long)r.nrb * r.ncb;
     }
@@ -195,6 +197,11 @@ static void triangle_regions(long long n, int rr, int key, std::vector<RegionDev
 }
 
 static int pick_cta_group(const fnb_options* o) { return (o->cta_group == 1 || o->cta_group == 2) ? o->cta_group : 2; }
+// CTA pairs per cluster of the histogram launches (multicast of the A operand): only with CTA pairs
+static int pick_pairs(const fnb_options* o, int cta_group) {
+    if (cta_group != 2) return 1;
+    return o->cluster_pairs == 2 ? 2 : 1;
+}
 
 static int pick_region_rows(const fnb_options* o, int tile) {
     int rr = o->region_rows > 0 ? o->region_rows : 2048;
@@ -315,12 +322,27 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;
     CK(cudaMemsetAsync(norm, 0, 4, h->stream));
     CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream));
-    int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d);
+    const int box_rows = side_b ? kRowsPerCta : kRowsPerCta / op.pairs;
+    if (!side_b) op.a_rows_pad = n_pad;
+    int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d, box_rows);
     if (rc) return rc;
-    if (op.num_pass == 3) rc = make_tmap(h, m_lo, lo.p, op.fmt, n_pad, d);
-    else if (f8) { rc = make_tmap(h, m_lo, lo.p, kFmtU8, n_pad, d); if (!rc) rc = make_tmap(h, m_h8, h8.p, kFmtU8, n_pad, d); }
+    if (op.num_pass == 3) rc = make_tmap(h, m_lo, lo.p, op.fmt, n_pad, d, box_rows);
+    else if (f8) { rc = make_tmap(h, m_lo, lo.p, kFmtU8, n_pad, d, box_rows); if (!rc) rc = make_tmap(h, m_h8, h8.p, kFmtU8, n_pad, d, box_rows); }
     else *m_lo = *m_hi;
     if (!f8) *m_h8 = *m_hi;
+    return rc;
+}
+
+int fnb::self_b_maps(fnb_context* h, GramOperands& op, int d) {
+    if (op.pairs == 1) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; return FNB_OK; }
+    // the A maps carry half-height boxes: encode full-height ones over the same arrays for the B side
+    const bool f8 = (op.num_pass == 2);
+    int rc = make_tmap(h, &op.b_hi, h->a_hi.p, op.fmt, op.a_rows_pad, d);
+    if (rc) return rc;
+    if (op.num_pass == 3) rc = make_tmap(h, &op.b_lo, h->a_lo.p, op.fmt, op.a_rows_pad, d);
+    else if (f8) { rc = make_tmap(h, &op.b_lo, h->a_lo.p, kFmtU8, op.a_rows_pad, d); if (!rc) rc = make_tmap(h, &op.b_h8, h->a_h8.p, kFmtU8, op.a_rows_pad, d); }
+    else op.b_lo = op.b_hi;
+    if (!f8) op.b_h8 = op.b_hi;
     return rc;
 }
 
@@ -388,7 +410,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     if ((rc = dl_to_device(h, va, (size_t)na * d * 4, h->stage_a, &da))) return rc;
     if (!self && (rc = dl_to_device(h, vb, (size_t)nb * d * 4, h->stage_b, &db))) return rc;
     if ((rc = prepare_operand(h, opt.mode, (const float*)da, nullptr, na, d, false, op))) return rc;
-    if (self) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; }
+    if (self) { if ((rc = self_b_maps(h, op, d))) return rc; }
     else if ((rc = prepare_operand(h, opt.mode, (const float*)db, nullptr, nb, d, true, op))) return rc;
 
     const int cg = pick_cta_group(&opt);
@@ -545,6 +567,7 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         stats->max_abs = amax;
         stats->eps_counted = (float)h->last_eps_counted;
         stats->kernel_launches += 1;
+        stats->grid_ctas = (uint32_t)h->last_grid;
     }
     return FNB_OK;
 }
@@ -606,14 +629,15 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
     if ((rc = dl_to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
-    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
-    op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8;
-
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
+    op.pairs = pick_pairs(&opt, cg);
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
+    if ((rc = self_b_maps(h, op, d))) return rc;
+
     std::vector<RegionDev> regs;
-    triangle_regions(n, pick_region_rows(&opt, tile), 0, regs);
-    finish_regions(regs, tile);
+    triangle_regions(n, pick_region_rows(&opt, tile * op.pairs), 0, regs);
+    finish_regions(regs, tile, op.pairs);
 
     HistLaunch hl;
     if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
@@ -704,6 +728,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     memset(bins_host, 0, out_bytes);
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
+    op.pairs = pick_pairs(&opt, cg);
     std::vector<RegionDev> regs;
     for (int i = 0; i < nregions; ++i) {
         const fnb_region& r = regions[i];
@@ -716,7 +741,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
         rd.tri = r.tri ? 1 : 0; rd.key = r.key;
         regs.push_back(rd);
     }
-    finish_regions(regs, tile);
+    finish_regions(regs, tile, op.pairs);
     if (regs.back().tile_begin == 0 || n < 1) { h->last_nkeys = 0; return FNB_OK; }
 
     const void* de = nullptr;
@@ -727,7 +752,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     CK(cudaMemcpyAsync(h->perm.p, perm, n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->cls.p, cls, n * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
-    op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8;
+    if ((rc = self_b_maps(h, op, d))) return rc;
 
     HistLaunch hl; hl.nkeys = nkeys;
     if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;

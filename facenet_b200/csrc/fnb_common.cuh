@@ -137,6 +137,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, ui
         : "memory");
 }
 
+// CTA-pair form with multicast: the box is written at the same CTA-relative offset `dst` in every CTA of
+// `cta_mask`, and each destination signals the bytes on the barrier at `bar_cluster_addr`'s offset in the
+// leader (even) CTA of ITS pair -- one L2 read feeds several CTAs of the cluster
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* dst, const void* tmap, uint32_t bar_cluster_addr, uint16_t cta_mask,
+                                                    int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // tcgen05: tensor memory + 5th-gen tensor core
 
@@ -232,14 +244,15 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_
 
 // mbarrier arrive when all previously issued MMAs of this thread have completed.
 // CTA-pair form arrives on the same barrier offset in both CTAs (mask 0b11).
+// `cta_mask`: CTAs of the cluster whose copy of the barrier receives the arrive.
 template <int kCtaGroup>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t cta_mask = 3) {
     if constexpr (kCtaGroup == 1) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                      :: "r"(smem_u32(bar)) : "memory");
     } else {
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     :: "r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+                     :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
     }
 }
 

@@ -1,6 +1,8 @@
 // facenet_b200 -- instantiations and launcher of the Gram kernel (see fnb_gram.cuh).
 #include "fnb_host.h"
 
+#include <algorithm>
+
 namespace fnb {
 
 static constexpr size_t kSmemLimit = 232448;   // 227 KB per CTA on sm_100
@@ -15,31 +17,53 @@ int gram_pick_slots(size_t hist_bytes) {
     return s;
 }
 
-template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi>
+template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi, int kPairs = 1>
 static int launch_one(fnb_context* h, int max_ctas, const GramOperands& op, const GramParams& p, size_t smem)
 {
-    auto kern = gram_kernel<kCtaGroup, kNumPass, kTf32, kEpi>;
+    constexpr int kCluster = kCtaGroup * kPairs;
+    auto kern = gram_kernel<kCtaGroup, kNumPass, kTf32, kEpi, kPairs>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    int ctas = h->sm_count;
-    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
-    ctas -= ctas % kCtaGroup;
-    if (ctas < kCtaGroup) ctas = kCtaGroup;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.gridDim = dim3((unsigned)(h->sm_count - h->sm_count % kCluster));
     cfg.blockDim = dim3(kGramThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.x = kCluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // persistent kernel, one CTA per SM: the grid is the number of CTAs that are co-resident.  Clusters larger than a
+    // TPC cannot use every SM (GPC boundaries), so ask the driver how many clusters fit.
+    int ctas = h->sm_count;
+    if (kCluster > 2) {
+        int nclusters = 0;
+        e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+        if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e));
+        ctas = std::min(ctas, nclusters * kCluster);
+    }
+    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+    ctas -= ctas % kCluster;
+    if (ctas < kCluster) ctas = kCluster;
+    cfg.gridDim = dim3((unsigned)ctas);
+    h->last_grid = ctas;
     e = cudaLaunchKernelEx(&cfg, kern, op.a_hi, op.a_lo, op.b_hi, op.b_lo, op.a_h8, op.b_h8, p);
     if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "gram kernel launch: %s", cudaGetErrorString(e));
     return FNB_OK;
+}
+
+// HIST with two CTA pairs per cluster (A operand multicast)
+static int launch_mode_pairs2(fnb_context* h, int max_ctas, const GramOperands& op, const GramParams& p, size_t smem)
+{
+    if (op.num_pass == 2 && !op.tf32) return launch_one<2, 2, false, EPI_HIST, 2>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 3 && !op.tf32) return launch_one<2, 3, false, EPI_HIST, 2>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 3 && op.tf32)  return launch_one<2, 3, true,  EPI_HIST, 2>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 1 && !op.tf32) return launch_one<2, 1, false, EPI_HIST, 2>(h, max_ctas, op, p, smem);
+    if (op.num_pass == 1 && op.tf32)  return launch_one<2, 1, true,  EPI_HIST, 2>(h, max_ctas, op, p, smem);
+    return h->fail(FNB_ERR_INVALID, "no kernel for num_pass=%d tf32=%d", op.num_pass, (int)op.tf32);
 }
 
 template <int kCtaGroup, int kEpi>
@@ -59,6 +83,10 @@ int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const Gram
     const size_t smem = gram_smem_bytes(p.num_slots, hist_bytes);
     if (smem > kSmemLimit) return h->fail(FNB_ERR_UNSUPPORTED, "shared memory budget exceeded (%zu bytes)", smem);
     if (op.num_pass == 2 && (p.kblocks & 1)) return h->fail(FNB_ERR_UNSUPPORTED, "fp16f8 mode needs an embedding dimension that is a multiple of 128");
+    if (op.pairs == 2) {
+        if (cta_group != 2 || epi != EPI_HIST) return h->fail(FNB_ERR_INVALID, "cluster pairs need cta_group 2 and the histogram epilogue");
+        return launch_mode_pairs2(h, max_ctas, op, p, smem);
+    }
     if (cta_group == 2) {
         if (epi == EPI_HIST)     return launch_mode<2, EPI_HIST>(h, max_ctas, op, p, smem);
         if (epi == EPI_PAIRWISE) return launch_mode<2, EPI_PAIRWISE>(h, max_ctas, op, p, smem);

@@ -87,9 +87,12 @@ struct TileInfo {
     int row0, col0, row_end, col_end, tri, key;
 };
 
-template <int kCtaGroup>
+// One scheduler step hands a cluster a SUPER-TILE of kTile rows x (kPairs * kTile) columns; CTA pair `pi` of the
+// cluster owns the columns [col0 + pi * kTile, + kTile).  kPairs == 1: the super-tile is the tile.
+template <int kCtaGroup, int kPairs = 1>
 struct TileScheduler {
     static constexpr int kTile = kRowsPerCta * kCtaGroup;
+    static constexpr int kSuperCols = kTile * kPairs;
     const RegionDev* regions;
     long long pos, stride, total;
     int cur;
@@ -107,12 +110,12 @@ struct TileScheduler {
             const int rb = li - cb * r.nrb;
             pos += stride;
             t.row0 = r.row_begin + rb * kTile;
-            t.col0 = r.col_begin + cb * kTile;
+            t.col0 = r.col_begin + cb * kSuperCols;
             t.row_end = r.row_end;
             t.col_end = r.col_end;
             t.tri = r.tri;
             t.key = r.key;
-            if (r.tri && t.col0 + kTile - 1 <= t.row0) continue;   // tile entirely on/below the diagonal
+            if (r.tri && t.col0 + kSuperCols - 1 <= t.row0) continue;   // entirely on/below the diagonal
             return true;
         }
         return false;
@@ -179,15 +182,22 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
 // ---------------------------------------------------------------------------------------
 // the kernel
 
-template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi>
+// kPairs == 2 (cta_group 2, HIST only): a cluster of two CTA pairs works on one 256 x 512 super-tile; the pairs share
+// the A rows, so every A box is read from L2 ONCE and multicast to the matching CTA of both pairs (each of the two
+// CTAs issues one 64-row half of it).  L2 -> SM operand traffic drops to 3/4; the two pairs run in lockstep
+// (a slot is refilled only after BOTH pairs' MMAs have consumed it).
+template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi, int kPairs = 1>
 __global__ void __launch_bounds__(kGramThreads, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
             const __grid_constant__ CUtensorMap tm_a_h8, const __grid_constant__ CUtensorMap tm_b_h8,
             const GramParams p)
 {
+    static_assert(kPairs == 1 || (kPairs == 2 && kCtaGroup == 2 && kEpi == EPI_HIST), "multicast clusters: CTA pairs, HIST only");
     constexpr int kTile   = kRowsPerCta * kCtaGroup;       // tile rows == tile cols
     constexpr int kUmmaN  = kTile;                         // accumulator columns per stage
+    constexpr int kClusterCtas = kCtaGroup * kPairs;
+    using Sched = TileScheduler<kCtaGroup, kPairs>;
     // kNumPass: 1 = one MMA per k-step; 3 = split operands x = hi + lo, hi*hi + hi*lo + lo*hi in the operand type;
     //           2 = hi*hi in fp16 plus the two cross terms in fp8 (e4m3) at twice the MMA rate (kSchemeF8)
     constexpr bool kF8    = (kNumPass == 2);
@@ -206,10 +216,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+    const uint32_t cluster_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+    const uint32_t cta_rank = cluster_rank & 1u;           // position inside the CTA pair: 0 = leader (issues the MMAs)
+    const uint32_t pair_idx = cluster_rank >> 1;           // which pair of the cluster (0 when kPairs == 1)
+    const uint32_t leader_rank = cluster_rank & ~1u;       // cluster rank of this pair's leader
     const bool is_leader = (cta_rank == 0);
-    const int cluster_id = blockIdx.x / kCtaGroup;
-    const int num_clusters = gridDim.x / kCtaGroup;
+    const int cluster_id = blockIdx.x / kClusterCtas;
+    const int num_clusters = gridDim.x / kClusterCtas;
+    const uint16_t pair_mask = (uint16_t)(3u << (pair_idx * 2));            // the two CTAs of this pair
+    const uint16_t cluster_mask = (uint16_t)((1u << kClusterCtas) - 1u);    // every CTA of the cluster
     const int num_slots = p.num_slots;
     // fp16 vs bf16 is a runtime choice (same instruction kind, one descriptor field)
     const uint32_t idesc = make_idesc((uint32_t)p.operand_fmt, kTile, kUmmaN);
@@ -217,7 +232,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < num_slots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], 1); }
+        for (int i = 0; i < num_slots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], kPairs); }
         for (int i = 0; i < 2; ++i) { mbar_init(&misc->tfull[i], 1); mbar_init(&misc->tempty[i], kEpiWarps * kCtaGroup); }
         fence_mbar_init();
     }
@@ -245,12 +260,12 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------------
         if (lane == 0) {
-            TileScheduler<kCtaGroup> sched(p, cluster_id, num_clusters);
+            Sched sched(p, cluster_id, num_clusters);
             TileInfo t;
             int slot = 0; uint32_t phase = 0;
             while (sched.next(t)) {
                 const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
-                const int brow = t.col0 + (int)cta_rank * kRowsPerCta;
+                const int brow = t.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
                 auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
                     mbar_wait<kCtaGroup == 2>(&misc->empty[slot], phase ^ 1u);
                     uint8_t* dst = slots + (size_t)slot * kSlotBytes;
@@ -262,19 +277,37 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         tma_load_2d(dst + kBoxBytes, mb, &misc->full[slot], kcol, brow);
                     } else {
                         if (is_leader) mbar_arrive_expect_tx(&misc->full[slot], 2 * kSlotBytes);
-                        const uint32_t bar = mapa_u32(smem_u32(&misc->full[slot]), 0);
-                        tma_load_2d_pair(dst, ma, bar, kcol, arow);
+                        const uint32_t bar = mapa_u32(smem_u32(&misc->full[slot]), leader_rank);
+                        if constexpr (kPairs == 1) {
+                            tma_load_2d_pair(dst, ma, bar, kcol, arow);
+                        } else {
+                            // `ma` has 64-row boxes: this CTA fetches half `pair_idx` of the A box and multicasts it to the
+                            // CTA with the same pair position in both pairs; the other half arrives from that CTA
+                            const uint16_t mc = (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank)));
+                            tma_load_2d_pair_mc(dst + pair_idx * (kBoxBytes / 2), ma, bar, mc, kcol, arow + (int)pair_idx * (kRowsPerCta / 2));
+                        }
                         tma_load_2d_pair(dst + kBoxBytes, mb, bar, kcol, brow);
                     }
                     if (++slot == num_slots) { slot = 0; phase ^= 1u; }
                 };
                 if constexpr (kF8) {
-                    // per 128 K-elements: two fp16 {hi, hi} slots, then {A e4m3(x), B e4m3(lo)} and {A e4m3(lo), B e4m3(x)}
+                    // The small cross terms first: {A e4m3(x), B e4m3(lo)} and {A e4m3(lo), B e4m3(x)} per 128 K-elements,
+                    // then the fp16 {hi, hi} slots.  The tensor core truncates when it adds into the fp32 accumulator, an
+                    // error proportional to the accumulator's magnitude per step: while the cross terms are summed the
+                    // accumulator is ~2^-11 of its final value, so only the hi*hi steps contribute (half as many).
+                    if (p.debug & 4) {       // A/B knob: interleaved order (2 fp16 slots, 2 e4m3 slots per 128 K-elements)
+                        for (int ks = 0; ks < p.kblocks / 2; ++ks) {
+                            load_slot(&tm_a_hi, &tm_b_hi, (2 * ks) * 64);
+                            load_slot(&tm_a_hi, &tm_b_hi, (2 * ks + 1) * 64);
+                            load_slot(&tm_a_h8, &tm_b_lo, ks * 128);
+                            load_slot(&tm_a_lo, &tm_b_h8, ks * 128);
+                        }
+                    } else {
                     for (int ks = 0; ks < p.kblocks / 2; ++ks) {
-                        load_slot(&tm_a_hi, &tm_b_hi, (2 * ks) * 64);
-                        load_slot(&tm_a_hi, &tm_b_hi, (2 * ks + 1) * 64);
                         load_slot(&tm_a_h8, &tm_b_lo, ks * 128);
                         load_slot(&tm_a_lo, &tm_b_h8, ks * 128);
+                    }
+                    for (int kb = 0; kb < p.kblocks; ++kb) load_slot(&tm_a_hi, &tm_b_hi, kb * 64);
                     }
                 } else {
                     for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -287,7 +320,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     } else if (warp == 1) {
         // ------------------------------ MMA issuer --------------------------------------
         if (lane == 0 && is_leader) {
-            TileScheduler<kCtaGroup> sched(p, cluster_id, num_clusters);
+            Sched sched(p, cluster_id, num_clusters);
             TileInfo t;
             int slot = 0; uint32_t phase = 0;
             uint32_t it = 0;
@@ -297,21 +330,20 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kUmmaN;
                 if constexpr (kF8) {
-                    for (int ks = 0; ks < p.kblocks / 2; ++ks) {
+                    const int nsteps = 2 * p.kblocks;              // kblocks e4m3 slots (K = 128 each), then kblocks fp16 slots (K = 64)
+                    for (int st = 0; st < nsteps; ++st) {
+                        mbar_wait<kCtaGroup == 2>(&misc->full[slot], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(slots + (size_t)slot * kSlotBytes);
+                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kBoxBytes);
 #pragma unroll
-                        for (int part = 0; part < 4; ++part) {
-                            mbar_wait<kCtaGroup == 2>(&misc->full[slot], phase);
-                            tc_fence_after();
-                            const uint32_t sa = smem_u32(slots + (size_t)slot * kSlotBytes);
-                            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kBoxBytes);
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                if (part < 2) umma<kCtaGroup, false>(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (ks | part | k4) != 0 ? 1u : 0u);
-                                else umma_f8<kCtaGroup>(d_tmem, da + 2 * k4, db + 2 * k4, idesc_f8, 1u);
-                            }
-                            umma_commit<kCtaGroup>(&misc->empty[slot]);
-                            if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const bool f8_slot = (p.debug & 4) ? ((st & 2) != 0) : (st < p.kblocks);
+                            if (f8_slot) umma_f8<kCtaGroup>(d_tmem, da + 2 * k4, db + 2 * k4, idesc_f8, (st | k4) != 0 ? 1u : 0u);
+                            else umma<kCtaGroup, false>(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (st | k4) != 0 ? 1u : 0u);
                         }
+                        umma_commit<kCtaGroup>(&misc->empty[slot], cluster_mask);
+                        if (++slot == num_slots) { slot = 0; phase ^= 1u; }
                     }
                 } else
                 for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -336,14 +368,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
                             umma<kCtaGroup, kTf32>(d_tmem, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
-                        umma_commit<kCtaGroup>(&misc->empty[slot_hi]);
-                        umma_commit<kCtaGroup>(&misc->empty[slot_lo]);
+                        umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
+                        umma_commit<kCtaGroup>(&misc->empty[slot_lo], cluster_mask);
                         if (++slot == num_slots) { slot = 0; phase ^= 1u; }
                     } else {
-                        umma_commit<kCtaGroup>(&misc->empty[slot_hi]);
+                        umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
                     }
                 }
-                umma_commit<kCtaGroup>(&misc->tfull[acc]);
+                umma_commit<kCtaGroup>(&misc->tfull[acc], pair_mask);
                 ++it;
             }
         }
@@ -357,7 +389,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float scale = p.acc_scale;
 
-        TileScheduler<kCtaGroup> sched(p, cluster_id, num_clusters);
+        Sched sched(p, cluster_id, num_clusters);
         TileInfo t;
         uint32_t it = 0;
 
@@ -410,6 +442,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
         while (sched.next(t)) {
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            if constexpr (kPairs > 1) t.col0 += (int)pair_idx * kTile;        // this pair's tile of the super-tile
+            // a pair whose tile lies outside the region / below the diagonal still runs the pipeline (lockstep) and drops the result
+            const bool null_tile = (kPairs > 1) && (t.col0 >= t.col_end || (t.tri && t.col0 + kTile - 1 <= t.row0));
             const int row = t.row0 + row_in_tile;
             const int colw = t.col0 + colq * kColsPerWarp;       // first column of this warp
             const uint32_t taddr0 = tmem_lane + acc * kUmmaN + colq * kColsPerWarp;
@@ -429,7 +464,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                  (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + rlast));
                 const bool slow = all_slow || edge || lab;
 
-                if (p.debug & 1) {
+                if ((p.debug & 1) || null_tile) {
                     mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
                 } else if (!slow) {
@@ -530,7 +565,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (kCtaGroup == 2) mbar_arrive_remote(&misc->tempty[acc], 0);
+                if (kCtaGroup == 2) mbar_arrive_remote(&misc->tempty[acc], leader_rank);
                 else mbar_arrive(&misc->tempty[acc]);
             }
             ++it; ++tiles_done;
@@ -547,7 +582,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 atomicMin(p.range_ord + 0, float_to_ordered(smin));
                 atomicMax(p.range_ord + 1, float_to_ordered(smax));
             }
-            if (e == 0 && is_leader) atomicAdd(p.counters + 1, (unsigned long long)tiles_done);
+            if (e == 0 && cluster_rank == 0) atomicAdd(p.counters + 1, (unsigned long long)tiles_done);
         }
     }
 

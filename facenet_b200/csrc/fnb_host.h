@@ -77,7 +77,7 @@ struct fnb_context {
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
-    int last_nkeys = 0, last_T = 0;
+    int last_nkeys = 0, last_T = 0, last_grid = 0;
     double last_eps_counted = 0;         // distance half-width of the near-threshold window counted by interior tiles
 
     int fail(int code, const char* fmt, ...);
@@ -98,6 +98,8 @@ struct GramOperands {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap a_h8, b_h8;        // fp16f8 mode only: e4m3(x) arrays (a_lo / b_lo then hold e4m3(lo))
     int num_pass = 3; bool tf32 = false; int fmt = 0; int elem_bytes = 2; float prescale = 1.f;
+    int pairs = 1;                 // CTA pairs per cluster (2: the A maps carry 64-row boxes, see gram_kernel kPairs)
+    long long a_rows_pad = 0;      // padded row count of the prepared A-side arrays
 };
 
 struct DeviceScalars {      // layout of fnb_context::counters
@@ -113,7 +115,8 @@ int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, c
 int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
                     bool side_b, GramOperands& op);
-void finish_regions(std::vector<RegionDev>& regs, int tile);
+void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1);
+int self_b_maps(fnb_context* h, GramOperands& op, int d);   // B side = the prepared A side (Gram of a set with itself)
 int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
 int reset_scalars(fnb_context* h);
 int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, float* prescale);

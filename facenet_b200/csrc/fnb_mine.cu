@@ -165,7 +165,7 @@ extern "C" int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* label
     if ((rc = dl_to_device(h, ve, (size_t)b * d * 4, h->stage_a, &de))) return rc;
     if ((rc = dl_to_device(h, vl, (size_t)b * (vl.bits / 8), h->stage_lab, &dl))) return rc;
     if ((rc = prepare_operand(h, opt.mode, (const float*)de, nullptr, b, d, false, op))) return rc;
-    op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8;
+    if ((rc = self_b_maps(h, op, d))) return rc;
 
     // stage 1: B x B distances (every ordered pair, diagonal included)
     const int cg = 1;                                   // 128 x 128 tiles: 225 tiles at B = 1800 fill the 148 SMs better than 64 pair-tiles

@@ -84,7 +84,9 @@ typedef struct {
                               eps window, per-pair range check) -- the reference the arithmetic path is tested against */
     int32_t debug;         /* profiling knob, results are MEANINGLESS when != 0: bit 0 skips the epilogue work,
                               bit 1 skips the operand loads (MMA on whatever shared memory holds) */
-    int32_t reserved[5];
+    int32_t cluster_pairs; /* histogram launches, cta_group 2 only: 2 = clusters of two CTA pairs that share (multicast) the
+                              A operand, so it is read from L2 once per 256 x 512 super-tile; 0/1 = one pair per cluster */
+    int32_t reserved[4];
 } fnb_options;
 
 typedef struct {
@@ -100,7 +102,8 @@ typedef struct {
     uint64_t tiles;        /* tiles processed by this rank                                      */
     uint32_t kernel_launches;
     float    eps_counted;  /* distance half-width actually counted by interior tiles (see eps_window)           */
-    uint32_t reserved[3];
+    uint32_t grid_ctas;    /* CTAs of the Gram launch (co-resident clusters x cluster size)                     */
+    uint32_t reserved[2];
 } fnb_stats;
 
 /* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:

@@ -41,7 +41,7 @@ def case_pairwise(mode, cg, na=200, nb=150, d=128):
     print('pairwise cross metric1: max|dd|=%.3e' % np.abs(got - ref).max())
 
 
-def case_hist(mode, cg, n_classes=40, d=128, seed=3):
+def case_hist(mode, cg, n_classes=40, d=128, seed=3, pairs=1):
     h = _capi.Handle(0)
     rng = np.random.default_rng(seed)
     sizes = rng.integers(1, 40, size=n_classes)
@@ -50,7 +50,9 @@ def case_hist(mode, cg, n_classes=40, d=128, seed=3):
         thr = so.default_thresholds(metric)
         ref = so.pair_histogram(x, labels, thr, metric)
         for force in ('fast', ):
-            out = h.pair_histogram(x, labels, thr, metric, mode=mode, cta_group=cg)
+            out = h.pair_histogram(x, labels, thr, metric, mode=mode, cta_group=cg, cluster_pairs=pairs)
+            base = h.pair_histogram(x, labels, thr, metric, mode=mode, cta_group=cg)
+            print('   pairs=%d bins identical to pairs=1: %s   grid %d' % (pairs, bool((out['bins'] == base['bins']).all()), out['stats']['grid_ctas']))
             ds = np.abs(out['same'] - ref['same']).sum()
             dd = np.abs(out['diff'] - ref['diff']).sum()
             print('hist mode=%s cg=%d N=%d metric=%d: n_same %d/%d n_diff %d/%d  L1(same)=%d L1(diff)=%d eps_window=%d tiles=%d kernel_ms=%.3f'
@@ -59,7 +61,7 @@ def case_hist(mode, cg, n_classes=40, d=128, seed=3):
             print('   range checked [%g, %g] max_abs %g' % (out['stats']['smin'], out['stats']['smax'], out['stats']['max_abs']))
 
 
-def case_bench(mode, cg, n=20000, d=512, reps=3):
+def case_bench(mode, cg, n=20000, d=512, reps=3, pairs=1):
     h = _capi.Handle(0)
     x, labels = so.synthetic_embeddings([50] * (n // 50), dim=d, sigma=1.1, seed=0)
     thr = so.default_thresholds(0)
@@ -68,12 +70,12 @@ def case_bench(mode, cg, n=20000, d=512, reps=3):
     lt = torch.from_numpy(labels).cuda()
     for r in range(reps):
         t0 = time.time()
-        bins, st = h.pair_histogram_bins(xt, lt, thr, 0, mode=mode, cta_group=cg)
+        bins, st = h.pair_histogram_bins(xt, lt, thr, 0, mode=mode, cta_group=cg, cluster_pairs=pairs)
         dt = time.time() - t0
-        pairs = n * (n - 1) / 2
-        print('bench mode=%s cg=%d N=%d: kernel %.3f ms  prepare %.3f ms  wall %.1f ms  -> %.1f Gpairs/s (kernel)  %.1f TFLOP/s  pairs=%d'
-              % (mode, cg, n, st['kernel_ms'], st['prepare_ms'], dt * 1e3, pairs / st['kernel_ms'] / 1e6,
-                 pairs * 1024 / st['kernel_ms'] / 1e9, st['n_pairs']))
+        npairs = n * (n - 1) / 2
+        print('bench mode=%s cg=%d pairs=%d grid=%d N=%d: kernel %.3f ms  prepare %.3f ms  wall %.1f ms  -> %.1f Gpairs/s (kernel)  %.1f TFLOP/s  pairs=%d'
+              % (mode, cg, pairs, st['grid_ctas'], n, st['kernel_ms'], st['prepare_ms'], dt * 1e3, npairs / st['kernel_ms'] / 1e6,
+                 npairs * 1024 / st['kernel_ms'] / 1e9, st['n_pairs']))
 
 
 def case_accuracy(mode, n=3000, d=512):
