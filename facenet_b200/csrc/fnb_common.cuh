@@ -88,26 +88,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-// same, acquiring at cluster scope (barrier completed by another CTA's arrive / async proxy)
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
 #ifndef FNB_SPIN_LIMIT
 #define FNB_SPIN_LIMIT (1u << 24)   // try_wait suspends ~us each; a stuck pipeline traps instead of hanging
 #endif
 
-template <bool kCluster>
+// CTA-scope acquire (the default of try_wait) is what the pipeline needs even across a CTA pair: the data behind
+// these barriers moves through the async proxy (TMA writes, tcgen05 reads) and tensor memory, ordered by
+// complete_tx / tcgen05.commit / tcgen05.fence -- no generic-proxy data of another CTA is read after the wait.  A
+// cluster-scope acquire here makes ptxas emit an L1 invalidate (CCTL.IVALL) after every successful wait.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spins = 0;; ++spins) {
-        bool ok = kCluster ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity);
-        if (ok) return;
+        if (mbar_try_wait(bar, parity)) return;
         if (spins > FNB_SPIN_LIMIT) __trap();
     }
 }

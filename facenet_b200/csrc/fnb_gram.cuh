@@ -259,15 +259,17 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // =====================================================================================
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------------
-        if (lane == 0) {
-            Sched sched(p, cluster_id, num_clusters);
-            TileInfo t;
-            int slot = 0; uint32_t phase = 0;
-            while (sched.next(t)) {
-                const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
-                const int brow = t.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
-                auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
-                    mbar_wait<kCtaGroup == 2>(&misc->empty[slot], phase ^ 1u);
+        // The whole warp walks the schedule and polls the barriers (warp-uniform control flow, so the compiler keeps
+        // addresses and descriptors in uniform registers); one elected lane issues the copies.
+        Sched sched(p, cluster_id, num_clusters);
+        TileInfo t;
+        int slot = 0; uint32_t phase = 0;
+        while (sched.next(t)) {
+            const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
+            const int brow = t.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
+            auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
+                mbar_wait(&misc->empty[slot], phase ^ 1u);
+                if (elect_one()) {
                     uint8_t* dst = slots + (size_t)slot * kSlotBytes;
                     if (p.debug & 2) {
                         if (is_leader) mbar_arrive(&misc->full[slot]);
@@ -288,94 +290,109 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         }
                         tma_load_2d_pair(dst + kBoxBytes, mb, bar, kcol, brow);
                     }
-                    if (++slot == num_slots) { slot = 0; phase ^= 1u; }
-                };
-                if constexpr (kF8) {
-                    // The small cross terms first: {A e4m3(x), B e4m3(lo)} and {A e4m3(lo), B e4m3(x)} per 128 K-elements,
-                    // then the fp16 {hi, hi} slots.  The tensor core truncates when it adds into the fp32 accumulator, an
-                    // error proportional to the accumulator's magnitude per step: while the cross terms are summed the
-                    // accumulator is ~2^-11 of its final value, so only the hi*hi steps contribute (half as many).
-                    if (p.debug & 4) {       // A/B knob: interleaved order (2 fp16 slots, 2 e4m3 slots per 128 K-elements)
-                        for (int ks = 0; ks < p.kblocks / 2; ++ks) {
-                            load_slot(&tm_a_hi, &tm_b_hi, (2 * ks) * 64);
-                            load_slot(&tm_a_hi, &tm_b_hi, (2 * ks + 1) * 64);
-                            load_slot(&tm_a_h8, &tm_b_lo, ks * 128);
-                            load_slot(&tm_a_lo, &tm_b_h8, ks * 128);
-                        }
-                    } else {
-                    for (int ks = 0; ks < p.kblocks / 2; ++ks) {
-                        load_slot(&tm_a_h8, &tm_b_lo, ks * 128);
-                        load_slot(&tm_a_lo, &tm_b_h8, ks * 128);
-                    }
-                    for (int kb = 0; kb < p.kblocks; ++kb) load_slot(&tm_a_hi, &tm_b_hi, kb * 64);
-                    }
-                } else {
-                    for (int kb = 0; kb < p.kblocks; ++kb) {
-                        load_slot(&tm_a_hi, &tm_b_hi, kb * kElemsPerBox);
-                        if (kParts == 2) load_slot(&tm_a_lo, &tm_b_lo, kb * kElemsPerBox);
-                    }
+                }
+                __syncwarp();
+                if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+            };
+            if constexpr (kF8) {
+                // The small cross terms first -- {A e4m3(x), B e4m3(lo)} and {A e4m3(lo), B e4m3(x)} per 128 K-elements --
+                // then the fp16 {hi, hi} slots.  The tensor core truncates when it adds into the fp32 accumulator, an error
+                // proportional to the accumulator's magnitude per step; while the cross terms are summed the accumulator
+                // is ~2^-11 of its final value, so only the hi*hi steps contribute.
+                for (int ks = 0; ks < p.kblocks / 2; ++ks) {
+                    load_slot(&tm_a_h8, &tm_b_lo, ks * 128);
+                    load_slot(&tm_a_lo, &tm_b_h8, ks * 128);
+                }
+                for (int kb = 0; kb < p.kblocks; ++kb) load_slot(&tm_a_hi, &tm_b_hi, kb * 64);
+            } else {
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    load_slot(&tm_a_hi, &tm_b_hi, kb * kElemsPerBox);
+                    if (kParts == 2) load_slot(&tm_a_lo, &tm_b_lo, kb * kElemsPerBox);
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer --------------------------------------
-        if (lane == 0 && is_leader) {
+        // Leader CTA of the pair only.  Warp-uniform control flow; one elected lane issues every tcgen05.mma and
+        // tcgen05.commit (the commits track the MMAs of the issuing thread: elect.sync picks the same lane each time).
+        if (is_leader) {
             Sched sched(p, cluster_id, num_clusters);
             TileInfo t;
             int slot = 0; uint32_t phase = 0;
             uint32_t it = 0;
             while (sched.next(t)) {
                 const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-                mbar_wait<kCtaGroup == 2>(&misc->tempty[acc], acc_phase ^ 1u);
+                mbar_wait(&misc->tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kUmmaN;
                 if constexpr (kF8) {
-                    const int nsteps = 2 * p.kblocks;              // kblocks e4m3 slots (K = 128 each), then kblocks fp16 slots (K = 64)
-                    for (int st = 0; st < nsteps; ++st) {
-                        mbar_wait<kCtaGroup == 2>(&misc->full[slot], phase);
+                    // kblocks e4m3 slots (K = 128 each: the cross terms), then kblocks fp16 slots (K = 64 each: hi*hi)
+                    for (int st = 0; st < p.kblocks; ++st) {
+                        mbar_wait(&misc->full[slot], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(slots + (size_t)slot * kSlotBytes);
-                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kBoxBytes);
+                        if (elect_one()) {
+                            const uint32_t sa = smem_u32(slots + (size_t)slot * kSlotBytes);
+                            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kBoxBytes);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const bool f8_slot = (p.debug & 4) ? ((st & 2) != 0) : (st < p.kblocks);
-                            if (f8_slot) umma_f8<kCtaGroup>(d_tmem, da + 2 * k4, db + 2 * k4, idesc_f8, (st | k4) != 0 ? 1u : 0u);
-                            else umma<kCtaGroup, false>(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (st | k4) != 0 ? 1u : 0u);
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma_f8<kCtaGroup>(d_tmem, da + 2 * k4, db + 2 * k4, idesc_f8, (st | k4) != 0 ? 1u : 0u);
+                            umma_commit<kCtaGroup>(&misc->empty[slot], cluster_mask);
                         }
-                        umma_commit<kCtaGroup>(&misc->empty[slot], cluster_mask);
+                        __syncwarp();
                         if (++slot == num_slots) { slot = 0; phase ^= 1u; }
                     }
-                } else
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    const int slot_hi = slot;
-                    mbar_wait<kCtaGroup == 2>(&misc->full[slot_hi], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(slots + (size_t)slot_hi * kSlotBytes);
-                    const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + kBoxBytes);
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
-                    if (++slot == num_slots) { slot = 0; phase ^= 1u; }
-                    if (kNumPass == 3) {
-                        const int slot_lo = slot;
-                        mbar_wait<kCtaGroup == 2>(&misc->full[slot_lo], phase);
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&misc->full[slot], phase);
                         tc_fence_after();
-                        const uint32_t sl = smem_u32(slots + (size_t)slot_lo * kSlotBytes);
-                        const uint64_t a_lo = make_smem_desc(sl), b_lo = make_smem_desc(sl + kBoxBytes);
+                        if (elect_one()) {
+                            const uint32_t sa = smem_u32(slots + (size_t)slot * kSlotBytes);
+                            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kBoxBytes);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1u);
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            umma<kCtaGroup, kTf32>(d_tmem, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
-                        umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
-                        umma_commit<kCtaGroup>(&misc->empty[slot_lo], cluster_mask);
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma<kCtaGroup, false>(d_tmem, da + 2 * k4, db + 2 * k4, idesc, 1u);
+                            umma_commit<kCtaGroup>(&misc->empty[slot], cluster_mask);
+                        }
+                        __syncwarp();
                         if (++slot == num_slots) { slot = 0; phase ^= 1u; }
-                    } else {
-                        umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
+                    }
+                } else {
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        const int slot_hi = slot;
+                        mbar_wait(&misc->full[slot_hi], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(slots + (size_t)slot_hi * kSlotBytes);
+                        const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + kBoxBytes);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                            if (kNumPass != 3) umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
+                        }
+                        __syncwarp();
+                        if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                        if (kNumPass == 3) {
+                            const int slot_lo = slot;
+                            mbar_wait(&misc->full[slot_lo], phase);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t sl = smem_u32(slots + (size_t)slot_lo * kSlotBytes);
+                                const uint64_t a_lo = make_smem_desc(sl), b_lo = make_smem_desc(sl + kBoxBytes);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4)
+                                    umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1u);
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; ++k4)
+                                    umma<kCtaGroup, kTf32>(d_tmem, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
+                                umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
+                                umma_commit<kCtaGroup>(&misc->empty[slot_lo], cluster_mask);
+                            }
+                            __syncwarp();
+                            if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                        }
                     }
                 }
-                umma_commit<kCtaGroup>(&misc->tfull[acc], pair_mask);
+                if (elect_one()) umma_commit<kCtaGroup>(&misc->tfull[acc], pair_mask);
+                __syncwarp();
                 ++it;
             }
         }
@@ -465,13 +482,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const bool slow = all_slow || edge || lab;
 
                 if ((p.debug & 1) || null_tile) {
-                    mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                    mbar_wait(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
                 } else if (!slow) {
                     // ---------------- interior tile: every element valid, no same-identity pair -------------
                     if (fast_since_flush >= kFlushEvery) flush_u8();
                     ++fast_since_flush;
-                    mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                    mbar_wait(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
                     const float s1 = p.f_s1, b1 = p.f_b1, k2 = p.f_k2, mk = p.f_magic_k, mn = p.f_magic_n;
                     const uint32_t nmask = p.near_mask;
@@ -497,7 +514,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     }
                 } else {
                     // ---------------- checked tile: edges, diagonal, same-identity pairs, general cuts --------
-                    mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                    mbar_wait(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
                     // stage this tile's column classes (kTile <= 256 columns).  Safe after the tfull wait:
                     // every epilogue warp has released the tile that last used col_cls[acc].
@@ -531,7 +548,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 }
             } else {
                 // ------------------- PAIRWISE / ROWSTRIP: materialise distances --------------
-                mbar_wait<kCtaGroup == 2>(&misc->tfull[acc], acc_phase);
+                mbar_wait(&misc->tfull[acc], acc_phase);
                 tc_fence_after();
                 const bool row_ok = row < t.row_end;
 #pragma unroll 1

@@ -1,0 +1,116 @@
+"""Timings + parity of the BASELINE.json configs that are not the bench.py headline (run on a B200):
+
+  c1  synthetic LFW-size 13,233 x 512 (5,749 identities): FaceToFaceValidation (10 folds, 100 thresholds,
+      FAR 1e-3) through the drop-in Python API, host arrays in, Report dict out; parity vs the vectorised
+      oracle (chosen thresholds, fold rates) and the oracle's CPU time beside it
+  c3  triplet mining, 1800-image batches (45 identities x 40 images), 512-d, alpha 0.2: steps/s with
+      host batches (H2D inside) and with device-resident batches; parity of one batch vs the mining oracle
+
+    python scripts/bench_configs.py [c1] [c3] [--steps N]   -> one JSON line per config
+"""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, '.')
+
+
+class Cfg:
+    def __init__(self, metric=0, nrof_folds=10, far_target=1.e-3):
+        self.metric, self.nrof_folds, self.far_target = metric, nrof_folds, far_target
+
+
+def run_c1(mode):
+    from facenet_b200 import statistics as fst
+    from oracle import statistics_oracle as so
+    fst.set_default_mode(mode=mode)
+    sizes = so.lfw_like_class_sizes()
+    x, labels = so.synthetic_embeddings(sizes, dim=512, sigma=1.1, seed=0)
+    cfg = Cfg()
+    fst.FaceToFaceValidation(x[:2000], labels[:2000], cfg)          # warm-up (context, workspaces)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        v = fst.FaceToFaceValidation(x, labels, cfg)
+        times.append(time.perf_counter() - t0)
+    got = v.dict
+    thr_acc = np.array([m.threshold[0] for m in v.reports[0].conf_matrix_test])
+    thr_far = np.array([m.threshold[0] for m in v.reports[1].conf_matrix_test])
+    t0 = time.perf_counter()
+    ref = so.face_to_face_validation(x, labels, 0, 10, 1.e-3)
+    cpu_s = time.perf_counter() - t0
+    n = x.shape[0]
+    ntr = n - n // 10
+    pair_evals = 10 * (ntr * (ntr - 1) // 2) + 20 * ((n // 10) * (n // 10 - 1) // 2)
+    worst = 0.0
+    for crit in got:
+        for k in got[crit]:
+            worst = max(worst, abs(float(got[crit][k]) - float(ref[crit][k])))
+    line = {'config': 'c1: synthetic LFW-size 13,233 x 512 fp32 (5,749 identities), FaceToFaceValidation 10 folds x 100 thresholds',
+            'mode': mode, 'seconds': min(times), 'seconds_all': times, 'pair_distance_evaluations': pair_evals,
+            'g_pair_distances_per_s': pair_evals / min(times) / 1e9,
+            'cpu_vectorised_oracle_seconds': cpu_s, 'cpu_literal_reference_seconds_extrapolated': 4.0e-3 * 5749 ** 2,
+            'accuracy_threshold_equal_folds': int(np.sum(thr_acc == ref['_thresholds'][:, 0])),
+            'far_threshold_max_abs_diff': float(np.abs(thr_far - ref['_thresholds'][:, 1]).max()),
+            'report_dict_max_abs_diff': worst,
+            'report': {k: {kk: float(vv) for kk, vv in d.items()} for k, d in got.items()}}
+    print(json.dumps(line))
+
+
+def run_c3(mode, steps):
+    import torch
+    from facenet_b200 import _capi
+    from oracle import mining_oracle as mo
+    from oracle import statistics_oracle as so
+    h = _capi.default_handle(0)
+    nb = 8
+    batches = []
+    for s in range(nb):
+        x, labels = so.synthetic_embeddings([40] * 45, dim=512, sigma=1.1, seed=100 + s, shuffle=False)
+        batches.append((x, labels))
+    out = h.mine(batches[0][0], batches[0][1], alpha=0.2, mode=mode, kmax=39)
+    ref = mo.mine(batches[0][0], batches[0][1], alpha=0.2)
+    agree = {k: float(np.mean(out[k] == ref[k])) for k in ref}
+    # host batches: H2D of the batch and D2H of the index arrays inside every step
+    for i in range(5):
+        h.mine(*batches[i % nb], alpha=0.2, mode=mode, kmax=39)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        h.mine(*batches[i % nb], alpha=0.2, mode=mode, kmax=39)
+    host_s = (time.perf_counter() - t0) / steps
+    dev = [(torch.from_numpy(x).cuda(), torch.from_numpy(l).cuda()) for x, l in batches]
+    torch.cuda.synchronize()
+    for i in range(5):
+        h.mine(*dev[i % nb], alpha=0.2, mode=mode, kmax=39)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        h.mine(*dev[i % nb], alpha=0.2, mode=mode, kmax=39)
+    dev_s = (time.perf_counter() - t0) / steps
+    t0 = time.perf_counter()
+    mo.mine(batches[1][0], batches[1][1], alpha=0.2)
+    cpu_s = time.perf_counter() - t0
+    b = 1800
+    line = {'config': 'c3: triplet mining, 1800-image batches (45 identities x 40 images), 512-d, alpha 0.2',
+            'mode': mode, 'steps': steps, 'ms_per_step_host_batches': host_s * 1e3, 'ms_per_step_device_batches': dev_s * 1e3,
+            'steps_per_s_device_batches': 1.0 / dev_s, 'seconds_for_10k_steps_device_batches': 1e4 * dev_s,
+            'g_ordered_pair_distances_per_s': b * b / dev_s / 1e9, 'cpu_oracle_ms_per_step': cpu_s * 1e3,
+            'index_agreement_with_oracle': agree}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    steps = 200
+    mode = 'fp16x3'
+    for i, a in enumerate(sys.argv):
+        if a == '--steps':
+            steps = int(sys.argv[i + 1])
+        if a == '--mode':
+            mode = sys.argv[i + 1]
+    args = [a for a in args if a not in (str(steps), mode)]
+    if not args or 'c1' in args:
+        run_c1(mode)
+    if not args or 'c3' in args:
+        run_c3(mode, steps)

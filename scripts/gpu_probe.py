@@ -96,6 +96,13 @@ def case_accuracy(mode, n=3000, d=512):
         e = np.abs(got - exact)
         print('accuracy mode=%s %-20s n=%d: max|dd|=%.3e rms=%.3e  vs oracle(fp32 sgemm): max=%.3e   [oracle vs f64: max=%.3e]'
               % (mode, name, n, e.max(), np.sqrt((e ** 2).mean()), np.abs(got - ref32).max(), np.abs(ref32 - exact).max()))
+        se = got - exact
+        j = int(np.argmax(e))
+        print('      bias=%.3e  p99.99=%.3e  worst pair (%d,%d): d=%.6f err=%.3e' %
+              (se.mean(), np.quantile(e, 0.9999), iu[0][j], iu[1][j], exact[j], se[j]))
+        near = exact < 0.5
+        if near.any():
+            print('      pairs with d<0.5: n=%d bias=%.3e rms=%.3e max=%.3e' % (near.sum(), se[near].mean(), np.sqrt((se[near]**2).mean()), e[near].max()))
 
 
 if __name__ == '__main__':

@@ -234,6 +234,38 @@ def test_histogram_sharded_ranks_sum_to_whole(handle):
         np.testing.assert_array_equal(acc, whole)
 
 
+def test_histogram_cluster_pairs_identical_bins(handle):
+    """Clusters of two CTA pairs (A operand multicast, 256 x 512 super-tiles) run the same MMAs in the same order
+    per tile: the integer bins are IDENTICAL to the one-pair kernel, for every mode, ragged edges, rank sharding
+    and the keyed (region) form."""
+    thr = so.default_thresholds(0)
+    for seed, nc, d in ((5, 80, 128), (9, 150, 512)):
+        x, labels = ragged(seed, n_classes=nc, d=d)
+        for mode in ('fp16x3', 'fp16f8', 'bf16', 'tf32x3'):
+            one, st1 = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode)
+            two, st2 = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode, cluster_pairs=2)
+            np.testing.assert_array_equal(one, two)
+            assert st2['eps_window'] == st1['eps_window'] and st2['grid_ctas'] % 4 == 0
+        acc = np.zeros_like(one)
+        for rank in range(3):
+            part, _ = handle.pair_histogram_bins(x, labels, thr, 0, mode='tf32x3', rank=rank, world=3, cluster_pairs=2)
+            acc += part
+        np.testing.assert_array_equal(acc, one)
+
+
+def test_histogram_fp16f8_mode(handle):
+    """fp16f8 (hi*hi in fp16 + e4m3 cross terms): distances within the 1e-5 tolerance of the oracle on dense
+    embeddings, histogram disagreements bounded by the counted eps-window pairs."""
+    for sigma in (1.1, 0.5):
+        x, labels = so.synthetic_embeddings([40] * 30 + [1] * 50 + [7] * 20, dim=512, sigma=sigma, seed=3)
+        d = handle.pairwise(x, None, 0, mode='fp16f8')
+        ref = so.pairwise_similarities(x.copy(), None, 0)
+        assert float(np.abs(d - ref).max()) <= DIST_TOL
+        thr = so.default_thresholds(0)
+        out = handle.pair_histogram(x, labels, thr, 0, mode='fp16f8')
+        check_hist(out, so.pair_histogram(x, labels, thr, 0), x.shape[0])
+
+
 def test_histogram_edge_cases(handle):
     thr = so.default_thresholds(0)
     x = unit(1, 64, 0)
@@ -338,6 +370,28 @@ def test_validation_golden(fst, golden_dir):
             else:
                 np.testing.assert_allclose(got_thr, g['far_thr_m%d' % metric], rtol=0, atol=2e-3)
         assert 'MaximumAccuracy' in repr(v)
+
+
+def test_validation_lfw_size_vs_oracle(fst):
+    """BASELINE config 1: 13,233 x 512, 5,749 identities (4,069 singletons, largest class 530), 10 folds, 100
+    thresholds, FAR 1e-3 -- the drop-in FaceToFaceValidation against the vectorised oracle of the same arithmetic.
+    The literal reference loop would take ~37 h at this size."""
+    sizes = so.lfw_like_class_sizes()
+    x, labels = so.synthetic_embeddings(sizes, dim=512, sigma=1.1, seed=0)
+
+    class Cfg:
+        metric, nrof_folds, far_target = 0, 10, 1.e-3
+
+    v = fst.FaceToFaceValidation(x, labels, Cfg)
+    ref = so.face_to_face_validation(x, labels, 0, 10, 1.e-3)
+    acc_thr = np.array([float(m.threshold[0]) for m in v.reports[0].conf_matrix_test])
+    far_thr = np.array([float(m.threshold[0]) for m in v.reports[1].conf_matrix_test])
+    np.testing.assert_array_equal(acc_thr, ref['_thresholds'][:, 0])                   # grid points: exact
+    np.testing.assert_allclose(far_thr, ref['_thresholds'][:, 1], rtol=0, atol=1e-4)   # interpolated between grid points
+    got = v.dict
+    for crit in got:
+        for k in got[crit]:
+            assert abs(float(got[crit][k]) - float(ref[crit][k])) <= 1e-4, (crit, k)
 
 
 # ------------------------------------------------------------------------------ threshold selection on the device
