@@ -52,11 +52,13 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='1m', choices=sorted(WORKLOADS))
-    ap.add_argument('--mode', default='fp16x3', choices=['fp16x3', 'fp16f8', 'tf32x3', 'tf32', 'bf16', 'fp16'])
+    ap.add_argument('--mode', default='auto', choices=['auto', 'fp16x3', 'fp16f8', 'tf32x3', 'tf32', 'bf16', 'fp16'])
     ap.add_argument('--cta-group', type=int, default=0)
     ap.add_argument('--cpu-sample-rows', type=int, default=16384)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--parity-rows', type=int, default=8192)
     return ap.parse_args()
 
 
@@ -226,13 +228,14 @@ def main():
     fst.set_default_mode(mode=args.mode, device=local_rank, cta_group=args.cta_group)
     stream = torch.cuda.current_stream()
     handle.set_stream(stream.cuda_stream)
-    kernel_ms, launches = [], [0]
+    kernel_ms, launches, modes_used = [], [0], set()
 
     def hist_fn(emb, labels, thresholds_, metric, rank_, world_, bins_out, **kw):
         _, st = handle.pair_histogram_bins(emb, labels, thresholds_, metric, rank=rank_, world=world_, bins_out=bins_out,
                                            mode=args.mode, cta_group=args.cta_group)
         kernel_ms.append(st['kernel_ms'])
         launches[0] += st['kernel_launches']
+        modes_used.add(_capi.MODE_NAMES[st['mode_used']])
         return st
 
     def step_device():
@@ -267,12 +270,46 @@ def main():
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float('nan')
     timed_launches = launches[0]
     value = pairs * args.steps / (total_ms * 1e-3) / 1e9
+    mode_used = sorted(modes_used)[0] if len(modes_used) == 1 else args.mode      # what 'auto' resolved to
 
     # sanity of the result (not timed): every pair counted once, same-identity total known analytically
     if rank == 0:
         out = fd.counts_from_bins(bins, thr, 0)
         assert out['n_same'] + out['n_diff'] == pairs, (out['n_same'], out['n_diff'], pairs)
         assert out['n_same'] == ids * (n // ids) * (n // ids - 1) // 2
+
+    # ---- parity of the timed arithmetic mode on a row sample of THIS workload (not timed; rank 0).  The checker is
+    #      plain torch float64 on the GPU (the CPU oracle is the checker in tests/ and smoke()):
+    #        max |d_mode - d_f64| over all pairs of the sample           (tolerance of BASELINE.json: 1e-5)
+    #        histogram of the sample in this mode vs bins of the float64 distances: L1 difference, which must be
+    #        covered by the pairs the kernel itself counted inside the eps window
+    parity = None
+    if rank == 0 and not args.no_parity:
+        ns = min(args.parity_rows, per_rank)
+        xs, ls = x_shard[:ns].contiguous(), labels_shard[:ns].contiguous()
+        d_mode = torch.empty(ns * (ns - 1) // 2, device=dev, dtype=torch.float32)
+        handle.pairwise(xs, None, 0, mode=mode_used, out=d_mode)
+        torch.cuda.synchronize()
+        x64 = xs.double()
+        iu = torch.triu_indices(ns, ns, 1, device=dev)
+        d64 = (2.0 * (1.0 - (x64 @ x64.T).clamp_(-1.0, 1.0)))[iu[0], iu[1]]
+        err = (d_mode.double() - d64).abs_()
+        same = (ls[iu[0]] == ls[iu[1]])
+        thr_t = torch.from_numpy(thr).to(dev)
+        # bin k of a distance = number of thresholds <= d  (d < t_n  <=>  k <= n), float64 compare like statistics.py:131
+        b64 = torch.searchsorted(thr_t, d64.float().double(), right=True)
+        ref_lt_all = torch.bincount(b64, minlength=thr.size + 1).cumsum(0)[:thr.size]
+        ref_lt_same = torch.bincount(b64[same], minlength=thr.size + 1).cumsum(0)[:thr.size]
+        hs = handle.pair_histogram(xs, ls, thr, 0, mode=mode_used, cta_group=args.cta_group)
+        got_same = torch.from_numpy(hs['same']).to(dev)
+        got_all = torch.from_numpy(hs['same'] + hs['diff']).to(dev)
+        l1 = int((got_same - ref_lt_same).abs().sum().item() + ((got_all - got_same) - (ref_lt_all - ref_lt_same)).abs().sum().item())
+        parity = {'sample_rows': ns, 'pairs': int(d64.numel()), 'max_abs_dd_vs_f64': float(err.max().item()),
+                  'rms_dd_vs_f64': float(err.pow(2).mean().sqrt().item()), 'tolerance': 1e-5,
+                  'hist_l1_vs_f64_bins': l1, 'eps_window_pairs_counted': int(hs['stats']['eps_window']),
+                  'hist_ok': bool(l1 <= 2 * hs['stats']['eps_window'])}
+        del d_mode, x64, d64, err, iu, same, b64
+        torch.cuda.empty_cache()
 
     # ---- end to end through the public API with pinned host buffers
     e2e = None
@@ -310,22 +347,27 @@ def main():
     clocks = sampler.summary(t0, t1)
     peaks, peak_src = measured_peaks()
     # TF32 tensor peak = half the bf16 rate (same datapath, 4-byte operands); the driver measures bf16 with cuBLAS
-    tf32_peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']) / 2.0
+    # (burst figure for a step of a few ms, sustained figure for a step long enough to sit under the power cap)
+    long_step = total_ms / args.steps > 100.0
+    peak_key = 'bf16_tflops_sustained' if (long_step and 'bf16_tflops_sustained' in peaks) else 'bf16_tflops'
+    tf32_peak = peaks[peak_key] / 2.0
     achieved = (pairs / world) * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12       # one launch covers 1/world of the pairs
     traffic = None
     tf = ROOT / 'profiles' / 'ncu_traffic.json'
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get('%s/%s' % (args.workload, args.mode))
+            traffic = json.loads(tf.read_text()).get('%s/%s' % (args.workload, mode_used))
         except ValueError:
             traffic = None
-    passes = 3 if args.mode.endswith('x3') else 2 if args.mode == 'fp16f8' else 1
+    passes = 3 if mode_used.endswith('x3') else 2 if mode_used == 'fp16f8' else 1
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
                 'traffic': traffic, 'kernel': 'gram_kernel<HIST>', 'kernel_ms': k_ms,
-                'peak_source': peak_src + ': bf16_tflops_sustained / 2 (TF32 rate = half the bf16 rate); of measured',
+                'peak_source': peak_src + ': %s / 2 (TF32 rate = half the bf16 rate); of measured' % peak_key,
                 'frac_of_nominal_tf32_1100': achieved / 1100.0,
                 'executed_mma_tflops': achieved * passes,
-                'executed_frac_of_pipe_peak': achieved * passes / (tf32_peak * (1 if 'tf32' in args.mode else 2))}
+                'executed_frac_of_pipe_peak': achieved * passes / (tf32_peak * (1 if 'tf32' in mode_used else 2)),
+                'note': 'achieved = pairs x 1024 algorithmic FLOP / Gram-kernel time; executed_mma_tflops counts the split passes '
+                        '(fp16-pass equivalents: an e4m3 pass counts 1/2)'}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -337,12 +379,13 @@ def main():
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': {'fp16x3': 'f16x3 split, f32 accumulate (fp32-equivalent)', 'tf32x3': 'tf32x3 split, f32 accumulate',
                       'tf32': 'tf32', 'bf16': 'bf16', 'fp16': 'f16',
-                      'fp16f8': 'f16 hi*hi + e4m3 cross terms, f32 accumulate'}[args.mode],
+                      'fp16f8': 'f16 hi*hi + e4m3 cross terms, f32 accumulate'}[mode_used],
             'data': 'synthetic',
-            'config': {'workload': wl['name'], 'mode': args.mode, 'parallelism': 'row-block tiles t %% %d == rank' % world,
+            'config': {'workload': wl['name'], 'mode': args.mode, 'mode_used': mode_used, 'parallelism': 'row-block tiles t %% %d == rank' % world,
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
                        'pairs_per_step': pairs},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': timed_launches, 'roofline': roofline, 'cpu_baseline': cpu,
+            'parity': parity,
             'pct_tf32_peak': 100.0 * value * 1e9 * FLOP_PER_PAIR / 1e12 / (tf32_peak * world)}
     print(json.dumps(line))
     if world > 1:

@@ -19,7 +19,8 @@ import numpy as np
 _LIB_PATH = Path(__file__).resolve().parent / '_lib' / 'libfacenet_b200.so'
 
 FNB_OK, FNB_ERR_INVALID, FNB_ERR_NOT_NORMALIZED, FNB_ERR_BAD_METRIC, FNB_ERR_CUDA, FNB_ERR_UNSUPPORTED = range(6)
-MODES = {'fp16x3': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3, 'fp16': 4, 'fp16f8': 5}
+MODES = {'fp16x3': 0, 'tf32x3': 1, 'tf32': 2, 'bf16': 3, 'fp16': 4, 'fp16f8': 5, 'auto': 6}
+MODE_NAMES = {v: k for k, v in MODES.items()}
 MAX_THRESHOLDS = 127
 
 EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info', 'fnb_set_stream',
@@ -53,7 +54,7 @@ class Stats(ctypes.Structure):
     _fields_ = [('n_pairs', ctypes.c_uint64), ('eps_window', ctypes.c_uint64), ('smin', ctypes.c_float),
                 ('smax', ctypes.c_float), ('max_abs', ctypes.c_float), ('kernel_ms', ctypes.c_float),
                 ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
-                ('eps_counted', ctypes.c_float), ('grid_ctas', ctypes.c_uint32), ('reserved', ctypes.c_uint32 * 2)]
+                ('eps_counted', ctypes.c_float), ('grid_ctas', ctypes.c_uint32), ('mode_used', ctypes.c_int32), ('peakedness', ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}

@@ -38,7 +38,8 @@ int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, fl
         case FNB_MODE_TF32:   *num_pass = 1; *tf32 = true;  *fmt = kFmtTF32; *elem_bytes = 4; *prescale = 1.f;   return 0;
         case FNB_MODE_BF16:   *num_pass = 1; *tf32 = false; *fmt = kFmtBF16; *elem_bytes = 2; *prescale = 1.f;   return 0;
         case FNB_MODE_FP16:   *num_pass = 1; *tf32 = false; *fmt = kFmtF16;  *elem_bytes = 2; *prescale = 1.f;   return 0;
-        case FNB_MODE_FP16F8: *num_pass = 2; *tf32 = false; *fmt = kFmtF16;  *elem_bytes = 2; *prescale = 4096.f; return 0;
+        case FNB_MODE_FP16F8: case FNB_MODE_AUTO:
+                              *num_pass = 2; *tf32 = false; *fmt = kFmtF16;  *elem_bytes = 2; *prescale = 4096.f; return 0;
     }
     return -1;
 }
@@ -159,6 +160,8 @@ static int make_tmap(fnb_context* h, CUtensorMap* m, void* base, int fmt, long l
     if (r != CUDA_SUCCESS) return h->fail(FNB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld d=%d", (int)r, rows, d);
     return FNB_OK;
 }
+
+constexpr float kAutoPeakLimit = 1.0f / 64.0f;       // FNB_MODE_AUTO: largest peakedness FP16F8 is used for
 
 static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 
@@ -306,6 +309,23 @@ extern "C" int fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* 
 // side of the Gram product and encode their TMA maps into `op`
 int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
                          bool side_b, GramOperands& op) {
+    if (mode == FNB_MODE_AUTO) {
+        // FP16F8 when the data satisfies its error model (see FNB_MODE_AUTO in the header), else FP16X3
+        int rc = (d % 128 == 0) ? prepare_operand(h, FNB_MODE_FP16F8, x, perm, n, d, side_b, op) : FNB_OK;
+        if (rc) return rc;
+        bool f8_ok = (d % 128 == 0);
+        if (f8_ok) {
+            unsigned int pk = 0;
+            CK(cudaMemcpyAsync(&pk, &h->counters.as<DeviceScalars>()->peak_max_ord, 4, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            op.peakedness = pk ? ordered_to_float(pk) : 0.f;
+            f8_ok = op.peakedness <= kAutoPeakLimit;            // false for NaN
+        }
+        if (f8_ok) return FNB_OK;
+        return prepare_operand(h, FNB_MODE_FP16X3, x, perm, n, d, side_b, op);
+    }
+    op.mode = mode;
+    if (mode_info(mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", mode);
     DevBuf& hi = side_b ? h->b_hi : h->a_hi;
     DevBuf& lo = side_b ? h->b_lo : h->a_lo;
     DevBuf& h8 = side_b ? h->b_h8 : h->a_h8;
@@ -319,8 +339,9 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     if (op.num_pass == 3) CK(lo.ensure(bytes));
     if (f8) { CK(lo.ensure((size_t)n_pad * d)); CK(h8.ensure((size_t)n_pad * d)); }
     CK(h->counters.ensure(sizeof(DeviceScalars)));
-    unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;
-    CK(cudaMemsetAsync(norm, 0, 4, h->stream));
+    unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;    // [0] max squared norm, [1] peakedness
+    static_assert(offsetof(DeviceScalars, peak_max_ord) == offsetof(DeviceScalars, norm_max_ord) + 4, "layout");
+    CK(cudaMemsetAsync(norm, 0, 8, h->stream));
     CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream));
     const int box_rows = side_b ? kRowsPerCta : kRowsPerCta / op.pairs;
     if (!side_b) op.a_rows_pad = n_pad;
@@ -386,6 +407,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
     CK(cudaSetDevice(h->device));
     GramOperands op;
+    if (opt.mode == FNB_MODE_AUTO) opt.mode = FNB_MODE_FP16X3;       // materialised distances: always the fp32-equivalent split
     if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
     DLView va, vb, vo;
     int rc = dl_view(h, xa, "xa", 2, 2, &va); if (rc) return rc;
@@ -456,6 +478,8 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
 // ---------------------------------------------------------------------------------------
 // histograms
 
+static double mode_slack(int mode);
+
 struct HistLaunch {
     CutTables ct;
     int nkeys = 1;
@@ -519,6 +543,16 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
             p.f_magic_n = (float)(12582912.0 + 0.5 * R + half);
             p.frac_bits = (unsigned)F;
             p.near_mask = ((1u << F) - 1u) & ~((1u << W) - 1u);
+            // Without clipping the bin index is floor(u + 1): it must stay inside the counter rows [0, nb8) for every
+            // similarity an interior tile can produce, |s| <= 1 + atol (row-norm bound) + the arithmetic error of the mode
+            const double lim = 1.0 + (double)opt.atol + mode_slack(opt.mode) + 1.0e-4;
+            const double idx_lo = (-lim - hl.ct.e0) / hl.ct.h + 1.0, idx_hi = (lim - hl.ct.e0) / hl.ct.h + 1.0;
+            if (idx_lo > 0.02 && idx_hi < (double)p.nb8 - 0.02) {
+                p.noclip = 1;
+                p.f_g1 = (float)((double)p.acc_scale / hl.ct.h * R);
+                p.f_g0 = (float)((-hl.ct.e0 / hl.ct.h + 1.0) * R + 12582912.0);
+                p.near_half = (unsigned)half;
+            }
             h->last_eps_counted = (opt.metric == 0 ? 2.0 : 1.0) * half / R * hl.ct.h;
         }
     }
@@ -538,7 +572,6 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     return FNB_OK;
 }
 
-static double mode_slack(int mode);
 static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats, float* smin_out, float* smax_out, bool* violated) {
     DeviceScalars hs;
     CK(cudaMemcpyAsync(h->pinned.p, h->counters.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
@@ -568,6 +601,8 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         stats->eps_counted = (float)h->last_eps_counted;
         stats->kernel_launches += 1;
         stats->grid_ctas = (uint32_t)h->last_grid;
+        stats->mode_used = h->last_mode;
+        stats->peakedness = hs.peak_max_ord ? ordered_to_float(hs.peak_max_ord) : 0.f;
     }
     return FNB_OK;
 }
@@ -634,6 +669,8 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     op.pairs = pick_pairs(&opt, cg);
     if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
     if ((rc = self_b_maps(h, op, d))) return rc;
+    opt.mode = op.mode;                                  // AUTO resolved
+    h->last_mode = op.mode; h->last_peak = op.peakedness;
 
     std::vector<RegionDev> regs;
     triangle_regions(n, pick_region_rows(&opt, tile * op.pairs), 0, regs);
@@ -753,6 +790,8 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     CK(cudaMemcpyAsync(h->cls.p, cls, n * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
     if ((rc = self_b_maps(h, op, d))) return rc;
+    opt.mode = op.mode;                                  // AUTO resolved
+    h->last_mode = op.mode; h->last_peak = op.peakedness;
 
     HistLaunch hl; hl.nkeys = nkeys;
     if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;

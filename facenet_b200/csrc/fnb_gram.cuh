@@ -70,6 +70,11 @@ struct GramParams {
     //   kw = v * f_k2 + 0.5 R  (R = 2^frac_bits)         = (u + 1) R  -> bin = kw >> frac_bits, clipped to T_fin
     float f_s1, f_b1, f_k2, f_magic_k, f_magic_n;
     unsigned int frac_bits, near_mask;
+    // single-FMA form, used when no clipping is needed (noclip != 0):  word = bits(acc * f_g1 + f_g0) = magic + (u + 1) R;
+    // near a threshold <=> ((word + near_half) & near_mask) == 0
+    int noclip;
+    float f_g1, f_g0;
+    unsigned int near_half;
     int nb8;                   // bins of the u8 counters (T_fin + 3)
     unsigned long long* bins;  // [nkeys][2][bins_stride]  (0: all pairs, 1: same-identity pairs)
     int bins_stride;
@@ -172,6 +177,11 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 __device__ __forceinline__ float fma_sat(float a, float b, float c) {
     float d;
@@ -490,26 +500,50 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     ++fast_since_flush;
                     mbar_wait(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
-                    const float s1 = p.f_s1, b1 = p.f_b1, k2 = p.f_k2, mk = p.f_magic_k, mn = p.f_magic_n;
                     const uint32_t nmask = p.near_mask;
+                    // two elements per step: both counters are read before either is written, so equal addresses add 2
+                    auto bump2 = [&](uint32_t k0, uint32_t k1) {     // k = bin index (+ the constant folded into hb)
+                        const uint32_t a0 = mad_lo(k0, (uint32_t)kHist8Row, hb), a1 = mad_lo(k1, (uint32_t)kHist8Row, hb);
+                        const uint32_t c0 = lds_u8(a0);
+                        const uint32_t c1 = lds_u8(a1);
+                        const uint32_t inc = (k0 == k1) ? 2u : 1u;
+                        sts_u8(a0, c0 + inc);
+                        sts_u8(a1, c1 + inc);
+                    };
+                    if (p.noclip) {
+                        // the cuts span the whole similarity range (guard bins absorb |s| <= 1 + atol + mode error):
+                        // one FMA takes the accumulator straight to the fixed-point bin word
+                        const float g1 = p.f_g1, g0 = p.f_g0;
+                        const uint32_t half = p.near_half;
 #pragma unroll 1
-                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
-                        uint32_t r[32];
-                        tmem_ld32(taddr0 + c * 32, r);
-                        tmem_ld_wait();
+                        for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                            uint32_t r[32];
+                            tmem_ld32(taddr0 + c * 32, r);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float v0 = fma_sat(__uint_as_float(r[j]), s1, b1);
-                            const float v1 = fma_sat(__uint_as_float(r[j + 1]), s1, b1);
-                            const uint32_t a0 = (__float_as_uint(fmaf(v0, k2, mk)) >> fbits) * (uint32_t)kHist8Row + hb;
-                            const uint32_t a1 = (__float_as_uint(fmaf(v1, k2, mk)) >> fbits) * (uint32_t)kHist8Row + hb;
-                            eps_cnt += ((__float_as_uint(fmaf(v0, k2, mn)) & nmask) == 0u) ? 1u : 0u;
-                            eps_cnt += ((__float_as_uint(fmaf(v1, k2, mn)) & nmask) == 0u) ? 1u : 0u;
-                            const uint32_t c0 = lds_u8(a0);
-                            const uint32_t c1 = lds_u8(a1);
-                            const uint32_t inc = (a0 == a1) ? 2u : 1u;
-                            sts_u8(a0, c0 + inc);
-                            sts_u8(a1, c1 + inc);
+                            for (int j = 0; j < 32; j += 2) {
+                                const uint32_t w0 = __float_as_uint(fmaf(__uint_as_float(r[j]), g1, g0));
+                                const uint32_t w1 = __float_as_uint(fmaf(__uint_as_float(r[j + 1]), g1, g0));
+                                eps_cnt += (((w0 + half) & nmask) == 0u) ? 1u : 0u;
+                                eps_cnt += (((w1 + half) & nmask) == 0u) ? 1u : 0u;
+                                bump2(w0 >> fbits, w1 >> fbits);
+                            }
+                        }
+                    } else {
+                        const float s1 = p.f_s1, b1 = p.f_b1, k2 = p.f_k2, mk = p.f_magic_k, mn = p.f_magic_n;
+#pragma unroll 1
+                        for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                            uint32_t r[32];
+                            tmem_ld32(taddr0 + c * 32, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float v0 = fma_sat(__uint_as_float(r[j]), s1, b1);
+                                const float v1 = fma_sat(__uint_as_float(r[j + 1]), s1, b1);
+                                eps_cnt += ((__float_as_uint(fmaf(v0, k2, mn)) & nmask) == 0u) ? 1u : 0u;
+                                eps_cnt += ((__float_as_uint(fmaf(v1, k2, mn)) & nmask) == 0u) ? 1u : 0u;
+                                bump2(__float_as_uint(fmaf(v0, k2, mk)) >> fbits, __float_as_uint(fmaf(v1, k2, mk)) >> fbits);
+                            }
                         }
                     }
                 } else {

@@ -77,7 +77,8 @@ struct fnb_context {
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
-    int last_nkeys = 0, last_T = 0, last_grid = 0;
+    int last_nkeys = 0, last_T = 0, last_grid = 0, last_mode = 0;
+    float last_peak = 0.f;
     double last_eps_counted = 0;         // distance half-width of the near-threshold window counted by interior tiles
 
     int fail(int code, const char* fmt, ...);
@@ -98,6 +99,8 @@ struct GramOperands {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap a_h8, b_h8;        // fp16f8 mode only: e4m3(x) arrays (a_lo / b_lo then hold e4m3(lo))
     int num_pass = 3; bool tf32 = false; int fmt = 0; int elem_bytes = 2; float prescale = 1.f;
+    int mode = 0;                  // FNB_MODE_* the operands were prepared for (AUTO resolved)
+    float peakedness = 0.f;        // max_row sum x^4 / (sum x^2)^2 (valid after prepare_operand in AUTO mode)
     int pairs = 1;                 // CTA pairs per cluster (2: the A maps carry 64-row boxes, see gram_kernel kPairs)
     long long a_rows_pad = 0;      // padded row count of the prepared A-side arrays
 };
@@ -106,7 +109,8 @@ struct DeviceScalars {      // layout of fnb_context::counters
     unsigned long long counters[2];
     unsigned int range_ord[4];
     unsigned int norm_max_ord;      // ordered-uint max squared row norm of the last prepared operand (not reset per launch)
-    unsigned int pad[7];
+    unsigned int peak_max_ord;      // ordered-uint max over rows of sum x^4 / (sum x^2)^2 (same lifetime)
+    unsigned int pad[6];
 };
 
 // fnb_api.cu
@@ -124,7 +128,7 @@ int build_cut_tables(const double* thresholds, int T, int metric, double eps, co
 
 // fnb_prepare.cu
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
-                              void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s);
+                              void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s);   // norm_max_ord[1] = peakedness
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
 
 // fnb_gram.cu

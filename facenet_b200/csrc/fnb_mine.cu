@@ -148,6 +148,7 @@ extern "C" int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* label
     CK(cudaSetDevice(h->device));
     if (stats) memset(stats, 0, sizeof(*stats));
     GramOperands op;
+    if (opt.mode == FNB_MODE_AUTO) opt.mode = FNB_MODE_FP16X3;
     if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
     DLView ve, vl;
     int rc = dl_view(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;

@@ -25,10 +25,10 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    float norm_max = 0.f;
+    float norm_max = 0.f, peak_max = 0.f;
     for (long long row = warp0; row < n_pad; row += nwarps) {
         const long long src = (row < n) ? (perm ? perm[row] : row) : 0;
-        float nrm = 0.f;
+        float nrm = 0.f, x4 = 0.f;
         for (int c8 = lane; c8 < vec_per_row; c8 += 32) {
             float f[8];
             if (row < n) {
@@ -40,7 +40,7 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
                 for (int i = 0; i < 8; ++i) f[i] = 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) nrm = fmaf(f[i], f[i], nrm);
+            for (int i = 0; i < 8; ++i) { const float sq = f[i] * f[i]; nrm += sq; x4 = fmaf(sq, sq, x4); }
             const long long o = row * d + (long long)c8 * 8;
             if (kMode == FNB_MODE_FP16X3 || kMode == FNB_MODE_FP16) {
                 const float pre = (kMode == FNB_MODE_FP16X3) ? 256.0f : 1.0f;
@@ -90,13 +90,17 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
             }
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        for (int o = 16; o; o >>= 1) { nrm += __shfl_xor_sync(0xffffffffu, nrm, o); x4 += __shfl_xor_sync(0xffffffffu, x4, o); }
         // NaN rows must not hide: an unordered compare keeps them as "too large"
         norm_max = (nrm <= norm_max) ? norm_max : nrm;
+        const float pk = (nrm > 0.f) ? x4 / (nrm * nrm) : 0.f;
+        peak_max = (pk <= peak_max) ? peak_max : pk;
     }
     if (norm_max_ord && lane == 0) {
         const float v = (norm_max == norm_max) ? norm_max : INFINITY;
         if (v > 0.f) atomicMax(norm_max_ord, float_to_ordered(v));
+        const float w = (peak_max == peak_max) ? peak_max : INFINITY;
+        if (w > 0.f) atomicMax(norm_max_ord + 1, float_to_ordered(w));
     }
 }
 

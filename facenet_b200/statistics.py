@@ -471,11 +471,15 @@ class FaceToFaceValidation:
         h5utils.write_dict(h5file, self.dict, group=tag)
 
 
-def pair_histogram(embeddings, labels, thresholds, metric=0, mode=None, **kw):
+def pair_histogram(embeddings, labels, thresholds, metric=0, mode='auto', **kw):
     """Whole-set verification histogram (BASELINE configs 2/4/5): integer numbers of same-identity and
     different-identity pairs with ``d < thresholds[n]`` over all N(N-1)/2 unordered pairs -- the
     reference's inner statement ``count_nonzero(sims < threshold)`` (statistics.py:131) without the
-    per-class weighting.  Returns a dict with ``same``, ``diff`` (int64 [T]), ``n_same``, ``n_diff``, ``stats``."""
+    per-class weighting.  Returns a dict with ``same``, ``diff`` (int64 [T]), ``n_same``, ``n_diff``, ``stats``.
+
+    ``mode='auto'`` (default here; the drop-in classes above default to the strict ``'fp16x3'``) lets the library use the
+    faster ``fp16f8`` contraction when the embeddings are dense enough for its error model and ``fp16x3`` otherwise;
+    ``stats['mode_used']`` reports the choice."""
     try:
         return _handle().pair_histogram(embeddings, labels, thresholds, metric, mode=mode or _state['mode'],
                                         cta_group=kw.pop('cta_group', _state['cta_group']), **kw)

@@ -65,7 +65,13 @@ enum {
  *           e4m3(x)*e4m3(lo) + e4m3(lo)*e4m3(x) in kind::f8f6f4 at twice the MMA rate -- two fp16-pass
  *           equivalents instead of three.  Error is statistical: |dd| ~ 1e-6 rms, < 1e-5 for dense
  *           embeddings (every element small against the norm); needs D % 128 == 0. */
-enum { FNB_MODE_FP16X3 = 0, FNB_MODE_TF32X3 = 1, FNB_MODE_TF32 = 2, FNB_MODE_BF16 = 3, FNB_MODE_FP16 = 4, FNB_MODE_FP16F8 = 5 };
+/*   AUTO    (histogram entry points only) FP16F8 when its error model holds for the data, else FP16X3: the e4m3
+ *           rounding errors of the 2 x D cross products are independent and each is bounded by 2^-16 |x_i y_i|, so
+ *           sigma(ds) ~ 2^-16.5 sqrt(sum_i x_i^2 y_i^2) <= 2^-16.5 max_row ||x||_4^2.  The split kernel measures
+ *           max_row sum x_i^4 / (sum x_i^2)^2 ("peakedness": 3/D for dense Gaussian-like rows, 1 for one-hot rows);
+ *           FP16F8 is used when it is <= 1/64 (5 sigma(dd) < 1e-5) and D % 128 == 0.  fnb_stats.mode_used tells. */
+enum { FNB_MODE_FP16X3 = 0, FNB_MODE_TF32X3 = 1, FNB_MODE_TF32 = 2, FNB_MODE_BF16 = 3, FNB_MODE_FP16 = 4, FNB_MODE_FP16F8 = 5,
+       FNB_MODE_AUTO = 6 };
 
 typedef struct {
     int32_t mode;          /* FNB_MODE_*                                        default FP16X3 */
@@ -103,7 +109,8 @@ typedef struct {
     uint32_t kernel_launches;
     float    eps_counted;  /* distance half-width actually counted by interior tiles (see eps_window)           */
     uint32_t grid_ctas;    /* CTAs of the Gram launch (co-resident clusters x cluster size)                     */
-    uint32_t reserved[2];
+    int32_t  mode_used;    /* FNB_MODE_* the contraction ran in (what AUTO resolved to)                         */
+    float    peakedness;   /* max over rows of sum x^4 / (sum x^2)^2 of the prepared embeddings                  */
 } fnb_stats;
 
 /* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:

@@ -266,6 +266,31 @@ def test_histogram_fp16f8_mode(handle):
         check_hist(out, so.pair_histogram(x, labels, thr, 0), x.shape[0])
 
 
+def test_histogram_auto_mode_selection(handle):
+    """mode='auto' uses fp16f8 for dense embeddings and falls back to the fp32-equivalent fp16x3 split when the rows
+    are too peaky for the e4m3 error model or the dimension is not a multiple of 128; results match the oracle
+    within the eps window either way."""
+    from facenet_b200 import _capi
+    thr = so.default_thresholds(0)
+    x, labels = so.synthetic_embeddings([30] * 20 + [1] * 30, dim=512, sigma=1.1, seed=4)
+    out = handle.pair_histogram(x, labels, thr, 0, mode='auto')
+    assert _capi.MODE_NAMES[out['stats']['mode_used']] == 'fp16f8' and 0 < out['stats']['peakedness'] < 1 / 64
+    check_hist(out, so.pair_histogram(x, labels, thr, 0), x.shape[0])
+    # peaky rows: 6 non-zero coordinates out of 512
+    rng = np.random.default_rng(5)
+    xs = np.zeros_like(x)
+    for r in range(xs.shape[0]):
+        xs[r, rng.choice(512, 6, replace=False)] = rng.standard_normal(6)
+    xs /= np.linalg.norm(xs, axis=1, keepdims=True)
+    out = handle.pair_histogram(xs, labels, thr, 0, mode='auto')
+    assert _capi.MODE_NAMES[out['stats']['mode_used']] == 'fp16x3' and out['stats']['peakedness'] > 1 / 64
+    check_hist(out, so.pair_histogram(xs, labels, thr, 0), xs.shape[0])
+    x192, l192 = so.synthetic_embeddings([30] * 10, dim=192, sigma=1.1, seed=6)
+    out = handle.pair_histogram(x192, l192, thr, 0, mode='auto')
+    assert _capi.MODE_NAMES[out['stats']['mode_used']] == 'fp16x3'
+    check_hist(out, so.pair_histogram(x192, l192, thr, 0), x192.shape[0])
+
+
 def test_histogram_edge_cases(handle):
     thr = so.default_thresholds(0)
     x = unit(1, 64, 0)
