@@ -72,10 +72,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// arrive on the copy of `bar` that lives in CTA `rank` of the cluster
+// arrive on the copy of `bar` that lives in CTA `rank` of the cluster.  Default semantics (release at CTA scope):
+// what crosses CTAs behind these barriers is tensor memory, ordered by tcgen05.wait::ld + tcgen05.fence; a
+// cluster-scope release costs a full memory barrier per arrive (ncu: "membar" was a top stall reason of the epilogue).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
     uint32_t a = mapa_u32(smem_u32(bar), rank);
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(a) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(a) : "memory");
 }
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -91,6 +93,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef FNB_SPIN_LIMIT
 #define FNB_SPIN_LIMIT (1u << 24)   // try_wait suspends ~us each; a stuck pipeline traps instead of hanging
 #endif
+
+// try_wait with a suspend-time hint (ns): the waiting warp sleeps in hardware instead of re-issuing the poll --
+// for waits whose wake-up latency is not on the critical path (epilogue waiting for an accumulator, producer waiting
+// for a free slot); fewer issued instructions under a power cap
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0;; ++spins) {
+        if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+        if (spins > FNB_SPIN_LIMIT) __trap();
+    }
+}
 
 // CTA-scope acquire (the default of try_wait) is what the pipeline needs even across a CTA pair: the data behind
 // these barriers moves through the async proxy (TMA writes, tcgen05 reads) and tensor memory, ordered by

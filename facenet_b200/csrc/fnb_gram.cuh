@@ -278,7 +278,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
             const int brow = t.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
             auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
-                mbar_wait(&misc->empty[slot], phase ^ 1u);
+                mbar_wait_relaxed(&misc->empty[slot], phase ^ 1u);
                 if (elect_one()) {
                     uint8_t* dst = slots + (size_t)slot * kSlotBytes;
                     if (p.debug & 2) {
@@ -492,13 +492,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const bool slow = all_slow || edge || lab;
 
                 if ((p.debug & 1) || null_tile) {
-                    mbar_wait(&misc->tfull[acc], acc_phase);
+                    mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
                 } else if (!slow) {
                     // ---------------- interior tile: every element valid, no same-identity pair -------------
                     if (fast_since_flush >= kFlushEvery) flush_u8();
                     ++fast_since_flush;
-                    mbar_wait(&misc->tfull[acc], acc_phase);
+                    mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
                     const uint32_t nmask = p.near_mask;
                     // two elements per step: both counters are read before either is written, so equal addresses add 2
@@ -548,7 +548,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     }
                 } else {
                     // ---------------- checked tile: edges, diagonal, same-identity pairs, general cuts --------
-                    mbar_wait(&misc->tfull[acc], acc_phase);
+                    mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
                     tc_fence_after();
                     // stage this tile's column classes (kTile <= 256 columns).  Safe after the tfull wait:
                     // every epilogue warp has released the tile that last used col_cls[acc].
@@ -582,7 +582,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 }
             } else {
                 // ------------------- PAIRWISE / ROWSTRIP: materialise distances --------------
-                mbar_wait(&misc->tfull[acc], acc_phase);
+                mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
                 tc_fence_after();
                 const bool row_ok = row < t.row_end;
 #pragma unroll 1

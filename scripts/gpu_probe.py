@@ -61,7 +61,7 @@ def case_hist(mode, cg, n_classes=40, d=128, seed=3, pairs=1):
             print('   range checked [%g, %g] max_abs %g' % (out['stats']['smin'], out['stats']['smax'], out['stats']['max_abs']))
 
 
-def case_bench(mode, cg, n=20000, d=512, reps=3, pairs=1):
+def case_bench(mode, cg, n=20000, d=512, reps=3, pairs=1, region_rows=0):
     h = _capi.Handle(0)
     x, labels = so.synthetic_embeddings([50] * (n // 50), dim=d, sigma=1.1, seed=0)
     thr = so.default_thresholds(0)
@@ -70,11 +70,11 @@ def case_bench(mode, cg, n=20000, d=512, reps=3, pairs=1):
     lt = torch.from_numpy(labels).cuda()
     for r in range(reps):
         t0 = time.time()
-        bins, st = h.pair_histogram_bins(xt, lt, thr, 0, mode=mode, cta_group=cg, cluster_pairs=pairs)
+        bins, st = h.pair_histogram_bins(xt, lt, thr, 0, mode=mode, cta_group=cg, cluster_pairs=pairs, region_rows=region_rows)
         dt = time.time() - t0
         npairs = n * (n - 1) / 2
-        print('bench mode=%s cg=%d pairs=%d grid=%d N=%d: kernel %.3f ms  prepare %.3f ms  wall %.1f ms  -> %.1f Gpairs/s (kernel)  %.1f TFLOP/s  pairs=%d'
-              % (mode, cg, pairs, st['grid_ctas'], n, st['kernel_ms'], st['prepare_ms'], dt * 1e3, npairs / st['kernel_ms'] / 1e6,
+        print('bench mode=%s cg=%d pairs=%d rr=%d grid=%d N=%d: kernel %.3f ms  prepare %.3f ms  wall %.1f ms  -> %.1f Gpairs/s (kernel)  %.1f TFLOP/s  pairs=%d'
+              % (mode, cg, pairs, region_rows, st['grid_ctas'], n, st['kernel_ms'], st['prepare_ms'], dt * 1e3, npairs / st['kernel_ms'] / 1e6,
                  npairs * 1024 / st['kernel_ms'] / 1e9, st['n_pairs']))
 
 
