@@ -228,7 +228,7 @@ def main():
     fst.set_default_mode(mode=args.mode, device=local_rank, cta_group=args.cta_group)
     stream = torch.cuda.current_stream()
     handle.set_stream(stream.cuda_stream)
-    kernel_ms, launches, modes_used = [], [0], set()
+    kernel_ms, launches, modes_used, grids = [], [0], set(), set()
 
     def hist_fn(emb, labels, thresholds_, metric, rank_, world_, bins_out, **kw):
         _, st = handle.pair_histogram_bins(emb, labels, thresholds_, metric, rank=rank_, world=world_, bins_out=bins_out,
@@ -236,6 +236,7 @@ def main():
         kernel_ms.append(st['kernel_ms'])
         launches[0] += st['kernel_launches']
         modes_used.add(_capi.MODE_NAMES[st['mode_used']])
+        grids.add(st['grid_ctas'])
         return st
 
     def step_device():
@@ -383,7 +384,8 @@ def main():
             'data': 'synthetic',
             'config': {'workload': wl['name'], 'mode': args.mode, 'mode_used': mode_used, 'parallelism': 'row-block tiles t %% %d == rank' % world,
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
-                       'pairs_per_step': pairs},
+                       'pairs_per_step': pairs,
+                       'grid_ctas': sorted(grids), 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': timed_launches, 'roofline': roofline, 'cpu_baseline': cpu,
             'parity': parity,
             'pct_tf32_peak': 100.0 * value * 1e9 * FLOP_PER_PAIR / 1e12 / (tf32_peak * world)}

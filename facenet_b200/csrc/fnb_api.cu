@@ -200,16 +200,32 @@ static void triangle_regions(long long n, int rr, int key, std::vector<RegionDev
 }
 
 static int pick_cta_group(const fnb_options* o) { return (o->cta_group == 1 || o->cta_group == 2) ? o->cta_group : 2; }
-// CTA pairs per cluster of the histogram launches (multicast of the A operand): only with CTA pairs
-static int pick_pairs(const fnb_options* o, int cta_group) {
+
+// CTA pairs per cluster of the histogram launches (multicast of the A operand): only with CTA pairs.
+// Auto (cluster_pairs == 0): a launch long enough to run into the board's power limit (measured: from ~5e10 pairs per
+// rank, profiles/r01c_tile_order_and_power.md) is bound by energy per pair, and reading the A operand from L2 once per
+// two tiles saves more than the 16 SMs that cannot host a 4-CTA cluster cost; shorter launches run at full clock,
+// are L2->SM bandwidth bound, and are faster on all 148 SMs.
+static int pick_pairs(const fnb_options* o, int cta_group, long long n = 0) {
     if (cta_group != 2) return 1;
-    return o->cluster_pairs == 2 ? 2 : 1;
+    if (o->cluster_pairs == 1 || o->cluster_pairs == 2) return o->cluster_pairs;
+    const double local_pairs = 0.5 * (double)n * (double)(n - 1) / (double)std::max(1, o->world);
+    return local_pairs >= 5.0e10 ? 2 : 1;
 }
 
-static int pick_region_rows(const fnb_options* o, int tile) {
-    int rr = o->region_rows > 0 ? o->region_rows : 2048;
-    rr = std::max(tile, (rr / tile) * tile);
-    return rr;
+// Rows per super-row of the tile order (row blocks fastest inside a super-row).  The CTAs working at any time then
+// share ONE column panel, and the super-row's row panels (rr x d x 4 bytes of split operands) are re-read from L2 for
+// every column panel: auto sizes them to 64 MiB, half of the 126 MB L2 (32768 rows at d = 512; measured 2048 -> 32768:
+// +13 % at 1M rows, HBM reads fall from 490 GB to 30 GB per pass).  Ranks interleave tiles (t % world), so each rank
+// touches 1/world of a super-row's row panels: scale by world.  Small sets keep >= 6 super-rows for balance.
+static int pick_region_rows(const fnb_options* o, int tile, long long n = 0, int d = 512) {
+    long long rr = o->region_rows;
+    if (rr <= 0) {
+        rr = (64ll << 20) / (4ll * std::max(d, 1)) * std::max(1, o->world);
+        if (n > 0) rr = std::min(rr, std::max<long long>(n / 6, 8ll * tile));
+    }
+    rr = std::max<long long>(tile, (rr / tile) * tile);
+    return (int)std::min<long long>(rr, 1ll << 30);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -438,7 +454,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
     std::vector<RegionDev> regs;
-    if (self) triangle_regions(na, pick_region_rows(&opt, tile), 0, regs);
+    if (self) triangle_regions(na, pick_region_rows(&opt, tile, na, d), 0, regs);
     else {
         RegionDev r = {}; r.row_end = (int)na; r.col_end = (int)nb; regs.push_back(r);
     }
@@ -513,7 +529,8 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
     p.force_slow = force_slow || opt.force_checked;
-    p.debug = opt.debug;
+    p.debug = opt.debug & 3;
+    p.l2_prefetch = (opt.debug >> 2) & 3;            // experiment knob until a default is measured
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
@@ -666,14 +683,14 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
-    op.pairs = pick_pairs(&opt, cg);
+    op.pairs = pick_pairs(&opt, cg, n);
     if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
     if ((rc = self_b_maps(h, op, d))) return rc;
     opt.mode = op.mode;                                  // AUTO resolved
     h->last_mode = op.mode; h->last_peak = op.peakedness;
 
     std::vector<RegionDev> regs;
-    triangle_regions(n, pick_region_rows(&opt, tile * op.pairs), 0, regs);
+    triangle_regions(n, pick_region_rows(&opt, tile * op.pairs, n, d), 0, regs);
     finish_regions(regs, tile, op.pairs);
 
     HistLaunch hl;

@@ -140,6 +140,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, uint64_
         : "memory");
 }
 
+// pull one box into L2 only (no shared-memory destination, no barrier): hides the HBM latency of a tile the producer
+// will need one tile-time from now
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 :: "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
+
 // CTA-pair form: data lands in the executing CTA, bytes are signalled on the barrier at
 // cluster address `bar_cluster_addr` (the leader CTA's copy)
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {

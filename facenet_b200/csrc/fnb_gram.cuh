@@ -54,6 +54,7 @@ struct GramParams {
     int operand_fmt;           // kFmtF16 / kFmtBF16 / kFmtTF32 (must agree with the kTf32 template flag)
     int force_slow;            // take the fully-checked epilogue path for every tile
     int debug;                 // profiling knob (fnb_options.debug): bit 0 no epilogue work, bit 1 no operand loads
+    int l2_prefetch;           // producer prefetches its next tile's operand boxes into L2: 1 = B panel, 3 = A and B
     const unsigned int* norm_max_ord;   // ordered-uint max squared row norm (written by the split kernel), may be NULL
     unsigned int norm_limit_ord;        // above this the interior tiles cannot be proven in range -> checked path
     // HIST epilogue
@@ -274,14 +275,43 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         Sched sched(p, cluster_id, num_clusters);
         TileInfo t;
         int slot = 0; uint32_t phase = 0;
+        int ntile = -1;
         while (sched.next(t)) {
+            ++ntile;
             const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
             const int brow = t.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
+            if (p.l2_prefetch) {
+                // pull the operand boxes of this CTA's NEXT tile into L2 now (one tile-time of lead): the first CTA to
+                // touch a B panel then pays the HBM latency here, off the critical path, instead of in its ring
+                Sched ahead = sched;
+                TileInfo tn;
+                if (ahead.next(tn) && elect_one()) {
+                    const int na = tn.row0 + (int)cta_rank * kRowsPerCta;
+                    const int nb = tn.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
+                    const bool pa = (p.l2_prefetch & 2) && na != arow, pb = nb != brow;
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        if (pb) tma_prefetch_l2_2d(&tm_b_hi, kb * kElemsPerBox, nb);
+                        if (pa) tma_prefetch_l2_2d(&tm_a_hi, kb * kElemsPerBox, na);
+                        if (kNumPass == 3) {
+                            if (pb) tma_prefetch_l2_2d(&tm_b_lo, kb * kElemsPerBox, nb);
+                            if (pa) tma_prefetch_l2_2d(&tm_a_lo, kb * kElemsPerBox, na);
+                        }
+                    }
+                    if (kF8) {
+                        for (int ks = 0; ks < p.kblocks / 2; ++ks) {
+                            if (pb) { tma_prefetch_l2_2d(&tm_b_lo, ks * 128, nb); tma_prefetch_l2_2d(&tm_b_h8, ks * 128, nb); }
+                            if (pa) { tma_prefetch_l2_2d(&tm_a_lo, ks * 128, na); tma_prefetch_l2_2d(&tm_a_h8, ks * 128, na); }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
             auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
                 mbar_wait_relaxed(&misc->empty[slot], phase ^ 1u);
                 if (elect_one()) {
                     uint8_t* dst = slots + (size_t)slot * kSlotBytes;
-                    if (p.debug & 2) {
+                    if ((p.debug & 2) && ntile > 0) {
+                        // profiling: only the first tile is really loaded, so that later MMAs run on representative data
                         if (is_leader) mbar_arrive(&misc->full[slot]);
                     } else if (kCtaGroup == 1) {
                         mbar_arrive_expect_tx(&misc->full[slot], kSlotBytes);

@@ -80,7 +80,7 @@ typedef struct {
     float   eps;           /* |d - threshold| <= eps pairs are counted            default 1e-5  */
     int32_t rank, world;   /* this process computes tiles t with t % world == rank  default 0,1 */
     int32_t cta_group;     /* 0 auto, 1: 128x128 tiles per CTA, 2: 256x256 per CTA pair           */
-    int32_t region_rows;   /* rows per L2 super-row, 0 = auto                                     */
+    int32_t region_rows;   /* rows per super-row of the tile order, 0 = auto (row panels sized to half of L2) */
     const float* cuts;     /* optional [T]: per threshold the smallest fp32 similarity whose distance is
                               < threshold (+inf if none); NULL = computed here with libm (metric 1:
                               acosf).  The Python host passes NumPy's so that results are bit-exact
@@ -88,10 +88,12 @@ typedef struct {
     int32_t max_ctas;      /* 0 = all SMs (debug / profiling knob) */
     int32_t force_checked; /* != 0: every tile takes the fully checked epilogue path (exact cut comparison, exact
                               eps window, per-pair range check) -- the reference the arithmetic path is tested against */
-    int32_t debug;         /* profiling knob, results are MEANINGLESS when != 0: bit 0 skips the epilogue work,
-                              bit 1 skips the operand loads (MMA on whatever shared memory holds) */
+    int32_t debug;         /* profiling knob, results are MEANINGLESS when bits 0-1 are set: bit 0 skips the epilogue work,
+                              bit 1 loads operands for the first tile only (later MMAs re-use that shared memory);
+                              bits 2-3: the producer prefetches its next tile's B (4) / A and B (12) boxes into L2 */
     int32_t cluster_pairs; /* histogram launches, cta_group 2 only: 2 = clusters of two CTA pairs that share (multicast) the
-                              A operand, so it is read from L2 once per 256 x 512 super-tile; 0/1 = one pair per cluster */
+                              A operand, so it is read from L2 once per 256 x 512 super-tile; 1 = one pair per cluster;
+                              0 = auto (2 for launches long enough to be power-limited, >= 5e10 pairs per rank) */
     int32_t reserved[4];
 } fnb_options;
 
