@@ -47,7 +47,8 @@ class Options(ctypes.Structure):
                 ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('cta_group', ctypes.c_int32),
                 ('region_rows', ctypes.c_int32), ('cuts', ctypes.POINTER(ctypes.c_float)),
                 ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('debug', ctypes.c_int32),
-                ('cluster_pairs', ctypes.c_int32), ('reserved', ctypes.c_int32 * 4)]
+                ('cluster_pairs', ctypes.c_int32), ('normalize', ctypes.c_int32), ('theta', ctypes.c_float),
+                ('raw_distance', ctypes.c_int32), ('reserved', ctypes.c_int32 * 1)]
 
 
 class Stats(ctypes.Structure):
@@ -265,7 +266,7 @@ class Handle:
         return {'sm_count': sm.value, 'cc': (ma.value, mi.value), 'total_mem': mem.value}
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
-                cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0):
+                cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0, normalize=0, theta=0.0, raw_distance=False):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -279,6 +280,9 @@ class Handle:
         o.force_checked = 1 if force_checked else 0
         o.debug = int(os.environ.get('FNB_DEBUG', '0'))     # profiling knob (see fnb_options.debug)
         o.cluster_pairs = int(cluster_pairs)
+        o.normalize = int(normalize)
+        o.theta = float(theta)
+        o.raw_distance = 1 if raw_distance else 0
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -286,7 +290,8 @@ class Handle:
         return o, keep
 
     # ---- pairwise_similarities (statistics.py:22-57)
-    def pairwise(self, xa, xb=None, metric=0, atol=1.e-5, mode='fp16x3', cta_group=0, out=None):
+    def pairwise(self, xa, xb=None, metric=0, atol=1.e-5, mode='fp16x3', cta_group=0, out=None, normalize=0, theta=0.0,
+                 raw_distance=False):
         xa = _as_f32_matrix(xa, 'xa')
         na = xa.shape[0]
         if xb is not None:
@@ -296,7 +301,8 @@ class Handle:
             shape = (na * (na - 1) // 2,)
         if out is None:
             out = np.empty(shape, dtype=np.float32)
-        o, keep = self.options(mode=mode, metric=metric, atol=atol, cta_group=cta_group)
+        o, keep = self.options(mode=mode, metric=metric, atol=atol, cta_group=cta_group, normalize=normalize, theta=theta,
+                               raw_distance=raw_distance)
         rng = (ctypes.c_float * 2)()
         ba, bo = Borrowed(xa), Borrowed(out)
         bb = Borrowed(xb) if xb is not None else None
@@ -309,7 +315,7 @@ class Handle:
     # ---- whole-set verification histogram
     def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
                             rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy',
-                            force_checked=False, cluster_pairs=0):
+                            force_checked=False, cluster_pairs=0, normalize=0):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
@@ -317,7 +323,7 @@ class Handle:
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
                                region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked,
-                               cluster_pairs=cluster_pairs)
+                               cluster_pairs=cluster_pairs, normalize=normalize)
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()
@@ -355,7 +361,8 @@ class Handle:
 
     # ---- keyed histogram over rectangles
     def region_histogram_bins(self, embeddings, perm, cls, regions, nkeys, thresholds, metric=0, atol=1.e-5, eps=1.e-5,
-                              mode='fp16x3', cta_group=0, cuts='numpy', rank=0, world=1, cluster_pairs=0):
+                              mode='fp16x3', cta_group=0, cuts='numpy', rank=0, world=1, cluster_pairs=0, normalize=0, theta=0.0,
+                              raw_distance=False):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         perm = np.ascontiguousarray(perm, dtype=np.int64)
         cls = np.ascontiguousarray(cls, dtype=np.int32)
@@ -364,7 +371,7 @@ class Handle:
         if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, cta_group=cta_group, cuts=cuts, rank=rank, world=world,
-                               cluster_pairs=cluster_pairs)
+                               cluster_pairs=cluster_pairs, normalize=normalize, theta=theta, raw_distance=raw_distance)
         bins = np.zeros((int(nkeys), 2, thr.size + 1), dtype=np.uint64)
         st = Stats()
         be = Borrowed(embeddings)

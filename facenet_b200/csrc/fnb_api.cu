@@ -289,7 +289,7 @@ extern "C" void fnb_destroy(fnb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->perm, &h->cls,
+    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_nrm, &h->b_nrm, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
                       &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io};
     for (DevBuf* b : bufs) b->release();
@@ -324,10 +324,10 @@ extern "C" int fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* 
 // split/convert `x` ([n, d] fp32 on the device, optionally gathered through perm) into the operand arrays of one
 // side of the Gram product and encode their TMA maps into `op`
 int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
-                         bool side_b, GramOperands& op) {
+                         bool side_b, GramOperands& op, int normalize) {
     if (mode == FNB_MODE_AUTO) {
         // FP16F8 when the data satisfies its error model (see FNB_MODE_AUTO in the header), else FP16X3
-        int rc = (d % 128 == 0) ? prepare_operand(h, FNB_MODE_FP16F8, x, perm, n, d, side_b, op) : FNB_OK;
+        int rc = (d % 128 == 0) ? prepare_operand(h, FNB_MODE_FP16F8, x, perm, n, d, side_b, op, normalize) : FNB_OK;
         if (rc) return rc;
         bool f8_ok = (d % 128 == 0);
         if (f8_ok) {
@@ -338,7 +338,7 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
             f8_ok = op.peakedness <= kAutoPeakLimit;            // false for NaN
         }
         if (f8_ok) return FNB_OK;
-        return prepare_operand(h, FNB_MODE_FP16X3, x, perm, n, d, side_b, op);
+        return prepare_operand(h, FNB_MODE_FP16X3, x, perm, n, d, side_b, op, normalize);
     }
     op.mode = mode;
     if (mode_info(mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", mode);
@@ -358,7 +358,15 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;    // [0] max squared norm, [1] peakedness
     static_assert(offsetof(DeviceScalars, peak_max_ord) == offsetof(DeviceScalars, norm_max_ord) + 4, "layout");
     CK(cudaMemsetAsync(norm, 0, 8, h->stream));
-    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream));
+    float* nrm_out = nullptr;
+    if (normalize) {
+        DevBuf& nb = side_b ? h->b_nrm : h->a_nrm;
+        CK(nb.ensure((size_t)n_pad * 4));
+        nrm_out = nb.as<float>();
+    }
+    (side_b ? op.b_nrm : op.a_nrm) = nrm_out;
+    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream,
+                         normalize, nrm_out));
     const int box_rows = side_b ? kRowsPerCta : kRowsPerCta / op.pairs;
     if (!side_b) op.a_rows_pad = n_pad;
     int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d, box_rows);
@@ -371,6 +379,7 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
 }
 
 int fnb::self_b_maps(fnb_context* h, GramOperands& op, int d) {
+    op.b_nrm = op.a_nrm;
     if (op.pairs == 1) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; return FNB_OK; }
     // the A maps carry half-height boxes: encode full-height ones over the same arrays for the B side
     const bool f8 = (op.num_pass == 2);
@@ -447,9 +456,9 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     const void* da = nullptr; const void* db = nullptr;
     if ((rc = dl_to_device(h, va, (size_t)na * d * 4, h->stage_a, &da))) return rc;
     if (!self && (rc = dl_to_device(h, vb, (size_t)nb * d * 4, h->stage_b, &db))) return rc;
-    if ((rc = prepare_operand(h, opt.mode, (const float*)da, nullptr, na, d, false, op))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)da, nullptr, na, d, false, op, opt.normalize))) return rc;
     if (self) { if ((rc = self_b_maps(h, op, d))) return rc; }
-    else if ((rc = prepare_operand(h, opt.mode, (const float*)db, nullptr, nb, d, true, op))) return rc;
+    else if ((rc = prepare_operand(h, opt.mode, (const float*)db, nullptr, nb, d, true, op, opt.normalize))) return rc;
 
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
@@ -476,6 +485,8 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     p.counters = sc->counters; p.range_ord = sc->range_ord;
     p.out = dout; p.out_ld = nb; p.tri_packed = self ? 1 : 0; p.metric = opt.metric;
     p.n_rows = (int)na; p.n_cols = (int)nb;
+    p.raw = opt.raw_distance;
+    if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
     if ((rc = launch_gram(h, cg, EPI_PAIRWISE, opt.max_ctas, op, p, 0))) return rc;
 
     DeviceScalars hs;
@@ -486,7 +497,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     const float smin = ordered_to_float(hs.range_ord[0]), smax = ordered_to_float(hs.range_ord[1]);
     if (range) { range[0] = smin; range[1] = smax; }
     const double lim = 1.0 + (double)opt.atol;
-    if ((double)smin < -lim || (double)smax > lim || smin != smin || smax != smax)
+    if (!opt.raw_distance && ((double)smin < -lim || (double)smax > lim || smin != smin || smax != smax))
         return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
     return FNB_OK;
 }
@@ -529,8 +540,12 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
     p.force_slow = force_slow || opt.force_checked;
+    p.raw = opt.raw_distance;
+    if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
     p.debug = opt.debug & 3;
     p.l2_prefetch = (opt.debug >> 2) & 3;            // experiment knob until a default is measured
+    p.l2_hints = (opt.debug >> 4) & 1;
+    p.serpentine = (opt.debug >> 5) & 1;
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
@@ -601,7 +616,7 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
     const unsigned int norm_ord = hs.norm_max_ord;
     const float amax = norm_ord ? ordered_to_float(norm_ord) : NAN;
     const double lim = 1.0 + (double)opt.atol + mode_slack(opt.mode);
-    *violated = have_checked && !((double)smin >= -lim && (double)smax <= lim);
+    *violated = !opt.raw_distance && have_checked && !((double)smin >= -lim && (double)smax <= lim);
     *smin_out = smin;
     *smax_out = smax;
     if (stats) {
@@ -684,7 +699,7 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
     op.pairs = pick_pairs(&opt, cg, n);
-    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op, opt.normalize))) return rc;
     if ((rc = self_b_maps(h, op, d))) return rc;
     opt.mode = op.mode;                                  // AUTO resolved
     h->last_mode = op.mode; h->last_peak = op.peakedness;
@@ -792,7 +807,8 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
         if (r.tri && (r.row_begin != r.col_begin || r.row_end != r.col_end)) return h->fail(FNB_ERR_INVALID, "region %d: tri needs row range == col range", i);
         RegionDev rd = {};
         rd.row_begin = r.row_begin; rd.row_end = r.row_end; rd.col_begin = r.col_begin; rd.col_end = r.col_end;
-        rd.tri = r.tri ? 1 : 0; rd.key = r.key;
+        rd.tri = r.tri == 2 ? 2 : (r.tri ? 1 : 0); rd.key = r.key;
+        if (rd.tri == 2 && r.key + 1 >= nkeys) return h->fail(FNB_ERR_INVALID, "region %d: tri == 2 bins the diagonal into slot key + 1", i);
         regs.push_back(rd);
     }
     finish_regions(regs, tile, op.pairs);
@@ -805,7 +821,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     CK(h->cls.ensure(n * 4));
     CK(cudaMemcpyAsync(h->perm.p, perm, n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->cls.p, cls, n * 4, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op, opt.normalize))) return rc;
     if ((rc = self_b_maps(h, op, d))) return rc;
     opt.mode = op.mode;                                  // AUTO resolved
     h->last_mode = op.mode; h->last_peak = op.peakedness;

@@ -169,6 +169,34 @@ __device__ __forceinline__ void tma_load_2d_pair_mc(void* dst, const void* tmap,
         : "memory");
 }
 
+// L2 eviction-priority policies for the operand stream: the row panels of a super-row are re-read for every column panel
+// (evict_last), a column panel is used by the CTAs working at that moment and then not again in this super-row (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_mc_hint(void* dst, const void* tmap, uint32_t bar_cluster_addr, uint16_t cta_mask,
+                                                         int c0, int c1, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // tcgen05: tensor memory + 5th-gen tensor core
 

@@ -55,6 +55,8 @@ struct GramParams {
     int force_slow;            // take the fully-checked epilogue path for every tile
     int debug;                 // profiling knob (fnb_options.debug): bit 0 no epilogue work, bit 1 no operand loads
     int l2_prefetch;           // producer prefetches its next tile's operand boxes into L2: 1 = B panel, 3 = A and B
+    int l2_hints;              // row panels evict_last, column panels evict_first (CTA-pair kernels)
+    int serpentine;            // tile order: odd column panels walk the row panels backwards
     const unsigned int* norm_max_ord;   // ordered-uint max squared row norm (written by the split kernel), may be NULL
     unsigned int norm_limit_ord;        // above this the interior tiles cannot be proven in range -> checked path
     // HIST epilogue
@@ -87,7 +89,19 @@ struct GramParams {
     int tri_packed;
     int metric;
     int n_rows, n_cols;
+    // classifier distances (facenet/faceclass.py): raw = no clamp; row_nrm / col_nrm = norms of the rows before they were
+    // normalised -> d = 2 (1 - s) + theta (2 (|x| - |y|) / (|x| + |y|))^2  (faceclass.py:71)
+    int raw;
+    const float* row_nrm;
+    const float* col_nrm;
+    float theta;
 };
+
+// faceclass.py:71 in float32, operation by operation (no contraction)
+__device__ __forceinline__ float classifier_distance(float s, float nr, float nc, float theta) {
+    const float g = __fdiv_rn(__fmul_rn(2.0f, __fsub_rn(nr, nc)), __fadd_rn(nr, nc));
+    return __fadd_rn(__fmul_rn(2.0f, __fsub_rn(1.0f, s)), __fmul_rn(theta, __fmul_rn(g, g)));
+}
 
 struct TileInfo {
     int row0, col0, row_end, col_end, tri, key;
@@ -102,10 +116,11 @@ struct TileScheduler {
     const RegionDev* regions;
     long long pos, stride, total;
     int cur;
+    int serpentine;
 
     __device__ TileScheduler(const GramParams& p, int cluster_id, int num_clusters)
         : regions(p.regions), pos((long long)cluster_id * p.world + p.rank),
-          stride((long long)num_clusters * p.world), total(p.total_tiles), cur(0) {}
+          stride((long long)num_clusters * p.world), total(p.total_tiles), cur(0), serpentine(p.serpentine) {}
 
     __device__ bool next(TileInfo& t) {
         while (pos < total) {
@@ -113,7 +128,10 @@ struct TileScheduler {
             const RegionDev r = regions[cur];
             const int li = (int)(pos - r.tile_begin);
             const int cb = li / r.nrb;
-            const int rb = li - cb * r.nrb;
+            int rb = li - cb * r.nrb;
+            // odd column panels walk the row panels backwards: the row panels used last are re-used first, so an L2 that
+            // holds only part of the super-row's row panels still hits on that part (a cyclic walk would evict them all)
+            if (serpentine && (cb & 1)) rb = r.nrb - 1 - rb;
             pos += stride;
             t.row0 = r.row_begin + rb * kTile;
             t.col0 = r.col_begin + cb * kSuperCols;
@@ -276,6 +294,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         TileInfo t;
         int slot = 0; uint32_t phase = 0;
         int ntile = -1;
+        const uint64_t pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
         while (sched.next(t)) {
             ++ntile;
             const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
@@ -320,6 +339,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     } else {
                         if (is_leader) mbar_arrive_expect_tx(&misc->full[slot], 2 * kSlotBytes);
                         const uint32_t bar = mapa_u32(smem_u32(&misc->full[slot]), leader_rank);
+                        if (p.l2_hints) {
+                            if constexpr (kPairs == 1) {
+                                tma_load_2d_pair_hint(dst, ma, bar, kcol, arow, pol_a);
+                            } else {
+                                const uint16_t mc = (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank)));
+                                tma_load_2d_pair_mc_hint(dst + pair_idx * (kBoxBytes / 2), ma, bar, mc, kcol, arow + (int)pair_idx * (kRowsPerCta / 2), pol_a);
+                            }
+                            tma_load_2d_pair_hint(dst + kBoxBytes, mb, bar, kcol, brow, pol_b);
+                        } else {
                         if constexpr (kPairs == 1) {
                             tma_load_2d_pair(dst, ma, bar, kcol, arow);
                         } else {
@@ -329,6 +357,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                             tma_load_2d_pair_mc(dst + pair_idx * (kBoxBytes / 2), ma, bar, mc, kcol, arow + (int)pair_idx * (kRowsPerCta / 2));
                         }
                         tma_load_2d_pair(dst + kBoxBytes, mb, bar, kcol, brow);
+                        }
                     }
                 }
                 __syncwarp();
@@ -456,7 +485,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         uint32_t fast_since_flush = 0, tiles_since_global = 0;
         // u8 counters hold <= 255: one fast tile adds at most kColsPerWarp (+1 for the pair rule) per counter
         constexpr uint32_t kFlushEvery = 254u / (uint32_t)kColsPerWarp;
-        const bool all_slow = p.force_slow || !p.uniform ||
+        const bool all_slow = p.force_slow || !p.uniform || p.row_nrm != nullptr ||
                               (p.norm_max_ord != nullptr && __ldg(p.norm_max_ord) > p.norm_limit_ord);
 
         // thread-private byte counters: bin b of thread (colq, q, lane) lives at byte b * 512 + (colq * 32 + lane) * 4 + q,
@@ -587,6 +616,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         misc->col_cls[acc][te] = (c < t.col_end) ? __ldg(p.col_cls + c) : -2;
                     }
                     const int my_cls = (row < t.row_end) ? __ldg(p.row_cls + row) : -1;
+                    const float my_nrm = (p.row_nrm != nullptr && row < t.row_end) ? __ldg(p.row_nrm + row) : 1.0f;
                     named_bar_sync(2, kEpiThreads);
                     const bool row_ok = row < t.row_end;
 #pragma unroll 1
@@ -597,15 +627,23 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int col = colw + c + j;
-                            const bool ok = row_ok && (col < t.col_end) && (!t.tri || col > row);
+                            const bool on_diag = (t.tri == 2) && (col == row);
+                            const bool ok = row_ok && (col < t.col_end) && (!t.tri || col > row || on_diag);
                             if (ok) {
                                 float s = __uint_as_float(r[j]) * scale;
-                                smin = fminf(smin, s); smax = fmaxf(smax, s);
-                                s = fminf(fmaxf(s, -1.0f), 1.0f);
+                                if (!on_diag) { smin = fminf(smin, s); smax = fmaxf(smax, s); }
+                                if (p.row_nrm != nullptr)      // classifier distance with the norm term, back on the similarity axis
+                                    s = __fsub_rn(1.0f, __fmul_rn(0.5f, classifier_distance(s, my_nrm, __ldg(p.col_nrm + col), p.theta)));
+                                else if (!p.raw) s = fminf(fmaxf(s, -1.0f), 1.0f);
                                 const int ke = exact_bin(s, misc->cuts);
-                                if (s <= misc->whi[ke] || s >= misc->wlo[ke]) ++eps_cnt;
-                                atomicAdd(&misc->cta_all[ke], 1u);
-                                if (misc->col_cls[acc][col - t.col0] == my_cls) atomicAdd(&misc->cta_same[ke], 1u);
+                                if (on_diag) {
+                                    // self pairs of the full n_i x n_i blocks of train_classifier.py:35: slot key + 1, N adds in total
+                                    atomicAdd(p.bins + ((size_t)(t.key + 1) * 2) * p.bins_stride + ke, 1ull);
+                                } else {
+                                    if (s <= misc->whi[ke] || s >= misc->wlo[ke]) ++eps_cnt;
+                                    atomicAdd(&misc->cta_all[ke], 1u);
+                                    if (misc->col_cls[acc][col - t.col0] == my_cls) atomicAdd(&misc->cta_same[ke], 1u);
+                                }
                             }
                         }
                     }
@@ -615,6 +653,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
                 tc_fence_after();
                 const bool row_ok = row < t.row_end;
+                const float my_nrm = (p.row_nrm != nullptr && row_ok) ? __ldg(p.row_nrm + row) : 1.0f;
 #pragma unroll 1
                 for (int c = 0; c < kColsPerWarp / 32; ++c) {
                     uint32_t r[32];
@@ -631,9 +670,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                             if (ok) {
                                 float s = __uint_as_float(r[j]) * scale;
                                 if (kEpi == EPI_PAIRWISE || col != row) { smin = fminf(smin, s); smax = fmaxf(smax, s); }
-                                s = fminf(fmaxf(s, -1.0f), 1.0f);
+                                if (!p.raw) s = fminf(fmaxf(s, -1.0f), 1.0f);
                                 float d;
-                                if (p.metric == 0) d = __fmul_rn(2.0f, __fsub_rn(1.0f, s));
+                                if (p.row_nrm != nullptr) d = classifier_distance(s, my_nrm, __ldg(p.col_nrm + col), p.theta);
+                                else if (p.metric == 0) d = __fmul_rn(2.0f, __fsub_rn(1.0f, s));
                                 else d = acosf(s);
                                 p.out[base + col] = d;
                             }

@@ -74,6 +74,7 @@ struct fnb_context {
 
     fnb::DevBuf stage_a, stage_b, stage_lab;          // H2D staging of kDLCPU inputs
     fnb::DevBuf a_hi, a_lo, b_hi, b_lo, a_h8, b_h8;   // split / converted operands
+    fnb::DevBuf a_nrm, b_nrm;                         // row norms before normalise-on-load (fnb_options.normalize)
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
@@ -103,6 +104,8 @@ struct GramOperands {
     float peakedness = 0.f;        // max_row sum x^4 / (sum x^2)^2 (valid after prepare_operand in AUTO mode)
     int pairs = 1;                 // CTA pairs per cluster (2: the A maps carry 64-row boxes, see gram_kernel kPairs)
     long long a_rows_pad = 0;      // padded row count of the prepared A-side arrays
+    const float* a_nrm = nullptr;  // norms of the rows before normalise-on-load (NULL without it)
+    const float* b_nrm = nullptr;
 };
 
 struct DeviceScalars {      // layout of fnb_context::counters
@@ -118,7 +121,7 @@ int dl_view(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_m
 int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, const void** out);
 int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
-                    bool side_b, GramOperands& op);
+                    bool side_b, GramOperands& op, int normalize = 0);
 void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1);
 int self_b_maps(fnb_context* h, GramOperands& op, int d);   // B side = the prepared A side (Gram of a set with itself)
 int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
@@ -128,7 +131,8 @@ int build_cut_tables(const double* thresholds, int T, int metric, double eps, co
 
 // fnb_prepare.cu
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
-                              void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s);   // norm_max_ord[1] = peakedness
+                              void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s,   // norm_max_ord[1] = peakedness
+                              int normalize = 0, float* row_nrm = nullptr);
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
 
 // fnb_gram.cu

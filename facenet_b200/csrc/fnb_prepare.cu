@@ -19,7 +19,8 @@ __device__ __forceinline__ float tf32_rn(float x) {
 template <int kMode>
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ perm, long long n, long long n_pad, int d,
-                  void* __restrict__ hi, void* __restrict__ lo, void* __restrict__ h8, unsigned int* __restrict__ norm_max_ord)
+                  void* __restrict__ hi, void* __restrict__ lo, void* __restrict__ h8, unsigned int* __restrict__ norm_max_ord,
+                  int normalize, float* __restrict__ row_nrm)
 {
     const int vec_per_row = d >> 3;
     const int lane = threadIdx.x & 31;
@@ -28,6 +29,25 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
     float norm_max = 0.f, peak_max = 0.f;
     for (long long row = warp0; row < n_pad; row += nwarps) {
         const long long src = (row < n) ? (perm ? perm[row] : row) : 0;
+        // normalise-on-load (fnb_options.normalize): a first pass over the row forms |x|; the second pass below re-reads
+        // the row (L1/L2 hit) and scales every element before the split.
+        //   1: x / |x|  (np.linalg.norm: sqrt of the fp32 sum of squares; faceclass.py:57-64)
+        //   2: x * rsqrt(max(sum x^2, 1e-10))  (tf.nn.l2_normalize, inception_resnet_v1.py:491-492)
+        float inv_or_nrm = 1.f;
+        if (normalize) {
+            float ss = 0.f;
+            if (row < n)
+                for (int c8 = lane; c8 < vec_per_row; c8 += 32) {
+                    const float4* s4 = reinterpret_cast<const float4*>(x + src * d + (long long)c8 * 8);
+                    const float4 p0 = __ldg(s4), p1 = __ldg(s4 + 1);
+                    ss += p0.x * p0.x + p0.y * p0.y + p0.z * p0.z + p0.w * p0.w + p1.x * p1.x + p1.y * p1.y + p1.z * p1.z + p1.w * p1.w;
+                }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float nr = __fsqrt_rn(ss);
+            inv_or_nrm = (normalize == 1) ? nr : __frsqrt_rn(fmaxf(ss, 1.0e-10f));
+            if (row_nrm && lane == 0) row_nrm[row] = (row < n) ? nr : 0.f;
+        }
         float nrm = 0.f, x4 = 0.f;
         for (int c8 = lane; c8 < vec_per_row; c8 += 32) {
             float f[8];
@@ -35,6 +55,13 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
                 const float4* s4 = reinterpret_cast<const float4*>(x + src * d + (long long)c8 * 8);
                 const float4 p0 = __ldg(s4), p1 = __ldg(s4 + 1);
                 f[0] = p0.x; f[1] = p0.y; f[2] = p0.z; f[3] = p0.w; f[4] = p1.x; f[5] = p1.y; f[6] = p1.z; f[7] = p1.w;
+                if (normalize == 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = __fdiv_rn(f[i], inv_or_nrm);
+                } else if (normalize == 2) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = __fmul_rn(f[i], inv_or_nrm);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = 0.f;
@@ -105,19 +132,20 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
 }
 
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
-                              void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s)
+                              void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s,
+                              int normalize, float* row_nrm)
 {
     if (n_pad == 0) return cudaSuccess;
     const int threads = 256;
     long long blocks = (n_pad + 7) / 8;                  // 8 warps (rows) per block
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     switch (mode) {
-        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord); break;
-        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord); break;
-        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord); break;
-        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord); break;
-        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord); break;
-        case FNB_MODE_FP16F8: split_rows_kernel<FNB_MODE_FP16F8><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord); break;
+        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
+        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
+        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
+        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
+        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
+        case FNB_MODE_FP16F8: split_rows_kernel<FNB_MODE_FP16F8><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -94,7 +94,14 @@ typedef struct {
     int32_t cluster_pairs; /* histogram launches, cta_group 2 only: 2 = clusters of two CTA pairs that share (multicast) the
                               A operand, so it is read from L2 once per 256 x 512 super-tile; 1 = one pair per cluster;
                               0 = auto (2 for launches long enough to be power-limited, >= 5e10 pairs per rank) */
-    int32_t reserved[4];
+    int32_t normalize;     /* rows are normalised while the operands are prepared (the raw norms are kept for `theta`):
+                              1: x / |x|                      (facenet/faceclass.py:63-64, np.linalg.norm)
+                              2: x * rsqrt(max(sum x^2, 1e-10))  (tf.nn.l2_normalize(axis=1, epsilon=1e-10),
+                                 facenet/models/inception_resnet_v1.py:491-492)                  default 0 */
+    float   theta;         /* normalize == 1 only: the pair distance becomes 2 (1 - s) + theta (2 (|x|-|y|) / (|x|+|y|))^2
+                              (FaceToFaceDistanceClassifier.distance, facenet/faceclass.py:71)   default 0 */
+    int32_t raw_distance;  /* != 0: classifier distance (facenet/faceclass.py:106-116): no range check, no clamp */
+    int32_t reserved[1];
 } fnb_options;
 
 typedef struct {
@@ -119,7 +126,7 @@ typedef struct {
  * row range == col range and only pairs col > row are counted. */
 typedef struct {
     int32_t row_begin, row_end, col_begin, col_end;
-    int32_t tri;
+    int32_t tri;           /* 2: like 1, and the diagonal elements (row == col) are binned too, into slot key + 1 */
     int32_t key;           /* histogram slot the rectangle accumulates into */
 } fnb_region;
 
