@@ -25,7 +25,8 @@ MAX_THRESHOLDS = 127
 
 EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info', 'fnb_set_stream',
            'fnb_pairwise', 'fnb_pair_histogram_bins', 'fnb_counts_from_bins', 'fnb_pair_histogram',
-           'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine')
+           'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine', 'fnb_pair_cross_entropy',
+           'fnb_logits_cross_entropy')
 
 
 class DLDevice(ctypes.Structure):
@@ -109,6 +110,8 @@ def load_library():
                                                       P(c.c_double), P(c.c_double), P(c.c_int32), P(c.c_double)]
         lib.fnb_mine.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), c.c_float, P(Options), P(c.c_int32), P(c.c_int32),
                                  c.c_int, P(c.c_int32), P(c.c_int32), P(c.c_int32), P(Stats)]
+        lib.fnb_pair_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, c.c_float, c.c_float, P(Options), P(c.c_double), P(Stats)]
+        lib.fnb_logits_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, P(c.c_double)]
         for name in EXPORTS:
             fn = getattr(lib, name)
             if fn.restype is c.c_int and name not in ('fnb_version',):
@@ -409,6 +412,29 @@ class Handle:
             self._raise(rc)
         return {'tp': out[0], 'tn': out[1], 'fp': out[2], 'fn': out[3], 'argmax_accuracy': int(amax.value),
                 'far_threshold': float(far.value)}
+
+    # ---- pair-classifier cross entropy over one P x K batch (train_classifier.py:60-84)
+    def pair_cross_entropy(self, batch, examples_per_class, alpha, threshold, normalize=0, theta=0.0):
+        batch = _as_f32_matrix(batch, 'batch')
+        o, keep = self.options(normalize=normalize, theta=theta, raw_distance=True)
+        out = (ctypes.c_double * 5)()
+        st = Stats()
+        bb = Borrowed(batch)
+        rc = self.lib.fnb_pair_cross_entropy(self.h, bb.ptr, int(examples_per_class), ctypes.c_float(alpha), ctypes.c_float(threshold),
+                                             ctypes.byref(o), out, ctypes.byref(st))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return {'loss': out[0], 'dalpha': out[1], 'dthreshold': out[2], 'dtheta': out[3], 'pos_weight': out[4],
+                'stats': st.as_dict()}
+
+    def logits_cross_entropy(self, logits, examples_per_class):
+        logits = _as_f32_matrix(logits, 'logits')
+        loss = ctypes.c_double(0.0)
+        bl = Borrowed(logits)
+        rc = self.lib.fnb_logits_cross_entropy(self.h, bl.ptr, int(examples_per_class), ctypes.byref(loss))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return float(loss.value)
 
     # ---- triplet mining (semantics: oracle/mining_oracle.py; not in the reference fork)
     def mine(self, embeddings, labels, alpha=0.2, kmax=None, mode='fp16x3', atol=1.e-5):

@@ -65,3 +65,28 @@ class ConfusionMatrix:
                 f'precision {self.precision}\n' +
                 f'tp rate   {self.tp_rate}\n' +
                 f'tn rate   {self.tn_rate}\n')
+
+
+def binary_cross_entropy_loss(logits, options):
+    """train_classifier.py:60-84 for a materialised ``[B, B]`` logits matrix (``B = nrof_classes_per_batch *
+    nrof_examples_per_class``): labels 1 for pairs of the same class on the strict upper triangle,
+    ``pos_weight = len(labels) / sum(labels) - 1``, mean weighted cross entropy.  Returns a float32 scalar like
+    ``session.run(loss)``.  The training loop should call ``pair_cross_entropy`` instead, which never forms the logits."""
+    batch_size = options.nrof_classes_per_batch * options.nrof_examples_per_class
+    logits = np.ascontiguousarray(logits, dtype=np.float32) if isinstance(logits, np.ndarray) or not hasattr(logits, '__dlpack__') else logits
+    if tuple(logits.shape) != (batch_size, batch_size):
+        raise ValueError('logits must be [{0}, {0}]'.format(batch_size))
+    return np.float32(_st._handle().logits_cross_entropy(logits, options.nrof_examples_per_class))
+
+
+def pair_cross_entropy(model, embeddings_batch, options):
+    """``binary_cross_entropy_loss(model(embeddings_batch), options)`` (train_classifier.py:109-110) and its derivatives with
+    respect to the classifier's variables, from ONE fused Gram launch -- what one optimiser step needs
+    (train_classifier.py:127).  Returns ``{'loss', 'grads': {'alpha', 'threshold'[, 'theta']}, 'pos_weight', 'stats'}``."""
+    opts = model._gram_options()
+    out = _st._handle().pair_cross_entropy(embeddings_batch, options.nrof_examples_per_class, float(model.variable('alpha')),
+                                           float(model.variable('threshold')), **opts)
+    grads = {'alpha': out['dalpha'], 'threshold': out['dthreshold']}
+    if 'theta' in model.variables:
+        grads['theta'] = out['dtheta']
+    return {'loss': out['loss'], 'grads': grads, 'pos_weight': out['pos_weight'], 'stats': out['stats']}

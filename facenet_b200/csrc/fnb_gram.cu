@@ -87,6 +87,12 @@ int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const Gram
         if (cta_group != 2 || epi != EPI_HIST) return h->fail(FNB_ERR_INVALID, "cluster pairs need cta_group 2 and the histogram epilogue");
         return launch_mode_pairs2(h, max_ctas, op, p, smem);
     }
+    if (epi == EPI_BCE) {
+        // one batch of a few thousand rows: the strict fp32-equivalent split only (the loss feeds an optimiser)
+        if (op.num_pass != 3 || op.tf32) return h->fail(FNB_ERR_INVALID, "the cross-entropy epilogue runs in fp16x3 mode");
+        return cta_group == 2 ? launch_one<2, 3, false, EPI_BCE>(h, max_ctas, op, p, smem)
+                              : launch_one<1, 3, false, EPI_BCE>(h, max_ctas, op, p, smem);
+    }
     if (cta_group == 2) {
         if (epi == EPI_HIST)     return launch_mode<2, EPI_HIST>(h, max_ctas, op, p, smem);
         if (epi == EPI_PAIRWISE) return launch_mode<2, EPI_PAIRWISE>(h, max_ctas, op, p, smem);

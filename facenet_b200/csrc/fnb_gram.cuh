@@ -33,7 +33,7 @@ constexpr int kSlotBytes    = 2 * kBoxBytes;       // {A part, B part}
 constexpr int kMaxSlots     = 8;
 constexpr int kHist8Row     = kEpiThreads;         // bytes per bin of the thread-private u8 counters
 
-enum EpiKind : int { EPI_HIST = 0, EPI_PAIRWISE = 1, EPI_ROWSTRIP = 2 };
+enum EpiKind : int { EPI_HIST = 0, EPI_PAIRWISE = 1, EPI_ROWSTRIP = 2, EPI_BCE = 3 };
 
 struct RegionDev {
     int32_t row_begin, row_end, col_begin, col_end;
@@ -95,6 +95,10 @@ struct GramParams {
     const float* row_nrm;
     const float* col_nrm;
     float theta;
+    // BCE epilogue (train_classifier.py:60-84 fused behind the classifier, faceclass.py:23-27): logits alpha (threshold - d)
+    // of the strict upper triangle, label = same group (row_cls == col_cls), weighted cross entropy and its derivatives
+    float bce_alpha, bce_threshold, bce_pos_weight;
+    double* bce_out;           // [4] sums over pairs: loss, dloss/dalpha, dloss/dthreshold, dloss/dtheta
 };
 
 // faceclass.py:71 in float32, operation by operation (no contraction)
@@ -480,6 +484,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         uint32_t it = 0;
 
         float smin = INFINITY, smax = -INFINITY;
+        double bce_acc[4] = {0.0, 0.0, 0.0, 0.0};
         uint32_t eps_cnt = 0, tiles_done = 0;
         int cur_key = -1;
         uint32_t fast_since_flush = 0, tiles_since_global = 0;
@@ -648,6 +653,51 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         }
                     }
                 }
+            } else if constexpr (kEpi == EPI_BCE) {
+                // ------------------- weighted binary cross entropy over the triangle ----------
+                mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
+                tc_fence_after();
+                const bool row_ok = row < t.row_end;
+                const float my_nrm = (p.row_nrm != nullptr && row_ok) ? __ldg(p.row_nrm + row) : 1.0f;
+                const int my_cls = row_ok ? __ldg(p.row_cls + row) : -1;
+                float t_loss = 0.f, t_da = 0.f, t_dt = 0.f, t_dth = 0.f;     // this tile's terms of this thread (<= 64)
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr0 + c * 32, r);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll 4
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = colw + c * 32 + j;
+                            if (col < t.col_end && col > row) {
+                                const float sv = __uint_as_float(r[j]) * scale;
+                                float d, g2 = 0.f;
+                                if (p.row_nrm != nullptr) {
+                                    const float nc = __ldg(p.col_nrm + col);
+                                    const float g = __fdiv_rn(__fmul_rn(2.0f, __fsub_rn(my_nrm, nc)), __fadd_rn(my_nrm, nc));
+                                    g2 = __fmul_rn(g, g);
+                                    d = __fadd_rn(__fmul_rn(2.0f, __fsub_rn(1.0f, sv)), __fmul_rn(p.theta, g2));
+                                } else {
+                                    d = __fmul_rn(2.0f, __fsub_rn(1.0f, sv));
+                                }
+                                const float margin = __fsub_rn(p.bce_threshold, d);
+                                const float x = __fmul_rn(p.bce_alpha, margin);           // the logit (faceclass.py:26)
+                                const float z = (__ldg(p.col_cls + col) == my_cls) ? 1.0f : 0.0f;
+                                const float lw = 1.0f + (p.bce_pos_weight - 1.0f) * z;
+                                // tf.nn.weighted_cross_entropy_with_logits: (1 - z) x + lw (log1p(exp(-|x|)) + max(-x, 0))
+                                const float e = expf(-fabsf(x));
+                                t_loss += (1.0f - z) * x + lw * (log1pf(e) + fmaxf(-x, 0.0f));
+                                const float sig_neg = (x >= 0.0f) ? e / (1.0f + e) : 1.0f / (1.0f + e);   // sigmoid(-x)
+                                const float gr = (1.0f - z) - lw * sig_neg;                                  // d loss / d logit
+                                t_da += gr * margin;
+                                t_dt += gr * p.bce_alpha;
+                                t_dth -= gr * p.bce_alpha * g2;
+                            }
+                        }
+                    }
+                }
+                bce_acc[0] += (double)t_loss; bce_acc[1] += (double)t_da; bce_acc[2] += (double)t_dt; bce_acc[3] += (double)t_dth;
             } else {
                 // ------------------- PAIRWISE / ROWSTRIP: materialise distances --------------
                 mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
@@ -696,6 +746,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             flush_cta(cur_key);
             eps_cnt = warp_sum(eps_cnt);
             if (lane == 0 && eps_cnt) atomicAdd(p.counters + 0, (unsigned long long)eps_cnt);
+        }
+        if constexpr (kEpi == EPI_BCE) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double v = bce_acc[i];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && v != 0.0) atomicAdd(p.bce_out + i, v);
+            }
         }
         smin = warp_min(smin); smax = warp_max(smax);
         if (lane == 0) {

@@ -193,6 +193,21 @@ int fnb_confidence_from_last_bins(fnb_handle h, int nkeys, const double* w_same,
                                   double* tp, double* tn, double* fp, double* fn,
                                   int32_t* argmax_accuracy, double* far_threshold);
 
+/* Weighted binary cross entropy of the pair classifier over one P x K batch, fused behind the Gram product
+ * (binary_cross_entropy_loss(model(embeddings_batch), options), facenet/apps/train_classifier.py:60-84,109-110, with the
+ * logits alpha * (threshold - distance) of facenet/faceclass.py:23-27):
+ *   batch float32 [B, D], rows grouped by class (row i belongs to group i / examples_per_class, facenet/facenet.py:108-113);
+ *   label 1 iff same group, on the strict upper triangle; pos_weight = len(labels) / sum(labels) - 1;
+ *   opt->normalize / opt->theta select FaceToFaceDistanceClassifier (normalize 1, theta) or
+ *   FaceToFaceNormalizedEmbeddingsClassifier (normalize 0) distances.
+ *   out [5] (host): mean loss, d loss / d alpha, d loss / d threshold, d loss / d theta (what TensorFlow's autodiff hands
+ *   the optimiser, train_classifier.py:127), pos_weight. */
+int fnb_pair_cross_entropy(fnb_handle h, const DLTensor* batch, int examples_per_class, float alpha, float threshold,
+                           const fnb_options* opt, double* out, fnb_stats* stats);
+
+/* binary_cross_entropy_loss(logits, options) for a materialised float32 [B, B] logits matrix (train_classifier.py:60-84). */
+int fnb_logits_cross_entropy(fnb_handle h, const DLTensor* logits, int examples_per_class, double* loss);
+
 /* Triplet mining on one batch (NOT in the reference fork -- semantics defined in
  * oracle/mining_oracle.py; batch layout facenet/facenet.py:89-123).  Distances are metric 0.
  *   hardest_pos, hardest_neg: int32 [B];  kmax >= max class size - 1;

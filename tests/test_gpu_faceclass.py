@@ -118,3 +118,67 @@ def test_normalise_on_load_histogram():
     assert mism <= 2 * got['stats']['eps_window']
     with pytest.raises(_capi.FnbError):
         h.pair_histogram(xu, labels, thr, 0)               # not normalised and not asked to: statistics.py:40-42
+
+
+# ------------------------------------------------------------------------------ f2 cross entropy
+
+class _Opt:
+    def __init__(self, p, k):
+        self.nrof_classes_per_batch, self.nrof_examples_per_class = p, k
+
+
+def test_cross_entropy_golden(golden_dir):
+    from facenet_b200 import faceclass
+    from facenet_b200.apps import train_classifier as tc
+    g = np.load(golden_dir / 'faceclass.npz')
+    P, K = (int(v) for v in g['PK'])
+    mn = faceclass.FaceToFaceNormalizedEmbeddingsClassifier()
+    out = tc.pair_cross_entropy(mn, g['batch'], _Opt(P, K))
+    assert abs(out['loss'] - float(g['bce_norm'])) <= 2e-5 * max(1.0, abs(float(g['bce_norm'])))
+    a, t, th = (float(v) for v in g['bce_dist_vars'])
+    md = faceclass.FaceToFaceDistanceClassifier()
+    md.variables.update(alpha=np.float32(a), threshold=np.float32(t), theta=np.float32(th))
+    out = tc.pair_cross_entropy(md, g['batch_u'], _Opt(P, K))
+    assert abs(out['loss'] - float(g['bce_dist'])) <= 2e-5 * max(1.0, abs(float(g['bce_dist'])))
+    # the reference's own signature on a materialised logits matrix
+    lg = md(g['batch_u'])
+    assert abs(float(tc.binary_cross_entropy_loss(lg, _Opt(P, K))) - float(g['bce_dist'])) <= 2e-5 * max(1.0, abs(float(g['bce_dist'])))
+
+
+@pytest.mark.parametrize('P,K,d', [(45, 40, 512), (7, 3, 64), (2, 130, 128)])
+def test_cross_entropy_and_grads_vs_oracle(P, K, d):
+    from facenet_b200 import faceclass
+    from facenet_b200.apps import train_classifier as tc
+    x, xu, _ = _unnormalised([K] * P, d, 100 + P)
+    for model, data, dist in ((faceclass.FaceToFaceNormalizedEmbeddingsClassifier(), x, fo.distance_normalized(x)),
+                              (faceclass.FaceToFaceDistanceClassifier(), xu, None)):
+        a, t = 6.0, 1.2
+        model.variables.update(alpha=np.float32(a), threshold=np.float32(t))
+        dth = None
+        if dist is None:
+            model.variables['theta'] = np.float32(0.8)
+            dist = fo.distance_unnormalized(xu, None, 0.8)
+            nrm = np.linalg.norm(xu.astype(np.float64), axis=1)
+            dth = (2 * (nrm[:, None] - nrm[None, :]) / (nrm[:, None] + nrm[None, :])) ** 2
+        ref = fo.binary_cross_entropy_loss_and_grads(dist, a, t, P, K, dtheta_term=dth)
+        out = tc.pair_cross_entropy(model, data, _Opt(P, K))
+        assert abs(out['pos_weight'] - ref['pos_weight']) < 1e-12
+        tol = 2e-5 * max(1.0, abs(ref['loss']))
+        assert abs(out['loss'] - ref['loss']) <= tol
+        assert abs(out['grads']['alpha'] - ref['dalpha']) <= 5e-5 * max(1.0, abs(ref['dalpha']))
+        assert abs(out['grads']['threshold'] - ref['dthreshold']) <= 5e-5 * max(1.0, abs(ref['dthreshold']))
+        if dth is not None:
+            assert abs(out['grads']['theta'] - ref['dtheta']) <= 5e-5 * max(1.0, abs(ref['dtheta']))
+        # float32 reference arithmetic (the golden form) agrees with the float64 statement to the same tolerance
+        ref32 = float(fo.binary_cross_entropy_loss(fo.logits(dist, a, t), P, K))
+        assert abs(out['loss'] - ref32) <= 5e-5 * max(1.0, abs(ref32))
+
+
+def test_cross_entropy_rejects_bad_batches():
+    from facenet_b200 import _capi
+    h = _capi.default_handle(0)
+    x = np.zeros((10, 64), dtype=np.float32)
+    with pytest.raises(_capi.FnbError):
+        h.pair_cross_entropy(x, 3, 10.0, 1.0)          # 10 rows are not P x 3
+    with pytest.raises(_capi.FnbError):
+        h.pair_cross_entropy(x, 1, 10.0, 1.0)          # K = 1: pos_weight undefined (division by zero in the reference)
