@@ -258,10 +258,24 @@ class Handle:
         raise FnbError(rc, self.lib.fnb_last_error(self.h).decode())
 
     def set_stream(self, cuda_stream=None):
-        """Run on ``cuda_stream`` (an int/ctypes handle, e.g. ``torch.cuda.current_stream().cuda_stream``); None = own stream."""
-        rc = self.lib.fnb_set_stream(self.h, ctypes.c_void_p(int(cuda_stream)) if cuda_stream else None)
+        """Run on ``cuda_stream`` (an int handle, e.g. ``torch.cuda.current_stream().cuda_stream``; 0 is the legacy default
+        stream); None = the handle's own stream."""
+        arg = ctypes.c_void_p(-1) if cuda_stream is None else ctypes.c_void_p(int(cuda_stream))
+        rc = self.lib.fnb_set_stream(self.h, arg)
         if rc != FNB_OK:
             self._raise(rc)
+        self._stream = None if cuda_stream is None else int(cuda_stream)
+
+    def _borrow(self, obj):
+        """Borrow a tensor for one call.  A torch CUDA tensor is ready on torch's CURRENT stream (its producer kernels,
+        an all-gather, a ``torch.zeros`` fill are queued there): the handle follows that stream so its work is ordered
+        after them -- never a host synchronisation, never its own unordered stream."""
+        if not isinstance(obj, np.ndarray) and getattr(obj, 'is_cuda', False):
+            import torch
+            s = int(torch.cuda.current_stream(obj.device).cuda_stream)
+            if getattr(self, '_stream', None) != s:
+                self.set_stream(s)
+        return Borrowed(obj)
 
     def device_info(self):
         sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_uint64()
@@ -307,8 +321,8 @@ class Handle:
         o, keep = self.options(mode=mode, metric=metric, atol=atol, cta_group=cta_group, normalize=normalize, theta=theta,
                                raw_distance=raw_distance)
         rng = (ctypes.c_float * 2)()
-        ba, bo = Borrowed(xa), Borrowed(out)
-        bb = Borrowed(xb) if xb is not None else None
+        ba, bo = self._borrow(xa), self._borrow(out)
+        bb = self._borrow(xb) if xb is not None else None
         rc = self.lib.fnb_pairwise(self.h, ba.ptr, bb.ptr if bb else None, ctypes.byref(o), bo.ptr, rng)
         self.last_range = (rng[0], rng[1])
         if rc != FNB_OK:
@@ -330,7 +344,7 @@ class Handle:
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()
-        be, bl, bb = Borrowed(embeddings), Borrowed(labels), Borrowed(bins_out)
+        be, bl, bb = self._borrow(embeddings), self._borrow(labels), self._borrow(bins_out)
         rc = self.lib.fnb_pair_histogram_bins(self.h, be.ptr, bl.ptr, thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                               thr.size, ctypes.byref(o), bb.ptr, ctypes.byref(st))
         if rc != FNB_OK:
@@ -377,7 +391,7 @@ class Handle:
                                cluster_pairs=cluster_pairs, normalize=normalize, theta=theta, raw_distance=raw_distance)
         bins = np.zeros((int(nkeys), 2, thr.size + 1), dtype=np.uint64)
         st = Stats()
-        be = Borrowed(embeddings)
+        be = self._borrow(embeddings)
         rc = self.lib.fnb_region_histogram_bins(
             self.h, be.ptr, perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), cls.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
             regions.ctypes.data_as(ctypes.POINTER(Region)), regions.size, int(nkeys),
@@ -419,7 +433,7 @@ class Handle:
         o, keep = self.options(normalize=normalize, theta=theta, raw_distance=True)
         out = (ctypes.c_double * 5)()
         st = Stats()
-        bb = Borrowed(batch)
+        bb = self._borrow(batch)
         rc = self.lib.fnb_pair_cross_entropy(self.h, bb.ptr, int(examples_per_class), ctypes.c_float(alpha), ctypes.c_float(threshold),
                                              ctypes.byref(o), out, ctypes.byref(st))
         if rc != FNB_OK:
@@ -430,7 +444,7 @@ class Handle:
     def logits_cross_entropy(self, logits, examples_per_class):
         logits = _as_f32_matrix(logits, 'logits')
         loss = ctypes.c_double(0.0)
-        bl = Borrowed(logits)
+        bl = self._borrow(logits)
         rc = self.lib.fnb_logits_cross_entropy(self.h, bl.ptr, int(examples_per_class), ctypes.byref(loss))
         if rc != FNB_OK:
             self._raise(rc)
@@ -452,7 +466,7 @@ class Handle:
         el = np.zeros((b, kmax), dtype=np.int32)
         o, keep = self.options(mode=mode, metric=0, atol=atol)
         st = Stats()
-        be, bl = Borrowed(embeddings), Borrowed(labels)
+        be, bl = self._borrow(embeddings), self._borrow(labels)
         ip = ctypes.POINTER(ctypes.c_int32)
         rc = self.lib.fnb_mine(self.h, be.ptr, bl.ptr, float(alpha), ctypes.byref(o), hp.ctypes.data_as(ip), hn.ctypes.data_as(ip),
                                kmax, pi.ctypes.data_as(ip), sh.ctypes.data_as(ip), el.ctypes.data_as(ip), ctypes.byref(st))

@@ -303,7 +303,11 @@ extern "C" int fnb_set_stream(fnb_handle h, void* cuda_stream) {
     if (!h) return FNB_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    // NULL is CUDA's legacy default stream (what torch reports as its current stream until another one is selected):
+    // it must NOT fall back to the handle's own non-blocking stream, which would not be ordered after the caller's
+    // kernels and collectives on stream 0
+    if (cuda_stream == FNB_STREAM_OWN) h->stream = h->own_stream;
+    else h->stream = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy;
     return FNB_OK;
 }
 

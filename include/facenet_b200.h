@@ -137,7 +137,10 @@ void fnb_destroy(fnb_handle h);
 const char* fnb_last_error(fnb_handle h);          /* h may be NULL: error of the last failed fnb_create */
 int  fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
 /* Enqueue all work of this handle on `cuda_stream` (a cudaStream_t, e.g. the framework's current stream) so that
- * it orders with the caller's kernels, collectives and events; NULL restores the handle's own stream. */
+ * it orders with the caller's kernels, collectives and events.  NULL is the legacy default stream (stream 0, the
+ * "current stream" of torch / TensorFlow until another one is selected); FNB_STREAM_OWN restores the handle's own
+ * non-blocking stream (the state after fnb_create).  Tensors handed over as kDLCUDA must be ready on that stream. */
+#define FNB_STREAM_OWN ((void*)(intptr_t)-1)
 int  fnb_set_stream(fnb_handle h, void* cuda_stream);
 
 /* Replaces pairwise_similarities(xa, xb=None, metric, atol)  (facenet/statistics.py:22-57).

@@ -6,7 +6,10 @@
   c3  triplet mining, 1800-image batches (45 identities x 40 images), 512-d, alpha 0.2: steps/s with
       host batches (H2D inside) and with device-resident batches; parity of one batch vs the mining oracle
 
-    python scripts/bench_configs.py [c1] [c3] [--steps N]   -> one JSON line per config
+  f1  ConfusionMatrix of the pair classifiers on the 26,489-row set of the published runs (section 8 f1)
+  f2  cross-entropy loss + gradients of one 1800-row P x K batch (section 8 f2)
+
+    python scripts/bench_configs.py [c1] [c3] [f1] [f2] [--steps N]   -> one JSON line per config
 """
 import json
 import sys
@@ -100,6 +103,103 @@ def run_c3(mode, steps):
     print(json.dumps(line))
 
 
+def run_f1():
+    """ConfusionMatrix (train_classifier.py:17-49) at the size of the published validation runs: 26,489 x 512, 530 classes of
+    45-50 images (models/20200724-231357/logs/report.txt:13-22); both classifiers; CPU oracle (vectorised) beside it and the
+    literal per-class-pair loop on a class subsample."""
+    from facenet_b200 import faceclass
+    from facenet_b200.apps import train_classifier as tc
+    from oracle import faceclass_oracle as fo
+    from oracle import statistics_oracle as so
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(45, 51, size=530).tolist()
+    x, _ = so.synthetic_embeddings(sizes, dim=512, sigma=1.1, seed=2, shuffle=False)
+    xu = (x * rng.uniform(0.6, 1.7, size=(x.shape[0], 1))).astype(np.float32)
+    b = np.concatenate([[0], np.cumsum(sizes)])
+    cls = np.repeat(np.arange(len(sizes)), sizes)
+    for tag, data, model, fn in (('normalized', x, faceclass.FaceToFaceNormalizedEmbeddingsClassifier(), fo.distance_normalized),
+                                 ('distance', xu, faceclass.FaceToFaceDistanceClassifier(), None)):
+        if fn is None:
+            model.variables['theta'] = np.float32(0.7)
+            fn = lambda a, c: fo.distance_unnormalized(a, c, 0.7)
+        model.variables['threshold'] = np.float32(1.1)
+        emb = [data[a:c] for a, c in zip(b[:-1], b[1:])]
+        tc.ConfusionMatrix(emb[:40], model)                 # warm-up
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            cm = tc.ConfusionMatrix(emb, model)
+            times.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        ref = fo.confusion_matrix_vectorized(data, cls, fn, 1.1)
+        cpu_vec = time.perf_counter() - t0
+        nsub = 60
+        t0 = time.perf_counter()
+        lit = fo.confusion_matrix(emb[:nsub], fn, 1.1)
+        cpu_lit = time.perf_counter() - t0
+        sub = tc.ConfusionMatrix(emb[:nsub], model)
+        n = data.shape[0]
+        line = {'config': 'f1: ConfusionMatrix, %s classifier, 26,489-row-class set (%d x 512, 530 classes of 45-50), threshold 1.1' % (tag, n),
+                'seconds': min(times), 'seconds_all': times, 'unordered_pairs': n * (n - 1) // 2,
+                'g_pair_distances_per_s': n * (n - 1) / 2 / min(times) / 1e9, 'kernel_ms': cm.stats['kernel_ms'],
+                'cpu_vectorised_oracle_seconds': cpu_vec,
+                'cpu_literal_loop_seconds_%d_classes' % nsub: cpu_lit,
+                'cpu_literal_loop_seconds_extrapolated_530_classes': cpu_lit * (530.0 / nsub) ** 2,
+                'rates': [cm.accuracy, cm.precision, cm.tp_rate, cm.tn_rate],
+                'max_abs_diff_vs_vectorised_oracle': float(np.max(np.abs(np.array([cm.accuracy, cm.precision, cm.tp_rate, cm.tn_rate]) -
+                                                                   np.array([ref.accuracy, ref.precision, ref.tp_rate, ref.tn_rate])))),
+                'max_abs_diff_vs_literal_loop_%d_classes' % nsub: float(np.max(np.abs(
+                    np.array([sub.accuracy, sub.precision, sub.tp_rate, sub.tn_rate]) - np.array([lit.accuracy, lit.precision, lit.tp_rate, lit.tn_rate])))),
+                'eps_window_pairs': int(cm.stats['eps_window'])}
+        print(json.dumps(line))
+
+
+def run_f2(steps):
+    """One optimiser step's loss + gradients of the pair classifier on an 1800-row P x K batch (45 x 40, 512-d)."""
+    import torch
+    from facenet_b200 import faceclass
+    from facenet_b200.apps import train_classifier as tc
+    from oracle import faceclass_oracle as fo
+    from oracle import statistics_oracle as so
+
+    class Opt:
+        nrof_classes_per_batch, nrof_examples_per_class = 45, 40
+    x, _ = so.synthetic_embeddings([40] * 45, dim=512, sigma=1.1, seed=9, shuffle=False)
+    xu = (x * np.random.default_rng(3).uniform(0.6, 1.7, size=(x.shape[0], 1))).astype(np.float32)
+    for tag, data, model in (('normalized', x, faceclass.FaceToFaceNormalizedEmbeddingsClassifier()),
+                             ('distance', xu, faceclass.FaceToFaceDistanceClassifier())):
+        out = tc.pair_cross_entropy(model, data, Opt)
+        for _ in range(5):
+            tc.pair_cross_entropy(model, data, Opt)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tc.pair_cross_entropy(model, data, Opt)
+        host_s = (time.perf_counter() - t0) / steps
+        dev = torch.from_numpy(data).cuda()
+        torch.cuda.synchronize()
+        for _ in range(5):
+            tc.pair_cross_entropy(model, dev, Opt)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tc.pair_cross_entropy(model, dev, Opt)
+        dev_s = (time.perf_counter() - t0) / steps
+        t0 = time.perf_counter()
+        if tag == 'normalized':
+            dist = fo.distance_normalized(data)
+        else:
+            dist = fo.distance_unnormalized(data, None, 1.0)
+        ref32 = float(fo.binary_cross_entropy_loss(fo.logits(dist, 10, 1), 45, 40))
+        cpu_s = time.perf_counter() - t0
+        ref = fo.binary_cross_entropy_loss_and_grads(dist, 10.0, 1.0, 45, 40)
+        line = {'config': 'f2: pair-classifier weighted cross entropy + gradients, %s classifier, 1800-row batch (45 x 40), 512-d' % tag,
+                'steps': steps, 'ms_per_step_host_batch': host_s * 1e3, 'ms_per_step_device_batch': dev_s * 1e3,
+                'kernel_ms': out['stats']['kernel_ms'], 'cpu_oracle_ms_per_step_loss_only': cpu_s * 1e3,
+                'loss': out['loss'], 'loss_oracle_f32': ref32, 'loss_oracle_f64': ref['loss'],
+                'rel_diff_vs_f64': abs(out['loss'] - ref['loss']) / max(1.0, abs(ref['loss'])),
+                'dalpha': [out['grads']['alpha'], ref['dalpha']], 'dthreshold': [out['grads']['threshold'], ref['dthreshold']]}
+        print(json.dumps(line))
+
+
 if __name__ == '__main__':
     args = [a for a in sys.argv[1:] if not a.startswith('--')]
     steps = 200
@@ -114,3 +214,7 @@ if __name__ == '__main__':
         run_c1(mode)
     if not args or 'c3' in args:
         run_c3(mode, steps)
+    if 'f1' in args:
+        run_f1()
+    if 'f2' in args:
+        run_f2(steps)

@@ -112,6 +112,32 @@ def test_pairwise_torch_cuda_zero_copy(handle):
     assert np.abs(out.cpu().numpy() - ref).max() <= DIST_TOL
 
 
+@pytest.mark.parametrize('side_stream', [False, True])
+def test_device_tensors_are_stream_ordered(handle, side_stream):
+    """Inputs and outputs that live on the GPU are produced / cleared by kernels queued on torch's CURRENT stream (stream 0
+    unless another one is selected).  The library must run after them without a host synchronisation: a long-running
+    producer is queued right before the call, and the output tensor is zero-filled on the same stream."""
+    import torch
+    x, labels = ragged(5, n_classes=40, d=128)
+    thr = so.default_thresholds(0)
+    ref = handle.pair_histogram_bins(x, labels, thr, 0)[0]
+    stream = torch.cuda.Stream() if side_stream else torch.cuda.current_stream()
+    big = torch.randn((6144, 6144), device='cuda')
+    xt0 = torch.from_numpy(x).cuda()
+    lt = torch.from_numpy(labels).cuda()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        junk = big
+        for _ in range(30):                       # tens of milliseconds of queued work ahead of the producer
+            junk = (junk @ big) * 1e-3
+        xt = xt0 + 0.0 * junk[:xt0.shape[0], :xt0.shape[1]]           # the embeddings depend on the queued work
+        bins = torch.zeros((2, thr.size + 1), dtype=torch.int64, device='cuda')
+        handle.pair_histogram_bins(xt, lt, thr, 0, bins_out=bins)
+        got = bins.cpu().numpy().astype(np.uint64)
+    np.testing.assert_array_equal(got, ref)
+    handle.set_stream(None)
+
+
 # ------------------------------------------------------------------------------ whole-set histogram
 
 def ragged(seed, n_classes=60, d=128, max_size=40, sigma=1.0, values=None):
