@@ -228,12 +228,13 @@ def main():
     fst.set_default_mode(mode=args.mode, device=local_rank, cta_group=args.cta_group)
     stream = torch.cuda.current_stream()
     handle.set_stream(stream.cuda_stream)
-    kernel_ms, launches, modes_used, grids = [], [0], set(), set()
+    kernel_ms, prepare_ms, launches, modes_used, grids = [], [], [0], set(), set()
 
     def hist_fn(emb, labels, thresholds_, metric, rank_, world_, bins_out, **kw):
         _, st = handle.pair_histogram_bins(emb, labels, thresholds_, metric, rank=rank_, world=world_, bins_out=bins_out,
                                            mode=args.mode, cta_group=args.cta_group)
         kernel_ms.append(st['kernel_ms'])
+        prepare_ms.append(st['prepare_ms'])
         launches[0] += st['kernel_launches']
         modes_used.add(_capi.MODE_NAMES[st['mode_used']])
         grids.add(st['grid_ctas'])
@@ -266,9 +267,15 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         step_device()
-    kernel_ms.clear(); launches[0] = 0
+    kernel_ms.clear(); prepare_ms.clear(); launches[0] = 0
     total_ms, bins, t0, t1 = timed(step_device, args.steps)
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float('nan')
+    p_ms = float(np.mean(prepare_ms)) if prepare_ms else float('nan')
+    # where the rest of the step goes (not part of `value`): the all-gather alone, timed the same way
+    gather_ms = 0.0
+    if world > 1:
+        g_total, _, _, _ = timed(lambda: fd.gather_shards(x_shard, labels_shard), args.steps)
+        gather_ms = g_total / args.steps
     timed_launches = launches[0]
     value = pairs * args.steps / (total_ms * 1e-3) / 1e9
     mode_used = sorted(modes_used)[0] if len(modes_used) == 1 else args.mode      # what 'auto' resolved to
@@ -386,6 +393,8 @@ def main():
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
                        'pairs_per_step': pairs,
                        'grid_ctas': sorted(grids), 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},
+            'breakdown_ms': {'all_gather': gather_ms, 'sort_split': p_ms, 'gram_kernel': k_ms,
+                             'rest (all-reduce, D2H of the bins, host)': total_ms / args.steps - gather_ms - p_ms - k_ms},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': timed_launches, 'roofline': roofline, 'cpu_baseline': cpu,
             'parity': parity,
             'pct_tf32_peak': 100.0 * value * 1e9 * FLOP_PER_PAIR / 1e12 / (tf32_peak * world)}

@@ -192,7 +192,23 @@ class FnbError(RuntimeError):
         self.code = code
 
 
+_cuts_cache = {}
+
+
 def numpy_cuts(thresholds, metric):
+    """Cached front of ``_numpy_cuts`` (the bisection costs ~1 ms; every step of a validation loop asks for the same grid)."""
+    thr = np.ascontiguousarray(np.atleast_1d(np.asarray(thresholds, dtype=np.float64)))
+    key = (int(metric), thr.tobytes())
+    hit = _cuts_cache.get(key)
+    if hit is None:
+        if len(_cuts_cache) > 64:
+            _cuts_cache.clear()
+        hit = _cuts_cache[key] = _numpy_cuts(thr, metric)
+        hit.setflags(write=False)
+    return hit
+
+
+def _numpy_cuts(thresholds, metric):
     """Per threshold, the smallest float32 similarity s in [-1, 1] with
     ``dist(s) < threshold`` (float64 compare of the float32 distance, statistics.py:131), +inf if
     none -- evaluated with NumPy's own float32 arithmetic (``2 * (1 - s)`` / ``np.arccos``), so the

@@ -1,0 +1,7 @@
+#!/bin/bash
+N=${1:-8}
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 400 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_1m_n$N.json 2> gpurun_out/bench_1m_n$N.err; echo "bench exit=$?"
+tail -c 2500 gpurun_out/bench_1m_n$N.json; tail -3 gpurun_out/bench_1m_n$N.err | cut -c1-300

@@ -4,10 +4,18 @@ where no GPU exists.  It follows the C ABI contract of include/facenet_b200.h li
 import numpy as np
 
 
-def region_histogram_bins(embeddings, perm, cls, regions, nkeys, thresholds, metric=0, cuts=None, **_):
+def region_histogram_bins(embeddings, perm, cls, regions, nkeys, thresholds, metric=0, cuts=None, raw_distance=False,
+                          normalize=0, theta=0.0, **_):
     x = np.ascontiguousarray(embeddings, dtype=np.float32)[np.asarray(perm)]
+    nrm = None
+    if normalize == 1:                                   # fnb_options.normalize = 1 (+ theta): faceclass.py:57-71
+        nrm = np.linalg.norm(x, axis=1, keepdims=True)
+        x = x / nrm
     cls = np.asarray(cls)
     assert np.all(np.diff(cls) >= 0), 'cls must be non-decreasing'
+    if cuts is None or isinstance(cuts, str):            # the library's default: NumPy-exact cuts
+        from facenet_b200 import _capi
+        cuts = _capi.numpy_cuts(thresholds, metric)
     order = np.sort(np.asarray(cuts, dtype=np.float32))
     nt = order.size
     bins = np.zeros((nkeys, 2, nt + 1), dtype=np.uint64)
@@ -15,7 +23,12 @@ def region_histogram_bins(embeddings, perm, cls, regions, nkeys, thresholds, met
         r0, r1, c0, c1 = int(r['row_begin']), int(r['row_end']), int(r['col_begin']), int(r['col_end'])
         if r1 <= r0 or c1 <= c0:
             continue
-        s = np.clip(x[r0:r1] @ x[c0:c1].T, -1, 1)
+        s = x[r0:r1] @ x[c0:c1].T
+        if nrm is not None and theta != 0.0:
+            g = 2 * (nrm[r0:r1] - nrm[c0:c1].T) / (nrm[r0:r1] + nrm[c0:c1].T)
+            s = np.float32(1) - np.float32(0.5) * (2 * (1 - s) + np.float32(theta) * g * g)
+        elif not raw_distance:
+            s = np.clip(s, -1, 1)
         k = np.searchsorted(order, s.ravel(), side='right').reshape(s.shape)
         valid = np.ones(s.shape, dtype=bool)
         if r['tri']:
@@ -24,6 +37,8 @@ def region_histogram_bins(embeddings, perm, cls, regions, nkeys, thresholds, met
         same = (cls[r0:r1, None] == cls[None, c0:c1]) & valid
         bins[r['key'], 0] += np.bincount(k[valid], minlength=nt + 1).astype(np.uint64)
         bins[r['key'], 1] += np.bincount(k[same], minlength=nt + 1).astype(np.uint64)
+        if r['tri'] == 2:                                # diagonal elements -> slot key + 1 (include/facenet_b200.h)
+            bins[r['key'] + 1, 0] += np.bincount(np.diagonal(k), minlength=nt + 1).astype(np.uint64)
     return bins, {'emulated': True}
 
 

@@ -202,3 +202,22 @@ def test_split_embeddings_matches_reference_semantics():
     assert len(got) == len(ref)
     for a, b in zip(got, ref):
         np.testing.assert_array_equal(a, b)
+
+
+def test_confusion_matrix_host_math_golden(emulated, golden_dir):
+    """ConfusionMatrix plan (size-group rectangles, diagonal slots, block-mean weights) with the library's keyed histogram
+    replaced by the NumPy stand-in: must reproduce the unmodified reference's rates (tests/golden/faceclass.npz)."""
+    from facenet_b200 import faceclass
+    from facenet_b200.apps import train_classifier as tc
+    g = np.load(golden_dir / 'faceclass.npz')
+    sizes = g['sizes']
+    b = np.concatenate([[0], np.cumsum(sizes)])
+    for tag, x, model in (('norm', g['x'], faceclass.FaceToFaceNormalizedEmbeddingsClassifier()),
+                          ('dist', g['xu'], faceclass.FaceToFaceDistanceClassifier())):
+        if tag == 'dist':
+            model.variables['theta'] = g['theta']
+        emb = [x[a:c] for a, c in zip(b[:-1], b[1:])]
+        for t, ref in zip(g['thresholds'], g['confusion_' + tag]):
+            model.variables['threshold'] = np.float32(t)
+            cm = tc.ConfusionMatrix(emb, model)
+            np.testing.assert_allclose([cm.accuracy, cm.precision, cm.tp_rate, cm.tn_rate], ref, rtol=0, atol=1e-12)
