@@ -271,6 +271,13 @@ def main():
     total_ms, bins, t0, t1 = timed(step_device, args.steps)
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float('nan')
     p_ms = float(np.mean(prepare_ms)) if prepare_ms else float('nan')
+    # per-rank Gram-kernel time: the all-reduce makes every step wait for the slowest rank
+    k_ranks = [k_ms]
+    if world > 1:
+        kt = torch.tensor([k_ms], device=dev, dtype=torch.float64)
+        allk = [torch.zeros_like(kt) for _ in range(world)]
+        dist.all_gather(allk, kt)
+        k_ranks = [float(t.item()) for t in allk]
     # where the rest of the step goes (not part of `value`): the all-gather alone, timed the same way
     gather_ms = 0.0
     if world > 1:
@@ -393,7 +400,7 @@ def main():
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
                        'pairs_per_step': pairs,
                        'grid_ctas': sorted(grids), 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},
-            'breakdown_ms': {'all_gather': gather_ms, 'sort_split': p_ms, 'gram_kernel': k_ms,
+            'breakdown_ms': {'all_gather': gather_ms, 'sort_split': p_ms, 'gram_kernel': k_ms, 'gram_kernel_per_rank': k_ranks,
                              'rest (all-reduce, D2H of the bins, host)': total_ms / args.steps - gather_ms - p_ms - k_ms},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': timed_launches, 'roofline': roofline, 'cpu_baseline': cpu,
             'parity': parity,

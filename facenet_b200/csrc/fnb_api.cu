@@ -171,9 +171,11 @@ static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 // tile grid of every region: `tile` rows x (`tile` * pairs) columns per scheduler step (see TileScheduler)
 void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs) {
     long long t = 0;
-    const int super_cols = tile * pairs;
+    // pair grid of a cluster: 1 x 1, 1 x 2 (pairs == 2) or 2 x 2 (pairs == 4) tiles per scheduler step
+    const int super_rows = tile * (pairs == 4 ? 2 : 1);
+    const int super_cols = tile * (pairs == 1 ? 1 : 2);
     for (auto& r : regs) {
-        r.nrb = (r.row_end - r.row_begin + tile - 1) / tile;
+        r.nrb = (r.row_end - r.row_begin + super_rows - 1) / super_rows;
         r.ncb = (r.col_end - r.col_begin + super_cols - 1) / super_cols;
         r.tile_begin = t;
         t += (long long)r.nrb * r.ncb;
@@ -208,7 +210,7 @@ static int pick_cta_group(const fnb_options* o) { return (o->cta_group == 1 || o
 // are L2->SM bandwidth bound, and are faster on all 148 SMs.
 static int pick_pairs(const fnb_options* o, int cta_group, long long n = 0) {
     if (cta_group != 2) return 1;
-    if (o->cluster_pairs == 1 || o->cluster_pairs == 2) return o->cluster_pairs;
+    if (o->cluster_pairs == 1 || o->cluster_pairs == 2 || o->cluster_pairs == 4) return o->cluster_pairs;
     const double local_pairs = 0.5 * (double)n * (double)(n - 1) / (double)std::max(1, o->world);
     return local_pairs >= 5.0e10 ? 2 : 1;
 }
@@ -377,7 +379,8 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     (side_b ? op.b_nrm : op.a_nrm) = nrm_out;
     CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream,
                          normalize, nrm_out));
-    const int box_rows = side_b ? kRowsPerCta : kRowsPerCta / op.pairs;
+    // an operand that two pairs of a cluster share is fetched as two 64-row halves (A: pairs 2 and 4, B: pairs 4)
+    const int box_rows = (side_b ? op.pairs == 4 : op.pairs > 1) ? kRowsPerCta / 2 : kRowsPerCta;
     if (!side_b) op.a_rows_pad = n_pad;
     int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d, box_rows);
     if (rc) return rc;
@@ -390,8 +393,8 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
 
 int fnb::self_b_maps(fnb_context* h, GramOperands& op, int d) {
     op.b_nrm = op.a_nrm;
-    if (op.pairs == 1) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; return FNB_OK; }
-    // the A maps carry half-height boxes: encode full-height ones over the same arrays for the B side
+    if (op.pairs == 1 || op.pairs == 4) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; return FNB_OK; }
+    // pairs == 2: the A maps carry half-height boxes, the B side is not shared: encode full-height boxes over the same arrays
     const bool f8 = (op.num_pass == 2);
     int rc = make_tmap(h, &op.b_hi, h->a_hi.p, op.fmt, op.a_rows_pad, d);
     if (rc) return rc;
@@ -553,9 +556,6 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.raw = opt.raw_distance;
     if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
     p.debug = opt.debug & 3;
-    p.l2_prefetch = (opt.debug >> 2) & 3;            // experiment knob until a default is measured
-    p.l2_hints = (opt.debug >> 4) & 1;
-    p.serpentine = (opt.debug >> 5) & 1;
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
@@ -715,7 +715,7 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     h->last_mode = op.mode; h->last_peak = op.peakedness;
 
     std::vector<RegionDev> regs;
-    triangle_regions(n, pick_region_rows(&opt, tile * op.pairs, n, d), 0, regs);
+    triangle_regions(n, pick_region_rows(&opt, tile * (op.pairs == 1 ? 1 : 2), n, d), 0, regs);
     finish_regions(regs, tile, op.pairs);
 
     HistLaunch hl;

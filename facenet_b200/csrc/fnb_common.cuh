@@ -140,13 +140,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, uint64_
         : "memory");
 }
 
-// pull one box into L2 only (no shared-memory destination, no barrier): hides the HBM latency of a tile the producer
-// will need one tile-time from now
-__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-                 :: "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
-}
-
 // CTA-pair form: data lands in the executing CTA, bytes are signalled on the barrier at
 // cluster address `bar_cluster_addr` (the leader CTA's copy)
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -166,34 +159,6 @@ __device__ __forceinline__ void tma_load_2d_pair_mc(void* dst, const void* tmap,
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
         " [%0], [%1, {%4, %5}], [%2], %3;"
         :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1)
-        : "memory");
-}
-
-// L2 eviction-priority policies for the operand stream: the row panels of a super-row are re-read for every column panel
-// (evict_last), a column panel is used by the CTAs working at that moment and then not again in this super-row (evict_first)
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(pol)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair_mc_hint(void* dst, const void* tmap, uint32_t bar_cluster_addr, uint16_t cta_mask,
-                                                         int c0, int c1, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
-        " [%0], [%1, {%4, %5}], [%2], %3, %6;"
-        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1), "l"(pol)
         : "memory");
 }
 

@@ -83,9 +83,13 @@ int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const Gram
     const size_t smem = gram_smem_bytes(p.num_slots, hist_bytes);
     if (smem > kSmemLimit) return h->fail(FNB_ERR_UNSUPPORTED, "shared memory budget exceeded (%zu bytes)", smem);
     if (op.num_pass == 2 && (p.kblocks & 1)) return h->fail(FNB_ERR_UNSUPPORTED, "fp16f8 mode needs an embedding dimension that is a multiple of 128");
-    if (op.pairs == 2) {
+    if (op.pairs == 2 || op.pairs == 4) {
         if (cta_group != 2 || epi != EPI_HIST) return h->fail(FNB_ERR_INVALID, "cluster pairs need cta_group 2 and the histogram epilogue");
-        return launch_mode_pairs2(h, max_ctas, op, p, smem);
+        if (op.pairs == 2) return launch_mode_pairs2(h, max_ctas, op, p, smem);
+        // 2 x 2 pair grids (8-CTA clusters): the two modes the headline workloads run in
+        if (op.num_pass == 2 && !op.tf32) return launch_one<2, 2, false, EPI_HIST, 4>(h, max_ctas, op, p, smem);
+        if (op.num_pass == 3 && !op.tf32) return launch_one<2, 3, false, EPI_HIST, 4>(h, max_ctas, op, p, smem);
+        return h->fail(FNB_ERR_UNSUPPORTED, "cluster_pairs = 4 is built for the fp16f8 and fp16x3 modes");
     }
     if (epi == EPI_BCE) {
         // one batch of a few thousand rows: the strict fp32-equivalent split only (the loss feeds an optimiser)

@@ -54,9 +54,6 @@ struct GramParams {
     int operand_fmt;           // kFmtF16 / kFmtBF16 / kFmtTF32 (must agree with the kTf32 template flag)
     int force_slow;            // take the fully-checked epilogue path for every tile
     int debug;                 // profiling knob (fnb_options.debug): bit 0 no epilogue work, bit 1 no operand loads
-    int l2_prefetch;           // producer prefetches its next tile's operand boxes into L2: 1 = B panel, 3 = A and B
-    int l2_hints;              // row panels evict_last, column panels evict_first (CTA-pair kernels)
-    int serpentine;            // tile order: odd column panels walk the row panels backwards
     const unsigned int* norm_max_ord;   // ordered-uint max squared row norm (written by the split kernel), may be NULL
     unsigned int norm_limit_ord;        // above this the interior tiles cannot be proven in range -> checked path
     // HIST epilogue
@@ -111,20 +108,24 @@ struct TileInfo {
     int row0, col0, row_end, col_end, tri, key;
 };
 
-// One scheduler step hands a cluster a SUPER-TILE of kTile rows x (kPairs * kTile) columns; CTA pair `pi` of the
-// cluster owns the columns [col0 + pi * kTile, + kTile).  kPairs == 1: the super-tile is the tile.
+// One scheduler step hands a cluster a SUPER-TILE of (kPR * kTile) rows x (kPC * kTile) columns; the CTA pair at
+// (pair_row, pair_col) of the cluster's kPR x kPC pair grid owns the tile at [row0 + pair_row * kTile, col0 + pair_col *
+// kTile).  kPairs == 1: the super-tile is the tile; 2: 1 x 2 pairs (A shared); 4: 2 x 2 pairs (A and B shared).
+template <int kPairs> struct Sched_PR { static constexpr int value = (kPairs == 4) ? 2 : 1; };
+template <int kPairs> struct Sched_PC { static constexpr int value = (kPairs == 1) ? 1 : 2; };
+
 template <int kCtaGroup, int kPairs = 1>
 struct TileScheduler {
     static constexpr int kTile = kRowsPerCta * kCtaGroup;
-    static constexpr int kSuperCols = kTile * kPairs;
+    static constexpr int kSuperRows = kTile * Sched_PR<kPairs>::value;
+    static constexpr int kSuperCols = kTile * Sched_PC<kPairs>::value;
     const RegionDev* regions;
     long long pos, stride, total;
     int cur;
-    int serpentine;
 
     __device__ TileScheduler(const GramParams& p, int cluster_id, int num_clusters)
         : regions(p.regions), pos((long long)cluster_id * p.world + p.rank),
-          stride((long long)num_clusters * p.world), total(p.total_tiles), cur(0), serpentine(p.serpentine) {}
+          stride((long long)num_clusters * p.world), total(p.total_tiles), cur(0) {}
 
     __device__ bool next(TileInfo& t) {
         while (pos < total) {
@@ -132,12 +133,9 @@ struct TileScheduler {
             const RegionDev r = regions[cur];
             const int li = (int)(pos - r.tile_begin);
             const int cb = li / r.nrb;
-            int rb = li - cb * r.nrb;
-            // odd column panels walk the row panels backwards: the row panels used last are re-used first, so an L2 that
-            // holds only part of the super-row's row panels still hits on that part (a cyclic walk would evict them all)
-            if (serpentine && (cb & 1)) rb = r.nrb - 1 - rb;
+            const int rb = li - cb * r.nrb;
             pos += stride;
-            t.row0 = r.row_begin + rb * kTile;
+            t.row0 = r.row_begin + rb * kSuperRows;
             t.col0 = r.col_begin + cb * kSuperCols;
             t.row_end = r.row_end;
             t.col_end = r.col_end;
@@ -215,6 +213,9 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
 // ---------------------------------------------------------------------------------------
 // the kernel
 
+// kPairs == 4 (cta_group 2, HIST only): a cluster of 2 x 2 CTA pairs works on one 512 x 512 super-tile; every A box is shared
+// by the two pairs of a pair-grid row and every B box by the two pairs of a pair-grid column, so each is read from L2 once
+// and multicast (L2 -> SM reads drop to 1/2).  All four pairs run in lockstep.
 // kPairs == 2 (cta_group 2, HIST only): a cluster of two CTA pairs works on one 256 x 512 super-tile; the pairs share
 // the A rows, so every A box is read from L2 ONCE and multicast to the matching CTA of both pairs (each of the two
 // CTAs issues one 64-row half of it).  L2 -> SM operand traffic drops to 3/4; the two pairs run in lockstep
@@ -226,7 +227,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             const __grid_constant__ CUtensorMap tm_a_h8, const __grid_constant__ CUtensorMap tm_b_h8,
             const GramParams p)
 {
-    static_assert(kPairs == 1 || (kPairs == 2 && kCtaGroup == 2 && kEpi == EPI_HIST), "multicast clusters: CTA pairs, HIST only");
+    static_assert(kPairs == 1 || ((kPairs == 2 || kPairs == 4) && kCtaGroup == 2 && kEpi == EPI_HIST), "multicast clusters: CTA pairs, HIST only");
+    constexpr int kPR = Sched_PR<kPairs>::value;           // pair grid of the cluster: kPR x kPC pairs (1x1, 1x2, 2x2)
+    constexpr int kPC = Sched_PC<kPairs>::value;
     constexpr int kTile   = kRowsPerCta * kCtaGroup;       // tile rows == tile cols
     constexpr int kUmmaN  = kTile;                         // accumulator columns per stage
     constexpr int kClusterCtas = kCtaGroup * kPairs;
@@ -252,6 +255,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const uint32_t cluster_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
     const uint32_t cta_rank = cluster_rank & 1u;           // position inside the CTA pair: 0 = leader (issues the MMAs)
     const uint32_t pair_idx = cluster_rank >> 1;           // which pair of the cluster (0 when kPairs == 1)
+    const uint32_t pair_row = pair_idx / kPC, pair_col = pair_idx % kPC;
     const uint32_t leader_rank = cluster_rank & ~1u;       // cluster rank of this pair's leader
     const bool is_leader = (cta_rank == 0);
     const int cluster_id = blockIdx.x / kClusterCtas;
@@ -298,37 +302,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         TileInfo t;
         int slot = 0; uint32_t phase = 0;
         int ntile = -1;
-        const uint64_t pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
         while (sched.next(t)) {
             ++ntile;
-            const int arow = t.row0 + (int)cta_rank * kRowsPerCta;
-            const int brow = t.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
-            if (p.l2_prefetch) {
-                // pull the operand boxes of this CTA's NEXT tile into L2 now (one tile-time of lead): the first CTA to
-                // touch a B panel then pays the HBM latency here, off the critical path, instead of in its ring
-                Sched ahead = sched;
-                TileInfo tn;
-                if (ahead.next(tn) && elect_one()) {
-                    const int na = tn.row0 + (int)cta_rank * kRowsPerCta;
-                    const int nb = tn.col0 + (int)pair_idx * kTile + (int)cta_rank * kRowsPerCta;
-                    const bool pa = (p.l2_prefetch & 2) && na != arow, pb = nb != brow;
-                    for (int kb = 0; kb < p.kblocks; ++kb) {
-                        if (pb) tma_prefetch_l2_2d(&tm_b_hi, kb * kElemsPerBox, nb);
-                        if (pa) tma_prefetch_l2_2d(&tm_a_hi, kb * kElemsPerBox, na);
-                        if (kNumPass == 3) {
-                            if (pb) tma_prefetch_l2_2d(&tm_b_lo, kb * kElemsPerBox, nb);
-                            if (pa) tma_prefetch_l2_2d(&tm_a_lo, kb * kElemsPerBox, na);
-                        }
-                    }
-                    if (kF8) {
-                        for (int ks = 0; ks < p.kblocks / 2; ++ks) {
-                            if (pb) { tma_prefetch_l2_2d(&tm_b_lo, ks * 128, nb); tma_prefetch_l2_2d(&tm_b_h8, ks * 128, nb); }
-                            if (pa) { tma_prefetch_l2_2d(&tm_a_lo, ks * 128, na); tma_prefetch_l2_2d(&tm_a_h8, ks * 128, na); }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            const int arow = t.row0 + (int)pair_row * kTile + (int)cta_rank * kRowsPerCta;
+            const int brow = t.col0 + (int)pair_col * kTile + (int)cta_rank * kRowsPerCta;
             auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
                 mbar_wait_relaxed(&misc->empty[slot], phase ^ 1u);
                 if (elect_one()) {
@@ -343,24 +320,22 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     } else {
                         if (is_leader) mbar_arrive_expect_tx(&misc->full[slot], 2 * kSlotBytes);
                         const uint32_t bar = mapa_u32(smem_u32(&misc->full[slot]), leader_rank);
-                        if (p.l2_hints) {
-                            if constexpr (kPairs == 1) {
-                                tma_load_2d_pair_hint(dst, ma, bar, kcol, arow, pol_a);
-                            } else {
-                                const uint16_t mc = (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank)));
-                                tma_load_2d_pair_mc_hint(dst + pair_idx * (kBoxBytes / 2), ma, bar, mc, kcol, arow + (int)pair_idx * (kRowsPerCta / 2), pol_a);
-                            }
-                            tma_load_2d_pair_hint(dst + kBoxBytes, mb, bar, kcol, brow, pol_b);
-                        } else {
-                        if constexpr (kPairs == 1) {
+                        // An operand box that two pairs of the cluster need is read from L2 once: the maps carry 64-row
+                        // boxes, each of the two CTAs that want the box (same position in their pair) fetches one half and
+                        // multicasts it to both; the other half arrives from the partner.
+                        if constexpr (kPC == 1) {
                             tma_load_2d_pair(dst, ma, bar, kcol, arow);
                         } else {
-                            // `ma` has 64-row boxes: this CTA fetches half `pair_idx` of the A box and multicasts it to the
-                            // CTA with the same pair position in both pairs; the other half arrives from that CTA
-                            const uint16_t mc = (uint16_t)((1u << cta_rank) | (1u << (2 + cta_rank)));
-                            tma_load_2d_pair_mc(dst + pair_idx * (kBoxBytes / 2), ma, bar, mc, kcol, arow + (int)pair_idx * (kRowsPerCta / 2));
+                            // A rows are shared along the pair-grid row: partners (pair_row, 0) and (pair_row, 1)
+                            const uint16_t mc = (uint16_t)((1u << ((pair_row * kPC + 0) * 2 + cta_rank)) | (1u << ((pair_row * kPC + 1) * 2 + cta_rank)));
+                            tma_load_2d_pair_mc(dst + pair_col * (kBoxBytes / 2), ma, bar, mc, kcol, arow + (int)pair_col * (kRowsPerCta / 2));
                         }
-                        tma_load_2d_pair(dst + kBoxBytes, mb, bar, kcol, brow);
+                        if constexpr (kPR == 1) {
+                            tma_load_2d_pair(dst + kBoxBytes, mb, bar, kcol, brow);
+                        } else {
+                            // B rows (tile columns) are shared along the pair-grid column: partners (0, pair_col) and (1, pair_col)
+                            const uint16_t mc = (uint16_t)((1u << ((0 * kPC + pair_col) * 2 + cta_rank)) | (1u << ((1 * kPC + pair_col) * 2 + cta_rank)));
+                            tma_load_2d_pair_mc(dst + kBoxBytes + pair_row * (kBoxBytes / 2), mb, bar, mc, kcol, brow + (int)pair_row * (kRowsPerCta / 2));
                         }
                     }
                 }
@@ -533,9 +508,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
         while (sched.next(t)) {
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-            if constexpr (kPairs > 1) t.col0 += (int)pair_idx * kTile;        // this pair's tile of the super-tile
+            if constexpr (kPairs > 1) { t.row0 += (int)pair_row * kTile; t.col0 += (int)pair_col * kTile; }   // this pair's tile of the super-tile
             // a pair whose tile lies outside the region / below the diagonal still runs the pipeline (lockstep) and drops the result
-            const bool null_tile = (kPairs > 1) && (t.col0 >= t.col_end || (t.tri && t.col0 + kTile - 1 <= t.row0));
+            const bool null_tile = (kPairs > 1) && (t.col0 >= t.col_end || t.row0 >= t.row_end || (t.tri && t.col0 + kTile - 1 <= t.row0));
             const int row = t.row0 + row_in_tile;
             const int colw = t.col0 + colq * kColsPerWarp;       // first column of this warp
             const uint32_t taddr0 = tmem_lane + acc * kUmmaN + colq * kColsPerWarp;

@@ -88,12 +88,13 @@ typedef struct {
     int32_t max_ctas;      /* 0 = all SMs (debug / profiling knob) */
     int32_t force_checked; /* != 0: every tile takes the fully checked epilogue path (exact cut comparison, exact
                               eps window, per-pair range check) -- the reference the arithmetic path is tested against */
-    int32_t debug;         /* profiling knob, results are MEANINGLESS when bits 0-1 are set: bit 0 skips the epilogue work,
-                              bit 1 loads operands for the first tile only (later MMAs re-use that shared memory);
-                              bits 2-3: the producer prefetches its next tile's B (4) / A and B (12) boxes into L2 */
+    int32_t debug;         /* profiling knob, results are MEANINGLESS when != 0: bit 0 skips the epilogue work,
+                              bit 1 loads operands for the first tile only (later MMAs re-use that shared memory) */
     int32_t cluster_pairs; /* histogram launches, cta_group 2 only: 2 = clusters of two CTA pairs that share (multicast) the
-                              A operand, so it is read from L2 once per 256 x 512 super-tile; 1 = one pair per cluster;
-                              0 = auto (2 for launches long enough to be power-limited, >= 5e10 pairs per rank) */
+                              A operand, so it is read from L2 once per 256 x 512 super-tile; 4 = clusters of 2 x 2 pairs on
+                              a 512 x 512 super-tile, A and B each read once per two tiles (fp16f8 / fp16x3 modes);
+                              1 = one pair per cluster; 0 = auto (for launches long enough to be power-limited,
+                              >= 5e10 pairs per rank) */
     int32_t normalize;     /* rows are normalised while the operands are prepared (the raw norms are kept for `theta`):
                               1: x / |x|                      (facenet/faceclass.py:63-64, np.linalg.norm)
                               2: x * rsqrt(max(sum x^2, 1e-10))  (tf.nn.l2_normalize(axis=1, epsilon=1e-10),

@@ -277,6 +277,20 @@ def test_histogram_cluster_pairs_identical_bins(handle):
             part, _ = handle.pair_histogram_bins(x, labels, thr, 0, mode='tf32x3', rank=rank, world=3, cluster_pairs=2)
             acc += part
         np.testing.assert_array_equal(acc, one)
+        # 2 x 2 pair grids (8-CTA clusters, A and B multicast, 512 x 512 super-tiles)
+        for mode in ('fp16x3', 'fp16f8'):
+            one, st1 = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode)
+            four, st4 = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode, cluster_pairs=4)
+            np.testing.assert_array_equal(one, four)
+            assert st4['eps_window'] == st1['eps_window'] and st4['grid_ctas'] % 8 == 0
+            for rr in (512, 1536):
+                four, _ = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode, cluster_pairs=4, region_rows=rr)
+                np.testing.assert_array_equal(one, four)
+            acc = np.zeros_like(one)
+            for rank in range(3):
+                part, _ = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode, rank=rank, world=3, cluster_pairs=4)
+                acc += part
+            np.testing.assert_array_equal(acc, one)
 
 
 def test_histogram_fp16f8_mode(handle):
