@@ -58,6 +58,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--equal-shares', action='store_true', help='N > 1: fixed equal shares instead of the speed-adaptive split')
     ap.add_argument('--parity-rows', type=int, default=8192)
     return ap.parse_args()
 
@@ -232,7 +233,7 @@ def main():
 
     def hist_fn(emb, labels, thresholds_, metric, rank_, world_, bins_out, **kw):
         _, st = handle.pair_histogram_bins(emb, labels, thresholds_, metric, rank=rank_, world=world_, bins_out=bins_out,
-                                           mode=args.mode, cta_group=args.cta_group)
+                                           mode=args.mode, cta_group=args.cta_group, shard=kw.get('shard'))
         kernel_ms.append(st['kernel_ms'])
         prepare_ms.append(st['prepare_ms'])
         launches[0] += st['kernel_launches']
@@ -240,8 +241,11 @@ def main():
         grids.add(st['grid_ctas'])
         return st
 
+    # shares of the pair matrix follow the measured speed of each GPU (adapts during the warm-up steps and keeps adapting)
+    balancer = fd.default_balancer(world) if (world > 1 and not args.equal_shares) else None
+
     def step_device():
-        bins, st = fd.pair_histogram_sharded(x_shard, labels_shard, thr, 0, hist_fn=hist_fn)
+        bins, st = fd.pair_histogram_sharded(x_shard, labels_shard, thr, 0, hist_fn=hist_fn, balancer=balancer)
         return bins.cpu() if rank == 0 else bins      # final histogram on the host (rank 0)
 
     def barrier():
@@ -343,7 +347,7 @@ def main():
 
             def step_e2e():
                 xd.copy_(x_host, non_blocking=True); ld.copy_(l_host, non_blocking=True)
-                b, _ = fd.pair_histogram_sharded(xd, ld, thr, 0, hist_fn=hist_fn)
+                b, _ = fd.pair_histogram_sharded(xd, ld, thr, 0, hist_fn=hist_fn, balancer=balancer)
                 return b.cpu()
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
@@ -396,7 +400,9 @@ def main():
                       'tf32': 'tf32', 'bf16': 'bf16', 'fp16': 'f16',
                       'fp16f8': 'f16 hi*hi + e4m3 cross terms, f32 accumulate'}[mode_used],
             'data': 'synthetic',
-            'config': {'workload': wl['name'], 'mode': args.mode, 'mode_used': mode_used, 'parallelism': 'row-block tiles t %% %d == rank' % world,
+            'config': {'workload': wl['name'], 'mode': args.mode, 'mode_used': mode_used,
+                       'parallelism': ('row blocks split over %d ranks' % world) +
+                                      (', shares adapted to per-GPU kernel time: %s / %d' % (balancer.widths, balancer.mod) if balancer else ', equal shares'),
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
                        'pairs_per_step': pairs,
                        'grid_ctas': sorted(grids), 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},

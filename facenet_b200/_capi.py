@@ -49,7 +49,8 @@ class Options(ctypes.Structure):
                 ('region_rows', ctypes.c_int32), ('cuts', ctypes.POINTER(ctypes.c_float)),
                 ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('debug', ctypes.c_int32),
                 ('cluster_pairs', ctypes.c_int32), ('normalize', ctypes.c_int32), ('theta', ctypes.c_float),
-                ('raw_distance', ctypes.c_int32), ('reserved', ctypes.c_int32 * 1)]
+                ('raw_distance', ctypes.c_int32), ('reserved', ctypes.c_int32 * 1), ('shard_mod', ctypes.c_int32),
+                ('shard_lo', ctypes.c_int32), ('shard_width', ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -299,7 +300,8 @@ class Handle:
         return {'sm_count': sm.value, 'cc': (ma.value, mi.value), 'total_mem': mem.value}
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
-                cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0, normalize=0, theta=0.0, raw_distance=False):
+                cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0, normalize=0, theta=0.0, raw_distance=False,
+                shard=None):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -316,6 +318,8 @@ class Handle:
         o.normalize = int(normalize)
         o.theta = float(theta)
         o.raw_distance = 1 if raw_distance else 0
+        if shard is not None:
+            o.shard_mod, o.shard_lo, o.shard_width = (int(v) for v in shard)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -348,7 +352,7 @@ class Handle:
     # ---- whole-set verification histogram
     def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
                             rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy',
-                            force_checked=False, cluster_pairs=0, normalize=0):
+                            force_checked=False, cluster_pairs=0, normalize=0, shard=None):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
@@ -356,7 +360,7 @@ class Handle:
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
                                region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked,
-                               cluster_pairs=cluster_pairs, normalize=normalize)
+                               cluster_pairs=cluster_pairs, normalize=normalize, shard=shard)
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()

@@ -169,7 +169,16 @@ static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 // regions
 
 // tile grid of every region: `tile` rows x (`tile` * pairs) columns per scheduler step (see TileScheduler)
-void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs) {
+int fnb::shard_from_options(fnb_context* h, const fnb_options& opt, ShardSpec* out) {
+    if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) return h->fail(FNB_ERR_INVALID, "bad rank/world %d/%d", opt.rank, opt.world);
+    if (opt.shard_mod == 0) { *out = ShardSpec{opt.world, opt.rank, 1}; return FNB_OK; }
+    if (opt.shard_mod < 1 || opt.shard_lo < 0 || opt.shard_width < 0 || opt.shard_lo + opt.shard_width > opt.shard_mod)
+        return h->fail(FNB_ERR_INVALID, "bad shard range [%d, %d + %d) mod %d", opt.shard_lo, opt.shard_lo, opt.shard_width, opt.shard_mod);
+    *out = ShardSpec{opt.shard_mod, opt.shard_lo, std::max(opt.shard_width, 0)};
+    return FNB_OK;
+}
+
+void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, ShardSpec shard) {
     long long t = 0;
     // pair grid of a cluster: 1 x 1, 1 x 2 (pairs == 2) or 2 x 2 (pairs == 4) tiles per scheduler step
     const int super_rows = tile * (pairs == 4 ? 2 : 1);
@@ -177,8 +186,9 @@ void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs) {
     for (auto& r : regs) {
         r.nrb = (r.row_end - r.row_begin + super_rows - 1) / super_rows;
         r.ncb = (r.col_end - r.col_begin + super_cols - 1) / super_cols;
+        r.own_cnt = shard.width > 0 ? shard.owned(r.nrb) : 0;
         r.tile_begin = t;
-        t += (long long)r.nrb * r.ncb;
+        t += (long long)r.own_cnt * r.ncb;
     }
     RegionDev sentinel = {};
     sentinel.tile_begin = t;
@@ -229,7 +239,7 @@ static int pick_region_rows(const fnb_options* o, int tile, long long n = 0, int
         // row blocks per super-row divisible by world: rank r then owns the SAME row blocks (r, r + world, ...) in every
         // column panel, i.e. 1/world of the row panels; otherwise its rows drift from column to column and it ends up
         // streaming all of them (measured at 8 GPUs: 114 ms per rank instead of 1/8 of the single-GPU 817 ms)
-        const long long q = (long long)tile * world;
+        const long long q = (long long)tile * (o->shard_mod > 0 ? o->shard_mod : world);
         if (rr >= q) rr = (rr / q) * q;
     }
     rr = std::max<long long>(tile, (rr / tile) * tile);
@@ -490,7 +500,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
 
     GramParams p = {};
     p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
-    p.rank = 0; p.world = 1;
+    p.shard = ShardSpec{1, 0, 1};
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
@@ -548,7 +558,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
 
     GramParams p = {};
     p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
-    p.rank = opt.rank; p.world = opt.world;
+    if ((rc = shard_from_options(h, opt, &p.shard))) return rc;
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
@@ -716,7 +726,9 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
 
     std::vector<RegionDev> regs;
     triangle_regions(n, pick_region_rows(&opt, tile * (op.pairs == 1 ? 1 : 2), n, d), 0, regs);
-    finish_regions(regs, tile, op.pairs);
+    ShardSpec shard;
+    if ((rc = shard_from_options(h, opt, &shard))) return rc;
+    finish_regions(regs, tile, op.pairs, shard);
 
     HistLaunch hl;
     if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
@@ -821,7 +833,9 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
         if (rd.tri == 2 && r.key + 1 >= nkeys) return h->fail(FNB_ERR_INVALID, "region %d: tri == 2 bins the diagonal into slot key + 1", i);
         regs.push_back(rd);
     }
-    finish_regions(regs, tile, op.pairs);
+    ShardSpec shard;
+    if ((rc = shard_from_options(h, opt, &shard))) return rc;
+    finish_regions(regs, tile, op.pairs, shard);
     if (regs.back().tile_begin == 0 || n < 1) { h->last_nkeys = 0; return FNB_OK; }
 
     const void* de = nullptr;

@@ -39,15 +39,28 @@ struct RegionDev {
     int32_t row_begin, row_end, col_begin, col_end;
     int32_t tri, key;
     int32_t nrb, ncb;          // tile grid of the region (row blocks fastest)
-    long long tile_begin;      // first global tile index of the region
+    int32_t own_cnt, pad;      // row blocks of the region that THIS rank owns (see ShardSpec)
+    long long tile_begin;      // first tile index of the region in this rank's own tile order (own_cnt * ncb tiles per region)
+};
+
+// Which row blocks of a region a rank owns: rb with lo <= rb % mod < lo + width.  The same subset in every column panel,
+// so a rank re-reads only its own row panels from L2; width / mod is the rank's share of the work (equal shares:
+// mod = world, lo = rank, width = 1; unequal ones follow measured per-GPU speed, facenet_b200/distributed.py).
+struct ShardSpec {
+    int mod, lo, width;
+    __host__ __device__ int owned(int nrb) const {             // number of owned row blocks among [0, nrb)
+        const int rem = nrb % mod - lo;
+        return (nrb / mod) * width + (rem < 0 ? 0 : (rem > width ? width : rem));
+    }
+    __host__ __device__ int block(int j) const { return (j / width) * mod + lo + (j % width); }   // j-th owned row block
 };
 
 struct GramParams {
     // schedule
     const RegionDev* regions;  // [nregions + 1], last entry is a sentinel with tile_begin = total_tiles
     int nregions;
-    long long total_tiles;
-    int rank, world;
+    long long total_tiles;     // of this rank
+    ShardSpec shard;
     int kblocks;               // D / (elements per 128 B)
     int num_slots;
     float acc_scale;           // similarity = accumulator * acc_scale
@@ -122,18 +135,18 @@ struct TileScheduler {
     const RegionDev* regions;
     long long pos, stride, total;
     int cur;
+    ShardSpec shard;
 
     __device__ TileScheduler(const GramParams& p, int cluster_id, int num_clusters)
-        : regions(p.regions), pos((long long)cluster_id * p.world + p.rank),
-          stride((long long)num_clusters * p.world), total(p.total_tiles), cur(0) {}
+        : regions(p.regions), pos(cluster_id), stride(num_clusters), total(p.total_tiles), cur(0), shard(p.shard) {}
 
     __device__ bool next(TileInfo& t) {
         while (pos < total) {
             while (pos >= regions[cur + 1].tile_begin) ++cur;
             const RegionDev r = regions[cur];
             const int li = (int)(pos - r.tile_begin);
-            const int cb = li / r.nrb;
-            const int rb = li - cb * r.nrb;
+            const int cb = li / r.own_cnt;
+            const int rb = shard.block(li - cb * r.own_cnt);
             pos += stride;
             t.row0 = r.row_begin + rb * kSuperRows;
             t.col0 = r.col_begin + cb * kSuperCols;

@@ -122,7 +122,8 @@ int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, c
 int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
                     bool side_b, GramOperands& op, int normalize = 0);
-void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1);
+void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1, ShardSpec shard = ShardSpec{1, 0, 1});
+int shard_from_options(fnb_context* h, const fnb_options& opt, ShardSpec* out);
 int self_b_maps(fnb_context* h, GramOperands& op, int d);   // B side = the prepared A side (Gram of a set with itself)
 int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
 int reset_scalars(fnb_context* h);

@@ -15,6 +15,57 @@ world_size 2) inject the NumPy stand-in to exercise this plumbing without a GPU.
 import numpy as np
 
 
+class ShardBalancer:
+    """Shares of the pair matrix per rank, adapted to the measured speed of each GPU.
+
+    Every rank computes the tiles of the row blocks ``rb`` (per super-row of the tile order) with
+    ``lo <= rb % mod < lo + width`` (``fnb_options.shard_*``); the ranges partition ``[0, mod)``.  The all-reduce at the
+    end of a step makes everybody wait for the slowest GPU, and under the board power limit the GPUs of one box differ
+    by several per cent; after each step the ranks exchange their Gram-kernel times (one tiny all-reduce) and the widths
+    move half-way towards ``speed / sum(speed)``.  The integer bins do not depend on the split, so adapting it never
+    changes a result.  All ranks hold identical state (it is updated from all-reduced values only)."""
+
+    def __init__(self, world, slots_per_rank=64):
+        self.world = int(world)
+        self.mod = self.world * int(slots_per_rank)
+        self.widths = [int(slots_per_rank)] * self.world
+        self.steps = 0
+
+    def spec(self, rank):
+        return self.mod, sum(self.widths[:rank]), self.widths[rank]
+
+    def update(self, kernel_ms):
+        ms = [float(v) for v in kernel_ms]
+        if len(ms) != self.world or min(ms) <= 0.0:
+            return
+        speed = [w / t for w, t in zip(self.widths, ms)]
+        total = sum(speed)
+        target = [0.5 * w + 0.5 * self.mod * sp / total for w, sp in zip(self.widths, speed)]
+        widths = [max(1, int(v)) for v in target]
+        # largest remainders first until the widths fill [0, mod) again
+        order = sorted(range(self.world), key=lambda r: (-(target[r] - int(target[r])), r))
+        i = 0
+        while sum(widths) < self.mod:
+            widths[order[i % self.world]] += 1
+            i += 1
+        while sum(widths) > self.mod:
+            r = max(range(self.world), key=lambda q: (widths[q], -q))
+            widths[r] -= 1
+        self.widths = widths
+        self.steps += 1
+
+
+_balancers = {}
+
+
+def default_balancer(world, group=None):
+    """Process-wide balancer per (group, world)."""
+    key = (id(group) if group is not None else None, int(world))
+    if key not in _balancers:
+        _balancers[key] = ShardBalancer(world)
+    return _balancers[key]
+
+
 def _default_hist_fn(device_index):
     from facenet_b200 import _capi
     handle = _capi.default_handle(device_index)
@@ -42,9 +93,12 @@ def gather_shards(emb_shard, labels_shard, group=None):
     return emb, labels
 
 
-def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=None, hist_fn=None, **kw):
+def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=None, hist_fn=None, balancer=None, **kw):
     """Every rank passes its shard (torch tensors on its device, equal row counts); returns on every
-    rank ``(bins [2, T+1] int64 torch tensor summed over ranks, stats of this rank)``."""
+    rank ``(bins [2, T+1] int64 torch tensor summed over ranks, stats of this rank)``.
+
+    ``balancer`` (a ``ShardBalancer``, e.g. ``default_balancer(world)``): split the work by measured GPU speed and keep
+    adapting; ``None`` = equal shares."""
     import torch
     import torch.distributed as dist
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
@@ -53,9 +107,16 @@ def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=
     bins = torch.zeros((2, thr.size + 1), dtype=torch.int64, device=emb.device)
     if hist_fn is None:
         hist_fn = _default_hist_fn(emb.device.index or 0)
+    if balancer is not None and world > 1:
+        kw = dict(kw, shard=balancer.spec(rank))
     stats = hist_fn(emb, labels, thr, metric, rank, world, bins, **kw)
     if world > 1:
         dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
+        if balancer is not None and isinstance(stats, dict) and 'kernel_ms' in stats:
+            times = torch.zeros(world, dtype=torch.float64, device=emb.device)
+            times[rank] = float(stats['kernel_ms'])
+            dist.all_reduce(times, op=dist.ReduceOp.SUM, group=group)
+            balancer.update(times.tolist())
     return bins, stats
 
 

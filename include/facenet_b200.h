@@ -78,7 +78,7 @@ typedef struct {
     int32_t metric;        /* 0: 2*(1-s)   1: arccos(s)   (statistics.py:48-55)  default 0     */
     float   atol;          /* normalisation tolerance (statistics.py:22,40)      default 1e-5  */
     float   eps;           /* |d - threshold| <= eps pairs are counted            default 1e-5  */
-    int32_t rank, world;   /* this process computes tiles t with t % world == rank  default 0,1 */
+    int32_t rank, world;   /* this process computes 1/world of the tiles (see shard_*)   default 0,1 */
     int32_t cta_group;     /* 0 auto, 1: 128x128 tiles per CTA, 2: 256x256 per CTA pair           */
     int32_t region_rows;   /* rows per super-row of the tile order, 0 = auto (row panels sized to half of L2) */
     const float* cuts;     /* optional [T]: per threshold the smallest fp32 similarity whose distance is
@@ -103,6 +103,11 @@ typedef struct {
                               (FaceToFaceDistanceClassifier.distance, facenet/faceclass.py:71)   default 0 */
     int32_t raw_distance;  /* != 0: classifier distance (facenet/faceclass.py:106-116): no range check, no clamp */
     int32_t reserved[1];
+    int32_t shard_mod, shard_lo, shard_width;
+                           /* multi-GPU work split by ROW BLOCK: this rank computes the tiles of the row blocks rb (per super-row
+                              of the tile order) with shard_lo <= rb % shard_mod < shard_lo + shard_width.  All 0 (default):
+                              mod = world, lo = rank, width = 1 (equal shares).  Unequal widths give faster GPUs more rows;
+                              the ranks' ranges must partition [0, shard_mod).  The integer bins do not depend on the split. */
 } fnb_options;
 
 typedef struct {

@@ -20,8 +20,8 @@ def _free_port():
 
 
 def _emulated_hist(emb, labels, thresholds, metric, rank, world, bins_out, **kw):
-    """Per-rank stand-in: rows sorted by label, strict upper triangle in 64x64 tiles, tile t handled by
-    rank t % world (mirrors the library's tile split)."""
+    """Per-rank stand-in: rows sorted by label, strict upper triangle in 64x64 tiles; a rank owns the row blocks rb with
+    lo <= rb % mod < lo + width (mirrors the library's split by row block; default mod = world, lo = rank, width = 1)."""
     from facenet_b200 import _capi
     x = emb.numpy()
     lab = labels.numpy()
@@ -31,14 +31,12 @@ def _emulated_hist(emb, labels, thresholds, metric, rank, world, bins_out, **kw)
     nt = cuts.size
     n = x.shape[0]
     tile = 64
-    t = 0
+    mod, lo, width = kw.get('shard') or (world, rank, 1)
     out = np.zeros((2, nt + 1), dtype=np.int64)
     for r0 in range(0, n, tile):
+        if not (lo <= (r0 // tile) % mod < lo + width):
+            continue
         for c0 in range(r0, n, tile):
-            mine = (t % world) == rank
-            t += 1
-            if not mine:
-                continue
             s = np.clip(x[r0:r0 + tile] @ x[c0:c0 + tile].T, -1, 1)
             k = np.searchsorted(cuts, s.ravel(), side='right').reshape(s.shape)
             valid = np.arange(c0, c0 + s.shape[1])[None, :] > np.arange(r0, r0 + s.shape[0])[:, None]
@@ -46,7 +44,7 @@ def _emulated_hist(emb, labels, thresholds, metric, rank, world, bins_out, **kw)
             out[0] += np.bincount(k[valid], minlength=nt + 1)
             out[1] += np.bincount(k[same], minlength=nt + 1)
     bins_out.copy_(torch.from_numpy(out))
-    return {'emulated': True}
+    return {'emulated': True, 'kernel_ms': 1.0 + 0.5 * rank}      # rank 1 pretends to be the slower GPU
 
 
 def _worker(rank, world, port, x, labels, result):
@@ -60,6 +58,12 @@ def _worker(rank, world, port, x, labels, result):
         ls = torch.from_numpy(labels[rank * per:(rank + 1) * per])
         thr = so.default_thresholds(0)
         bins, _ = fd.pair_histogram_sharded(xs, ls, thr, 0, hist_fn=_emulated_hist)
+        # speed-weighted shares: same bins, and the slower rank's share shrinks step by step (identically on both ranks)
+        bal = fd.ShardBalancer(world, slots_per_rank=8)
+        for step in range(3):
+            again, _ = fd.pair_histogram_sharded(xs, ls, thr, 0, hist_fn=_emulated_hist, balancer=bal)
+            assert torch.equal(again, bins)
+        assert sum(bal.widths) == bal.mod and bal.widths[0] > bal.widths[1] >= 1
         out = fd.counts_from_bins(bins, thr, 0)
         if rank == 0:
             result['same'] = out['same']
@@ -83,3 +87,21 @@ def test_two_rank_histogram_equals_single_process():
     mp.spawn(_worker, args=(2, port, x, labels, result), nprocs=2, join=True)
     assert result['n'] == (ref['n_same'], ref['n_diff'])
     assert np.abs(result['same'] - ref['same']).sum() + np.abs(result['diff'] - ref['diff']).sum() <= 2
+
+
+def test_shard_balancer_shares():
+    from facenet_b200 import distributed as fd
+    b = fd.ShardBalancer(8)
+    assert [b.spec(r) for r in (0, 7)] == [(512, 0, 64), (512, 448, 64)]
+    ms = [110, 111, 105, 109, 104, 109, 101, 107]
+    for _ in range(6):
+        b.update(ms)
+        # the ranges always partition [0, mod)
+        assert sum(b.widths) == b.mod and min(b.widths) >= 1
+        assert all(b.spec(r)[1] == sum(b.widths[:r]) for r in range(8))
+        # pretend every GPU keeps its speed: its time follows its share
+        speed = [64 / t for t in [110, 111, 105, 109, 104, 109, 101, 107]]
+        ms = [w / s for w, s in zip(b.widths, speed)]
+    assert max(ms) / min(ms) < 1.03                       # was 1.10 with equal shares
+    b.update([0.0] * 8)                                   # unusable measurement: ignored
+    assert sum(b.widths) == b.mod

@@ -260,6 +260,26 @@ def test_histogram_sharded_ranks_sum_to_whole(handle):
         np.testing.assert_array_equal(acc, whole)
 
 
+def test_histogram_weighted_shards_sum_to_whole(handle):
+    """Unequal shares (fnb_options.shard_*: row blocks rb with lo <= rb % mod < lo + width): any partition of [0, mod)
+    gives the same summed integer bins, for one-pair and two-pair clusters and several super-row heights."""
+    x, labels = ragged(11, n_classes=260, d=128, max_size=30)
+    thr = so.default_thresholds(0)
+    whole, st = handle.pair_histogram_bins(x, labels, thr, 0)
+    for mod, widths in ((16, (9, 1, 6)), (5, (1, 1, 1, 1, 1)), (7, (0, 7)), (64, (20, 23, 21))):
+        for pairs, rr in ((1, 0), (2, 1024), (1, 512)):
+            acc = np.zeros_like(whole)
+            lo = 0
+            for w in widths:
+                part, _ = handle.pair_histogram_bins(x, labels, thr, 0, rank=0, world=len(widths), shard=(mod, lo, w),
+                                                     cluster_pairs=pairs, region_rows=rr)
+                acc += part
+                lo += w
+            np.testing.assert_array_equal(acc, whole)
+    with pytest.raises(Exception):
+        handle.pair_histogram_bins(x, labels, thr, 0, shard=(4, 3, 2))      # range leaves [0, mod)
+
+
 def test_histogram_cluster_pairs_identical_bins(handle):
     """Clusters of two CTA pairs (A operand multicast, 256 x 512 super-tiles) run the same MMAs in the same order
     per tile: the integer bins are IDENTICAL to the one-pair kernel, for every mode, ragged edges, rank sharding
