@@ -50,7 +50,7 @@ class Options(ctypes.Structure):
                 ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('debug', ctypes.c_int32),
                 ('cluster_pairs', ctypes.c_int32), ('normalize', ctypes.c_int32), ('theta', ctypes.c_float),
                 ('raw_distance', ctypes.c_int32), ('reserved', ctypes.c_int32 * 1), ('shard_mod', ctypes.c_int32),
-                ('shard_lo', ctypes.c_int32), ('shard_width', ctypes.c_int32)]
+                ('shard_lo', ctypes.c_int32), ('shard_width', ctypes.c_int32), ('shard_slots', ctypes.POINTER(ctypes.c_int32))]
 
 
 class Stats(ctypes.Structure):
@@ -318,12 +318,19 @@ class Handle:
         o.normalize = int(normalize)
         o.theta = float(theta)
         o.raw_distance = 1 if raw_distance else 0
-        if shard is not None:
-            o.shard_mod, o.shard_lo, o.shard_width = (int(v) for v in shard)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
             o.cuts = keep.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        if shard is not None:
+            # (mod, lo, width): a contiguous residue range; (mod, [residues]): an explicit ascending list
+            if len(shard) == 2:
+                slots = np.ascontiguousarray(shard[1], dtype=np.int32)
+                o.shard_mod, o.shard_lo, o.shard_width = int(shard[0]), 0, int(slots.size)
+                o.shard_slots = slots.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+                keep = (keep, slots)
+            else:
+                o.shard_mod, o.shard_lo, o.shard_width = (int(v) for v in shard)
         return o, keep
 
     # ---- pairwise_similarities (statistics.py:22-57)

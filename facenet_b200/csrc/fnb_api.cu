@@ -169,16 +169,37 @@ static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 // regions
 
 // tile grid of every region: `tile` rows x (`tile` * pairs) columns per scheduler step (see TileScheduler)
-int fnb::shard_from_options(fnb_context* h, const fnb_options& opt, ShardSpec* out) {
+int fnb::shard_from_options(fnb_context* h, const fnb_options& opt, ShardHost* out) {
     if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) return h->fail(FNB_ERR_INVALID, "bad rank/world %d/%d", opt.rank, opt.world);
-    if (opt.shard_mod == 0) { *out = ShardSpec{opt.world, opt.rank, 1}; return FNB_OK; }
-    if (opt.shard_mod < 1 || opt.shard_lo < 0 || opt.shard_width < 0 || opt.shard_lo + opt.shard_width > opt.shard_mod)
-        return h->fail(FNB_ERR_INVALID, "bad shard range [%d, %d + %d) mod %d", opt.shard_lo, opt.shard_lo, opt.shard_width, opt.shard_mod);
-    *out = ShardSpec{opt.shard_mod, opt.shard_lo, std::max(opt.shard_width, 0)};
+    out->residues.clear();
+    if (opt.shard_mod == 0) {
+        out->spec = ShardSpec{opt.world, opt.rank, 1, nullptr};
+        out->residues.push_back(opt.rank);
+        return FNB_OK;
+    }
+    const int mod = opt.shard_mod, width = opt.shard_width;
+    if (mod < 1 || width < 0 || width > mod) return h->fail(FNB_ERR_INVALID, "bad shard width %d of %d", width, mod);
+    if (opt.shard_slots) {
+        for (int i = 0; i < width; ++i) {
+            const int r = opt.shard_slots[i];
+            if (r < 0 || r >= mod || (i > 0 && r <= opt.shard_slots[i - 1])) return h->fail(FNB_ERR_INVALID, "shard_slots must be ascending residues in [0, %d)", mod);
+            out->residues.push_back(r);
+        }
+        CK(h->shard_slots.ensure((size_t)std::max(width, 1) * 4));
+        if (width) CK(cudaMemcpyAsync(h->shard_slots.p, out->residues.data(), (size_t)width * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));            // `residues` is the caller's stack object
+        out->spec = ShardSpec{mod, 0, width, h->shard_slots.as<int32_t>()};
+    } else {
+        if (opt.shard_lo < 0 || opt.shard_lo + width > mod) return h->fail(FNB_ERR_INVALID, "bad shard range [%d, %d + %d) mod %d", opt.shard_lo, opt.shard_lo, width, mod);
+        for (int i = 0; i < width; ++i) out->residues.push_back(opt.shard_lo + i);
+        out->spec = ShardSpec{mod, opt.shard_lo, width, nullptr};
+    }
     return FNB_OK;
 }
 
-void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, ShardSpec shard) {
+void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, const ShardHost* shard) {
+    const ShardHost whole;
+    if (!shard) shard = &whole;
     long long t = 0;
     // pair grid of a cluster: 1 x 1, 1 x 2 (pairs == 2) or 2 x 2 (pairs == 4) tiles per scheduler step
     const int super_rows = tile * (pairs == 4 ? 2 : 1);
@@ -186,7 +207,7 @@ void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, Shar
     for (auto& r : regs) {
         r.nrb = (r.row_end - r.row_begin + super_rows - 1) / super_rows;
         r.ncb = (r.col_end - r.col_begin + super_cols - 1) / super_cols;
-        r.own_cnt = shard.width > 0 ? shard.owned(r.nrb) : 0;
+        r.own_cnt = shard->spec.width > 0 ? shard->owned(r.nrb) : 0;
         r.tile_begin = t;
         t += (long long)r.own_cnt * r.ncb;
     }
@@ -307,7 +328,7 @@ extern "C" void fnb_destroy(fnb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_nrm, &h->b_nrm, &h->perm, &h->cls,
+    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
                       &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io};
     for (DevBuf* b : bufs) b->release();
@@ -500,7 +521,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
 
     GramParams p = {};
     p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
-    p.shard = ShardSpec{1, 0, 1};
+    p.shard = ShardSpec{1, 0, 1, nullptr};
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
@@ -558,7 +579,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
 
     GramParams p = {};
     p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
-    if ((rc = shard_from_options(h, opt, &p.shard))) return rc;
+    p.shard = h->last_shard;
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
@@ -726,9 +747,10 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
 
     std::vector<RegionDev> regs;
     triangle_regions(n, pick_region_rows(&opt, tile * (op.pairs == 1 ? 1 : 2), n, d), 0, regs);
-    ShardSpec shard;
+    ShardHost shard;
     if ((rc = shard_from_options(h, opt, &shard))) return rc;
-    finish_regions(regs, tile, op.pairs, shard);
+    h->last_shard = shard.spec;
+    finish_regions(regs, tile, op.pairs, &shard);
 
     HistLaunch hl;
     if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
@@ -833,9 +855,10 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
         if (rd.tri == 2 && r.key + 1 >= nkeys) return h->fail(FNB_ERR_INVALID, "region %d: tri == 2 bins the diagonal into slot key + 1", i);
         regs.push_back(rd);
     }
-    ShardSpec shard;
+    ShardHost shard;
     if ((rc = shard_from_options(h, opt, &shard))) return rc;
-    finish_regions(regs, tile, op.pairs, shard);
+    h->last_shard = shard.spec;
+    finish_regions(regs, tile, op.pairs, &shard);
     if (regs.back().tile_begin == 0 || n < 1) { h->last_nkeys = 0; return FNB_OK; }
 
     const void* de = nullptr;

@@ -94,7 +94,7 @@ extern "C" int fnb_pair_cross_entropy(fnb_handle h, const DLTensor* batch, int e
     if ((rc = reset_scalars(h))) return rc;
     GramParams p = {};
     p.regions = h->regions.as<RegionDev>(); p.nregions = 1; p.total_tiles = regs.back().tile_begin;
-    p.shard = ShardSpec{1, 0, 1};
+    p.shard = ShardSpec{1, 0, 1, nullptr};
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;

@@ -43,16 +43,18 @@ struct RegionDev {
     long long tile_begin;      // first tile index of the region in this rank's own tile order (own_cnt * ncb tiles per region)
 };
 
-// Which row blocks of a region a rank owns: rb with lo <= rb % mod < lo + width.  The same subset in every column panel,
-// so a rank re-reads only its own row panels from L2; width / mod is the rank's share of the work (equal shares:
-// mod = world, lo = rank, width = 1; unequal ones follow measured per-GPU speed, facenet_b200/distributed.py).
+// Which row blocks of a region a rank owns: rb with rb % mod in the rank's set of `width` residues (a contiguous range or an
+// explicit list).  The same subset in every column panel, so a rank re-reads only its own row panels from L2; width / mod
+// is the rank's share of the work (equal shares: mod = world, the single residue `rank`; unequal ones follow measured
+// per-GPU speed, with the residues of a rank spread evenly over [0, mod) so that the short rows at the bottom of a
+// triangular region are shared out fairly -- facenet_b200/distributed.py).
 struct ShardSpec {
     int mod, lo, width;
-    __host__ __device__ int owned(int nrb) const {             // number of owned row blocks among [0, nrb)
-        const int rem = nrb % mod - lo;
-        return (nrb / mod) * width + (rem < 0 ? 0 : (rem > width ? width : rem));
+    const int32_t* slots;      // device array [width] of owned residues, ascending; NULL: the contiguous range [lo, lo + width)
+    __device__ int block(int j) const {                        // j-th owned row block
+        const int q = j / width, r = j - q * width;
+        return q * mod + (slots ? __ldg(slots + r) : lo + r);
     }
-    __host__ __device__ int block(int j) const { return (j / width) * mod + lo + (j % width); }   // j-th owned row block
 };
 
 struct GramParams {

@@ -75,11 +75,13 @@ struct fnb_context {
     fnb::DevBuf stage_a, stage_b, stage_lab;          // H2D staging of kDLCPU inputs
     fnb::DevBuf a_hi, a_lo, b_hi, b_lo, a_h8, b_h8;   // split / converted operands
     fnb::DevBuf a_nrm, b_nrm;                         // row norms before normalise-on-load (fnb_options.normalize)
+    fnb::DevBuf shard_slots;                          // residues of fnb_options.shard_slots on the device
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
     int last_nkeys = 0, last_T = 0, last_grid = 0, last_mode = 0;
     float last_peak = 0.f;
+    fnb::ShardSpec last_shard = fnb::ShardSpec{1, 0, 1, nullptr};   // share of the launch being prepared
     double last_eps_counted = 0;         // distance half-width of the near-threshold window counted by interior tiles
 
     int fail(int code, const char* fmt, ...);
@@ -122,8 +124,19 @@ int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, c
 int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
                     bool side_b, GramOperands& op, int normalize = 0);
-void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1, ShardSpec shard = ShardSpec{1, 0, 1});
-int shard_from_options(fnb_context* h, const fnb_options& opt, ShardSpec* out);
+// host view of a rank's share: the residues it owns (ascending) and the device spec
+struct ShardHost {
+    ShardSpec spec = ShardSpec{1, 0, 1, nullptr};
+    std::vector<int> residues = {0};
+    int owned(int nrb) const {                                 // number of owned row blocks among [0, nrb)
+        int c = (nrb / spec.mod) * spec.width;
+        const int rem = nrb % spec.mod;
+        for (int r : residues) c += (r < rem) ? 1 : 0;
+        return c;
+    }
+};
+void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1, const ShardHost* shard = nullptr);
+int shard_from_options(fnb_context* h, const fnb_options& opt, ShardHost* out);
 int self_b_maps(fnb_context* h, GramOperands& op, int d);   // B side = the prepared A side (Gram of a set with itself)
 int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
 int reset_scalars(fnb_context* h);

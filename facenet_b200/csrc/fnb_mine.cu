@@ -180,7 +180,7 @@ extern "C" int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* label
     CK(h->strip.ensure((size_t)b * ld * 4));
     GramParams p = {};
     p.regions = h->regions.as<RegionDev>(); p.nregions = 1; p.total_tiles = regs.back().tile_begin;
-    p.shard = ShardSpec{1, 0, 1};
+    p.shard = ShardSpec{1, 0, 1, nullptr};
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;

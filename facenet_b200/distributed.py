@@ -18,8 +18,8 @@ import numpy as np
 class ShardBalancer:
     """Shares of the pair matrix per rank, adapted to the measured speed of each GPU.
 
-    Every rank computes the tiles of the row blocks ``rb`` (per super-row of the tile order) with
-    ``lo <= rb % mod < lo + width`` (``fnb_options.shard_*``); the ranges partition ``[0, mod)``.  The all-reduce at the
+    Every rank computes the tiles of the row blocks ``rb`` (per super-row of the tile order) whose residue ``rb % mod`` it
+    owns (``fnb_options.shard_*``); the ranks' residue sets partition ``[0, mod)`` and their sizes are the shares.  The all-reduce at the
     end of a step makes everybody wait for the slowest GPU, and under the board power limit the GPUs of one box differ
     by several per cent; after each step the ranks exchange their Gram-kernel times (one tiny all-reduce) and the widths
     move half-way towards ``speed / sum(speed)``.  The integer bins do not depend on the split, so adapting it never
@@ -30,9 +30,26 @@ class ShardBalancer:
         self.mod = self.world * int(slots_per_rank)
         self.widths = [int(slots_per_rank)] * self.world
         self.steps = 0
+        self._table = None
+
+    def owners(self):
+        """Owner of each residue in [0, mod): weighted round-robin (the rank furthest behind its share gets the next
+        residue), so every rank's residues are spread evenly -- the long rows at the top and the short rows at the bottom
+        of a triangular region are shared out in proportion, and equal widths give the plain ``residue % world``."""
+        if self._table is None:
+            got = [0] * self.world
+            table = []
+            for s in range(self.mod):
+                r = max(range(self.world), key=lambda q: (self.widths[q] * (s + 1) - got[q] * self.mod, -q))
+                got[r] += 1
+                table.append(r)
+            assert got == self.widths
+            self._table = table
+        return self._table
 
     def spec(self, rank):
-        return self.mod, sum(self.widths[:rank]), self.widths[rank]
+        """``(mod, residues)`` of ``rank`` -- the ``shard`` argument of ``Handle.pair_histogram_bins``."""
+        return self.mod, [s for s, r in enumerate(self.owners()) if r == rank]
 
     def update(self, kernel_ms):
         ms = [float(v) for v in kernel_ms]
@@ -52,6 +69,7 @@ class ShardBalancer:
             r = max(range(self.world), key=lambda q: (widths[q], -q))
             widths[r] -= 1
         self.widths = widths
+        self._table = None
         self.steps += 1
 
 

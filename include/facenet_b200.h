@@ -104,10 +104,13 @@ typedef struct {
     int32_t raw_distance;  /* != 0: classifier distance (facenet/faceclass.py:106-116): no range check, no clamp */
     int32_t reserved[1];
     int32_t shard_mod, shard_lo, shard_width;
+    const int32_t* shard_slots;
                            /* multi-GPU work split by ROW BLOCK: this rank computes the tiles of the row blocks rb (per super-row
-                              of the tile order) with shard_lo <= rb % shard_mod < shard_lo + shard_width.  All 0 (default):
-                              mod = world, lo = rank, width = 1 (equal shares).  Unequal widths give faster GPUs more rows;
-                              the ranks' ranges must partition [0, shard_mod).  The integer bins do not depend on the split. */
+                              of the tile order) whose residue rb % shard_mod is one of its shard_width residues: the host array
+                              shard_slots[shard_width] (ascending), or, when that is NULL, the range [shard_lo, shard_lo +
+                              shard_width).  shard_mod == 0 (default): mod = world and the single residue `rank` (equal shares).
+                              Unequal widths give faster GPUs more rows; the ranks' residue sets must partition [0, shard_mod).
+                              The integer bins do not depend on the split. */
 } fnb_options;
 
 typedef struct {

@@ -21,7 +21,7 @@ def _free_port():
 
 def _emulated_hist(emb, labels, thresholds, metric, rank, world, bins_out, **kw):
     """Per-rank stand-in: rows sorted by label, strict upper triangle in 64x64 tiles; a rank owns the row blocks rb with
-    lo <= rb % mod < lo + width (mirrors the library's split by row block; default mod = world, lo = rank, width = 1)."""
+    rb % mod in its residue list (mirrors the library's split by row block; default mod = world, the residue `rank`)."""
     from facenet_b200 import _capi
     x = emb.numpy()
     lab = labels.numpy()
@@ -31,10 +31,10 @@ def _emulated_hist(emb, labels, thresholds, metric, rank, world, bins_out, **kw)
     nt = cuts.size
     n = x.shape[0]
     tile = 64
-    mod, lo, width = kw.get('shard') or (world, rank, 1)
+    mod, mine = kw.get('shard') or (world, [rank])
     out = np.zeros((2, nt + 1), dtype=np.int64)
     for r0 in range(0, n, tile):
-        if not (lo <= (r0 // tile) % mod < lo + width):
+        if (r0 // tile) % mod not in mine:
             continue
         for c0 in range(r0, n, tile):
             s = np.clip(x[r0:r0 + tile] @ x[c0:c0 + tile].T, -1, 1)
@@ -92,13 +92,16 @@ def test_two_rank_histogram_equals_single_process():
 def test_shard_balancer_shares():
     from facenet_b200 import distributed as fd
     b = fd.ShardBalancer(8)
-    assert [b.spec(r) for r in (0, 7)] == [(512, 0, 64), (512, 448, 64)]
+    assert b.spec(3) == (512, list(range(3, 512, 8)))              # equal shares: residue % world == rank
     ms = [110, 111, 105, 109, 104, 109, 101, 107]
     for _ in range(6):
         b.update(ms)
         # the ranges always partition [0, mod)
         assert sum(b.widths) == b.mod and min(b.widths) >= 1
-        assert all(b.spec(r)[1] == sum(b.widths[:r]) for r in range(8))
+        owned = [b.spec(r)[1] for r in range(8)]
+        assert sorted(sum(owned, [])) == list(range(b.mod)) and [len(o) for o in owned] == b.widths
+        # a rank's residues are spread evenly: the largest gap is close to mod / width
+        assert all(max(np.diff(o)) <= 2 * b.mod / len(o) for o in owned)
         # pretend every GPU keeps its speed: its time follows its share
         speed = [64 / t for t in [110, 111, 105, 109, 104, 109, 101, 107]]
         ms = [w / s for w, s in zip(b.widths, speed)]

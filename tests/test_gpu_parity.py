@@ -276,8 +276,20 @@ def test_histogram_weighted_shards_sum_to_whole(handle):
                 acc += part
                 lo += w
             np.testing.assert_array_equal(acc, whole)
+    # explicit residue lists, spread evenly by the balancer (what the multi-GPU layer passes)
+    from facenet_b200.distributed import ShardBalancer
+    bal = ShardBalancer(3, slots_per_rank=8)
+    bal.widths, bal._table = [11, 4, 9], None
+    acc = np.zeros_like(whole)
+    for rank in range(3):
+        mod, residues = bal.spec(rank)
+        part, _ = handle.pair_histogram_bins(x, labels, thr, 0, rank=rank, world=3, shard=(mod, residues), region_rows=2048)
+        acc += part
+    np.testing.assert_array_equal(acc, whole)
     with pytest.raises(Exception):
         handle.pair_histogram_bins(x, labels, thr, 0, shard=(4, 3, 2))      # range leaves [0, mod)
+    with pytest.raises(Exception):
+        handle.pair_histogram_bins(x, labels, thr, 0, shard=(8, [5, 2]))    # residues must ascend
 
 
 def test_histogram_cluster_pairs_identical_bins(handle):
