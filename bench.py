@@ -58,7 +58,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
-    ap.add_argument('--equal-shares', action='store_true', help='N > 1: fixed equal shares instead of the speed-adaptive split')
+    ap.add_argument('--adaptive-shares', action='store_true', help='N > 1: speed-adaptive shares instead of equal ones')
     ap.add_argument('--parity-rows', type=int, default=8192)
     return ap.parse_args()
 
@@ -241,8 +241,9 @@ def main():
         grids.add(st['grid_ctas'])
         return st
 
-    # shares of the pair matrix follow the measured speed of each GPU (adapts during the warm-up steps and keeps adapting)
-    balancer = fd.default_balancer(world) if (world > 1 and not args.equal_shares) else None
+    # equal shares by default; --adaptive-shares lets the shares follow the measured speed of each GPU (measured on two
+    # 8-GPU boxes: the per-rank kernel times level out, but the step is no shorter -- profiles/r01c_multi_gpu.md)
+    balancer = fd.default_balancer(world) if (world > 1 and args.adaptive_shares) else None
 
     def step_device():
         bins, st = fd.pair_histogram_sharded(x_shard, labels_shard, thr, 0, hist_fn=hist_fn, balancer=balancer)

@@ -2,7 +2,7 @@
 NCCL over NVLink/NVSwitch for the plumbing).
 
 The pair matrix shards naturally: every rank needs all N embeddings (columns) but computes only the
-tiles ``t`` with ``t % world == rank`` of the global tile order, so each rank does 1/world of the upper
+tiles of the row blocks ``rb % world == rank`` of every super-row of the tile order, so each rank does 1/world of the upper
 triangle regardless of N (no triangle imbalance).  Exchange steps:
 
   1. all-gather of the embedding / label shards (N * 512 * 4 bytes in total; 2 GB at N = 1M);
@@ -30,26 +30,24 @@ class ShardBalancer:
         self.mod = self.world * int(slots_per_rank)
         self.widths = [int(slots_per_rank)] * self.world
         self.steps = 0
+        self.gain = 0.5            # how far the shares move towards speed / sum(speed) per step
         self._table = None
+        self._pending = None       # all-reduced kernel times of the previous step, read at the start of the next one
 
     def owners(self):
-        """Owner of each residue in [0, mod): weighted round-robin (the rank furthest behind its share gets the next
-        residue), so every rank's residues are spread evenly -- the long rows at the top and the short rows at the bottom
-        of a triangular region are shared out in proportion, and equal widths give the plain ``residue % world``."""
+        """Owner of each residue in [0, mod): rank r's k-th residue sits at position (k + 1/2) / width_r of the unit interval
+        and the residues are handed out in the order of those positions, so every rank's residues are spread evenly -- the
+        long rows at the top and the short rows at the bottom of a triangular region are shared out in proportion, and
+        equal widths give the plain ``residue % world``."""
         if self._table is None:
-            got = [0] * self.world
-            table = []
-            for s in range(self.mod):
-                r = max(range(self.world), key=lambda q: (self.widths[q] * (s + 1) - got[q] * self.mod, -q))
-                got[r] += 1
-                table.append(r)
-            assert got == self.widths
-            self._table = table
+            pos = np.concatenate([(np.arange(w) + 0.5) / w for w in self.widths])
+            who = np.concatenate([np.full(w, r, dtype=np.int64) for r, w in enumerate(self.widths)])
+            self._table = who[np.lexsort((who, pos))]
         return self._table
 
     def spec(self, rank):
         """``(mod, residues)`` of ``rank`` -- the ``shard`` argument of ``Handle.pair_histogram_bins``."""
-        return self.mod, [s for s, r in enumerate(self.owners()) if r == rank]
+        return self.mod, np.flatnonzero(self.owners() == rank).tolist()
 
     def update(self, kernel_ms):
         ms = [float(v) for v in kernel_ms]
@@ -57,7 +55,8 @@ class ShardBalancer:
             return
         speed = [w / t for w, t in zip(self.widths, ms)]
         total = sum(speed)
-        target = [0.5 * w + 0.5 * self.mod * sp / total for w, sp in zip(self.widths, speed)]
+        g = self.gain
+        target = [(1.0 - g) * w + g * self.mod * sp / total for w, sp in zip(self.widths, speed)]
         widths = [max(1, int(v)) for v in target]
         # largest remainders first until the widths fill [0, mod) again
         order = sorted(range(self.world), key=lambda r: (-(target[r] - int(target[r])), r))
@@ -126,6 +125,10 @@ def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=
     if hist_fn is None:
         hist_fn = _default_hist_fn(emb.device.index or 0)
     if balancer is not None and world > 1:
+        if balancer._pending is not None:
+            # times of the previous step: that all-reduce finished long ago, reading it now does not stall the GPU
+            balancer.update(balancer._pending.tolist())
+            balancer._pending = None
         kw = dict(kw, shard=balancer.spec(rank))
     stats = hist_fn(emb, labels, thr, metric, rank, world, bins, **kw)
     if world > 1:
@@ -134,7 +137,7 @@ def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=
             times = torch.zeros(world, dtype=torch.float64, device=emb.device)
             times[rank] = float(stats['kernel_ms'])
             dist.all_reduce(times, op=dist.ReduceOp.SUM, group=group)
-            balancer.update(times.tolist())
+            balancer._pending = times
     return bins, stats
 
 
