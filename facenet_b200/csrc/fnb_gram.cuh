@@ -8,12 +8,14 @@
 //   :130-131  count_nonzero(sims < threshold)   -> epilogue per-thread histogram over similarity bins
 //   :124-126  per-class-pair blocking           -> rows sorted by class, rectangles ("regions") with a key
 //
-// Structure (one CTA per SM, or one CTA PAIR per two SMs with cta_group::2):
-//   warp 0   TMA producer   : 128-row x 128-byte operand boxes (SWIZZLE_128B) into a ring of 32 KB slots
-//   warp 1   MMA issuer     : one thread issues tcgen05.mma (leader CTA only in pair mode)
-//   warp 2   TMEM allocator
-//   warps 4-11 epilogue     : tcgen05.ld the finished accumulator (double buffered in TMEM) and
-//                             consume it while the next tile's MMAs run
+// Structure (one CTA per SM, or one CTA PAIR per two SMs with cta_group::2; 640 threads per CTA):
+//   warp 0      TMA producer  : 128-row x 128-byte operand boxes (SWIZZLE_128B) into a ring of 32 KB slots; boxes that two
+//                               pairs of a cluster share are fetched once and multicast (kPairs = 2, 4)
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma (leader CTA only in pair mode)
+//   warp 2      TMEM allocator
+//   warps 4-19  epilogue      : tcgen05.ld the finished accumulator (double buffered in TMEM) and consume it while the
+//                               next tile's MMAs run: HIST (per-threshold counts), PAIRWISE / ROWSTRIP (distances),
+//                               BCE (pair-classifier cross entropy and its gradients)
 // Tile = 128x128 (cta_group 1) or 256x256 per CTA pair (each CTA owns 128 rows x 256 columns).
 #pragma once
 
@@ -68,7 +70,7 @@ struct GramParams {
     float acc_scale;           // similarity = accumulator * acc_scale
     int operand_fmt;           // kFmtF16 / kFmtBF16 / kFmtTF32 (must agree with the kTf32 template flag)
     int force_slow;            // take the fully-checked epilogue path for every tile
-    int debug;                 // profiling knob (fnb_options.debug): bit 0 no epilogue work, bit 1 no operand loads
+    int debug;                 // profiling knob (fnb_options.debug): bit 0 no epilogue work, bit 1 operands loaded for the first tile only
     const unsigned int* norm_max_ord;   // ordered-uint max squared row norm (written by the split kernel), may be NULL
     unsigned int norm_limit_ord;        // above this the interior tiles cannot be proven in range -> checked path
     // HIST epilogue
@@ -138,24 +140,36 @@ struct TileScheduler {
     long long pos, stride, total;
     int cur;
     ShardSpec shard;
+    // position inside the current region, advanced incrementally (18 warps per CTA walk the schedule: no divisions per tile)
+    RegionDev r;
+    int cb, j;                 // column panel; index among this rank's row blocks of the region
+    bool fresh;                // (cb, j) must be recomputed from pos (first call, or a new region)
 
     __device__ TileScheduler(const GramParams& p, int cluster_id, int num_clusters)
-        : regions(p.regions), pos(cluster_id), stride(num_clusters), total(p.total_tiles), cur(0), shard(p.shard) {}
+        : regions(p.regions), pos(cluster_id), stride(num_clusters), total(p.total_tiles), cur(0), shard(p.shard),
+          cb(0), j(0), fresh(true) {}
 
     __device__ bool next(TileInfo& t) {
         while (pos < total) {
-            while (pos >= regions[cur + 1].tile_begin) ++cur;
-            const RegionDev r = regions[cur];
-            const int li = (int)(pos - r.tile_begin);
-            const int cb = li / r.own_cnt;
-            const int rb = shard.block(li - cb * r.own_cnt);
-            pos += stride;
+            if (fresh || pos >= regions[cur + 1].tile_begin) {
+                while (pos >= regions[cur + 1].tile_begin) ++cur;
+                r = regions[cur];
+                const int li = (int)(pos - r.tile_begin);
+                cb = li / r.own_cnt;
+                j = li - cb * r.own_cnt;
+                fresh = false;
+            }
+            const int rb = (shard.width == 1 && shard.slots == nullptr) ? j * shard.mod + shard.lo : shard.block(j);
             t.row0 = r.row_begin + rb * kSuperRows;
             t.col0 = r.col_begin + cb * kSuperCols;
             t.row_end = r.row_end;
             t.col_end = r.col_end;
             t.tri = r.tri;
             t.key = r.key;
+            // advance by `stride` tiles inside the region (row blocks fastest)
+            pos += stride;
+            j += (int)stride;
+            while (j >= r.own_cnt) { j -= r.own_cnt; ++cb; }
             if (r.tri && t.col0 + kSuperCols - 1 <= t.row0) continue;   // entirely on/below the diagonal
             return true;
         }
