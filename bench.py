@@ -389,6 +389,30 @@ def main():
                 'note': 'achieved = pairs x 1024 algorithmic FLOP / Gram-kernel time; executed_mma_tflops counts the split passes '
                         '(fp16-pass equivalents: an e4m3 pass counts 1/2)'}
 
+    # TF32 tensor peak measured live, the way MEASURED_PEAKS.json measures bf16 (SURVEY.md section 8 d): cuBLAS through
+    # torch.matmul, fp32 8192^3 with allow_tf32, best of 5 (burst) -- reported beside the bf16/2 figure, not on the product path
+    tf32_live = None
+    try:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ma = torch.randn((8192, 8192), device=dev)
+        mb = torch.randn((8192, 8192), device=dev)
+        torch.matmul(ma, mb)
+        best = None
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(ma, mb); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        tf32_live = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del ma, mb
+    except Exception:
+        tf32_live = None
+    if tf32_live:
+        roofline['tf32_cublas_tflops_live'] = tf32_live
+        roofline['frac_of_live_tf32'] = achieved / tf32_live
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, ms, sample, cores = cpu_arm(args.cpu_sample_rows, ids, n, 2, 1)
