@@ -49,7 +49,7 @@ class Options(ctypes.Structure):
                 ('region_rows', ctypes.c_int32), ('cuts', ctypes.POINTER(ctypes.c_float)),
                 ('max_ctas', ctypes.c_int32), ('force_checked', ctypes.c_int32), ('debug', ctypes.c_int32),
                 ('cluster_pairs', ctypes.c_int32), ('normalize', ctypes.c_int32), ('theta', ctypes.c_float),
-                ('raw_distance', ctypes.c_int32), ('reserved', ctypes.c_int32 * 1), ('shard_mod', ctypes.c_int32),
+                ('raw_distance', ctypes.c_int32), ('subset_rows', ctypes.c_int32), ('shard_mod', ctypes.c_int32),
                 ('shard_lo', ctypes.c_int32), ('shard_width', ctypes.c_int32), ('shard_slots', ctypes.POINTER(ctypes.c_int32))]
 
 
@@ -301,7 +301,7 @@ class Handle:
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
                 cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0, normalize=0, theta=0.0, raw_distance=False,
-                shard=None):
+                shard=None, subset_rows=0):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -318,6 +318,7 @@ class Handle:
         o.normalize = int(normalize)
         o.theta = float(theta)
         o.raw_distance = 1 if raw_distance else 0
+        o.subset_rows = int(subset_rows)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -406,7 +407,9 @@ class Handle:
     # ---- keyed histogram over rectangles
     def region_histogram_bins(self, embeddings, perm, cls, regions, nkeys, thresholds, metric=0, atol=1.e-5, eps=1.e-5,
                               mode='fp16x3', cta_group=0, cuts='numpy', rank=0, world=1, cluster_pairs=0, normalize=0, theta=0.0,
-                              raw_distance=False):
+                              raw_distance=False, subset=False):
+        """``subset=True``: ``perm`` / ``cls`` describe ``len(perm)`` rows of ``embeddings`` (``perm`` indexes the full array),
+        e.g. one fold of a validation whose embeddings stay resident on the GPU."""
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         perm = np.ascontiguousarray(perm, dtype=np.int64)
         cls = np.ascontiguousarray(cls, dtype=np.int32)
@@ -415,7 +418,10 @@ class Handle:
         if isinstance(cuts, str) and cuts == 'numpy':
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, cta_group=cta_group, cuts=cuts, rank=rank, world=world,
-                               cluster_pairs=cluster_pairs, normalize=normalize, theta=theta, raw_distance=raw_distance)
+                               cluster_pairs=cluster_pairs, normalize=normalize, theta=theta, raw_distance=raw_distance,
+                               subset_rows=perm.size if subset else 0)
+        if cls.size != perm.size or (not subset and perm.size != int(embeddings.shape[0])):
+            raise ValueError('perm / cls must have one entry per row')
         bins = np.zeros((int(nkeys), 2, thr.size + 1), dtype=np.uint64)
         st = Stats()
         be = self._borrow(embeddings)

@@ -835,7 +835,11 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     DLView ve;
     int rc = dl_view(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
     if ((rc = dl_check_embeddings(h, ve, "embeddings"))) return rc;
-    const long long n = ve.rows;
+    const long long n_all = ve.rows;
+    if (opt.subset_rows < 0 || opt.subset_rows > n_all) return h->fail(FNB_ERR_INVALID, "subset_rows %d out of range", opt.subset_rows);
+    const long long n = opt.subset_rows > 0 ? opt.subset_rows : n_all;      // rows of the (permuted) subset
+    for (long long i = 0; i < n; ++i)
+        if (perm[i] < 0 || perm[i] >= n_all) return h->fail(FNB_ERR_INVALID, "perm[%lld] = %lld out of range", i, (long long)perm[i]);
     const int d = (int)ve.cols;
     const size_t out_bytes = (size_t)nkeys * 2 * (T + 1) * 8;
     memset(bins_host, 0, out_bytes);
@@ -863,7 +867,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
 
     const void* de = nullptr;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    if ((rc = dl_to_device(h, ve, (size_t)n_all * d * 4, h->stage_a, &de))) return rc;
     CK(h->perm.ensure(n * 8));
     CK(h->cls.ensure(n * 4));
     CK(cudaMemcpyAsync(h->perm.p, perm, n * 8, cudaMemcpyHostToDevice, h->stream));

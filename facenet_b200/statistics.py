@@ -107,17 +107,41 @@ def split_embeddings(embeddings, labels):
     return np.split(embeddings[order], np.cumsum(counts)[:-1])
 
 
+def _on_gpu(x):
+    """True for a tensor that lives in CUDA memory and speaks DLPack (torch, TensorFlow via tf.experimental.dlpack, CuPy)."""
+    if isinstance(x, np.ndarray) or not hasattr(x, '__dlpack_device__'):
+        return False
+    try:
+        return int(x.__dlpack_device__()[0]) == 2          # kDLCUDA
+    except Exception:
+        return False
+
+
+def _host_array(x):
+    return np.asarray(x.cpu() if hasattr(x, 'cpu') else x)
+
+
 class SimilarityCalculator:
     """Class to evaluate similarities according to defined metric (statistics.py:82-108).
 
     Holds the whole subset; ``ConfidenceMatrix`` hands it to the GPU in one call.  ``.embeddings`` (the
-    per-class list of the reference) is materialised lazily for callers that index it."""
+    per-class list of the reference) is materialised lazily for callers that index it.
 
-    def __init__(self, embeddings, labels, metric=0):
+    Beyond the reference (the hand-off of ``facenet.evaluate_embeddings``, facenet.py:184-201):
+    ``embeddings`` may be a float32 tensor that is already on the GPU (torch / TensorFlow through DLPack) -- it is used in
+    place, never copied to the host; ``_rows`` selects the rows of it this calculator covers (one fold of a validation)
+    and ``normalize=True`` applies ``tf.nn.l2_normalize(axis=1, epsilon=1e-10)`` (inception_resnet_v1.py:491-492) while
+    the operands are prepared, so raw network outputs can be handed over."""
+
+    def __init__(self, embeddings, labels, metric=0, _rows=None, normalize=False):
         self.metric = metric
-        self._x = np.ascontiguousarray(embeddings, dtype=np.float32)
-        self._labels = np.asarray(labels)
-        if self._x.shape[0] != len(self._labels):
+        self._gpu = _on_gpu(embeddings)
+        self._x = embeddings if self._gpu else np.ascontiguousarray(embeddings, dtype=np.float32)
+        self._rows = None if _rows is None else np.ascontiguousarray(_rows, dtype=np.int64)
+        self._normalize = 2 if normalize else 0
+        self._labels = _host_array(labels)
+        self._n = int(self._x.shape[0]) if self._rows is None else int(self._rows.size)
+        if self._n != len(self._labels):
             raise ValueError('embeddings and labels have different lengths')
         values, self._cls, self._sizes = np.unique(self._labels, return_inverse=True, return_counts=True)
         self._cls = np.asarray(self._cls).reshape(-1)
@@ -126,8 +150,13 @@ class SimilarityCalculator:
     @property
     def embeddings(self):
         if self._split is None:
+            x = _host_array(self._x) if self._gpu else self._x
+            if self._rows is not None:
+                x = x[self._rows]
+            if self._normalize:
+                x = (x * (1.0 / np.sqrt(np.maximum((x.astype(np.float32) ** 2).sum(axis=1, keepdims=True), np.float32(1e-10))))).astype(np.float32)
             order = np.argsort(self._cls, kind='stable')
-            self._split = np.split(self._x[order], np.cumsum(self._sizes)[:-1])
+            self._split = np.split(x[order], np.cumsum(self._sizes)[:-1])
         return self._split
 
     def evaluate(self, i, k):
@@ -211,7 +240,7 @@ class ConfidenceMatrix:
         # filled by the device selection kernel when the whole threshold grid went through one launch
         self._argmax_accuracy = None
         self._far_threshold = None
-        if nt == 0 or calculator._x.shape[0] < 2:
+        if nt == 0 or calculator._n < 2:
             return
         thr = self.threshold.astype(np.float64).reshape(-1)
         metric = calculator.metric
@@ -233,9 +262,11 @@ class ConfidenceMatrix:
             sl = slice(t0, min(nt, t0 + _capi.MAX_THRESHOLDS))
             cuts = _capi.numpy_cuts(thr[sl], metric)
             try:
-                bins, self.stats = h.region_histogram_bins(calculator._x, perm, cls_sorted, regions, regions.size,
-                                                           thr[sl], metric=metric, mode=_state['mode'],
-                                                           cta_group=_state['cta_group'], cuts=cuts)
+                rows = calculator._rows
+                bins, self.stats = h.region_histogram_bins(calculator._x, perm if rows is None else rows[perm], cls_sorted,
+                                                           regions, regions.size, thr[sl], metric=metric, mode=_state['mode'],
+                                                           cta_group=_state['cta_group'], cuts=cuts,
+                                                           subset=rows is not None, normalize=calculator._normalize)
                 sel = h.confidence_from_last_bins(regions.size, w_same, w_diff, thr[sl], metric=metric, cuts=cuts,
                                                   far_target=0.0 if _far_target is None else float(_far_target))
             except _capi.FnbError as err:
@@ -404,15 +435,26 @@ class FaceToFaceValidation:
         return info
 
     def _evaluate(self):
-        embeddings = np.asarray(self.embeddings)
-        labels = np.asarray(self.labels)
+        # embeddings that already live on the GPU (torch / TensorFlow through DLPack) stay there: every fold is a row
+        # subset of the one resident tensor (no D2H -> H2D round trip, facenet.py:184-201); ``config.normalize`` (not in
+        # the reference's config) applies l2_normalize on load for raw network outputs
+        gpu = _on_gpu(self.embeddings)
+        embeddings = self.embeddings if gpu else np.asarray(self.embeddings)
+        labels = _host_array(self.labels)
+        normalize = bool(getattr(self.config, 'normalize', False))
+
+        def subset(rows):
+            if gpu or normalize:
+                return SimilarityCalculator(embeddings, labels[rows], metric=self.config.metric, _rows=rows, normalize=normalize)
+            return SimilarityCalculator(embeddings[rows], labels[rows], metric=self.config.metric)
+
         self.reports = (
             Report(criterion='MaximumAccuracy'),
             Report(criterion='FalseAlarmRate(FAR = {})'.format(self.config.far_target))
         )
         for train_set, test_set in kfold_split(len(labels), self.config.nrof_folds):
             # evaluations with train set and define the best threshold for the fold
-            calculator = SimilarityCalculator(embeddings[train_set], labels[train_set], metric=self.config.metric)
+            calculator = subset(train_set)
             matrix = ConfidenceMatrix(calculator, self.thresholds, _far_target=self.config.far_target)
             for report in self.reports:
                 report.append_fold('train', matrix)
@@ -436,7 +478,7 @@ class FaceToFaceValidation:
                     far_threshold = _slinear(matrix.fp_rates, self.thresholds, self.config.far_target)
 
             # evaluations with test set: both thresholds in ONE launch, then split per report
-            calculator = SimilarityCalculator(embeddings[test_set], labels[test_set], metric=self.config.metric)
+            calculator = subset(test_set)
             both = ConfidenceMatrix(calculator, np.array([accuracy_threshold, float(far_threshold)]))
             for idx, thr in enumerate((accuracy_threshold, far_threshold)):
                 one = ConfidenceMatrix.__new__(ConfidenceMatrix)

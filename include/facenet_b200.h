@@ -102,7 +102,9 @@ typedef struct {
     float   theta;         /* normalize == 1 only: the pair distance becomes 2 (1 - s) + theta (2 (|x|-|y|) / (|x|+|y|))^2
                               (FaceToFaceDistanceClassifier.distance, facenet/faceclass.py:71)   default 0 */
     int32_t raw_distance;  /* != 0: classifier distance (facenet/faceclass.py:106-116): no range check, no clamp */
-    int32_t reserved[1];
+    int32_t subset_rows;   /* fnb_region_histogram_bins: perm / cls describe a SUBSET of subset_rows rows of emb (perm[r] indexes emb);
+                              0 = all rows.  Lets a k-fold validation keep the embeddings resident on the GPU (one tensor, 20
+                              subsets) instead of copying every fold's rows (facenet/statistics.py:284-305) */
     int32_t shard_mod, shard_lo, shard_width;
     const int32_t* shard_slots;
                            /* multi-GPU work split by ROW BLOCK: this rank computes the tiles of the row blocks rb (per super-row
@@ -186,8 +188,8 @@ int fnb_pair_histogram(fnb_handle h, const DLTensor* emb, const DLTensor* labels
 
 /* Keyed histogram over caller-defined rectangles of the pair matrix -- the building block of the
  * class-balanced ConfidenceMatrix (facenet/statistics.py:111-138) and of k-fold validation
- * (statistics.py:277-311).  perm [N] (host): row r of the permuted order is emb[perm[r]];
- * cls [N] (host): class id of permuted row r, NON-DECREASING in r.
+ * (statistics.py:277-311).  perm [n] (host): row r of the permuted order is emb[perm[r]];
+ * cls [n] (host): class id of permuted row r, NON-DECREASING in r; n = opt->subset_rows, or all rows of emb when 0.
  *   bins_host: uint64 [nkeys][2][T+1]. */
 int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, const int64_t* perm, const int32_t* cls,
                               const fnb_region* regions, int nregions, int nkeys,

@@ -11,6 +11,8 @@ def region_histogram_bins(embeddings, perm, cls, regions, nkeys, thresholds, met
     if normalize == 1:                                   # fnb_options.normalize = 1 (+ theta): faceclass.py:57-71
         nrm = np.linalg.norm(x, axis=1, keepdims=True)
         x = x / nrm
+    elif normalize == 2:                                 # tf.nn.l2_normalize(axis=1, epsilon=1e-10)
+        x = (x * (1.0 / np.sqrt(np.maximum((x * x).sum(axis=1, keepdims=True), np.float32(1e-10))))).astype(np.float32)
     cls = np.asarray(cls)
     assert np.all(np.diff(cls) >= 0), 'cls must be non-decreasing'
     if cuts is None or isinstance(cuts, str):            # the library's default: NumPy-exact cuts

@@ -618,3 +618,35 @@ def test_mining_python_surface_and_errors(handle):
     out_t = handle.mine(xt, lt, alpha=0.3, kmax=5)
     for k in ('hardest_pos', 'hardest_neg', 'pos_index', 'semi_hard', 'eligible'):
         np.testing.assert_array_equal(out[k], out_t[k])
+
+
+def test_validation_with_gpu_resident_embeddings(fst, golden_dir):
+    """embeddings that are already on the GPU (a torch tensor, handed over through DLPack) are used in
+    place -- every fold is a row subset of the resident tensor -- and give the same reports as host arrays; raw network
+    outputs with config.normalize (l2_normalize on load) give the reports of the normalised embeddings."""
+    import torch
+    g = np.load(golden_dir / 'validation.npz')
+    x, labels = g['embeddings'], g['labels']
+
+    class Cfg:
+        metric, nrof_folds, far_target = 0, 10, 1.e-3
+
+    host = fst.FaceToFaceValidation(x, labels, Cfg)
+    dev = fst.FaceToFaceValidation(torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda(), Cfg)
+    for a, b in zip(host.reports, dev.reports):
+        da, db = a.dict, b.dict
+        assert da.keys() == db.keys()
+        for k in da:
+            assert float(da[k]) == float(db[k]), k                 # same integer counts, same float64 arithmetic
+    scale = torch.from_numpy(np.random.default_rng(0).uniform(0.5, 3.0, size=(x.shape[0], 1)).astype(np.float32)).cuda()
+    Cfg.normalize = True
+    raw = fst.FaceToFaceValidation((torch.from_numpy(x).cuda() * scale).contiguous(), labels, Cfg)
+    for a, b in zip(host.reports, raw.reports):
+        da, db = a.dict, b.dict
+        for k in da:
+            assert abs(float(da[k]) - float(db[k])) <= 2e-3, k     # re-normalised rows differ in the last ulp: eps-window pairs may move
+    del Cfg.normalize
+    cm = fst.ConfidenceMatrix(fst.SimilarityCalculator(torch.from_numpy(x).cuda(), labels, 0), np.linspace(0, 4, 100))
+    ref = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, 0), np.linspace(0, 4, 100))
+    np.testing.assert_array_equal(cm.tp, ref.tp)
+    np.testing.assert_array_equal(cm.fp, ref.fp)

@@ -221,3 +221,23 @@ def test_confusion_matrix_host_math_golden(emulated, golden_dir):
             model.variables['threshold'] = np.float32(t)
             cm = tc.ConfusionMatrix(emb, model)
             np.testing.assert_allclose([cm.accuracy, cm.precision, cm.tp_rate, cm.tn_rate], ref, rtol=0, atol=1e-12)
+
+
+def test_validation_subset_rows_and_normalise_on_load(emulated, golden_dir):
+    """The GPU-resident hand-off path (every fold = a row subset of ONE array, l2_normalize on load) through the NumPy
+    stand-in: raw (scaled) embeddings with config.normalize give the golden reports of the normalised embeddings."""
+    g = np.load(golden_dir / 'validation.npz')
+    x, labels = g['embeddings'], g['labels']
+    scale = np.random.default_rng(0).uniform(0.5, 3.0, size=(x.shape[0], 1)).astype(np.float32)
+
+    class Cfg:
+        metric, nrof_folds, far_target, normalize = 0, 10, 1.e-3, True
+
+    v = fst.FaceToFaceValidation((x * scale).astype(np.float32), labels, Cfg)
+    for r, tag in zip(v.reports, ('acc', 'far')):
+        dct = r.dict
+        keys = [str(k) for k in g['%s_keys_m0' % tag]]
+        np.testing.assert_allclose([float(dct[k]) for k in keys], g['%s_vals_m0' % tag], rtol=0, atol=2e-3)
+    calc = fst.SimilarityCalculator((x * scale).astype(np.float32), labels[10:50], _rows=np.arange(10, 50), normalize=True)
+    assert calc.nrof_classes == np.unique(labels[10:50]).size
+    assert abs(float(np.linalg.norm(calc.embeddings[0][0])) - 1.0) < 1e-6
