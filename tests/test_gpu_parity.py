@@ -650,3 +650,20 @@ def test_validation_with_gpu_resident_embeddings(fst, golden_dir):
     ref = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, 0), np.linspace(0, 4, 100))
     np.testing.assert_array_equal(cm.tp, ref.tp)
     np.testing.assert_array_equal(cm.fp, ref.fp)
+
+
+def test_pair_histogram_equals_reference_counts_summed(handle, golden_dir):
+    """The headline kernel against integer counts of the UNMODIFIED reference: per-class-pair count_nonzero(sims < threshold)
+    (statistics.py:131, tests/golden/confidence.npz) summed over diagonal / off-diagonal class pairs, both metrics, every
+    arithmetic mode that meets the tolerance; disagreements bounded by the pairs the kernel counted in the eps window."""
+    g = np.load(golden_dir / 'confidence.npz')
+    x, labels = g['embeddings'], g['labels']
+    for metric in (0, 1):
+        thr = so.default_thresholds(metric)
+        counts = g['counts_m%d' % metric]
+        same = np.einsum('iit->t', counts)
+        diff = counts.sum(axis=(0, 1)) - same
+        for mode in ('fp16x3', 'tf32x3', 'auto'):
+            got = handle.pair_histogram(x, labels, thr, metric, mode=mode)
+            mism = int(np.abs(got['same'] - same).sum() + np.abs(got['diff'] - diff).sum())
+            assert mism <= 2 * got['stats']['eps_window'] + 2, (metric, mode, mism, got['stats']['eps_window'])

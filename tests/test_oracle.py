@@ -140,3 +140,19 @@ def test_mining_oracle_small():
             if s >= 0:
                 assert labels[s] != labels[a] and d[a, s] > d[a, p] and np.float32(d[a, s] - d[a, p]) < np.float32(0.2)
     assert out['pos_index'].shape == (12, 3)
+
+
+def test_pair_histogram_equals_reference_counts_summed(golden_dir):
+    """The whole-set same / different histogram is the reference's per-class-pair counts (count_nonzero(sims < threshold),
+    statistics.py:131, taken from the UNMODIFIED reference in tests/golden/confidence.npz) summed over the diagonal /
+    off-diagonal class pairs."""
+    g = np.load(golden_dir / 'confidence.npz')
+    x, labels = g['embeddings'], g['labels']
+    for metric in (0, 1):
+        thr = so.default_thresholds(metric)
+        counts = g['counts_m%d' % metric]                       # [C, C, T], lower triangle incl. diagonal
+        same = np.einsum('iit->t', counts)
+        diff = counts.sum(axis=(0, 1)) - same
+        got = so.pair_histogram(x, labels, thr, metric)
+        # whole-Gram vs per-block sgemm may differ in the last ulp for a pair sitting on a threshold
+        assert np.abs(got['same'] - same).sum() + np.abs(got['diff'] - diff).sum() <= 2
