@@ -200,6 +200,7 @@ int fnb::shard_from_options(fnb_context* h, const fnb_options& opt, ShardHost* o
 void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, const ShardHost* shard) {
     const ShardHost whole;
     if (!shard) shard = &whole;
+    int cp = 0;
     long long t = 0;
     // pair grid of a cluster: 1 x 1, 1 x 2 (pairs == 2) or 2 x 2 (pairs == 4) tiles per scheduler step
     const int super_rows = tile * (pairs == 4 ? 2 : 1);
@@ -208,6 +209,8 @@ void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, cons
         r.nrb = (r.row_end - r.row_begin + super_rows - 1) / super_rows;
         r.ncb = (r.col_end - r.col_begin + super_cols - 1) / super_cols;
         r.own_cnt = shard->spec.width > 0 ? shard->owned(r.nrb) : 0;
+        r.cp_begin = cp;
+        cp += r.ncb;
         r.tile_begin = t;
         t += (long long)r.own_cnt * r.ncb;
     }
@@ -328,7 +331,7 @@ extern "C" void fnb_destroy(fnb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->perm, &h->cls,
+    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->progress, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
                       &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io};
     for (DevBuf* b : bufs) b->release();
@@ -587,6 +590,24 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.raw = opt.raw_distance;
     if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
     p.debug = opt.debug & 3;
+    // cluster-progress window (fnb_options.panel_window, GramParams::sync_window): auto = on for the launches long enough for the
+    // clusters to drift apart (this rank's share of the pair matrix >= 5e10 pairs, the same launches pick_pairs calls long)
+    p.sync_window = opt.panel_window > 0 ? std::min(opt.panel_window, 7) : 0;
+    if (opt.panel_window == 0) {
+        double own_pairs = 0.0;
+        for (size_t i = 0; i + 1 < regs.size(); ++i) {
+            const RegionDev& r = regs[i];
+            const double area = (double)(r.row_end - r.row_begin) * (double)(r.col_end - r.col_begin) * (r.tri ? 0.5 : 1.0);
+            if (r.nrb > 0) own_pairs += area * (double)r.own_cnt / (double)r.nrb;
+        }
+        if (own_pairs >= 5.0e10) p.sync_window = 2;
+    }
+    h->last_window = p.sync_window;
+    if (p.sync_window) {
+        CK(h->progress.ensure(1024 * 4));
+        CK(cudaMemsetAsync(h->progress.p, 0, 1024 * 4, h->stream));
+        p.progress = h->progress.as<unsigned int>();
+    }
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
@@ -675,6 +696,7 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         stats->kernel_launches += 1;
         stats->grid_ctas = (uint32_t)h->last_grid;
         stats->mode_used = h->last_mode;
+        stats->panel_window = h->last_window;
         stats->peakedness = hs.peak_max_ord ? ordered_to_float(hs.peak_max_ord) : 0.f;
     }
     return FNB_OK;

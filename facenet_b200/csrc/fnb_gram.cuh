@@ -41,7 +41,8 @@ struct RegionDev {
     int32_t row_begin, row_end, col_begin, col_end;
     int32_t tri, key;
     int32_t nrb, ncb;          // tile grid of the region (row blocks fastest)
-    int32_t own_cnt, pad;      // row blocks of the region that THIS rank owns (see ShardSpec)
+    int32_t own_cnt;           // row blocks of the region that THIS rank owns (see ShardSpec)
+    int32_t cp_begin;          // column panels of all earlier regions (a launch-wide column-panel counter: cp_begin + cb)
     long long tile_begin;      // first tile index of the region in this rank's own tile order (own_cnt * ncb tiles per region)
 };
 
@@ -113,6 +114,16 @@ struct GramParams {
     // of the strict upper triangle, label = same group (row_cls == col_cls), weighted cross entropy and its derivatives
     float bce_alpha, bce_threshold, bce_pos_weight;
     double* bce_out;           // [4] sums over pairs: loss, dloss/dalpha, dloss/dthreshold, dloss/dtheta
+    // Cluster-progress window (off unless sync_window > 0).  The clusters walk a static schedule, and over a long launch
+    // they drift apart by many column panels: each then streams its own column panel AND evicts the row panels the
+    // others still need (measured at 1M rows: 824 GB of DRAM reads per launch).  Every cluster publishes the column
+    // panel it is entering and waits while it is more than sync_window panels ahead of the slowest one, so the clusters
+    // share column panels inside L2 (1M rows: 193-208 GB, kernel 834 -> 800 ms, profiles/r01d_panel_window.md).
+    // The wait is BOUNDED (kSyncSpinLimit polls, a few ms): a cluster that runs into the bound stops waiting for the rest
+    // of the launch, so clusters that are not co-resident (SMs held by somebody else's kernel) cost time, never a hang.
+    // Timing only: the integer bins do not depend on it.
+    unsigned int* progress;    // [number of clusters], zeroed before the launch; 0xffffffff = finished
+    int sync_window;
 };
 
 // faceclass.py:71 in float32, operation by operation (no contraction)
@@ -121,8 +132,13 @@ __device__ __forceinline__ float classifier_distance(float s, float nr, float nc
     return __fadd_rn(__fmul_rn(2.0f, __fsub_rn(1.0f, s)), __fmul_rn(theta, __fmul_rn(g, g)));
 }
 
+// polls (about 1 us each: a 400 ns sleep plus one L2 round trip) before a cluster gives up the progress window; the waits of a
+// healthy launch are tens of microseconds (one column panel of one cluster is ~30 us of work)
+constexpr int kSyncSpinLimit = 4096;
+
 struct TileInfo {
     int row0, col0, row_end, col_end, tri, key;
+    int gcp;                   // launch-wide index of the tile's column panel (non-decreasing along a cluster's tile sequence)
 };
 
 // One scheduler step hands a cluster a SUPER-TILE of (kPR * kTile) rows x (kPC * kTile) columns; the CTA pair at
@@ -166,6 +182,7 @@ struct TileScheduler {
             t.col_end = r.col_end;
             t.tri = r.tri;
             t.key = r.key;
+            t.gcp = r.cp_begin + cb;
             // advance by `stride` tiles inside the region (row blocks fastest)
             pos += stride;
             j += (int)stride;
@@ -331,8 +348,28 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         TileInfo t;
         int slot = 0; uint32_t phase = 0;
         int ntile = -1;
+        int last_gcp = -1;
+        const bool sync_on = p.sync_window > 0 && cluster_rank == 0;
+        bool sync_wait = true;        // cleared for good when a wait runs into kSyncSpinLimit
         while (sched.next(t)) {
             ++ntile;
+            if (sync_on && t.gcp != last_gcp) {
+                // entering a new column panel: publish it, then wait for the stragglers (the slowest cluster never waits)
+                last_gcp = t.gcp;
+                volatile unsigned int* prog = p.progress;
+                if (lane == 0) prog[cluster_id] = (unsigned int)t.gcp + 1u;
+                __syncwarp();
+                int spins = 0;
+                while (sync_wait) {
+                    unsigned int mn = 0xffffffffu;
+                    for (int i = lane; i < num_clusters; i += 32) mn = min(mn, prog[i]);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    if (mn + (unsigned int)p.sync_window >= (unsigned int)t.gcp + 1u) break;
+                    if (++spins >= kSyncSpinLimit) sync_wait = false;      // warp-uniform (mn is): give up waiting for good
+                    __nanosleep(400);
+                }
+            }
             const int arow = t.row0 + (int)pair_row * kTile + (int)cta_rank * kRowsPerCta;
             const int brow = t.col0 + (int)pair_col * kTile + (int)cta_rank * kRowsPerCta;
             auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
@@ -387,6 +424,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     if (kParts == 2) load_slot(&tm_a_lo, &tm_b_lo, kb * kElemsPerBox);
                 }
             }
+        }
+        if (sync_on && lane == 0) {
+            volatile unsigned int* prog = p.progress;
+            prog[cluster_id] = 0xffffffffu;              // finished: nobody waits for this cluster any more
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer --------------------------------------

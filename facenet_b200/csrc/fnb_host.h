@@ -76,10 +76,11 @@ struct fnb_context {
     fnb::DevBuf a_hi, a_lo, b_hi, b_lo, a_h8, b_h8;   // split / converted operands
     fnb::DevBuf a_nrm, b_nrm;                         // row norms before normalise-on-load (fnb_options.normalize)
     fnb::DevBuf shard_slots;                          // residues of fnb_options.shard_slots on the device
+    fnb::DevBuf progress;                             // per-cluster column-panel progress (GramParams::sync_window)
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
     fnb::HostBuf pinned;
-    int last_nkeys = 0, last_T = 0, last_grid = 0, last_mode = 0;
+    int last_nkeys = 0, last_T = 0, last_grid = 0, last_mode = 0, last_window = 0;
     float last_peak = 0.f;
     fnb::ShardSpec last_shard = fnb::ShardSpec{1, 0, 1, nullptr};   // share of the launch being prepared
     double last_eps_counted = 0;         // distance half-width of the near-threshold window counted by interior tiles

@@ -113,6 +113,13 @@ typedef struct {
                               shard_width).  shard_mod == 0 (default): mod = world and the single residue `rank` (equal shares).
                               Unequal widths give faster GPUs more rows; the ranks' residue sets must partition [0, shard_mod).
                               The integer bins do not depend on the split. */
+    int32_t panel_window;  /* histogram launches: the clusters of the persistent Gram kernel publish the column panel they work
+                              on, and one that is more than panel_window panels ahead of the slowest waits (bounded: it gives
+                              up after a few ms, so this can cost time but never hang).  Keeps the clusters inside the same
+                              column panels, which keeps the super-row's row panels in L2 over long launches (1M rows: DRAM
+                              reads 824 -> 193-208 GB per launch, kernel 834 -> 800 ms).  1..7 = window, -1 = off, 0 = auto (2 when this
+                              rank's share is >= 5e10 pairs, the launches long enough to drift; else off).  Timing only:
+                              the integer bins do not depend on it. */
 } fnb_options;
 
 typedef struct {
@@ -131,6 +138,7 @@ typedef struct {
     uint32_t grid_ctas;    /* CTAs of the Gram launch (co-resident clusters x cluster size)                     */
     int32_t  mode_used;    /* FNB_MODE_* the contraction ran in (what AUTO resolved to)                         */
     float    peakedness;   /* max over rows of sum x^4 / (sum x^2)^2 of the prepared embeddings                  */
+    int32_t  panel_window; /* cluster-progress window the histogram launch ran with (0 = off; fnb_options.panel_window)  */
 } fnb_stats;
 
 /* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:
