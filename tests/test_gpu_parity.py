@@ -325,6 +325,29 @@ def test_histogram_cluster_pairs_identical_bins(handle):
             np.testing.assert_array_equal(acc, one)
 
 
+def test_histogram_panel_window_identical_bins(handle):
+    """fnb_options.panel_window (clusters wait for the slowest one at column-panel granularity) changes timing only: the
+    integer bins are identical for every window, cluster shape, super-row height and for row-block shards; the auto rule
+    leaves it off for launches this small (profiles/r01d_panel_window.md has the 1M launch, where auto switches it on)."""
+    x, labels = ragged(11, n_classes=260, d=128, max_size=30)
+    thr = so.default_thresholds(0)
+    whole, st = handle.pair_histogram_bins(x, labels, thr, 0, panel_window=-1)
+    assert st['panel_window'] == 0
+    auto, st = handle.pair_histogram_bins(x, labels, thr, 0)
+    assert st['panel_window'] == 0
+    np.testing.assert_array_equal(auto, whole)
+    for pairs, rr in ((1, 0), (1, 512), (2, 1024), (4, 1024)):
+        for w in (1, 3, 7):
+            got, st = handle.pair_histogram_bins(x, labels, thr, 0, panel_window=w, cluster_pairs=pairs, region_rows=rr)
+            assert st['panel_window'] == w
+            np.testing.assert_array_equal(got, whole)
+    acc = np.zeros_like(whole)
+    for rank in range(3):
+        part, _ = handle.pair_histogram_bins(x, labels, thr, 0, rank=rank, world=3, panel_window=2, cluster_pairs=2, region_rows=768)
+        acc += part
+    np.testing.assert_array_equal(acc, whole)
+
+
 def test_histogram_fp16f8_mode(handle):
     """fp16f8 (hi*hi in fp16 + e4m3 cross terms): distances within the 1e-5 tolerance of the oracle on dense
     embeddings, histogram disagreements bounded by the counted eps-window pairs."""
