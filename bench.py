@@ -59,6 +59,8 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--adaptive-shares', action='store_true', help='N > 1: speed-adaptive shares instead of equal ones')
+    ap.add_argument('--panel-window', type=int, default=0,
+                    help='fnb_options.panel_window: 0 auto (on for launches of >= 5e10 pairs per rank), -1 off, 1..7 window')
     ap.add_argument('--parity-rows', type=int, default=8192)
     return ap.parse_args()
 
@@ -229,16 +231,18 @@ def main():
     fst.set_default_mode(mode=args.mode, device=local_rank, cta_group=args.cta_group)
     stream = torch.cuda.current_stream()
     handle.set_stream(stream.cuda_stream)
-    kernel_ms, prepare_ms, launches, modes_used, grids = [], [], [0], set(), set()
+    kernel_ms, prepare_ms, launches, modes_used, grids, windows = [], [], [0], set(), set(), set()
 
     def hist_fn(emb, labels, thresholds_, metric, rank_, world_, bins_out, **kw):
         _, st = handle.pair_histogram_bins(emb, labels, thresholds_, metric, rank=rank_, world=world_, bins_out=bins_out,
-                                           mode=args.mode, cta_group=args.cta_group, shard=kw.get('shard'))
+                                           mode=args.mode, cta_group=args.cta_group, shard=kw.get('shard'),
+                                           panel_window=args.panel_window)
         kernel_ms.append(st['kernel_ms'])
         prepare_ms.append(st['prepare_ms'])
         launches[0] += st['kernel_launches']
         modes_used.add(_capi.MODE_NAMES[st['mode_used']])
         grids.add(st['grid_ctas'])
+        windows.add(st['panel_window'])
         return st
 
     # equal shares by default; --adaptive-shares lets the shares follow the measured speed of each GPU (measured on two
@@ -376,7 +380,9 @@ def main():
     tf = ROOT / 'profiles' / 'ncu_traffic.json'
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get('%s/%s' % (args.workload, mode_used))
+            # the DRAM bytes of the long launches depend on the cluster-progress window (profiles/r01d_panel_window.md)
+            key = '%s/%s' % (args.workload, mode_used) + ('' if (windows != {0} or args.workload != '1m') else '/window_off')
+            traffic = json.loads(tf.read_text()).get(key)
         except ValueError:
             traffic = None
     passes = 3 if mode_used.endswith('x3') else 2 if mode_used == 'fp16f8' else 1
@@ -430,7 +436,7 @@ def main():
                                       (', shares adapted to per-GPU kernel time: %s / %d' % (balancer.widths, balancer.mod) if balancer else ', equal shares'),
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
                        'pairs_per_step': pairs,
-                       'grid_ctas': sorted(grids), 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},
+                       'grid_ctas': sorted(grids), 'panel_window': sorted(windows), 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},
             'breakdown_ms': {'all_gather': gather_ms, 'sort_split': p_ms, 'gram_kernel': k_ms, 'gram_kernel_per_rank': k_ranks,
                              'rest (all-reduce, D2H of the bins, host)': total_ms / args.steps - gather_ms - p_ms - k_ms},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': timed_launches, 'roofline': roofline, 'cpu_baseline': cpu,
