@@ -378,7 +378,7 @@ def main():
     achieved = (pairs / world) * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12       # one launch covers 1/world of the pairs
     traffic = None
     tf = ROOT / 'profiles' / 'ncu_traffic.json'
-    if tf.exists():
+    if tf.exists() and world == 1:                     # the captures are single-GPU launches of the whole pair matrix
         try:
             # the DRAM bytes of the long launches depend on the cluster-progress window (profiles/r01d_panel_window.md)
             key = '%s/%s' % (args.workload, mode_used) + ('' if (windows != {0} or args.workload != '1m') else '/window_off')
