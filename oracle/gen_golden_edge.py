@@ -1,0 +1,54 @@
+"""Generate ``tests/golden/validation_edge.npz``: edge cases of FaceToFaceValidation (facenet/statistics.py:237-331) from
+the UNMODIFIED reference (``oracle.reference_loader``).  Build container only:
+
+    python -m oracle.gen_golden_edge
+
+Cases (inputs are stored in the fixture):
+  folds3    N = 64 (not divisible), 3 folds, far_target 0.1 -- the first N % k folds are one longer (:278-287), a FAR
+            target in the steep part of the curve (:299-302)
+  sparse    many singletons + a few pairs, 5 folds -- test folds where no class has two images: tp + fn == 0, the
+            rates fall back to 1 (:144-165) and the report's means carry those defaults
+  twoclass  two classes only, 2 folds, metric 1 -- the smallest C(C-1)/2 weight (:99) and the arccos grid (:258)
+
+The seeds are chosen so that no pair distance lies within 3e-5 of a grid threshold or of a chosen FAR threshold: any
+implementation whose distances are within the 1e-5 tolerance must reproduce these outputs EXACTLY (no eps-window pairs),
+(D = 64 everywhere: the CUDA path needs D % 64 == 0),
+which is what lets the GPU leg (tests/test_gpu_parity.py) use tight tolerances.
+"""
+import numpy as np
+
+from oracle import statistics_oracle as so
+from oracle.gen_golden import OUT, Cfg, versions
+from oracle.reference_loader import load_reference_statistics
+
+CASES = {
+    'folds3': dict(sizes=[9, 7, 5, 3, 2, 1, 1, 14, 11, 6, 4, 1], dim=64, sigma=2.0, seed=41, metric=0, folds=3, far=1.e-1),
+    'sparse': dict(sizes=[1] * 30 + [2] * 6 + [3, 4], dim=64, sigma=1.6, seed=49, metric=0, folds=5, far=1.e-2),
+    'twoclass': dict(sizes=[17, 23], dim=64, sigma=1.8, seed=39, metric=1, folds=2, far=1.e-2),
+}
+
+
+def main():
+    st = load_reference_statistics()
+    out = {'versions': versions(), 'cases': np.array(sorted(CASES))}
+    for name, c in sorted(CASES.items()):
+        x, labels = so.synthetic_embeddings(c['sizes'], dim=c['dim'], sigma=c['sigma'], seed=c['seed'], shuffle=True)
+        v = st.FaceToFaceValidation(x, labels, Cfg(c['metric'], c['folds'], c['far']))
+        out[name + '_embeddings'], out[name + '_labels'] = x, labels
+        out[name + '_cfg'] = np.array([c['metric'], c['folds'], c['far']], dtype=np.float64)
+        for r, tag in zip(v.reports, ('acc', 'far')):
+            dct = r.dict
+            out['%s_%s_keys' % (name, tag)] = np.array(sorted(dct.keys()))
+            out['%s_%s_vals' % (name, tag)] = np.array([float(dct[k]) for k in sorted(dct.keys())])
+            out['%s_%s_thr' % (name, tag)] = np.array([float(m.threshold[0]) for m in r.conf_matrix_test])
+            out['%s_%s_test' % (name, tag)] = np.array([[m.tp[0], m.tn[0], m.fp[0], m.fn[0]] for m in r.conf_matrix_test])
+        out[name + '_train_tp'] = np.array([m.tp for m in v.reports[0].conf_matrix_train])
+        out[name + '_train_fp'] = np.array([m.fp for m in v.reports[0].conf_matrix_train])
+        out[name + '_repr'] = np.array(repr(v).split('elapsed_time')[0])
+        out[name + '_criteria'] = np.array(sorted(v.dict.keys()))
+    np.savez_compressed(OUT / 'validation_edge.npz', **out)
+    print('validation_edge.npz', (OUT / 'validation_edge.npz').stat().st_size, 'bytes')
+
+
+if __name__ == '__main__':
+    main()

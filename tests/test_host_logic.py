@@ -241,3 +241,33 @@ def test_validation_subset_rows_and_normalise_on_load(emulated, golden_dir):
     calc = fst.SimilarityCalculator((x * scale).astype(np.float32), labels[10:50], _rows=np.arange(10, 50), normalize=True)
     assert calc.nrof_classes == np.unique(labels[10:50]).size
     assert abs(float(np.linalg.norm(calc.embeddings[0][0])) - 1.0) < 1e-6
+
+
+def test_validation_edge_cases_host_math_golden(emulated, golden_dir):
+    """The drop-in FaceToFaceValidation (host logic over the emulated library) on the reference's outputs for ragged folds
+    (N % k != 0), test folds without a same-identity pair and a two-class set (tests/golden/validation_edge.npz)."""
+    g = np.load(golden_dir / 'validation_edge.npz')
+    for name in (str(c) for c in g['cases']):
+        x, labels = g[name + '_embeddings'], g[name + '_labels']
+
+        class Cfg:
+            metric, nrof_folds, far_target = int(g[name + '_cfg'][0]), int(g[name + '_cfg'][1]), float(g[name + '_cfg'][2])
+
+        v = fst.FaceToFaceValidation(x, labels, Cfg)
+        assert sorted(v.dict.keys()) == [str(k) for k in g[name + '_criteria']]
+        for r, tag in zip(v.reports, ('acc', 'far')):
+            dct = r.dict
+            keys = [str(k) for k in g['%s_%s_keys' % (name, tag)]]
+            assert sorted(dct.keys()) == keys
+            np.testing.assert_allclose([float(dct[k]) for k in keys], g['%s_%s_vals' % (name, tag)], rtol=0, atol=1e-6,
+                                       err_msg='%s %s' % (name, tag))
+            got_thr = np.array([float(m.threshold[0]) for m in r.conf_matrix_test])
+            if tag == 'acc':
+                np.testing.assert_array_equal(got_thr, g[name + '_acc_thr'])
+            else:
+                np.testing.assert_allclose(got_thr, g[name + '_far_thr'], rtol=0, atol=1e-9)
+            got_test = np.array([[m.tp[0], m.tn[0], m.fp[0], m.fn[0]] for m in r.conf_matrix_test])
+            np.testing.assert_allclose(got_test, g['%s_%s_test' % (name, tag)], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(np.array([m.tp for m in v.reports[0].conf_matrix_train]), g[name + '_train_tp'], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(np.array([m.fp for m in v.reports[0].conf_matrix_train]), g[name + '_train_fp'], rtol=0, atol=1e-12)
+        assert repr(v).split('elapsed_time')[0].splitlines()[:3] == str(g[name + '_repr']).splitlines()[:3]

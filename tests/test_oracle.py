@@ -156,3 +156,28 @@ def test_pair_histogram_equals_reference_counts_summed(golden_dir):
         got = so.pair_histogram(x, labels, thr, metric)
         # whole-Gram vs per-block sgemm may differ in the last ulp for a pair sitting on a threshold
         assert np.abs(got['same'] - same).sum() + np.abs(got['diff'] - diff).sum() <= 2
+
+
+def _edge_cases(golden_dir):
+    g = np.load(golden_dir / 'validation_edge.npz')
+    for name in (str(c) for c in g['cases']):
+        metric, folds, far = g[name + '_cfg']
+        yield g, name, int(metric), int(folds), float(far)
+
+
+def test_validation_edge_cases_golden(golden_dir):
+    """Edge cases of statistics.py:277-313 from the unmodified reference (oracle/gen_golden_edge.py): ragged folds, test
+    folds without a same-identity pair (rates default to 1), two classes only."""
+    for g, name, metric, folds, far in _edge_cases(golden_dir):
+        x, labels = g[name + '_embeddings'], g[name + '_labels']
+        for conf in (so.confidence_matrix_exact_order, so.confidence_matrix_weighted):
+            out = so.face_to_face_validation(x, labels, metric, folds, far, confidence=conf)
+            crit = [str(k) for k in g[name + '_criteria']]
+            assert sorted(k for k in out if not k.startswith('_')) == crit
+            for tag, key in (('acc', 'MaximumAccuracy'), ('far', [k for k in crit if k != 'MaximumAccuracy'][0])):
+                keys = [str(k) for k in g['%s_%s_keys' % (name, tag)]]
+                assert sorted(out[key].keys()) == keys
+                got = np.array([float(out[key][k]) for k in keys])
+                np.testing.assert_allclose(got, g['%s_%s_vals' % (name, tag)], rtol=0, atol=1e-9, err_msg='%s %s' % (name, key))
+            np.testing.assert_array_equal(out['_thresholds'][:, 0], g[name + '_acc_thr'])
+            np.testing.assert_allclose(out['_thresholds'][:, 1], g[name + '_far_thr'], rtol=0, atol=1e-12)
