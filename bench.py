@@ -376,18 +376,20 @@ def main():
     peak_key = 'bf16_tflops_sustained' if (long_step and 'bf16_tflops_sustained' in peaks) else 'bf16_tflops'
     tf32_peak = peaks[peak_key] / 2.0
     achieved = (pairs / world) * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12       # one launch covers 1/world of the pairs
-    traffic = None
+    traffic, traffic_src = None, None
     tf = ROOT / 'profiles' / 'ncu_traffic.json'
     if tf.exists() and world == 1:                     # the captures are single-GPU launches of the whole pair matrix
         try:
             # the DRAM bytes of the long launches depend on the cluster-progress window (profiles/r01d_panel_window.md)
             key = '%s/%s' % (args.workload, mode_used) + ('' if (windows != {0} or args.workload != '1m') else '/window_off')
-            traffic = json.loads(tf.read_text()).get(key)
+            table = json.loads(tf.read_text())
+            traffic = table.get(key)
+            traffic_src = 'profiles/ncu_traffic.json[%s]: %s' % (key, table.get('_note', '')) if traffic is not None else None
         except ValueError:
             traffic = None
     passes = 3 if mode_used.endswith('x3') else 2 if mode_used == 'fp16f8' else 1
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
-                'traffic': traffic, 'kernel': 'gram_kernel<HIST>', 'kernel_ms': k_ms,
+                'traffic': traffic, 'traffic_source': traffic_src, 'kernel': 'gram_kernel<HIST>', 'kernel_ms': k_ms,
                 'peak_source': peak_src + ': %s / 2 (TF32 rate = half the bf16 rate); of measured' % peak_key,
                 'frac_of_nominal_tf32_1100': achieved / 1100.0,
                 'executed_mma_tflops': achieved * passes,
