@@ -47,7 +47,9 @@ def build(force=False, verbose=True):
         obj = obj_dir / (src.replace('.cu', '.o'))
         cmd = [cc] + NVCC_FLAGS + ['-c', str(CSRC / src), '-o', str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        (obj_dir / (src + '.log')).write_text(r.stdout + r.stderr)
+        # tracked ptxas -v log (registers, spills, barriers per kernel); compile times would make every rebuild a diff
+        log = ''.join(ln for ln in (r.stdout + r.stderr).splitlines(keepends=True) if 'Compile time' not in ln)
+        (obj_dir / (src + '.log')).write_text(log)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s' % (src, r.stdout + r.stderr))
         return obj

@@ -558,6 +558,9 @@ struct HistLaunch {
     CutTables ct;
     int nkeys = 1;
     int stride = kMaxBins + 1;
+    // the auto rule of fnb_options.panel_window applies (whole-set launches: every region is a super-row whose column panels
+    // hold many tiles per cluster; keyed launches can have one-tile regions, where a progress window would serialise the clusters)
+    bool auto_window = false;
 };
 
 // uploads tables, zeroes bins, launches the HIST kernel over `regs`; leaves bins on the device
@@ -593,7 +596,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     // cluster-progress window (fnb_options.panel_window, GramParams::sync_window): auto = on for the launches long enough for the
     // clusters to drift apart (this rank's share of the pair matrix >= 5e10 pairs, the same launches pick_pairs calls long)
     p.sync_window = opt.panel_window > 0 ? std::min(opt.panel_window, 7) : 0;
-    if (opt.panel_window == 0) {
+    if (opt.panel_window == 0 && hl.auto_window) {
         double own_pairs = 0.0;
         for (size_t i = 0; i + 1 < regs.size(); ++i) {
             const RegionDev& r = regs[i];
@@ -774,7 +777,7 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     h->last_shard = shard.spec;
     finish_regions(regs, tile, op.pairs, &shard);
 
-    HistLaunch hl;
+    HistLaunch hl; hl.auto_window = true;
     if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
     float smin, smax; bool violated = false;
     if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;

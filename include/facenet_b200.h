@@ -117,8 +117,9 @@ typedef struct {
                               on, and one that is more than panel_window panels ahead of the slowest waits (bounded: it gives
                               up after a few ms, so this can cost time but never hang).  Keeps the clusters inside the same
                               column panels, which keeps the super-row's row panels in L2 over long launches (1M rows: DRAM
-                              reads 824 -> 193-208 GB per launch, kernel 834 -> 800 ms).  1..7 = window, -1 = off, 0 = auto (2 when this
-                              rank's share is >= 5e10 pairs, the launches long enough to drift; else off).  Timing only:
+                              reads 824 -> 193-208 GB per launch, kernel 834 -> 800 ms).  1..7 = window, -1 = off, 0 = auto (whole-set
+                              launches -- fnb_pair_histogram[_bins] -- whose share on this rank is >= 5e10 pairs, the ones long
+                              enough to drift: window 2; off otherwise and for keyed launches, whose regions can be one tile wide).  Timing only:
                               the integer bins do not depend on it. */
 } fnb_options;
 
