@@ -14,6 +14,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -s 1 -c 1 -o gpurun_out/r2_prof_gram_1m -f \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --no-e2e > gpurun_out/r2_ncu_full.log 2>&1
 timeout 200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none \
-  -k regex:gram_kernel -c 13 python scripts/probe_rr_window.py 1000000 2 32768,32768,16384,8192,49152,65536 -1,2 2>&1 \
+  -k regex:gram_kernel -c 13 python scripts/probe_rr_window.py 1000000 2 32768,32768,24576,16384,8192,49152 -1,2 2>&1 \
   | grep -E "dram__bytes|gpu__time_duration|hit_rate|rr=|rror" > gpurun_out/r2_rr_window.log
 tail -3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_smoke.log; cat gpurun_out/r2_bench_1m.json | cut -c1-400; cut -c1-160 gpurun_out/r2_rr_window.log
