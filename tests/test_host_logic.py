@@ -271,3 +271,25 @@ def test_validation_edge_cases_host_math_golden(emulated, golden_dir):
         np.testing.assert_allclose(np.array([m.tp for m in v.reports[0].conf_matrix_train]), g[name + '_train_tp'], rtol=0, atol=1e-12)
         np.testing.assert_allclose(np.array([m.fp for m in v.reports[0].conf_matrix_train]), g[name + '_train_fp'], rtol=0, atol=1e-12)
         assert repr(v).split('elapsed_time')[0].splitlines()[:3] == str(g[name + '_repr']).splitlines()[:3]
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_confidence_matrix_host_math_random_ragged_sets(emulated, seed):
+    """Size-group rectangles + fp64 weights (statistics._size_group_plan) against the literal class-pair loop of the oracle
+    (statistics.py:115-138) on random ragged sets: singletons, repeated sizes, one dominant class, shuffled rows,
+    non-contiguous label values, both metrics, grids and single thresholds."""
+    rng = np.random.default_rng(1000 + seed)
+    nc = int(rng.integers(2, 40))
+    sizes = rng.choice([1, 1, 2, 2, 3, 5, 8, 13], size=nc).tolist()
+    if seed % 2:
+        sizes[int(rng.integers(0, nc))] = int(rng.integers(40, 90))
+    values = rng.choice(np.arange(-50, 5000), size=nc, replace=False)
+    x, labels = so.synthetic_embeddings(sizes, dim=64, sigma=float(rng.uniform(0.8, 2.5)), seed=seed, shuffle=True, label_values=values)
+    metric = seed % 2
+    for thr in (so.default_thresholds(metric), np.array(float(rng.uniform(0.5, 2.5)))):
+        cm = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, metric), thr)
+        ref = so.confidence_matrix_exact_order(x, labels, thr, metric)
+        for name in ('tp', 'tn', 'fp', 'fn'):
+            np.testing.assert_allclose(getattr(cm, name), getattr(ref, name), rtol=0, atol=1e-13, err_msg='%s seed %d' % (name, seed))
+        for name in ('accuracy', 'precision', 'tp_rates', 'tn_rates', 'fp_rates', 'fn_rates'):
+            np.testing.assert_allclose(getattr(cm, name), getattr(ref, name), rtol=0, atol=1e-12, err_msg=name)
