@@ -25,8 +25,8 @@ MAX_THRESHOLDS = 127
 
 EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info', 'fnb_set_stream',
            'fnb_pairwise', 'fnb_pair_histogram_bins', 'fnb_counts_from_bins', 'fnb_pair_histogram',
-           'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine', 'fnb_pair_cross_entropy',
-           'fnb_logits_cross_entropy')
+           'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine', 'fnb_mine_batched', 'fnb_mine_check',
+           'fnb_mine_select_kth', 'fnb_pair_cross_entropy', 'fnb_logits_cross_entropy')
 
 
 class DLDevice(ctypes.Structure):
@@ -51,7 +51,7 @@ class Options(ctypes.Structure):
                 ('cluster_pairs', ctypes.c_int32), ('normalize', ctypes.c_int32), ('theta', ctypes.c_float),
                 ('raw_distance', ctypes.c_int32), ('subset_rows', ctypes.c_int32), ('shard_mod', ctypes.c_int32),
                 ('shard_lo', ctypes.c_int32), ('shard_width', ctypes.c_int32), ('shard_slots', ctypes.POINTER(ctypes.c_int32)),
-                ('panel_window', ctypes.c_int32)]
+                ('panel_window', ctypes.c_int32), ('strict_tiles', ctypes.c_int32), ('bias_correction', ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -59,7 +59,7 @@ class Stats(ctypes.Structure):
                 ('smax', ctypes.c_float), ('max_abs', ctypes.c_float), ('kernel_ms', ctypes.c_float),
                 ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
                 ('eps_counted', ctypes.c_float), ('grid_ctas', ctypes.c_uint32), ('mode_used', ctypes.c_int32), ('peakedness', ctypes.c_float),
-                ('panel_window', ctypes.c_int32)]
+                ('panel_window', ctypes.c_int32), ('error_bound', ctypes.c_float), ('fallback', ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
@@ -113,6 +113,10 @@ def load_library():
                                                       P(c.c_double), P(c.c_double), P(c.c_int32), P(c.c_double)]
         lib.fnb_mine.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), c.c_float, P(Options), P(c.c_int32), P(c.c_int32),
                                  c.c_int, P(c.c_int32), P(c.c_int32), P(c.c_int32), P(Stats)]
+        lib.fnb_mine_batched.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), c.c_int, c.c_float, P(Options), c.c_int, P(DLTensor),
+                                         P(DLTensor), P(DLTensor), P(DLTensor), P(DLTensor), P(DLTensor), P(Stats)]
+        lib.fnb_mine_check.argtypes = [c.c_void_p, P(c.c_int32), P(Stats)]
+        lib.fnb_mine_select_kth.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(DLTensor), c.c_float, P(DLTensor)]
         lib.fnb_pair_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, c.c_float, c.c_float, P(Options), P(c.c_double), P(Stats)]
         lib.fnb_logits_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, P(c.c_double)]
         for name in EXPORTS:
@@ -303,7 +307,7 @@ class Handle:
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
                 cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0, normalize=0, theta=0.0, raw_distance=False,
-                shard=None, subset_rows=0, panel_window=None):
+                shard=None, subset_rows=0, panel_window=None, strict_tiles=None, bias_correction=None):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -323,6 +327,9 @@ class Handle:
         o.subset_rows = int(subset_rows)
         # None: FNB_PANEL_WINDOW from the environment (probe scripts), else 0 = auto (see fnb_options.panel_window)
         o.panel_window = int(os.environ.get('FNB_PANEL_WINDOW', '0')) if panel_window is None else int(panel_window)
+        # measurement knobs (None: environment, else 0 = on, -1 = off)
+        o.strict_tiles = int(os.environ.get('FNB_STRICT_TILES', '0')) if strict_tiles is None else int(strict_tiles)
+        o.bias_correction = int(os.environ.get('FNB_BIAS_CORRECTION', '0')) if bias_correction is None else int(bias_correction)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -340,7 +347,7 @@ class Handle:
 
     # ---- pairwise_similarities (statistics.py:22-57)
     def pairwise(self, xa, xb=None, metric=0, atol=1.e-5, mode='fp16x3', cta_group=0, out=None, normalize=0, theta=0.0,
-                 raw_distance=False):
+                 raw_distance=False, bias_correction=None):
         xa = _as_f32_matrix(xa, 'xa')
         na = xa.shape[0]
         if xb is not None:
@@ -351,7 +358,7 @@ class Handle:
         if out is None:
             out = np.empty(shape, dtype=np.float32)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, cta_group=cta_group, normalize=normalize, theta=theta,
-                               raw_distance=raw_distance)
+                               raw_distance=raw_distance, bias_correction=bias_correction)
         rng = (ctypes.c_float * 2)()
         ba, bo = self._borrow(xa), self._borrow(out)
         bb = self._borrow(xb) if xb is not None else None
@@ -364,7 +371,8 @@ class Handle:
     # ---- whole-set verification histogram
     def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
                             rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy',
-                            force_checked=False, cluster_pairs=0, normalize=0, shard=None, panel_window=None):
+                            force_checked=False, cluster_pairs=0, normalize=0, shard=None, panel_window=None,
+                            strict_tiles=None, bias_correction=None):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
@@ -372,7 +380,8 @@ class Handle:
             cuts = numpy_cuts(thr, metric)
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
                                region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked,
-                               cluster_pairs=cluster_pairs, normalize=normalize, shard=shard, panel_window=panel_window)
+                               cluster_pairs=cluster_pairs, normalize=normalize, shard=shard, panel_window=panel_window,
+                               strict_tiles=strict_tiles, bias_correction=bias_correction)
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()
@@ -488,13 +497,30 @@ class Handle:
         return float(loss.value)
 
     # ---- triplet mining (semantics: oracle/mining_oracle.py; not in the reference fork)
+    _kmax_cache = {}
+
+    @classmethod
+    def _kmax_of(cls, labels, nbatches=1):
+        """largest class size - 1 over the batches (host labels; cached on the label bytes: a training loop re-uses its P x K labels)"""
+        lab = np.ascontiguousarray(labels)
+        key = (lab.shape, lab.dtype.str, int(nbatches), hash(lab.tobytes()))
+        hit = cls._kmax_cache.get(key)
+        if hit is None:
+            if len(cls._kmax_cache) > 256:
+                cls._kmax_cache.clear()
+            hit = 0
+            for part in np.split(lab, int(nbatches)) if lab.size else []:
+                hit = max(hit, int(np.unique(part, return_counts=True)[1].max()) - 1)
+            cls._kmax_cache[key] = hit
+        return hit
+
     def mine(self, embeddings, labels, alpha=0.2, kmax=None, mode='fp16x3', atol=1.e-5):
+        """One batch, host (NumPy) results: the synchronous form (``fnb_mine``)."""
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         b = int(embeddings.shape[0])
         if kmax is None:
-            lab_np = labels if isinstance(labels, np.ndarray) else np.asarray(labels.cpu())
-            kmax = int(np.unique(lab_np, return_counts=True)[1].max()) - 1 if b else 0
+            kmax = self._kmax_of(labels if isinstance(labels, np.ndarray) else np.asarray(labels.cpu())) if b else 0
         kmax = int(kmax)
         hp = np.full(b, -1, dtype=np.int32)
         hn = np.full(b, -1, dtype=np.int32)
@@ -510,6 +536,77 @@ class Handle:
         if rc != FNB_OK:
             self._raise(rc)
         return {'hardest_pos': hp, 'hardest_neg': hn, 'pos_index': pi, 'semi_hard': sh, 'eligible': el, 'stats': st.as_dict()}
+
+    def mine_batched(self, embeddings, labels, nbatches=1, alpha=0.2, kmax=None, mode='fp16x3', atol=1.e-5, out=None):
+        """``nbatches`` batches of equal size packed as ``[S * B, D]`` / ``[S * B]`` in ONE call (``fnb_mine_batched``); all indices
+        are local to their batch.  torch CUDA inputs give torch CUDA int32 outputs WITHOUT a host synchronisation (pass ``kmax``;
+        ``out`` = the dict of a previous call re-uses its tensors; data-dependent errors surface in ``mine_check``); NumPy inputs
+        give NumPy outputs (synchronous).  ``kmax=0``: hardest positive / negative only -- fully fused in the Gram epilogue, no
+        distance strip."""
+        embeddings = _as_f32_matrix(embeddings, 'embeddings')
+        labels = _as_labels(labels)
+        rows = int(embeddings.shape[0])
+        on_gpu = not isinstance(embeddings, np.ndarray) and getattr(embeddings, 'is_cuda', False)
+        if kmax is None:
+            kmax = self._kmax_of(labels if isinstance(labels, np.ndarray) else np.asarray(labels.cpu()), nbatches) if rows else 0
+        kmax = int(kmax)
+        names = ('hardest_pos', 'hardest_neg', 'pos_index', 'semi_hard', 'eligible', 'status')
+        shapes = ((rows,), (rows,), (rows, kmax), (rows, kmax), (rows, kmax), (4,))
+        if out is None:
+            out = {}
+        for name, shape in zip(names, shapes):
+            cur = out.get(name)
+            if cur is not None and tuple(cur.shape) == shape:
+                continue
+            if on_gpu:
+                import torch
+                out[name] = torch.empty(shape, dtype=torch.int32, device=embeddings.device)
+            else:
+                out[name] = np.empty(shape, dtype=np.int32)
+        o, keep = self.options(mode=mode, metric=0, atol=atol)
+        st = Stats()
+        be, bl = self._borrow(embeddings), self._borrow(labels)
+        bo = [self._borrow(out[name]) for name in names]
+        none = ctypes.POINTER(DLTensor)()
+        ptrs = [b.ptr for b in bo]
+        if kmax == 0:
+            ptrs[2] = ptrs[3] = ptrs[4] = none
+        rc = self.lib.fnb_mine_batched(self.h, be.ptr, bl.ptr, int(nbatches), float(alpha), ctypes.byref(o), kmax,
+                                       ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ctypes.byref(st))
+        if rc != FNB_OK:
+            self._raise(rc)
+        out['stats'] = st.as_dict()
+        return out
+
+    def mine_check(self):
+        """Synchronise and raise what the last ``mine_batched`` call on device tensors could not report; returns
+        ``{'kmax_needed', 'smin', 'smax', 'kernel_ms', 'prepare_ms'}``."""
+        status = (ctypes.c_int32 * 4)()
+        st = Stats()
+        rc = self.lib.fnb_mine_check(self.h, status, ctypes.byref(st))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return {'kmax_needed': int(status[0]), 'smin': st.smin, 'smax': st.smax, 'kernel_ms': st.kernel_ms, 'prepare_ms': st.prepare_ms}
+
+    def mine_select_kth(self, anchors, positives, kth, alpha=0.2, out=None):
+        """The ``kth[i]``-th (0-based, ascending index) margin-eligible negative of ``(anchors[i], positives[i])`` over the distance
+        strips of the last mining call (``fnb_mine_select_kth``); -1 if there are fewer.  int32 arrays (NumPy or torch CUDA)."""
+        def as_i32(x):
+            if isinstance(x, np.ndarray) or not hasattr(x, '__dlpack__'):
+                return np.ascontiguousarray(x, dtype=np.int32)
+            return x
+        anchors, positives, kth = as_i32(anchors), as_i32(positives), as_i32(kth)
+        if out is None:
+            if isinstance(anchors, np.ndarray):
+                out = np.empty(anchors.shape, dtype=np.int32)
+            else:
+                import torch
+                out = torch.empty(anchors.shape, dtype=torch.int32, device=anchors.device)
+        ba, bp, bk, bo = self._borrow(anchors), self._borrow(positives), self._borrow(kth), self._borrow(out)
+        rc = self.lib.fnb_mine_select_kth(self.h, ba.ptr, bp.ptr, bk.ptr, float(alpha), bo.ptr)
+        if rc != FNB_OK:
+            self._raise(rc)
+        return out
 
 
 _default_handles = {}

@@ -1,6 +1,7 @@
 // facenet_b200 -- C-ABI entry points (include/facenet_b200.h): argument checking, DLPack
 // ingestion, workspace management, similarity-cut tables, region schedules and kernel launches.
 #include "fnb_host.h"
+#include "fnb_bias.h"
 
 #include <algorithm>
 #include <cmath>
@@ -44,6 +45,47 @@ int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, fl
     return -1;
 }
 
+// beta(|s|) knots of `mode` at dimension d (fnb_bias.h); zeros for the modes without a calibration
+void bias_table(int mode, int d, float* knots /* [kBiasStride] */) {
+    for (int i = 0; i < kBiasStride; ++i) knots[i] = 0.f;
+    const float* src = nullptr;
+    double f = std::pow((double)d / 512.0, 1.09);
+    switch (mode) {
+        case FNB_MODE_FP16X3: src = kBiasBetaX3; break;
+        case FNB_MODE_TF32X3: src = kBiasBetaX3; f *= 1.41; break;     // same 96 steps, coarser product alignment (relu probe: 5.7 vs 4.0e-6)
+        case FNB_MODE_FP16F8: case FNB_MODE_AUTO: src = kBiasBetaF8; break;
+        default: return;
+    }
+    for (int i = 0; i < kBiasKnots; ++i) knots[i] = (float)(src[i] * f);
+    for (int i = kBiasKnots; i < kBiasStride; ++i) knots[i] = knots[kBiasKnots - 1];
+}
+
+static double beta_at(const float* knots, double a) {
+    a = std::min(std::fabs(a), 1.0) * (kBiasKnots - 1);
+    int i = std::min((int)a, kBiasKnots - 2);
+    const double f = a - i;
+    return knots[i] + f * (knots[i + 1] - knots[i]);
+}
+
+// Error model of one pair's similarity in `mode` AFTER the bias correction (profiles/r02a_bias_fine.log, D = 512, dense rows):
+// spread of the truncating accumulation (fp16x3: 0.05e-6 .. 0.32e-6, ~ D^0.8) and, for fp16f8, of the 2 D e4m3 roundings of
+// the cross terms (0.46e-6 .. 0.83e-6 for Gaussian rows, ~ sqrt(sum x_i^2 y_i^2) <= sqrt(peakedness)); the single-pass modes
+// carry the rounding of the operands themselves.  Returns sigma(s).
+double mode_sigma_s(int mode, int d, double abs_s, double peakedness) {
+    const double trunc = (0.05e-6 + 0.27e-6 * abs_s) * std::pow((double)d / 512.0, 0.8);
+    switch (mode) {
+        case FNB_MODE_FP16X3: return trunc;
+        case FNB_MODE_TF32X3: return 1.41 * trunc;
+        case FNB_MODE_FP16F8: case FNB_MODE_AUTO: {
+            const double pk = peakedness > 0 ? peakedness : 3.0 / d;
+            const double e4m3 = (0.455e-6 + 0.375e-6 * abs_s) * std::sqrt(pk / (3.0 / 512.0));
+            return std::sqrt(e4m3 * e4m3 + trunc * trunc / 3.0);
+        }
+        case FNB_MODE_BF16: return 1.5e-4;
+        default: return 1.75e-5;                          // tf32 / fp16 single pass
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // similarity cuts.  dist32() restates statistics.py:45-53 on one fp32 value.
 
@@ -67,7 +109,8 @@ static float cut_for_threshold(double t, int metric) {
     return ordered_to_float(hi);
 }
 
-int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out) {
+int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out,
+                     const float* beta_knots) {
     if (T < 1 || T >= kMaxBins) return -1;
     CutTables& c = *out;
     c.T = T;
@@ -92,13 +135,20 @@ int build_cut_tables(const double* thresholds, int T, int metric, double eps, co
     }
     for (int n = 0; n < T; ++n)
         c.pos[n] = (int)(std::upper_bound(c.cuts, c.cuts + T, cut[n]) - c.cuts);
-    // arithmetic-progression fit of the finite cuts (true for np.linspace thresholds with metric 0)
+    // arithmetic-progression fit of the finite cuts (true for np.linspace thresholds with metric 0) in RAW similarity: the
+    // interior tiles bin the uncorrected accumulator, s_raw = s (1 - beta(|s|)) (fnb_bias.h), so the progression is fitted to
+    // the raw positions of the cuts and the curvature of beta goes into `dev`, i.e. into the counted near-threshold window
     c.uniform = 0;
     if (c.T_fin >= 2) {
-        c.e0 = c.cuts[0];
-        c.h = ((double)c.cuts[c.T_fin - 1] - (double)c.cuts[0]) / (c.T_fin - 1);
+        std::vector<double> raw(c.T_fin);
+        for (int j = 0; j < c.T_fin; ++j) {
+            const double cj = (double)c.cuts[j];
+            raw[j] = beta_knots ? cj * (1.0 - beta_at(beta_knots, cj)) : cj;
+        }
+        c.e0 = raw[0];
+        c.h = (raw[c.T_fin - 1] - raw[0]) / (c.T_fin - 1);
         double dev = 0;
-        for (int j = 0; j < c.T_fin; ++j) dev = std::max(dev, std::fabs((double)c.cuts[j] - (c.e0 + j * c.h)));
+        for (int j = 0; j < c.T_fin; ++j) dev = std::max(dev, std::fabs(raw[j] - (c.e0 + j * c.h)));
         c.dev = dev;
         if (c.h > 1e-4 && dev / c.h < 2e-4) c.uniform = 1;
     }
@@ -161,7 +211,9 @@ static int make_tmap(fnb_context* h, CUtensorMap* m, void* base, int fmt, long l
     return FNB_OK;
 }
 
-constexpr float kAutoPeakLimit = 1.0f / 64.0f;       // FNB_MODE_AUTO: largest peakedness FP16F8 is used for
+// FNB_MODE_AUTO: largest peakedness FP16F8 is used for.  Dense Gaussian-like rows have 3 / D: 512-d embeddings pass (0.0059),
+// 256-d ones (0.0117: measured max |dd| 1.3e-5 in fp16f8, profiles/r02a_bias_d256.log) and sparse / heavy-tailed rows do not
+constexpr float kAutoPeakLimit = 1.0f / 128.0f;
 
 static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 
@@ -258,7 +310,7 @@ static int pick_region_rows(const fnb_options* o, int tile, long long n = 0, int
     long long rr = o->region_rows;
     const int world = std::max(1, o->world);
     if (rr <= 0) {
-        rr = (64ll << 20) / (4ll * std::max(d, 1)) * world;
+        rr = (48ll << 20) / (4ll * std::max(d, 1)) * world;
         if (n > 0) rr = std::min(rr, std::max<long long>(n / 6, 8ll * tile));
         // row blocks per super-row divisible by world: rank r then owns the SAME row blocks (r, r + world, ...) in every
         // column panel, i.e. 1/world of the row panels; otherwise its rows drift from column to column and it ends up
@@ -331,9 +383,9 @@ extern "C" void fnb_destroy(fnb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->progress, &h->perm, &h->cls,
+    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_l16, &h->b_l16, &h->bias_tab, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->progress, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
-                      &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io};
+                      &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io, &h->mine_lab, &h->mine_keys, &h->mine_status};
     for (DevBuf* b : bufs) b->release();
     h->pinned.release();
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -400,6 +452,9 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     CK(hi.ensure(bytes));
     if (op.num_pass == 3) CK(lo.ensure(bytes));
     if (f8) { CK(lo.ensure((size_t)n_pad * d)); CK(h8.ensure((size_t)n_pad * d)); }
+    DevBuf& l16 = side_b ? h->b_l16 : h->a_l16;
+    const bool want_l16 = f8 && op.want_l16;
+    if (want_l16) CK(l16.ensure(bytes));
     CK(h->counters.ensure(sizeof(DeviceScalars)));
     unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;    // [0] max squared norm, [1] peakedness
     static_assert(offsetof(DeviceScalars, peak_max_ord) == offsetof(DeviceScalars, norm_max_ord) + 4, "layout");
@@ -412,7 +467,7 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     }
     (side_b ? op.b_nrm : op.a_nrm) = nrm_out;
     CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream,
-                         normalize, nrm_out));
+                         normalize, nrm_out, want_l16 ? l16.p : nullptr));
     // an operand that two pairs of a cluster share is fetched as two 64-row halves (A: pairs 2 and 4, B: pairs 4)
     const int box_rows = (side_b ? op.pairs == 4 : op.pairs > 1) ? kRowsPerCta / 2 : kRowsPerCta;
     if (!side_b) op.a_rows_pad = n_pad;
@@ -422,12 +477,15 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     else if (f8) { rc = make_tmap(h, m_lo, lo.p, kFmtU8, n_pad, d, box_rows); if (!rc) rc = make_tmap(h, m_h8, h8.p, kFmtU8, n_pad, d, box_rows); }
     else *m_lo = *m_hi;
     if (!f8) *m_h8 = *m_hi;
+    CUtensorMap* m_l16 = side_b ? &op.b_l16 : &op.a_l16;
+    *m_l16 = *m_hi;
+    if (!rc && want_l16) { rc = make_tmap(h, m_l16, l16.p, kFmtF16, n_pad, d, box_rows); if (!side_b) op.have_l16 = true; }
     return rc;
 }
 
 int fnb::self_b_maps(fnb_context* h, GramOperands& op, int d) {
     op.b_nrm = op.a_nrm;
-    if (op.pairs == 1 || op.pairs == 4) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; return FNB_OK; }
+    if (op.pairs == 1 || op.pairs == 4) { op.b_hi = op.a_hi; op.b_lo = op.a_lo; op.b_h8 = op.a_h8; op.b_l16 = op.a_l16; return FNB_OK; }
     // pairs == 2: the A maps carry half-height boxes, the B side is not shared: encode full-height boxes over the same arrays
     const bool f8 = (op.num_pass == 2);
     int rc = make_tmap(h, &op.b_hi, h->a_hi.p, op.fmt, op.a_rows_pad, d);
@@ -436,6 +494,8 @@ int fnb::self_b_maps(fnb_context* h, GramOperands& op, int d) {
     else if (f8) { rc = make_tmap(h, &op.b_lo, h->a_lo.p, kFmtU8, op.a_rows_pad, d); if (!rc) rc = make_tmap(h, &op.b_h8, h->a_h8.p, kFmtU8, op.a_rows_pad, d); }
     else op.b_lo = op.b_hi;
     if (!f8) op.b_h8 = op.b_hi;
+    op.b_l16 = op.b_hi;
+    if (!rc && op.have_l16) rc = make_tmap(h, &op.b_l16, h->a_l16.p, kFmtF16, op.a_rows_pad, d);
     return rc;
 }
 
@@ -455,10 +515,27 @@ int fnb::reset_scalars(fnb_context* h) {
     init.range_ord[1] = 0;                              // max
     init.range_ord[2] = float_to_ordered(0.f);          // max |s|
     init.range_ord[3] = 0;
-    CK(h->pinned.ensure(4096));
+    CK(h->pinned.ensure(16384));                          // [0, 1 KB) scalars, [1 KB, 4 KB) tables, [4 KB, ..) bins of a whole-set launch
     memcpy(h->pinned.p, &init, sizeof(init));
     // the row-norm word behind the first 32 bytes is written by the split kernel and survives the reset
     CK(cudaMemcpyAsync(h->counters.p, h->pinned.p, offsetof(DeviceScalars, norm_max_ord), cudaMemcpyHostToDevice, h->stream));
+    return FNB_OK;
+}
+
+// device copy of the accumulation-bias knots: [0] the launch's mode, [1] the fp16x3 contraction of strict tiles in an fp16f8
+// launch (hi / l16 at the 2^12 pre-scale: the same 96 accumulation steps as FP16X3)
+int fnb::upload_bias(fnb_context* h, int mode, int d, bool off, const float** dev) {
+    if (off) { *dev = nullptr; return FNB_OK; }
+    CK(h->bias_tab.ensure(2 * kBiasStride * 4));
+    if (h->bias_mode != mode || h->bias_d != d) {
+        float tab[2 * kBiasStride];
+        bias_table(mode, d, tab);
+        bias_table(FNB_MODE_FP16X3, d, tab + kBiasStride);
+        // pageable source: the runtime stages the 352 bytes before the call returns
+        CK(cudaMemcpyAsync(h->bias_tab.p, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
+        h->bias_mode = mode; h->bias_d = d;
+    }
+    *dev = h->bias_tab.as<float>();
     return FNB_OK;
 }
 
@@ -534,6 +611,7 @@ extern "C" int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb
     p.n_rows = (int)na; p.n_cols = (int)nb;
     p.raw = opt.raw_distance;
     if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
+    if ((rc = upload_bias(h, op.mode, d, opt.bias_correction < 0, &p.bias_beta))) return rc;
     if ((rc = launch_gram(h, cg, EPI_PAIRWISE, opt.max_ctas, op, p, 0))) return rc;
 
     DeviceScalars hs;
@@ -567,7 +645,10 @@ struct HistLaunch {
 static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, const std::vector<RegionDev>& regs, int cg,
                     int d, const int32_t* cls_dev, const double* thresholds, int T, HistLaunch& hl, int force_slow)
 {
-    if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &hl.ct))
+    float knots[kBiasStride];
+    bias_table(op.mode, d, knots);
+    const bool bias_off = opt.bias_correction < 0;
+    if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &hl.ct, bias_off ? nullptr : knots))
         return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
     int rc;
     if ((rc = upload_regions(h, regs))) return rc;
@@ -590,6 +671,9 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
     p.operand_fmt = op.fmt;
     p.force_slow = force_slow || opt.force_checked;
+    if ((rc = upload_bias(h, op.mode, d, bias_off, &p.bias_beta))) return rc;
+    p.strict_tiles = (op.num_pass == 2 && op.have_l16 && opt.strict_tiles >= 0) ? 1 : 0;
+    h->last_strict = p.strict_tiles;
     p.raw = opt.raw_distance;
     if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
     p.debug = opt.debug & 3;
@@ -718,6 +802,39 @@ static double mode_slack(int mode) {
 
 static uint64_t sum_bins(const uint64_t* b, int n) { uint64_t s = 0; for (int i = 0; i < n; ++i) s += b[i]; return s; }
 
+// A-posteriori error bound of one histogram launch (fnb_stats.error_bound).  The histogram tells how many pairs were found in
+// every similarity bin; for each non-empty bin the model error of the arithmetic that binned those pairs is
+//     residual of the bias correction (35 % of beta |s|: the data dependence seen in profiles/r02a_bias_{relu,sparse,t3}.log)
+//   + z sigma(|s|),  z = sqrt(2 ln(1000 (T + 1) M))  -- a union bound over the M pairs of the bin and all bins at 1e-3,
+// in distance units (metric 0: dd = 2 ds; metric 1 keeps similarity units like the eps window).  Same-identity pairs of an
+// fp16f8 launch with strict tiles ran in the fp16x3 contraction.  all / same: [T + 1] counts summed over keys.
+static double error_certificate(const fnb_options& opt, int mode, bool strict_tiles, int d, double peak, const CutTables& ct,
+                                const uint64_t* all, const uint64_t* same, int T)
+{
+    float tab_mode[kBiasStride], tab_x3[kBiasStride];
+    bias_table(mode, d, tab_mode);
+    bias_table(FNB_MODE_FP16X3, d, tab_x3);
+    const bool corrected = opt.bias_correction >= 0;
+    double worst = 0.0;
+    for (int k = 0; k <= T && k <= ct.T_fin; ++k) {
+        const double lo = k > 0 ? (double)ct.cuts[k - 1] : -1.0, hi = k < ct.T_fin ? (double)ct.cuts[k] : 1.0;
+        const double a = std::min(1.0, std::max(std::fabs(lo), std::fabs(hi)));
+        const uint64_t m_same = same[k], m_diff = all[k] - same[k];
+        for (int which = 0; which < 2; ++which) {
+            const uint64_t m = which ? m_same : m_diff;
+            if (!m) continue;
+            const bool x3 = which && strict_tiles && mode == FNB_MODE_FP16F8;
+            const int md = x3 ? FNB_MODE_FP16X3 : mode;
+            const double beta = beta_at(x3 ? tab_x3 : tab_mode, a);
+            const double resid = (corrected ? 0.35 : 1.0) * beta * a;
+            const double z = std::sqrt(2.0 * std::log(1000.0 * (T + 1) * (double)m));
+            const double e_s = resid + z * mode_sigma_s(md, d, a, peak);
+            worst = std::max(worst, opt.metric == 0 ? 2.0 * e_s : e_s);
+        }
+    }
+    return worst;
+}
+
 extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const DLTensor* labels,
                                        const double* thresholds, int T, const fnb_options* opt_in,
                                        DLTensor* bins_out, fnb_stats* stats)
@@ -764,38 +881,67 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
-    op.pairs = pick_pairs(&opt, cg, n);
-    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op, opt.normalize))) return rc;
-    if ((rc = self_b_maps(h, op, d))) return rc;
-    opt.mode = op.mode;                                  // AUTO resolved
-    h->last_mode = op.mode; h->last_peak = op.peakedness;
-
-    std::vector<RegionDev> regs;
-    triangle_regions(n, pick_region_rows(&opt, tile * (op.pairs == 1 ? 1 : 2), n, d), 0, regs);
+    const int requested = opt.mode;
     ShardHost shard;
     if ((rc = shard_from_options(h, opt, &shard))) return rc;
     h->last_shard = shard.spec;
-    finish_regions(regs, tile, op.pairs, &shard);
+    uint64_t host_bins[2 * (kMaxBins + 1)];
 
-    HistLaunch hl; hl.auto_window = true;
-    if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
-    float smin, smax; bool violated = false;
-    if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
-    if (violated) {
-        // re-run with every tile on the checked path to report the exact similarity range
-        if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 1))) return rc;
-        if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
-        return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
+    // one pass in `mode`: operands, schedule, launch, range check, bins to the host, error certificate
+    auto pass = [&](int mode, double* bound) -> int {
+        int rc2;
+        op = GramOperands();
+        op.pairs = pick_pairs(&opt, cg, n);
+        op.want_l16 = opt.strict_tiles >= 0;
+        if ((rc2 = prepare_operand(h, mode, (const float*)de, h->perm.as<long long>(), n, d, false, op, opt.normalize))) return rc2;
+        if ((rc2 = self_b_maps(h, op, d))) return rc2;
+        opt.mode = op.mode;                              // AUTO resolved
+        h->last_mode = op.mode; h->last_peak = op.peakedness;
+        std::vector<RegionDev> regs;
+        triangle_regions(n, pick_region_rows(&opt, tile * (op.pairs == 1 ? 1 : 2), n, d), 0, regs);
+        finish_regions(regs, tile, op.pairs, &shard);
+        HistLaunch hl; hl.auto_window = true;
+        if ((rc2 = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc2;
+        float smin, smax; bool violated = false;
+        if ((rc2 = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc2;
+        if (violated) {
+            // re-run with every tile on the checked path to report the exact similarity range
+            if ((rc2 = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 1))) return rc2;
+            if ((rc2 = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc2;
+            return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
+        }
+        CK(cudaMemcpyAsync(h->pinned.as<char>() + 4096, h->bins.p, 2 * (size_t)hl.stride * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const uint64_t* pb = reinterpret_cast<const uint64_t*>(h->pinned.as<char>() + 4096);
+        for (int r = 0; r < 2; ++r) memcpy(host_bins + (size_t)r * (T + 1), pb + (size_t)r * hl.stride, row_bytes);
+        float pk = 0.f;
+        if (stats) pk = stats->peakedness;
+        *bound = error_certificate(opt, op.mode, h->last_strict != 0, d, pk, hl.ct, host_bins, host_bins + (T + 1), T);
+        return FNB_OK;
+    };
+
+    double bound = 0.0;
+    int fallback = 0;
+    if ((rc = pass(requested, &bound))) return rc;
+    if (requested == FNB_MODE_AUTO && op.mode == FNB_MODE_FP16F8 && bound > (double)opt.eps) {
+        // the fast contraction cannot vouch for this data (e.g. many different-identity pairs at high similarity): strict pass
+        if ((rc = pass(FNB_MODE_FP16X3, &bound))) return rc;
+        if (stats) stats->kernel_launches += 1;          // the second split_rows
+        fallback = 1;
     }
-    if ((rc = write_bins(h->bins.as<unsigned long long>(), hl.stride))) return rc;
+    // the bins are already on the host; hand them over (device output: one small copy on the stream)
+    if (vb.on_device) {
+        for (int r = 0; r < 2; ++r)
+            CK(cudaMemcpyAsync((char*)vb.data + r * row_bytes, h->bins.as<unsigned long long>() + (size_t)r * (kMaxBins + 1), row_bytes,
+                               cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        memcpy(vb.data, host_bins, 2 * row_bytes);
+    }
     if (stats) {
         stats->kernel_launches += 3;      // labels_to_keys, boundary_flags, split_rows (+ the Gram kernel counted above)
-        if (!vb.on_device) stats->n_pairs = sum_bins((const uint64_t*)vb.data, T + 1);
-        else {
-            uint64_t tmp[kMaxBins + 1];
-            CK(cudaMemcpy(tmp, h->bins.p, row_bytes, cudaMemcpyDeviceToHost));
-            stats->n_pairs = sum_bins(tmp, T + 1);
-        }
+        stats->n_pairs = sum_bins(host_bins, T + 1);
+        stats->error_bound = (float)bound;
+        stats->fallback = fallback;
     }
     return FNB_OK;
 }
@@ -871,6 +1017,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
     op.pairs = pick_pairs(&opt, cg);
+    op.want_l16 = opt.strict_tiles >= 0;
     std::vector<RegionDev> regs;
     for (int i = 0; i < nregions; ++i) {
         const fnb_region& r = regions[i];
@@ -917,11 +1064,16 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     CK(cudaMemcpyAsync(stage, h->bins.p, (size_t)nkeys * 2 * hl.stride * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     uint64_t total = 0;
+    uint64_t sums[2][kMaxBins + 1] = {};
     for (int k = 0; k < nkeys * 2; ++k) {
         memcpy(bins_host + (size_t)k * (T + 1), stage + (size_t)k * hl.stride, (size_t)(T + 1) * 8);
         if ((k & 1) == 0) total += sum_bins(stage + (size_t)k * hl.stride, T + 1);
+        for (int b = 0; b <= T; ++b) sums[k & 1][b] += stage[(size_t)k * hl.stride + b];
     }
-    if (stats) stats->n_pairs = total;
+    if (stats) {
+        stats->n_pairs = total;
+        stats->error_bound = (float)error_certificate(opt, op.mode, h->last_strict != 0, d, stats->peakedness, hl.ct, sums[0], sums[1], T);
+    }
     return FNB_OK;
 }
 

@@ -106,6 +106,7 @@ extern "C" int fnb_pair_cross_entropy(fnb_handle h, const DLTensor* batch, int e
     if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
     p.bce_alpha = alpha; p.bce_threshold = threshold; p.bce_pos_weight = (float)pos_weight;
     p.bce_out = h->scan.as<double>();
+    if ((rc = upload_bias(h, op.mode, d, opt.bias_correction < 0, &p.bias_beta))) return rc;
     CK(cudaEventRecord(h->ev[1], h->stream));
     if ((rc = launch_gram(h, cg, EPI_BCE, opt.max_ctas, op, p, 0))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));

@@ -114,6 +114,15 @@ struct GramParams {
     // of the strict upper triangle, label = same group (row_cls == col_cls), weighted cross entropy and its derivatives
     float bce_alpha, bce_threshold, bce_pos_weight;
     double* bce_out;           // [4] sums over pairs: loss, dloss/dalpha, dloss/dthreshold, dloss/dtheta
+    // ROWSTRIP epilogue, mining (fnb_mine_batched): running per-anchor arg-extrema folded into the Gram epilogue.  Every
+    // region is one batch (rows == columns == the batch); mine_lab holds the label of every (global) row; each thread folds
+    // its row's 64 columns into packed (distance, index) keys and merges them with one 64-bit atomic per row and tile:
+    //   mine_pos_key[row] = max over same-label columns != row of (d << 32 | ~index)   -> hardest positive, ties -> lowest index
+    //   mine_neg_key[row] = min over other-label columns of (d << 32 | index)          -> hardest negative
+    // Column indices are local to the batch.  out == NULL: the distance strip is not materialised (hardest-only mining).
+    const long long* mine_lab;
+    unsigned long long* mine_pos_key;
+    unsigned long long* mine_neg_key;
     // Cluster-progress window (off unless sync_window > 0).  The clusters walk a static schedule, and over a long launch
     // they drift apart by many column panels: each then streams its own column panel AND evicts the row panels the
     // others still need (measured at 1M rows: 824 GB of DRAM reads per launch).  Every cluster publishes the column
@@ -124,7 +133,31 @@ struct GramParams {
     // Timing only: the integer bins do not depend on it.
     unsigned int* progress;    // [number of clusters], zeroed before the launch; 0xffffffff = finished
     int sync_window;
+    // Accumulation-bias correction (fnb_bias.h).  The tensor core truncates (towards zero) when it aligns the products and
+    // adds them into the fp32 accumulator, so a raw similarity comes out SMALLER in magnitude than the exact one by a
+    // calibrated relative amount beta(|s|) (profiles/r02a_bias_vs_similarity.log: 1.5e-6 .. 3.3e-6 for fp16x3 at D = 512).
+    // Wherever a similarity is evaluated exactly (checked HIST tiles, PAIRWISE / ROWSTRIP / BCE) it is first corrected,
+    // s <- s (1 + beta(|s|)), beta piecewise linear over kBiasKnots knots in |s|; the arithmetic binning of interior tiles
+    // folds the same correction into its linear map (host: CutTables::raw).  Two tables: [0] the launch's arithmetic,
+    // [1] the fp16x3 arithmetic of strict tiles inside an fp16f8 launch.  NULL: no correction.
+    const float* bias_beta;    // [2][kBiasStride]
+    // fp16f8 launches: tiles that can hold a same-identity pair, and ragged / diagonal tiles, run the fp16x3 contraction
+    // (hi*hi + hi*l16 + l16*hi, l16 = fp16 low part) instead of the e4m3 cross terms -- the pairs behind TP / FN get the
+    // strict arithmetic, the e4m3 error model only has to hold for different-identity pairs.  Needs row_cls / col_cls.
+    int strict_tiles;
 };
+
+constexpr int kBiasKnots  = 41;                    // |s| = 0, 0.025, ..., 1
+constexpr int kBiasStride = 44;
+
+// s (1 + beta(|s|)), beta linear between the knots of `tab` (shared memory)
+__device__ __forceinline__ float bias_correct(const float* tab, float s) {
+    const float a = fminf(fabsf(s) * (float)(kBiasKnots - 1), (float)(kBiasKnots - 1) - 0.001f);
+    const int i = (int)a;
+    const float f = a - (float)i;
+    const float b = fmaf(f, tab[i + 1] - tab[i], tab[i]);
+    return fmaf(s, b, s);
+}
 
 // faceclass.py:71 in float32, operation by operation (no contraction)
 __device__ __forceinline__ float classifier_distance(float s, float nr, float nc, float theta) {
@@ -139,6 +172,7 @@ constexpr int kSyncSpinLimit = 4096;
 struct TileInfo {
     int row0, col0, row_end, col_end, tri, key;
     int gcp;                   // launch-wide index of the tile's column panel (non-decreasing along a cluster's tile sequence)
+    int cbeg;                  // first column of the tile's region (ROWSTRIP writes region-local column indices)
 };
 
 // One scheduler step hands a cluster a SUPER-TILE of (kPR * kTile) rows x (kPC * kTile) columns; the CTA pair at
@@ -183,6 +217,7 @@ struct TileScheduler {
             t.tri = r.tri;
             t.key = r.key;
             t.gcp = r.cp_begin + cb;
+            t.cbeg = r.col_begin;
             // advance by `stride` tiles inside the region (row blocks fastest)
             pos += stride;
             j += (int)stride;
@@ -207,6 +242,7 @@ struct __align__(16) GramSmemMisc {
     uint32_t cta_all[kMaxBins + 4];     // CTA-level counters (all pairs / same-identity pairs) of the current key
     uint32_t cta_same[kMaxBins + 4];
     int32_t col_cls[2][256];
+    float beta[2][kBiasStride];         // accumulation-bias tables (GramParams::bias_beta), zeros without correction
 };
 
 __device__ __forceinline__ int exact_bin(float s, const float* cuts_s) {
@@ -271,6 +307,7 @@ __global__ void __launch_bounds__(kGramThreads, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
             const __grid_constant__ CUtensorMap tm_a_h8, const __grid_constant__ CUtensorMap tm_b_h8,
+            const __grid_constant__ CUtensorMap tm_a_l16, const __grid_constant__ CUtensorMap tm_b_l16,
             const GramParams p)
 {
     static_assert(kPairs == 1 || ((kPairs == 2 || kPairs == 4) && kCtaGroup == 2 && kEpi == EPI_HIST), "multicast clusters: CTA pairs, HIST only");
@@ -323,8 +360,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_b_hi);
         if (kNumPass != 1) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
         if (kF8) { tma_prefetch_desc(&tm_a_h8); tma_prefetch_desc(&tm_b_h8); }
+        if (kF8 && p.strict_tiles) { tma_prefetch_desc(&tm_a_l16); tma_prefetch_desc(&tm_b_l16); }
     }
     if (warp == 2) tmem_alloc<kCtaGroup>(&misc->tmem_base, kTmemCols);
+    if (warp >= kFirstEpiWarp) {
+        const int te = threadIdx.x - kFirstEpiWarp * 32;
+        for (int i = te; i < 2 * kBiasStride; i += kEpiThreads) (&misc->beta[0][0])[i] = p.bias_beta ? p.bias_beta[i] : 0.f;
+    }
     if (kEpi == EPI_HIST && warp >= kFirstEpiWarp) {
         const int te = threadIdx.x - kFirstEpiWarp * 32;
         for (int i = te; i < kMaxBins; i += kEpiThreads) misc->cuts[i] = p.cuts[i];
@@ -338,6 +380,18 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = misc->tmem_base;
+
+    // fp16f8 launches: does the cluster's super-tile run the strict fp16x3 contraction (GramParams::strict_tiles)?  Identical
+    // in every role and every CTA of the cluster (decided on the super-tile, from the class ranks of its corner rows).
+    auto strict_tile = [&](const TileInfo& t) -> bool {
+        if (!kF8 || !p.strict_tiles) return false;
+        const int r_last = min(t.row0 + Sched::kSuperRows, t.row_end) - 1;
+        const int c_last = min(t.col0 + Sched::kSuperCols, t.col_end) - 1;
+        const bool edge = (t.row0 + Sched::kSuperRows > t.row_end) || (t.col0 + Sched::kSuperCols > t.col_end) ||
+                          (t.tri && t.col0 <= t.row0 + Sched::kSuperRows - 1);
+        if (edge) return true;
+        return (__ldg(p.row_cls + t.row0) <= __ldg(p.col_cls + c_last)) && (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + r_last));
+    };
 
     // =====================================================================================
     if (warp == 0) {
@@ -408,7 +462,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 __syncwarp();
                 if (++slot == num_slots) { slot = 0; phase ^= 1u; }
             };
-            if constexpr (kF8) {
+            if (kF8 && strict_tile(t)) {
+                // strict tile of an fp16f8 launch: the fp16x3 slots {hi, hi}, {l16, l16} per k-block (same slot count)
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    load_slot(&tm_a_hi, &tm_b_hi, kb * 64);
+                    load_slot(&tm_a_l16, &tm_b_l16, kb * 64);
+                }
+            } else if constexpr (kF8) {
                 // The small cross terms first -- {A e4m3(x), B e4m3(lo)} and {A e4m3(lo), B e4m3(x)} per 128 K-elements --
                 // then the fp16 {hi, hi} slots.  The tensor core truncates when it adds into the fp32 accumulator, an error
                 // proportional to the accumulator's magnitude per step; while the cross terms are summed the accumulator
@@ -443,7 +503,43 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 mbar_wait(&misc->tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kUmmaN;
-                if constexpr (kF8) {
+                // one k-block pass of the split contraction hi*hi + hi*lo + lo*hi over two slots {hi, hi}, {lo, lo}
+                auto x3_tile = [&]() {
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        const int slot_hi = slot;
+                        mbar_wait(&misc->full[slot_hi], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(slots + (size_t)slot_hi * kSlotBytes);
+                        const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + kBoxBytes);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        }
+                        __syncwarp();
+                        if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                        const int slot_lo = slot;
+                        mbar_wait(&misc->full[slot_lo], phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t sl = smem_u32(slots + (size_t)slot_lo * kSlotBytes);
+                            const uint64_t a_lo = make_smem_desc(sl), b_lo = make_smem_desc(sl + kBoxBytes);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1u);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma<kCtaGroup, kTf32>(d_tmem, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
+                            umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
+                            umma_commit<kCtaGroup>(&misc->empty[slot_lo], cluster_mask);
+                        }
+                        __syncwarp();
+                        if (++slot == num_slots) { slot = 0; phase ^= 1u; }
+                    }
+                };
+                if (kF8 && strict_tile(t)) {
+                    x3_tile();
+                } else if constexpr (kF8) {
                     // kblocks e4m3 slots (K = 128 each: the cross terms), then kblocks fp16 slots (K = 64 each: hi*hi)
                     for (int st = 0; st < p.kblocks; ++st) {
                         mbar_wait(&misc->full[slot], phase);
@@ -473,40 +569,22 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         __syncwarp();
                         if (++slot == num_slots) { slot = 0; phase ^= 1u; }
                     }
+                } else if constexpr (kNumPass == 3) {
+                    x3_tile();
                 } else {
                     for (int kb = 0; kb < p.kblocks; ++kb) {
-                        const int slot_hi = slot;
-                        mbar_wait(&misc->full[slot_hi], phase);
+                        mbar_wait(&misc->full[slot], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(slots + (size_t)slot_hi * kSlotBytes);
-                        const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + kBoxBytes);
                         if (elect_one()) {
+                            const uint32_t sa = smem_u32(slots + (size_t)slot * kSlotBytes);
+                            const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + kBoxBytes);
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4)
                                 umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
-                            if (kNumPass != 3) umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
+                            umma_commit<kCtaGroup>(&misc->empty[slot], cluster_mask);
                         }
                         __syncwarp();
                         if (++slot == num_slots) { slot = 0; phase ^= 1u; }
-                        if (kNumPass == 3) {
-                            const int slot_lo = slot;
-                            mbar_wait(&misc->full[slot_lo], phase);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint32_t sl = smem_u32(slots + (size_t)slot_lo * kSlotBytes);
-                                const uint64_t a_lo = make_smem_desc(sl), b_lo = make_smem_desc(sl + kBoxBytes);
-#pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4)
-                                    umma<kCtaGroup, kTf32>(d_tmem, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1u);
-#pragma unroll
-                                for (int k4 = 0; k4 < 4; ++k4)
-                                    umma<kCtaGroup, kTf32>(d_tmem, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
-                                umma_commit<kCtaGroup>(&misc->empty[slot_hi], cluster_mask);
-                                umma_commit<kCtaGroup>(&misc->empty[slot_lo], cluster_mask);
-                            }
-                            __syncwarp();
-                            if (++slot == num_slots) { slot = 0; phase ^= 1u; }
-                        }
                     }
                 }
                 if (elect_one()) umma_commit<kCtaGroup>(&misc->tfull[acc], pair_mask);
@@ -578,6 +656,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
         while (sched.next(t)) {
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const TileInfo t_super = t;
             if constexpr (kPairs > 1) { t.row0 += (int)pair_row * kTile; t.col0 += (int)pair_col * kTile; }   // this pair's tile of the super-tile
             // a pair whose tile lies outside the region / below the diagonal still runs the pipeline (lockstep) and drops the result
             const bool null_tile = (kPairs > 1) && (t.col0 >= t.col_end || t.row0 >= t.row_end || (t.tri && t.col0 + kTile - 1 <= t.row0));
@@ -596,9 +675,12 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                   (t.tri && t.col0 <= t.row0 + kTile - 1);
                 const int rlast = min(t.row0 + kTile, t.row_end) - 1;
                 const int clast = min(t.col0 + kTile, t.col_end) - 1;
-                const bool lab = (__ldg(p.row_cls + t.row0) <= __ldg(p.col_cls + clast)) &&
+                // (a pair tile outside the region is dropped below: its corner rows may lie past the class array)
+                const bool lab = !null_tile && (__ldg(p.row_cls + t.row0) <= __ldg(p.col_cls + clast)) &&
                                  (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + rlast));
-                const bool slow = all_slow || edge || lab;
+                const bool strict = strict_tile(t_super);
+                const bool slow = all_slow || edge || lab || strict;
+                const float* beta = misc->beta[strict ? 1 : 0];
 
                 if ((p.debug & 1) || null_tile) {
                     mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
@@ -682,6 +764,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                             if (ok) {
                                 float s = __uint_as_float(r[j]) * scale;
                                 if (!on_diag) { smin = fminf(smin, s); smax = fmaxf(smax, s); }
+                                s = bias_correct(beta, s);
                                 if (p.row_nrm != nullptr)      // classifier distance with the norm term, back on the similarity axis
                                     s = __fsub_rn(1.0f, __fmul_rn(0.5f, classifier_distance(s, my_nrm, __ldg(p.col_nrm + col), p.theta)));
                                 else if (!p.raw) s = fminf(fmaxf(s, -1.0f), 1.0f);
@@ -716,7 +799,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         for (int j = 0; j < 32; ++j) {
                             const int col = colw + c * 32 + j;
                             if (col < t.col_end && col > row) {
-                                const float sv = __uint_as_float(r[j]) * scale;
+                                const float sv = bias_correct(misc->beta[0], __uint_as_float(r[j]) * scale);
                                 float d, g2 = 0.f;
                                 if (p.row_nrm != nullptr) {
                                     const float nc = __ldg(p.col_nrm + col);
@@ -749,6 +832,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 tc_fence_after();
                 const bool row_ok = row < t.row_end;
                 const float my_nrm = (p.row_nrm != nullptr && row_ok) ? __ldg(p.row_nrm + row) : 1.0f;
+                const bool mining = (kEpi == EPI_ROWSTRIP) && (p.mine_lab != nullptr);
+                const long long my_lab = (mining && row_ok) ? __ldg(p.mine_lab + row) : 0;
+                unsigned long long best_pos = 0ull, best_neg = ~0ull;
+                const int cbeg = (kEpi == EPI_ROWSTRIP) ? t.cbeg : 0;
 #pragma unroll 1
                 for (int c = 0; c < kColsPerWarp / 32; ++c) {
                     uint32_t r[32];
@@ -757,7 +844,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     if (row_ok) {
                         long long base;
                         if (p.tri_packed) base = (long long)row * p.n_rows - ((long long)row * (row + 1)) / 2 - row - 1;
-                        else base = (long long)row * p.out_ld;
+                        else base = (long long)row * p.out_ld - cbeg;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int col = colw + c * 32 + j;
@@ -765,15 +852,26 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                             if (ok) {
                                 float s = __uint_as_float(r[j]) * scale;
                                 if (kEpi == EPI_PAIRWISE || col != row) { smin = fminf(smin, s); smax = fmaxf(smax, s); }
+                                s = bias_correct(misc->beta[0], s);
                                 if (!p.raw) s = fminf(fmaxf(s, -1.0f), 1.0f);
                                 float d;
                                 if (p.row_nrm != nullptr) d = classifier_distance(s, my_nrm, __ldg(p.col_nrm + col), p.theta);
                                 else if (p.metric == 0) d = __fmul_rn(2.0f, __fsub_rn(1.0f, s));
                                 else d = acosf(s);
-                                p.out[base + col] = d;
+                                if (kEpi == EPI_PAIRWISE || p.out != nullptr) p.out[base + col] = d;
+                                if (kEpi == EPI_ROWSTRIP && mining && col != row) {
+                                    const unsigned long long dk = (unsigned long long)__float_as_uint(d) << 32;
+                                    const unsigned int ci = (unsigned int)(col - cbeg);
+                                    if (__ldg(p.mine_lab + col) == my_lab) best_pos = max(best_pos, dk | (0xFFFFFFFFu - ci));
+                                    else best_neg = min(best_neg, dk | ci);
+                                }
                             }
                         }
                     }
+                }
+                if (kEpi == EPI_ROWSTRIP && mining && row_ok) {
+                    if (best_pos != 0ull) atomicMax(p.mine_pos_key + row, best_pos);
+                    if (best_neg != ~0ull) atomicMin(p.mine_neg_key + row, best_neg);
                 }
             }
 

@@ -74,13 +74,19 @@ struct fnb_context {
 
     fnb::DevBuf stage_a, stage_b, stage_lab;          // H2D staging of kDLCPU inputs
     fnb::DevBuf a_hi, a_lo, b_hi, b_lo, a_h8, b_h8;   // split / converted operands
+    fnb::DevBuf a_l16, b_l16;                         // fp16f8 mode: fp16 low parts (strict tiles)
     fnb::DevBuf a_nrm, b_nrm;                         // row norms before normalise-on-load (fnb_options.normalize)
     fnb::DevBuf shard_slots;                          // residues of fnb_options.shard_slots on the device
     fnb::DevBuf progress;                             // per-cluster column-panel progress (GramParams::sync_window)
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
+    fnb::DevBuf bias_tab;                             // [2][kBiasStride] accumulation-bias knots of the current (mode, d)
+    int bias_mode = -1, bias_d = 0;
+    fnb::DevBuf mine_lab, mine_keys, mine_status;     // mining: labels as int64, packed arg-extrema keys, status words
+    long long mine_rows = 0, mine_b = 0, mine_ld = 0; // geometry of the last mining call (its strips stay in `strip`)
+    int mine_kmax = 0; float mine_atol = 0.f; bool mine_has_strip = false;
     fnb::HostBuf pinned;
-    int last_nkeys = 0, last_T = 0, last_grid = 0, last_mode = 0, last_window = 0;
+    int last_nkeys = 0, last_T = 0, last_grid = 0, last_mode = 0, last_window = 0, last_strict = 0;
     float last_peak = 0.f;
     fnb::ShardSpec last_shard = fnb::ShardSpec{1, 0, 1, nullptr};   // share of the launch being prepared
     double last_eps_counted = 0;         // distance half-width of the near-threshold window counted by interior tiles
@@ -102,6 +108,9 @@ struct DLView {
 struct GramOperands {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap a_h8, b_h8;        // fp16f8 mode only: e4m3(x) arrays (a_lo / b_lo then hold e4m3(lo))
+    CUtensorMap a_l16, b_l16;      // fp16f8 mode only: fp16 low parts for the strict (fp16x3) tiles of a histogram launch
+    bool have_l16 = false;         // a_l16 / b_l16 were prepared (prepare_operand with want_l16 in fp16f8 mode)
+    bool want_l16 = false;         // set by the histogram entry points before prepare_operand
     int num_pass = 3; bool tf32 = false; int fmt = 0; int elem_bytes = 2; float prescale = 1.f;
     int mode = 0;                  // FNB_MODE_* the operands were prepared for (AUTO resolved)
     float peakedness = 0.f;        // max_row sum x^4 / (sum x^2)^2 (valid after prepare_operand in AUTO mode)
@@ -142,12 +151,17 @@ int self_b_maps(fnb_context* h, GramOperands& op, int d);   // B side = the prep
 int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
 int reset_scalars(fnb_context* h);
 int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, float* prescale);
-int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out);
+inline float gram_acc_scale(const GramOperands& op) { return 1.0f / (op.prescale * op.prescale); }
+int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out,
+                     const float* beta_knots = nullptr);
+void bias_table(int mode, int d, float* knots);
+double mode_sigma_s(int mode, int d, double abs_s, double peakedness);
+int upload_bias(fnb_context* h, int mode, int d, bool strict_x3, const float** dev);
 
 // fnb_prepare.cu
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
                               void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s,   // norm_max_ord[1] = peakedness
-                              int normalize = 0, float* row_nrm = nullptr);
+                              int normalize = 0, float* row_nrm = nullptr, void* l16 = nullptr);
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
 
 // fnb_gram.cu

@@ -20,7 +20,7 @@ template <int kMode>
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ perm, long long n, long long n_pad, int d,
                   void* __restrict__ hi, void* __restrict__ lo, void* __restrict__ h8, unsigned int* __restrict__ norm_max_ord,
-                  int normalize, float* __restrict__ row_nrm)
+                  int normalize, float* __restrict__ row_nrm, void* __restrict__ l16)
 {
     const int vec_per_row = d >> 3;
     const int lane = threadIdx.x & 31;
@@ -84,17 +84,20 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
             } else if (kMode == FNB_MODE_FP16F8) {
                 // x * 2^12 = hi + lo, hi fp16; the cross terms hi*lo are formed from e4m3(x * 2^8) and e4m3(lo * 2^4):
                 // both stay in the normal range of e4m3 for |x| >= 6e-5 and the product keeps the 2^24 scale of hi*hi
-                __half hh[8];
+                // l16 (optional) = the same low part in fp16: the operand of the strict fp16x3 tiles of a histogram launch
+                __half hh[8], ll[8];
                 __align__(8) __nv_fp8_storage_t q8[8], l8[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float xs = f[i] * 4096.0f;
                     hh[i] = __float2half_rn(xs);
                     const float lo_f = xs - __half2float(hh[i]);
+                    ll[i] = __float2half_rn(lo_f);
                     q8[i] = __nv_cvt_float_to_fp8(xs * 0.0625f, __NV_SATFINITE, __NV_E4M3);
                     l8[i] = __nv_cvt_float_to_fp8(lo_f * 16.0f, __NV_SATFINITE, __NV_E4M3);
                 }
                 *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(hi) + o) = *reinterpret_cast<uint4*>(hh);
+                if (l16) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(l16) + o) = *reinterpret_cast<uint4*>(ll);
                 *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(h8) + o) = *reinterpret_cast<uint2*>(q8);
                 *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(lo) + o) = *reinterpret_cast<uint2*>(l8);
             } else if (kMode == FNB_MODE_BF16) {
@@ -133,19 +136,19 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
 
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
                               void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s,
-                              int normalize, float* row_nrm)
+                              int normalize, float* row_nrm, void* l16)
 {
     if (n_pad == 0) return cudaSuccess;
     const int threads = 256;
     long long blocks = (n_pad + 7) / 8;                  // 8 warps (rows) per block
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     switch (mode) {
-        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
-        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
-        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
-        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
-        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
-        case FNB_MODE_FP16F8: split_rows_kernel<FNB_MODE_FP16F8><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm); break;
+        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
+        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
+        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
+        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
+        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
+        case FNB_MODE_FP16F8: split_rows_kernel<FNB_MODE_FP16F8><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -16,7 +16,7 @@ import numpy as np
 from facenet_b200 import _capi
 from facenet_b200.statistics import _handle, _raise_like_reference, _state
 
-__all__ = ['mine', 'hardest_triplets', 'semi_hard_triplets', 'select_triplets']
+__all__ = ['mine', 'mine_batched', 'mine_check', 'select_kth_eligible', 'hardest_triplets', 'semi_hard_triplets', 'select_triplets']
 
 
 def mine(embeddings, labels, alpha=0.2, mode=None):
@@ -35,6 +35,34 @@ def mine(embeddings, labels, alpha=0.2, mode=None):
         return _handle().mine(embeddings, labels, alpha=alpha, mode=mode or _state['mode'])
     except _capi.FnbError as err:
         _raise_like_reference(err, 0)
+
+
+def mine_batched(embeddings, labels, nbatches=1, alpha=0.2, kmax=None, mode=None, out=None):
+    """``nbatches`` P x K batches packed as ``[S * B, D]`` / ``[S * B]`` mined in ONE call (indices local to each batch).
+
+    torch CUDA tensors in -> torch CUDA int32 tensors out and NO host synchronisation (a training loop keeps the mined
+    indices on the GPU; pass ``kmax`` = K - 1 and re-use ``out``); data-dependent errors (un-normalised embeddings, ``kmax``
+    too small) are raised by ``mine_check()``.  NumPy in -> NumPy out, synchronous.  ``kmax=0`` mines the hardest positive /
+    negative only, fully fused in the Gram epilogue."""
+    try:
+        return _handle().mine_batched(embeddings, labels, nbatches=nbatches, alpha=alpha, kmax=kmax, mode=mode or _state['mode'], out=out)
+    except _capi.FnbError as err:
+        _raise_like_reference(err, 0)
+
+
+def mine_check():
+    """Synchronise with the last device-resident ``mine_batched`` call and raise its data-dependent errors."""
+    try:
+        return _handle().mine_check()
+    except _capi.FnbError as err:
+        _raise_like_reference(err, 0)
+
+
+def select_kth_eligible(anchors, positives, kth, alpha=0.2):
+    """For every query ``(a, p, k)``: the ``k``-th (0-based, ascending index) negative ``n`` of anchor ``a`` with
+    ``fp32(d(a, n) - d(a, p)) < alpha`` in the batch mined last (``a`` = row of that call, ``p`` / result local to a's batch);
+    -1 when fewer exist.  With ``k = randint(eligible[a, p])`` this is the draw of upstream ``select_triplets``."""
+    return _handle().mine_select_kth(anchors, positives, kth, alpha=alpha)
 
 
 def hardest_triplets(embeddings, labels, mode=None):
@@ -57,14 +85,17 @@ def semi_hard_triplets(embeddings, labels, alpha=0.2, mode=None, unique_pairs=Tr
     return np.stack([a[ok], pos[ok], neg[ok]], axis=1)
 
 
-def select_triplets(embeddings, nrof_images_per_class, image_paths=None, people_per_batch=None, alpha=0.2, mode=None):
+def select_triplets(embeddings, nrof_images_per_class, image_paths=None, people_per_batch=None, alpha=0.2, mode=None, rng=None):
     """Call shape of upstream ``select_triplets(embeddings, nrof_images_per_class, image_paths,
-    people_per_batch, alpha)``: rows are grouped by class with the given class sizes.  Upstream draws a
-    RANDOM negative among the margin-eligible ones; this deterministic variant returns the semi-hard
-    argmin and, for callers that want to replay the random draw, the eligible-set sizes.
+    people_per_batch, alpha)``: rows are grouped by class with the given class sizes.
 
-    Returns ``(triplets, nrof_eligible)``: triplets is int32 [M, 3] of row indices, or a list of
-    ``(path_a, path_p, path_n)`` when ``image_paths`` is given."""
+    ``rng=None`` (deterministic variant): the negative of every (a, p), p after a, is the semi-hard argmin; returns
+    ``(triplets, nrof_eligible)``.  ``rng`` = a ``np.random.RandomState`` (or the ``np.random`` module): upstream's selection
+    is replayed -- for every (a, p) in upstream's loop order whose eligible set ``{n : d(a,n) - d(a,p) < alpha}`` is not
+    empty, ``rng.randint(len(eligible))`` picks the entry of the ascending candidate list (``fnb_mine_select_kth``), then the
+    triplets are shuffled with ``rng.shuffle``; returns upstream's ``(triplets, num_trips, len(triplets))``.
+
+    triplets is int32 [M, 3] of row indices, or a list of ``(path_a, path_p, path_n)`` when ``image_paths`` is given."""
     sizes = np.asarray(nrof_images_per_class, dtype=np.int64)
     if people_per_batch is not None:
         sizes = sizes[:people_per_batch]
@@ -73,9 +104,24 @@ def select_triplets(embeddings, nrof_images_per_class, image_paths=None, people_
     out = mine(embeddings, labels, alpha=alpha, mode=mode)
     pos, neg = out['pos_index'], out['semi_hard']
     a = np.broadcast_to(np.arange(pos.shape[0], dtype=np.int32)[:, None], pos.shape)
-    ok = (pos > a) & (neg >= 0)
-    trip = np.stack([a[ok], pos[ok], neg[ok]], axis=1)
-    elig = out['eligible'][pos > a]
+    if rng is None:
+        ok = (pos > a) & (neg >= 0)
+        trip = np.stack([a[ok], pos[ok], neg[ok]], axis=1)
+        elig = out['eligible'][pos > a]
+        if image_paths is not None:
+            trip = [(image_paths[i], image_paths[j], image_paths[k]) for i, j, k in trip]
+        return trip, elig
+    # upstream order: anchors ascending, for each the positives after it ascending (row-major over [B, K-1] is that order)
+    visit = pos > a
+    num_trips = int(np.count_nonzero(visit))
+    take = visit & (out['eligible'] > 0)
+    qa, qp, qe = a[take], pos[take], out['eligible'][take]
+    kth = np.array([rng.randint(int(e)) for e in qe], dtype=np.int32)
+    qn = select_kth_eligible(qa.astype(np.int32), qp.astype(np.int32), kth, alpha=alpha) if qa.size else np.zeros(0, dtype=np.int32)
+    trip = [(int(i), int(j), int(k)) for i, j, k in zip(qa, qp, qn)]
     if image_paths is not None:
         trip = [(image_paths[i], image_paths[j], image_paths[k]) for i, j, k in trip]
-    return trip, elig
+    rng.shuffle(trip)
+    if image_paths is None:
+        trip = np.asarray(trip, dtype=np.int32).reshape(-1, 3)
+    return trip, num_trips, len(trip)

@@ -56,20 +56,25 @@ enum {
 
 /* Arithmetic of the Gram contraction (all accumulate in fp32 in tensor memory):
  *   FP16X3  x = hi + lo with hi, lo fp16 (pre-scaled by 2^8): hi*hi + hi*lo + lo*hi, three
- *           kind::f16 MMAs per k-step -- fp32-equivalent (|ds| ~ 1e-7); the DEFAULT, and the only
- *           modes that meet the reference tolerance (|dd| <= 1e-5) are the two X3 modes;
+ *           kind::f16 MMAs per k-step.  The operands carry 22 bits; what limits the accuracy is the tensor core's
+ *           truncating accumulation: a bias of up to -3.3e-6 |s| at D = 512 (growing ~ D^1.09), which is calibrated
+ *           and corrected (csrc/fnb_bias.h) -- after the correction |dd| <~ 3e-6.  The DEFAULT of the drop-in classes;
  *   TF32X3  same split with tf32 operands, kind::tf32;
  *   TF32    single kind::tf32 pass on RN-rounded operands (|dd| ~ 3.5e-5 rms);
  *   BF16    single kind::f16 pass on bf16 operands;  FP16: single pass on fp16 operands;
  *   FP16F8  x = hi + lo, hi fp16 (pre-scaled by 2^12): hi*hi in kind::f16 plus the cross terms
  *           e4m3(x)*e4m3(lo) + e4m3(lo)*e4m3(x) in kind::f8f6f4 at twice the MMA rate -- two fp16-pass
- *           equivalents instead of three.  Error is statistical: |dd| ~ 1e-6 rms, < 1e-5 for dense
- *           embeddings (every element small against the norm); needs D % 128 == 0. */
+ *           equivalents instead of three.  Error (after the bias correction) is statistical: sigma(dd) ~ 0.9e-6 for
+ *           dense 512-d rows, growing with the peakedness of the rows and with |s| (1.7e-6 at |s| ~ 1); histogram
+ *           launches therefore run every tile that can hold a same-identity pair in FP16X3 (strict_tiles) and report
+ *           fnb_stats.error_bound; needs D % 128 == 0. */
 /*   AUTO    (histogram entry points only) FP16F8 when its error model holds for the data, else FP16X3: the e4m3
  *           rounding errors of the 2 x D cross products are independent and each is bounded by 2^-16 |x_i y_i|, so
  *           sigma(ds) ~ 2^-16.5 sqrt(sum_i x_i^2 y_i^2) <= 2^-16.5 max_row ||x||_4^2.  The split kernel measures
  *           max_row sum x_i^4 / (sum x_i^2)^2 ("peakedness": 3/D for dense Gaussian-like rows, 1 for one-hot rows);
- *           FP16F8 is used when it is <= 1/64 (5 sigma(dd) < 1e-5) and D % 128 == 0.  fnb_stats.mode_used tells. */
+ *           FP16F8 is used when it is <= 1/128 and D % 128 == 0 (a-priori gate), and its result is KEPT only when the
+ *           a-posteriori fnb_stats.error_bound -- evaluated on the histogram it produced -- is <= eps; otherwise the
+ *           launch is repeated in FP16X3 (fnb_stats.fallback).  fnb_stats.mode_used tells. */
 enum { FNB_MODE_FP16X3 = 0, FNB_MODE_TF32X3 = 1, FNB_MODE_TF32 = 2, FNB_MODE_BF16 = 3, FNB_MODE_FP16 = 4, FNB_MODE_FP16F8 = 5,
        FNB_MODE_AUTO = 6 };
 
@@ -121,6 +126,11 @@ typedef struct {
                               launches -- fnb_pair_histogram[_bins] -- whose share on this rank is >= 5e10 pairs, the ones long
                               enough to drift: window 2; off otherwise and for keyed launches, whose regions can be one tile wide).  Timing only:
                               the integer bins do not depend on it. */
+    int32_t strict_tiles;  /* FP16F8 histogram launches: tiles that can hold a same-identity pair (and ragged / diagonal tiles) run
+                              the FP16X3 contraction inside the same launch, so the pairs behind TP / FN never depend on the e4m3
+                              error model.  0 = on (default), -1 = off (measurement knob) */
+    int32_t bias_correction; /* the calibrated correction of the tensor core's accumulation bias (fnb_stats.error_bound, DESIGN.md
+                              section 2): 0 = on (default), -1 = off (measurement knob: scripts/probe_bias.py) */
 } fnb_options;
 
 typedef struct {
@@ -140,6 +150,10 @@ typedef struct {
     int32_t  mode_used;    /* FNB_MODE_* the contraction ran in (what AUTO resolved to)                         */
     float    peakedness;   /* max over rows of sum x^4 / (sum x^2)^2 of the prepared embeddings                  */
     int32_t  panel_window; /* cluster-progress window the histogram launch ran with (0 = off; fnb_options.panel_window)  */
+    float    error_bound;  /* a-posteriori bound on |dd| of any binned pair under the error model of mode_used (calibrated spread of
+                              the arithmetic x a union bound over the pairs actually found in each similarity bin + the residual
+                              of the bias correction); the contract needs <= eps.  AUTO re-runs in FP16X3 when FP16F8 exceeds it */
+    int32_t  fallback;     /* 1: AUTO ran FP16F8, its error_bound exceeded eps and the launch was repeated in FP16X3 */
 } fnb_stats;
 
 /* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:
@@ -231,13 +245,34 @@ int fnb_pair_cross_entropy(fnb_handle h, const DLTensor* batch, int examples_per
 /* binary_cross_entropy_loss(logits, options) for a materialised float32 [B, B] logits matrix (train_classifier.py:60-84). */
 int fnb_logits_cross_entropy(fnb_handle h, const DLTensor* logits, int examples_per_class, double* loss);
 
-/* Triplet mining on one batch (NOT in the reference fork -- semantics defined in
- * oracle/mining_oracle.py; batch layout facenet/facenet.py:89-123).  Distances are metric 0.
- *   hardest_pos, hardest_neg: int32 [B];  kmax >= max class size - 1;
- *   pos_index, semi_hard, eligible: int32 [B, kmax] (host). */
+/* Triplet mining on P x K batches (NOT in the reference fork -- semantics defined in oracle/mining_oracle.py; batch layout
+ * facenet/facenet.py:89-123; hardest pairs = within-class argmax / cross-class argmin of the distance, the commented search of
+ * facenet/statistics.py:357-387).  Distances are metric 0.  The hardest positive / negative of every anchor are folded into
+ * the Gram epilogue as running packed-key arg-extrema; the semi-hard selection reads the B x B distance strip of the batch.
+ *
+ * fnb_mine_batched: emb float32 [S * B, D] = S batches of B rows each (S = nbatches), labels int32 / int64 [S * B]; every
+ *   batch is mined on its own (all indices written are LOCAL to the batch, 0 .. B-1; -1 = empty set).
+ *     hardest_pos, hardest_neg: int32 [S * B];  kmax >= max class size - 1, or 0 for hardest-only mining (the strip is then
+ *     not materialised);  pos_index, semi_hard, eligible: int32 [S * B, kmax] (NULL when kmax == 0);
+ *     status: optional int32 [4]: {largest number of positives seen if > kmax else 0, min s, max s (float bits), 0}.
+ *   When EVERY output tensor is kDLCUDA the call only enqueues work on the handle's stream and returns (no host
+ *   synchronisation; a training loop keeps the indices on the GPU): errors that depend on the data (embeddings not
+ *   normalised, kmax too small) are then reported by fnb_mine_check, which synchronises.  With host outputs the call
+ *   synchronises and returns those errors itself.
+ * fnb_mine: one batch, host outputs (the synchronous form).
+ * fnb_mine_select_kth: for queries (anchor a = global row of the last mining call, positive p local to a's batch, k >= 0):
+ *   out = the k-th negative n (ascending index, local) with fp32(d(a, n) - d(a, p)) < alpha, or -1 -- the candidate list upstream
+ *   davidsandberg/facenet select_triplets indexes with np.random.randint; with eligible[] as the range of the draw it replays
+ *   that selection.  Needs the strips of a preceding call with kmax > 0 on this handle.  int32 tensors, host or device. */
 int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* labels, float alpha, const fnb_options* opt,
              int32_t* hardest_pos, int32_t* hardest_neg,
              int kmax, int32_t* pos_index, int32_t* semi_hard, int32_t* eligible, fnb_stats* stats);
+int fnb_mine_batched(fnb_handle h, const DLTensor* emb, const DLTensor* labels, int nbatches, float alpha,
+                     const fnb_options* opt, int kmax, DLTensor* hardest_pos, DLTensor* hardest_neg,
+                     DLTensor* pos_index, DLTensor* semi_hard, DLTensor* eligible, DLTensor* status, fnb_stats* stats);
+int fnb_mine_check(fnb_handle h, int32_t* status /* [4], may be NULL */, fnb_stats* stats);
+int fnb_mine_select_kth(fnb_handle h, const DLTensor* anchors, const DLTensor* positives, const DLTensor* kth,
+                        float alpha, DLTensor* out);
 
 #ifdef __cplusplus
 }

@@ -73,3 +73,46 @@ def mine(embeddings, labels, alpha=0.2, dist=None):
                     semi_hard[a, j] = neg[idx[np.argmin(dn[idx])]]
     return {'hardest_pos': hardest_pos, 'hardest_neg': hardest_neg,
             'pos_index': pos_index, 'semi_hard': semi_hard, 'eligible': eligible}
+
+
+def select_kth_eligible(embeddings, labels, anchors, positives, kth, alpha=0.2, dist=None):
+    """``kth[i]``-th entry (0-based) of ``np.where(fp32(d[a] - d[a, p]) < alpha)[0]`` restricted to the negatives of ``a``; -1
+    if the list is shorter -- the candidate list upstream ``select_triplets`` indexes with ``np.random.randint``."""
+    labels = np.asarray(labels)
+    d = distance_matrix(embeddings) if dist is None else np.asarray(dist, dtype=np.float32)
+    alpha32 = np.float32(alpha)
+    out = np.full(len(anchors), -1, dtype=np.int32)
+    for i, (a, p, k) in enumerate(zip(anchors, positives, kth)):
+        cand = np.nonzero((labels != labels[a]) & ((d[a] - d[a, p]) < alpha32))[0]
+        if 0 <= k < cand.size:
+            out[i] = cand[k]
+    return out
+
+
+def select_triplets_upstream(embeddings, nrof_images_per_class, people_per_batch, alpha, rng, dist=None):
+    """Restatement of upstream davidsandberg/facenet ``src/train_tripletloss.py:select_triplets`` (NOT in the sMedX fork --
+    SURVEY.md section 8 A8; written from its published algorithm, PARITY UNPINNED): for every anchor ``a`` and every positive
+    ``p`` after it in the class, a uniformly random negative among ``{n : d(a,n) - d(a,p) < alpha}`` drawn with
+    ``rng.randint``; the list is shuffled at the end.  Distances are this repo's metric 0 (== upstream's squared L2 for
+    unit-norm embeddings).  Returns ``(triplets int32 [M, 3], num_trips, M)``."""
+    sizes = np.asarray(nrof_images_per_class, dtype=np.int64)[:people_per_batch]
+    labels = np.repeat(np.arange(sizes.size), sizes)
+    d = distance_matrix(np.asarray(embeddings)[:labels.size]) if dist is None else np.asarray(dist, dtype=np.float32)
+    alpha32 = np.float32(alpha)
+    triplets, num_trips, start = [], 0, 0
+    for n_img in sizes:
+        n_img = int(n_img)
+        for j in range(1, n_img):
+            a = start + j - 1
+            neg = d[a].copy()
+            neg[start:start + n_img] = np.nan
+            for pair in range(j, n_img):
+                p = start + pair
+                with np.errstate(invalid='ignore'):
+                    all_neg = np.where((neg - d[a, p]) < alpha32)[0]
+                if all_neg.size > 0:
+                    triplets.append((a, p, int(all_neg[rng.randint(all_neg.size)])))
+                num_trips += 1
+        start += n_img
+    rng.shuffle(triplets)
+    return np.asarray(triplets, dtype=np.int32).reshape(-1, 3), num_trips, len(triplets)

@@ -458,6 +458,16 @@ def face_to_face_validation(embeddings, labels, metric=0, nrof_folds=10, far_tar
 # synthetic inputs (SURVEY.md section 8 d)
 
 
+def pair_histogram_window(embeddings, labels, thresholds, metric=0, eps=1.e-5, threads=1):
+    """Per threshold, the exact number of same-identity / different-identity pairs whose ORACLE distance lies within ``eps``
+    of it (``t - eps <= d <= t + eps``): the only pairs the contract (BASELINE.json north_star) allows an implementation
+    to count on the other side of that threshold.  Returns ``(window_same, window_diff)`` int64 [T]."""
+    thr = np.atleast_1d(np.asarray(thresholds, dtype=np.float64))
+    hi = pair_histogram(embeddings, labels, np.nextafter(thr + eps, np.inf), metric, threads=threads)     # d <= t + eps
+    lo = pair_histogram(embeddings, labels, thr - eps, metric, threads=threads)                            # d <  t - eps
+    return hi['same'] - lo['same'], hi['diff'] - lo['diff']
+
+
 def synthetic_embeddings(class_sizes, dim=512, sigma=1.1, seed=0, shuffle=True, label_values=None):
     """Clustered unit-norm fp32 embeddings: centre ~ N(0,I), sample = centre +
     sigma*N(0,I), L2-normalised in fp32.  Returns (embeddings [N,dim] f32, labels [N] i64)."""

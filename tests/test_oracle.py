@@ -142,6 +142,39 @@ def test_mining_oracle_small():
     assert out['pos_index'].shape == (12, 3)
 
 
+def test_mining_oracle_kth_eligible_and_upstream_selection():
+    """select_kth_eligible walks the ascending candidate list; the upstream restatement draws from exactly those lists."""
+    sizes = [6] * 5 + [2, 1]
+    x, labels = so.synthetic_embeddings(sizes, dim=32, sigma=1.0, seed=4, shuffle=False)
+    alpha = 0.6
+    d = mo.distance_matrix(x)
+    out = mo.mine(x, labels, alpha=alpha)
+    for a in range(x.shape[0]):
+        for j, p in enumerate(out['pos_index'][a]):
+            if p < 0:
+                continue
+            cand = [n for n in range(x.shape[0]) if labels[n] != labels[a] and np.float32(d[a, n] - d[a, p]) < np.float32(alpha)]
+            assert len(cand) == out['eligible'][a, j]
+            ks = np.arange(len(cand) + 1)
+            got = mo.select_kth_eligible(x, labels, [a] * ks.size, [p] * ks.size, ks, alpha=alpha)
+            np.testing.assert_array_equal(got, cand + [-1])
+    trip, num_trips, m = mo.select_triplets_upstream(x, sizes, len(sizes), alpha, np.random.RandomState(0))
+    assert num_trips == sum(k * (k - 1) // 2 for k in sizes) and m == trip.shape[0] > 0
+    for a, p, n in trip:
+        assert labels[a] == labels[p] and p > a and labels[n] != labels[a]
+        assert np.float32(d[a, n] - d[a, p]) < np.float32(alpha)
+    # the draw is reproducible from the RNG stream and the eligible counts alone (what the GPU replay relies on)
+    rng = np.random.RandomState(0)
+    replay = []
+    for a in range(x.shape[0]):
+        for j, p in enumerate(out['pos_index'][a]):
+            if p > a and out['eligible'][a, j] > 0:
+                k = rng.randint(int(out['eligible'][a, j]))
+                replay.append((a, int(p), int(mo.select_kth_eligible(x, labels, [a], [p], [k], alpha=alpha)[0])))
+    rng.shuffle(replay)
+    np.testing.assert_array_equal(np.asarray(replay, dtype=np.int32), trip)
+
+
 def test_pair_histogram_equals_reference_counts_summed(golden_dir):
     """The whole-set same / different histogram is the reference's per-class-pair counts (count_nonzero(sims < threshold),
     statistics.py:131, taken from the UNMODIFIED reference in tests/golden/confidence.npz) summed over the diagonal /
