@@ -59,7 +59,7 @@ class Stats(ctypes.Structure):
                 ('smax', ctypes.c_float), ('max_abs', ctypes.c_float), ('kernel_ms', ctypes.c_float),
                 ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
                 ('eps_counted', ctypes.c_float), ('grid_ctas', ctypes.c_uint32), ('mode_used', ctypes.c_int32), ('peakedness', ctypes.c_float),
-                ('panel_window', ctypes.c_int32), ('error_bound', ctypes.c_float), ('fallback', ctypes.c_int32)]
+                ('panel_window', ctypes.c_int32), ('error_bound', ctypes.c_float), ('fallback', ctypes.c_int32), ('h2d_ms', ctypes.c_float), ('h2d_bytes', ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
@@ -139,6 +139,67 @@ _pyapi.PyCapsule_IsValid.argtypes = [ctypes.py_object, ctypes.c_char_p]
 _NP_CODES = {'i': 0, 'u': 1, 'f': 2}
 
 
+class DLManagedTensor(ctypes.Structure):
+    pass
+
+
+DLManagedTensor._fields_ = [('dl_tensor', DLTensor), ('manager_ctx', ctypes.c_void_p),
+                            ('deleter', ctypes.CFUNCTYPE(None, ctypes.POINTER(DLManagedTensor)))]
+
+_pyapi.PyCapsule_SetName.restype = ctypes.c_int
+_pyapi.PyCapsule_SetName.argtypes = [ctypes.py_object, ctypes.c_char_p]
+_USED_NAME = b'used_dltensor'            # PyCapsule_SetName keeps the pointer, not a copy: module lifetime
+
+
+def is_capsule(obj):
+    return type(obj).__name__ == 'PyCapsule'
+
+
+class DLPackTensor:
+    """A tensor taken over from a raw ``"dltensor"`` PyCapsule -- what ``tf.experimental.dlpack.to_dlpack(t)`` and
+    ``torch.utils.dlpack.to_dlpack(t)`` return -- per the DLPack protocol: the capsule is renamed ``"used_dltensor"`` (its
+    producer will not free the tensor any more) and this object owns the ``DLManagedTensor``: its ``deleter`` runs when the
+    object is released.  Exposes what the statistics classes need from an embedding matrix: ``shape``, ``dtype`` info,
+    ``__dlpack_device__`` and the borrowed ``DLTensor*`` for the C ABI (the memory is used in place, never copied here)."""
+
+    def __init__(self, capsule):
+        if not is_capsule(capsule) or not _pyapi.PyCapsule_IsValid(capsule, b'dltensor'):
+            raise ValueError('expected an un-consumed "dltensor" PyCapsule')
+        addr = _pyapi.PyCapsule_GetPointer(capsule, b'dltensor')
+        _pyapi.PyCapsule_SetName(capsule, _USED_NAME)
+        self._managed = ctypes.cast(addr, ctypes.POINTER(DLManagedTensor))
+        self._capsule = capsule                      # keeps the (now inert) capsule object alive with us
+        t = self._managed.contents.dl_tensor
+        self.ptr = ctypes.cast(addr, ctypes.POINTER(DLTensor))      # dl_tensor is the first member
+        self.shape = tuple(int(t.shape[i]) for i in range(t.ndim))
+        self.ndim = int(t.ndim)
+        self.device = (int(t.device.device_type), int(t.device.device_id))
+        self.is_cuda = self.device[0] == 2
+        self.dtype_code, self.dtype_bits = int(t.dtype.code), int(t.dtype.bits)
+
+    def __dlpack_device__(self):
+        return self.device
+
+    def __len__(self):
+        return self.shape[0]
+
+    def release(self):
+        m, self._managed = self._managed, None
+        if m is not None and m.contents.deleter:
+            m.contents.deleter(m)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def from_dlpack(obj):
+    """``DLPackTensor`` for a raw capsule; anything else (NumPy, torch, objects with ``__dlpack__``) is returned unchanged."""
+    return DLPackTensor(obj) if is_capsule(obj) else obj
+
+
 class Borrowed:
     """A DLTensor borrowed from ``obj``; keeps whatever owns the memory alive."""
 
@@ -146,6 +207,12 @@ class Borrowed:
         self.keep = [obj]
         self.ptr = None
         capsule = None
+        if is_capsule(obj):
+            obj = DLPackTensor(obj)                  # consumed per protocol; lives as long as this borrow
+            self.keep.append(obj)
+        if isinstance(obj, DLPackTensor):
+            self.ptr = obj.ptr
+            return
         if hasattr(obj, '__dlpack__') and not (isinstance(obj, np.ndarray) and not obj.flags.writeable):
             try:
                 capsule = obj.__dlpack__()
@@ -177,6 +244,10 @@ class Borrowed:
 
 def _as_f32_matrix(x, name):
     """float32 C-contiguous [N, D]; NumPy inputs are converted if needed, GPU tensors must already comply."""
+    if is_capsule(x):
+        x = DLPackTensor(x)
+    if isinstance(x, DLPackTensor):
+        return x
     if isinstance(x, np.ndarray) or not hasattr(x, '__dlpack__'):
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 2:
@@ -185,6 +256,10 @@ def _as_f32_matrix(x, name):
 
 
 def _as_labels(x):
+    if is_capsule(x):
+        x = DLPackTensor(x)
+    if isinstance(x, DLPackTensor):
+        return x
     if isinstance(x, np.ndarray) or not hasattr(x, '__dlpack__'):
         x = np.asarray(x)
         if x.dtype.kind not in 'iu' or x.dtype.itemsize not in (4, 8) or x.dtype.kind == 'u':
@@ -295,7 +370,8 @@ class Handle:
         after them -- never a host synchronisation, never its own unordered stream."""
         if not isinstance(obj, np.ndarray) and getattr(obj, 'is_cuda', False):
             import torch
-            s = int(torch.cuda.current_stream(obj.device).cuda_stream)
+            dev = obj.device[1] if isinstance(obj, DLPackTensor) else obj.device
+            s = int(torch.cuda.current_stream(dev).cuda_stream)
             if getattr(self, '_stream', None) != s:
                 self.set_stream(s)
         return Borrowed(obj)

@@ -52,7 +52,7 @@ void bias_table(int mode, int d, float* knots /* [kBiasStride] */) {
     double f = std::pow((double)d / 512.0, 1.09);
     switch (mode) {
         case FNB_MODE_FP16X3: src = kBiasBetaX3; break;
-        case FNB_MODE_TF32X3: src = kBiasBetaX3; f *= 1.41; break;     // same 96 steps, coarser product alignment (relu probe: 5.7 vs 4.0e-6)
+        case FNB_MODE_TF32X3: src = kBiasBetaX3; f *= 1.50; break;     // same 96 steps, K = 8 per MMA: 4.57e-6 vs 3.05e-6 (profiles/r02a_bias_raw_tf32x3.log)
         case FNB_MODE_FP16F8: case FNB_MODE_AUTO: src = kBiasBetaF8; break;
         default: return;
     }
@@ -75,7 +75,7 @@ double mode_sigma_s(int mode, int d, double abs_s, double peakedness) {
     const double trunc = (0.05e-6 + 0.27e-6 * abs_s) * std::pow((double)d / 512.0, 0.8);
     switch (mode) {
         case FNB_MODE_FP16X3: return trunc;
-        case FNB_MODE_TF32X3: return 1.41 * trunc;
+        case FNB_MODE_TF32X3: return 1.5 * trunc;
         case FNB_MODE_FP16F8: case FNB_MODE_AUTO: {
             const double pk = peakedness > 0 ? peakedness : 3.0 / d;
             const double e4m3 = (0.455e-6 + 0.375e-6 * abs_s) * std::sqrt(pk / (3.0 / 512.0));
@@ -189,7 +189,8 @@ int fnb::dl_view(fnb_context* h, const DLTensor* t, const char* name, int want_n
 int fnb::dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, const void** out) {
     if (v.on_device || bytes == 0) { *out = v.data; return FNB_OK; }
     CK(stage.ensure(bytes));
-    CK(cudaMemcpyAsync(stage.p, v.data, bytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = stage_to_device(h, stage.p, v.data, bytes);       // pinned ring + copy threads for pageable memory (fnb_stage.cu)
+    if (rc) return rc;
     *out = stage.p;
     return FNB_OK;
 }
@@ -211,9 +212,11 @@ static int make_tmap(fnb_context* h, CUtensorMap* m, void* base, int fmt, long l
     return FNB_OK;
 }
 
-// FNB_MODE_AUTO: largest peakedness FP16F8 is used for.  Dense Gaussian-like rows have 3 / D: 512-d embeddings pass (0.0059),
-// 256-d ones (0.0117: measured max |dd| 1.3e-5 in fp16f8, profiles/r02a_bias_d256.log) and sparse / heavy-tailed rows do not
-constexpr float kAutoPeakLimit = 1.0f / 128.0f;
+// FNB_MODE_AUTO, a-priori gate: largest peakedness of any row FP16F8 is tried for.  Dense Gaussian-like rows have 3 / D on
+// average (512-d: 0.0059, the largest of 1M rows ~0.010); 256-d rows (mean 0.0117, largest of a few thousand > 1/64; measured
+// max |dd| 1.3e-5 in fp16f8, profiles/r02a_bias_d256.log) and sparse / heavy-tailed rows do not pass.  The a-posteriori
+// error bound (error_certificate) decides whether the result of the fast pass is kept.
+constexpr float kAutoPeakLimit = 1.0f / 64.0f;
 
 static long long pad_rows(long long n) { return ((n + 255) / 256) * 256 + 256; }
 
@@ -306,16 +309,26 @@ static int pick_pairs(const fnb_options* o, int cta_group, long long n = 0) {
 // every column panel: auto sizes them to 64 MiB, half of the 126 MB L2 (32768 rows at d = 512; measured 2048 -> 32768:
 // +13 % at 1M rows, HBM reads fall from 490 GB to 30 GB per pass).  Ranks interleave tiles (t % world), so each rank
 // touches 1/world of a super-row's row panels: scale by world.  Small sets keep >= 6 super-rows for balance.
-static int pick_region_rows(const fnb_options* o, int tile, long long n = 0, int d = 512) {
+static int pick_region_rows(const fnb_options* o, int tile, long long n = 0, int d = 512, int clusters = 0, int row_block = 0) {
     long long rr = o->region_rows;
     const int world = std::max(1, o->world);
     if (rr <= 0) {
-        rr = (48ll << 20) / (4ll * std::max(d, 1)) * world;
+        rr = (64ll << 20) / (4ll * std::max(d, 1)) * world;
         if (n > 0) rr = std::min(rr, std::max<long long>(n / 6, 8ll * tile));
         // row blocks per super-row divisible by world: rank r then owns the SAME row blocks (r, r + world, ...) in every
         // column panel, i.e. 1/world of the row panels; otherwise its rows drift from column to column and it ends up
         // streaming all of them (measured at 8 GPUs: 114 ms per rank instead of 1/8 of the single-GPU 817 ms)
-        const long long q = (long long)tile * (o->shard_mod > 0 ? o->shard_mod : world);
+        long long q = (long long)tile * (o->shard_mod > 0 ? o->shard_mod : world);
+        // ... and this rank's row blocks per super-row a multiple of the number of clusters: every cluster then gets the same
+        // number of tiles in every column panel -- no cluster waits at the progress window for one that has an extra tile, and
+        // each cluster re-reads the same row panels (measured at 1M, 33 clusters of two pairs: 132 row blocks per super-row
+        // 849-854 ms and 64-66 GB of DRAM reads, 96 row blocks 890-894 ms and 78-85 GB; profiles/r02b_rr_window_dram.log)
+        if (clusters > 0 && row_block > 0) {
+            long long unit = (long long)clusters * row_block * (o->shard_mod > 0 ? o->shard_mod : world);
+            while (unit % tile) unit *= 2;
+            if (rr >= unit) q = unit;
+            if (rr >= unit && rr % unit >= unit / 2 && (n <= 0 || rr + unit <= std::max<long long>(n / 3, unit))) rr += unit;   // round to nearest
+        }
         if (rr >= q) rr = (rr / q) * q;
     }
     rr = std::max<long long>(tile, (rr / tile) * tile);
@@ -375,6 +388,7 @@ extern "C" int fnb_create(int device, fnb_handle* out) {
     }
     h->stream = h->own_stream;
     for (int i = 0; i < 4; ++i) cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < 3; ++i) cudaEventCreate(&h->copy_ev[i]);
     *out = h;
     return FNB_OK;
 }
@@ -383,11 +397,16 @@ extern "C" void fnb_destroy(fnb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_l16, &h->b_l16, &h->bias_tab, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->progress, &h->perm, &h->cls,
+    DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_l16, &h->b_l16, &h->bias_tab, &h->strict_bits, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->progress, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
                       &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io, &h->mine_lab, &h->mine_keys, &h->mine_status};
     for (DevBuf* b : bufs) b->release();
     h->pinned.release();
+    if (h->copier) { destroy_copier(h->copier); h->copier = nullptr; }
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    h->ring.release();
+    for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    for (int i = 0; i < 3; ++i) if (h->copy_ev[i]) cudaEventDestroy(h->copy_ev[i]);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -396,12 +415,16 @@ extern "C" void fnb_destroy(fnb_handle h) {
 extern "C" int fnb_set_stream(fnb_handle h, void* cuda_stream) {
     if (!h) return FNB_ERR_INVALID;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
     // NULL is CUDA's legacy default stream (what torch reports as its current stream until another one is selected):
     // it must NOT fall back to the handle's own non-blocking stream, which would not be ordered after the caller's
     // kernels and collectives on stream 0
-    if (cuda_stream == FNB_STREAM_OWN) h->stream = h->own_stream;
-    else h->stream = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy;
+    cudaStream_t next = (cuda_stream == FNB_STREAM_OWN) ? h->own_stream : (cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy);
+    if (next != h->stream) {
+        // no host synchronisation: the new stream is ordered after the handle's work on the old one (workspaces are shared)
+        if (cudaEventRecord(h->ev[3], h->stream) == cudaSuccess) cudaStreamWaitEvent(next, h->ev[3], 0);
+        else cudaGetLastError();                         // the old stream is gone (destroyed by its owner): nothing to order after
+        h->stream = next;
+    }
     return FNB_OK;
 }
 
@@ -456,9 +479,10 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     const bool want_l16 = f8 && op.want_l16;
     if (want_l16) CK(l16.ensure(bytes));
     CK(h->counters.ensure(sizeof(DeviceScalars)));
-    unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;    // [0] max squared norm, [1] peakedness
+    unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;    // [0] max squared norm, [1] max peakedness, [2] its sum over rows
     static_assert(offsetof(DeviceScalars, peak_max_ord) == offsetof(DeviceScalars, norm_max_ord) + 4, "layout");
-    CK(cudaMemsetAsync(norm, 0, 8, h->stream));
+    static_assert(offsetof(DeviceScalars, peak_sum) == offsetof(DeviceScalars, norm_max_ord) + 8, "layout");
+    CK(cudaMemsetAsync(norm, 0, 12, h->stream));
     float* nrm_out = nullptr;
     if (normalize) {
         DevBuf& nb = side_b ? h->b_nrm : h->a_nrm;
@@ -470,7 +494,7 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
                          normalize, nrm_out, want_l16 ? l16.p : nullptr));
     // an operand that two pairs of a cluster share is fetched as two 64-row halves (A: pairs 2 and 4, B: pairs 4)
     const int box_rows = (side_b ? op.pairs == 4 : op.pairs > 1) ? kRowsPerCta / 2 : kRowsPerCta;
-    if (!side_b) op.a_rows_pad = n_pad;
+    if (!side_b) { op.a_rows_pad = n_pad; h->last_rows = n; }
     int rc = make_tmap(h, m_hi, hi.p, op.fmt, n_pad, d, box_rows);
     if (rc) return rc;
     if (op.num_pass == 3) rc = make_tmap(h, m_lo, lo.p, op.fmt, n_pad, d, box_rows);
@@ -672,7 +696,17 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.operand_fmt = op.fmt;
     p.force_slow = force_slow || opt.force_checked;
     if ((rc = upload_bias(h, op.mode, d, bias_off, &p.bias_beta))) return rc;
-    p.strict_tiles = (op.num_pass == 2 && op.have_l16 && opt.strict_tiles >= 0) ? 1 : 0;
+    // whole-set launches decide per global 512 x 512 block (bins independent of the tiling); keyed launches have arbitrary
+    // rectangles: every tile strict
+    p.strict_tiles = (op.num_pass == 2 && op.have_l16 && opt.strict_tiles >= 0) ? (hl.auto_window ? 1 : 2) : 0;
+    if (p.strict_tiles == 1) {
+        const int n_rows = (int)h->last_rows, nb = (n_rows + 511) / 512;
+        const size_t words = ((size_t)nb * nb + 31) / 32 + 1;
+        CK(h->strict_bits.ensure(words * 4));
+        CK(cudaMemsetAsync(h->strict_bits.p, 0, words * 4, h->stream));
+        CK(launch_strict_blocks(cls_dev, n_rows, kRowsPerCta * cg, nb, h->strict_bits.as<unsigned int>(), h->stream));
+        p.strict_bits = h->strict_bits.as<unsigned int>(); p.strict_nb = nb;
+    }
     h->last_strict = p.strict_tiles;
     p.raw = opt.raw_distance;
     if (opt.normalize == 1 && opt.theta != 0.f) { p.row_nrm = op.a_nrm; p.col_nrm = op.b_nrm; p.theta = opt.theta; }
@@ -768,6 +802,8 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
     *violated = !opt.raw_distance && have_checked && !((double)smin >= -lim && (double)smax <= lim);
     *smin_out = smin;
     *smax_out = smax;
+    h->last_peak = hs.peak_max_ord ? ordered_to_float(hs.peak_max_ord) : 0.f;
+    h->last_peak_mean = h->last_rows > 0 ? hs.peak_sum / (float)h->last_rows : 0.f;
     if (stats) {
         float ms = 0.f, pm = 0.f;
         cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
@@ -785,6 +821,8 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         stats->mode_used = h->last_mode;
         stats->panel_window = h->last_window;
         stats->peakedness = hs.peak_max_ord ? ordered_to_float(hs.peak_max_ord) : 0.f;
+        stats->h2d_bytes = h->last_h2d_bytes;
+        if (h->h2d_timed) { float hm = 0.f; if (cudaEventElapsedTime(&hm, h->copy_ev[1], h->copy_ev[2]) == cudaSuccess) stats->h2d_ms = hm; }
     }
     return FNB_OK;
 }
@@ -808,9 +846,10 @@ static uint64_t sum_bins(const uint64_t* b, int n) { uint64_t s = 0; for (int i 
 //   + z sigma(|s|),  z = sqrt(2 ln(1000 (T + 1) M))  -- a union bound over the M pairs of the bin and all bins at 1e-3,
 // in distance units (metric 0: dd = 2 ds; metric 1 keeps similarity units like the eps window).  Same-identity pairs of an
 // fp16f8 launch with strict tiles ran in the fp16x3 contraction.  all / same: [T + 1] counts summed over keys.
-static double error_certificate(const fnb_options& opt, int mode, bool strict_tiles, int d, double peak, const CutTables& ct,
-                                const uint64_t* all, const uint64_t* same, int T)
+static double error_certificate(const fnb_options& opt, int mode, bool strict_tiles, int d, double peak_mean, double peak_max,
+                                long long n_rows, const CutTables& ct, const uint64_t* all, const uint64_t* same, int T)
 {
+    const double share = (double)std::max(1, opt.world);     // a rank sees 1 / world of every bin: bound the whole job
     float tab_mode[kBiasStride], tab_x3[kBiasStride];
     bias_table(mode, d, tab_mode);
     bias_table(FNB_MODE_FP16X3, d, tab_x3);
@@ -827,8 +866,13 @@ static double error_certificate(const fnb_options& opt, int mode, bool strict_ti
             const int md = x3 ? FNB_MODE_FP16X3 : mode;
             const double beta = beta_at(x3 ? tab_x3 : tab_mode, a);
             const double resid = (corrected ? 0.35 : 1.0) * beta * a;
-            const double z = std::sqrt(2.0 * std::log(1000.0 * (T + 1) * (double)m));
-            const double e_s = resid + z * mode_sigma_s(md, d, a, peak);
+            // bulk of the bin: typical rows (mean peakedness); and the pairs of the peakiest row with typical rows
+            // (sum x^2 y^2 <= sqrt(sum x^4 sum y^4)): at most n_rows of them fall into the bin
+            const double z = std::sqrt(2.0 * std::log(1000.0 * (T + 1) * (double)m * share));
+            const double m_row = std::min((double)m, (double)std::max<long long>(n_rows, 1));
+            const double z_row = std::sqrt(2.0 * std::log(1000.0 * (T + 1) * m_row));
+            const double pk_row = std::sqrt(std::max(peak_mean, 0.0) * std::max(peak_max, peak_mean));
+            const double e_s = resid + std::max(z * mode_sigma_s(md, d, a, peak_mean), z_row * mode_sigma_s(md, d, a, pk_row));
             worst = std::max(worst, opt.metric == 0 ? 2.0 * e_s : e_s);
         }
     }
@@ -876,9 +920,11 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
 
     const void* de = nullptr; const void* dl = nullptr;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    h->last_h2d_bytes = 0; h->h2d_timed = false; h->h2d_timed_bytes = 0;
+    // labels first: the class sort (np.unique ranks, statistics.py:68-79) runs on the stream while the embeddings are staged
     if ((rc = dl_to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
+    if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
     const int requested = opt.mode;
@@ -898,7 +944,11 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
         opt.mode = op.mode;                              // AUTO resolved
         h->last_mode = op.mode; h->last_peak = op.peakedness;
         std::vector<RegionDev> regs;
-        triangle_regions(n, pick_region_rows(&opt, tile * (op.pairs == 1 ? 1 : 2), n, d), 0, regs);
+        // 512-aligned regions (see strict_tile in the kernel), super-row height matched to the cluster count of the launch
+        const int cl_size = cg * op.pairs;
+        const int clusters = h->hist_grid[op.pairs] > 0 ? h->hist_grid[op.pairs] / cl_size
+                                                        : (op.pairs == 1 ? h->sm_count / cl_size : op.pairs == 2 ? h->sm_count / cl_size - 4 : 15);
+        triangle_regions(n, pick_region_rows(&opt, 512, n, d, clusters, tile * (op.pairs == 4 ? 2 : 1)), 0, regs);
         finish_regions(regs, tile, op.pairs, &shard);
         HistLaunch hl; hl.auto_window = true;
         if ((rc2 = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc2;
@@ -914,15 +964,15 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
         CK(cudaStreamSynchronize(h->stream));
         const uint64_t* pb = reinterpret_cast<const uint64_t*>(h->pinned.as<char>() + 4096);
         for (int r = 0; r < 2; ++r) memcpy(host_bins + (size_t)r * (T + 1), pb + (size_t)r * hl.stride, row_bytes);
-        float pk = 0.f;
-        if (stats) pk = stats->peakedness;
-        *bound = error_certificate(opt, op.mode, h->last_strict != 0, d, pk, hl.ct, host_bins, host_bins + (T + 1), T);
+        *bound = error_certificate(opt, op.mode, h->last_strict != 0, d, h->last_peak_mean, h->last_peak, n, hl.ct, host_bins, host_bins + (T + 1), T);
         return FNB_OK;
     };
 
     double bound = 0.0;
     int fallback = 0;
     if ((rc = pass(requested, &bound))) return rc;
+    // (every rank of a sharded job evaluates the same model on its share scaled to the whole; the shares are interleaved
+    // row blocks, so the ranks agree except at the very edge of the bound)
     if (requested == FNB_MODE_AUTO && op.mode == FNB_MODE_FP16F8 && bound > (double)opt.eps) {
         // the fast contraction cannot vouch for this data (e.g. many different-identity pairs at high similarity): strict pass
         if ((rc = pass(FNB_MODE_FP16X3, &bound))) return rc;
@@ -1039,6 +1089,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
 
     const void* de = nullptr;
     CK(cudaEventRecord(h->ev[0], h->stream));
+    h->last_h2d_bytes = 0; h->h2d_timed = false; h->h2d_timed_bytes = 0;
     if ((rc = dl_to_device(h, ve, (size_t)n_all * d * 4, h->stage_a, &de))) return rc;
     CK(h->perm.ensure(n * 8));
     CK(h->cls.ensure(n * 4));
@@ -1072,7 +1123,7 @@ extern "C" int fnb_region_histogram_bins(fnb_handle h, const DLTensor* emb, cons
     }
     if (stats) {
         stats->n_pairs = total;
-        stats->error_bound = (float)error_certificate(opt, op.mode, h->last_strict != 0, d, stats->peakedness, hl.ct, sums[0], sums[1], T);
+        stats->error_bound = (float)error_certificate(opt, op.mode, h->last_strict != 0, d, h->last_peak_mean, h->last_peak, n, hl.ct, sums[0], sums[1], T);
     }
     return FNB_OK;
 }

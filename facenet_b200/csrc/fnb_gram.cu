@@ -50,6 +50,7 @@ static int launch_one(fnb_context* h, int max_ctas, const GramOperands& op, cons
     if (ctas < kCluster) ctas = kCluster;
     cfg.gridDim = dim3((unsigned)ctas);
     h->last_grid = ctas;
+    if (kEpi == EPI_HIST) h->hist_grid[kPairs] = ctas;
     e = cudaLaunchKernelEx(&cfg, kern, op.a_hi, op.a_lo, op.b_hi, op.b_lo, op.a_h8, op.b_h8, op.a_l16, op.b_l16, p);
     if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "gram kernel launch: %s", cudaGetErrorString(e));
     return FNB_OK;

@@ -143,8 +143,11 @@ struct GramParams {
     const float* bias_beta;    // [2][kBiasStride]
     // fp16f8 launches: tiles that can hold a same-identity pair, and ragged / diagonal tiles, run the fp16x3 contraction
     // (hi*hi + hi*l16 + l16*hi, l16 = fp16 low part) instead of the e4m3 cross terms -- the pairs behind TP / FN get the
-    // strict arithmetic, the e4m3 error model only has to hold for different-identity pairs.  Needs row_cls / col_cls.
+    // strict arithmetic, the e4m3 error model only has to hold for different-identity pairs.  1: whole-set launches (row_cls ==
+    // col_cls over n_valid rows, strictness decided per global 512 x 512 block); 2: every tile (keyed launches).
     int strict_tiles;
+    const unsigned int* strict_bits;   // strict_tiles == 1: bit (R / 512) * strict_nb + C / 512 of the block at (R, C)
+    int strict_nb;
 };
 
 constexpr int kBiasKnots  = 41;                    // |s| = 0, 0.025, ..., 1
@@ -382,15 +385,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const uint32_t tmem_base = misc->tmem_base;
 
     // fp16f8 launches: does the cluster's super-tile run the strict fp16x3 contraction (GramParams::strict_tiles)?  Identical
-    // in every role and every CTA of the cluster (decided on the super-tile, from the class ranks of its corner rows).
+    // in every role and every CTA of the cluster.  The rule is a function of the GLOBAL 512 x 512 block of the pair matrix the
+    // super-tile lies in -- strict iff any tile of that block is ragged, touches the diagonal or can hold a same-identity pair
+    // (class ranks of its corner rows) -- so it does not depend on the cluster shape, the super-row height or the rank split:
+    // the integer bins of an fp16f8 launch stay identical across all of them (regions are 512-aligned, fnb_api.cu).
     auto strict_tile = [&](const TileInfo& t) -> bool {
         if (!kF8 || !p.strict_tiles) return false;
-        const int r_last = min(t.row0 + Sched::kSuperRows, t.row_end) - 1;
-        const int c_last = min(t.col0 + Sched::kSuperCols, t.col_end) - 1;
-        const bool edge = (t.row0 + Sched::kSuperRows > t.row_end) || (t.col0 + Sched::kSuperCols > t.col_end) ||
-                          (t.tri && t.col0 <= t.row0 + Sched::kSuperRows - 1);
-        if (edge) return true;
-        return (__ldg(p.row_cls + t.row0) <= __ldg(p.col_cls + c_last)) && (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + r_last));
+        if (p.strict_tiles == 2) return true;
+        const unsigned int idx = (unsigned int)(t.row0 >> 9) * (unsigned int)p.strict_nb + (unsigned int)(t.col0 >> 9);
+        return (__ldg(p.strict_bits + (idx >> 5)) >> (idx & 31u)) & 1u;          // one bit per 512 x 512 block (strict_blocks_kernel)
     };
 
     // =====================================================================================

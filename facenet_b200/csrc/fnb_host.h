@@ -61,6 +61,8 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 }  // namespace fnb
 
+namespace fnb { struct HostCopier; void destroy_copier(HostCopier*); }
+
 struct fnb_context {
     int device = 0;
     int sm_count = 0;
@@ -80,14 +82,26 @@ struct fnb_context {
     fnb::DevBuf progress;                             // per-cluster column-panel progress (GramParams::sync_window)
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
+    fnb::DevBuf strict_bits;                          // one bit per 512 x 512 block of the pair matrix (fp16f8 strict tiles)
     fnb::DevBuf bias_tab;                             // [2][kBiasStride] accumulation-bias knots of the current (mode, d)
     int bias_mode = -1, bias_d = 0;
     fnb::DevBuf mine_lab, mine_keys, mine_status;     // mining: labels as int64, packed arg-extrema keys, status words
     long long mine_rows = 0, mine_b = 0, mine_ld = 0; // geometry of the last mining call (its strips stay in `strip`)
     int mine_kmax = 0; float mine_atol = 0.f; bool mine_has_strip = false;
     fnb::HostBuf pinned;
+    // pipelined staging of pageable host tensors (fnb_stage.cu)
+    cudaStream_t copy_stream = nullptr;
+    fnb::HostBuf ring;
+    cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};
+    fnb::HostCopier* copier = nullptr;
+    size_t last_h2d_bytes = 0;           // host -> device bytes of the call in progress
+    size_t h2d_timed_bytes = 0;          // size of the copy those events bracket
+    bool h2d_timed = false;              // copy_ev[1] .. copy_ev[2] bracket a staged copy of the call in progress
+    int hist_grid[5] = {0, 0, 0, 0, 0};  // CTAs of the last histogram launch per cluster_pairs (co-resident clusters x cluster size)
     int last_nkeys = 0, last_T = 0, last_grid = 0, last_mode = 0, last_window = 0, last_strict = 0;
-    float last_peak = 0.f;
+    float last_peak = 0.f, last_peak_mean = 0.f;
+    long long last_rows = 0;             // rows of the last prepared A operand (mean peakedness = peak_sum / rows)
     fnb::ShardSpec last_shard = fnb::ShardSpec{1, 0, 1, nullptr};   // share of the launch being prepared
     double last_eps_counted = 0;         // distance half-width of the near-threshold window counted by interior tiles
 
@@ -125,12 +139,14 @@ struct DeviceScalars {      // layout of fnb_context::counters
     unsigned int range_ord[4];
     unsigned int norm_max_ord;      // ordered-uint max squared row norm of the last prepared operand (not reset per launch)
     unsigned int peak_max_ord;      // ordered-uint max over rows of sum x^4 / (sum x^2)^2 (same lifetime)
-    unsigned int pad[6];
+    float peak_sum;                 // sum over rows of the same quantity (mean peakedness = peak_sum / rows)
+    unsigned int pad[5];
 };
 
 // fnb_api.cu
 int dl_view(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_min, int want_ndim_max, DLView* v);
 int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, const void** out);
+int stage_to_device(fnb_context* h, void* dst, const void* src, size_t bytes);   // fnb_stage.cu
 int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
                     bool side_b, GramOperands& op, int normalize = 0);
@@ -162,6 +178,7 @@ int upload_bias(fnb_context* h, int mode, int d, bool strict_x3, const float** d
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
                               void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s,   // norm_max_ord[1] = peakedness
                               int normalize = 0, float* row_nrm = nullptr, void* l16 = nullptr);
+cudaError_t launch_strict_blocks(const int32_t* cls, int n, int tile, int nb, unsigned int* bits, cudaStream_t s);
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
 
 // fnb_gram.cu

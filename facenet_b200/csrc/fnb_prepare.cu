@@ -26,7 +26,7 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    float norm_max = 0.f, peak_max = 0.f;
+    float norm_max = 0.f, peak_max = 0.f, peak_sum = 0.f;
     for (long long row = warp0; row < n_pad; row += nwarps) {
         const long long src = (row < n) ? (perm ? perm[row] : row) : 0;
         // normalise-on-load (fnb_options.normalize): a first pass over the row forms |x|; the second pass below re-reads
@@ -125,12 +125,14 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
         norm_max = (nrm <= norm_max) ? norm_max : nrm;
         const float pk = (nrm > 0.f) ? x4 / (nrm * nrm) : 0.f;
         peak_max = (pk <= peak_max) ? peak_max : pk;
+        if (row < n && pk == pk) peak_sum += pk;
     }
     if (norm_max_ord && lane == 0) {
         const float v = (norm_max == norm_max) ? norm_max : INFINITY;
         if (v > 0.f) atomicMax(norm_max_ord, float_to_ordered(v));
         const float w = (peak_max == peak_max) ? peak_max : INFINITY;
         if (w > 0.f) atomicMax(norm_max_ord + 1, float_to_ordered(w));
+        if (peak_sum > 0.f) atomicAdd(reinterpret_cast<float*>(norm_max_ord + 2), peak_sum);      // DeviceScalars::peak_sum
     }
 }
 
@@ -151,6 +153,36 @@ cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, l
         case FNB_MODE_FP16F8: split_rows_kernel<FNB_MODE_FP16F8><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
         default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+// One thread per 512 x 512 block of the (upper triangle of the) pair matrix of a class-sorted set of n rows: the block is strict
+// iff any of its tile x tile tiles is ragged (crosses n), touches the diagonal, or can hold a same-identity pair (the class
+// ranks of its corner rows overlap).  bits must be zeroed before the launch.
+__global__ void strict_blocks_kernel(const int32_t* __restrict__ cls, int n, int tile, int nb, unsigned int* __restrict__ bits)
+{
+    const long long total = (long long)nb * nb;
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int br = (int)(id / nb), bc = (int)(id - (long long)br * nb);
+        if (bc < br) continue;                                       // below the diagonal: never scheduled
+        const int R = br << 9, C = bc << 9;
+        bool strict = false;
+        for (int i = 0; i < 512 / tile && !strict; ++i) {
+            for (int j = 0; j < 512 / tile && !strict; ++j) {
+                const int r0 = R + i * tile, c0 = C + j * tile;
+                if (r0 >= n || c0 >= n || c0 + tile - 1 <= r0) continue;           // outside the set / below the diagonal: never binned
+                if (r0 + tile > n || c0 + tile > n || c0 <= r0 + tile - 1) strict = true;
+                else strict = (cls[r0] <= cls[c0 + tile - 1]) && (cls[c0] <= cls[r0 + tile - 1]);
+            }
+        }
+        if (strict) atomicOr(bits + (id >> 5), 1u << (id & 31));
+    }
+}
+
+cudaError_t launch_strict_blocks(const int32_t* cls, int n, int tile, int nb, unsigned int* bits, cudaStream_t s) {
+    const long long total = (long long)nb * nb;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+    strict_blocks_kernel<<<blocks, 256, 0, s>>>(cls, n, tile, nb, bits);
     return cudaGetLastError();
 }
 

@@ -36,8 +36,8 @@ _state = {'mode': 'fp16x3', 'device': 0, 'cta_group': 0}
 
 
 def set_default_mode(mode=None, device=None, cta_group=None):
-    """Select the Gram arithmetic ('fp16x3' default, 'tf32x3', 'tf32', 'bf16', 'fp16'), the CUDA device
-    and the tile variant used by the functions of this module."""
+    """Select the Gram arithmetic ('fp16x3' default; 'tf32x3', 'fp16f8', 'auto' -- fp16f8 where its error model holds, else fp16x3
+    --, and the single-pass 'tf32', 'bf16', 'fp16'), the CUDA device and the tile variant used by the functions of this module."""
     if mode is not None:
         if mode not in _capi.MODES:
             raise ValueError('unknown mode {}'.format(mode))
@@ -72,16 +72,37 @@ def std(x):
     return np.std(np.array(x))
 
 
+def _pad64(x):
+    """The tensor-core tiles take embedding dimensions that are multiples of 64 (64 .. 4096); the reference takes any D.  Zero
+    columns change no dot product and no norm, so other dimensions are padded here (a copy; 512-d embeddings pass through)."""
+    d = int(x.shape[1])
+    dp = max(64, -(-d // 64) * 64)
+    if dp == d or x.shape[0] == 0:
+        return x
+    if isinstance(x, np.ndarray):
+        out = np.zeros((x.shape[0], dp), dtype=np.float32)
+        out[:, :d] = x
+        return out
+    if isinstance(x, _capi.DLPackTensor):
+        raise ValueError('a raw DLPack capsule must carry an embedding dimension that is a multiple of 64 (got {})'.format(d))
+    import torch
+    return torch.nn.functional.pad(x if hasattr(x, 'storage') else torch.from_dlpack(x), (0, dp - d)).contiguous()
+
+
 def pairwise_similarities(xa, xb=None, metric=0, atol=1.e-5):
     """Evaluate pairwise distances between vectors xa and xb (statistics.py:22-57).
 
     ``xb is None``: 1-D float32 array of the strict upper triangle of the Gram matrix in row-major
     ``np.triu_indices(n, k=1)`` order; otherwise the 2-D ``[n_a, n_b]`` matrix.  metric 0 gives
     ``2 * (1 - s)``, metric 1 ``arccos(s)``.  Raises ``ValueError`` exactly where the reference does."""
-    xa = np.ascontiguousarray(xa, dtype=np.float32)
+    xa = np.ascontiguousarray(xa, dtype=np.float32)        # (float64 input is computed in float32 here, in float64 by NumPy)
     if xb is not None:
         xb = np.ascontiguousarray(xb, dtype=np.float32)
     n_out = xa.shape[0] * (xa.shape[0] - 1) // 2 if xb is None else xa.shape[0] * xb.shape[0]
+    if n_out and xa.ndim == 2:
+        xa = _pad64(xa)
+        if xb is not None and xb.ndim == 2:
+            xb = _pad64(xb)
     if n_out == 0:
         # statistics.py:38 -- empty in, empty out (no checks)
         return np.empty((0,) if xb is None else (xa.shape[0], xb.shape[0]), dtype=np.float32)
@@ -118,6 +139,16 @@ def _on_gpu(x):
 
 
 def _host_array(x):
+    if isinstance(x, _capi.DLPackTensor):
+        # labels handed over as a capsule: a small host copy through torch (any DLPack consumer would do)
+        n = int(np.prod(x.shape))
+        if not x.is_cuda:
+            ct = {(0, 32): np.int32, (0, 64): np.int64, (2, 32): np.float32, (2, 64): np.float64}[(x.dtype_code, x.dtype_bits)]
+            import ctypes
+            t = x.ptr.contents
+            buf = (ctypes.c_char * (n * x.dtype_bits // 8)).from_address(t.data + t.byte_offset)
+            return np.frombuffer(buf, dtype=ct).reshape(x.shape).copy()
+        raise TypeError('labels in a raw DLPack capsule must live on the host (hand GPU labels over as a tensor object)')
     return np.asarray(x.cpu() if hasattr(x, 'cpu') else x)
 
 
@@ -135,8 +166,13 @@ class SimilarityCalculator:
 
     def __init__(self, embeddings, labels, metric=0, _rows=None, normalize=False):
         self.metric = metric
+        embeddings = _capi.from_dlpack(embeddings)   # a raw "dltensor" capsule (tf.experimental.dlpack.to_dlpack) is taken over
+        labels = _capi.from_dlpack(labels)
         self._gpu = _on_gpu(embeddings)
-        self._x = embeddings if self._gpu else np.ascontiguousarray(embeddings, dtype=np.float32)
+        self._x = embeddings if (self._gpu or isinstance(embeddings, _capi.DLPackTensor)) else np.ascontiguousarray(embeddings, dtype=np.float32)
+        self._dim = int(self._x.shape[1]) if len(self._x.shape) == 2 else None
+        if len(self._x.shape) == 2:
+            self._x = _pad64(self._x)
         self._rows = None if _rows is None else np.ascontiguousarray(_rows, dtype=np.int64)
         self._normalize = 2 if normalize else 0
         self._labels = _host_array(labels)
@@ -150,13 +186,15 @@ class SimilarityCalculator:
     @property
     def embeddings(self):
         if self._split is None:
+            if isinstance(self._x, _capi.DLPackTensor):
+                raise TypeError('.embeddings needs a tensor object (torch / NumPy); a raw DLPack capsule is consumed by the GPU path only')
             x = _host_array(self._x) if self._gpu else self._x
             if self._rows is not None:
                 x = x[self._rows]
             if self._normalize:
                 x = (x * (1.0 / np.sqrt(np.maximum((x.astype(np.float32) ** 2).sum(axis=1, keepdims=True), np.float32(1e-10))))).astype(np.float32)
             order = np.argsort(self._cls, kind='stable')
-            self._split = np.split(x[order], np.cumsum(self._sizes)[:-1])
+            self._split = np.split(x[order][:, :self._dim], np.cumsum(self._sizes)[:-1])
         return self._split
 
     def evaluate(self, i, k):
@@ -240,6 +278,15 @@ class ConfidenceMatrix:
         # filled by the device selection kernel when the whole threshold grid went through one launch
         self._argmax_accuracy = None
         self._far_threshold = None
+        if not hasattr(calculator, '_cls'):
+            # a reference-style calculator (facenet/statistics.py:82-108: ``.embeddings`` = list of per-class arrays, ``.metric``,
+            # ``.nrof_classes``): rebuild the row set from the list -- still ONE launch for the whole matrix
+            parts = [np.asarray(e, dtype=np.float32).reshape(-1, np.asarray(e).shape[-1]) if np.asarray(e).size else
+                     np.zeros((0, 1), dtype=np.float32) for e in calculator.embeddings]
+            dim = max((p.shape[1] for p in parts if p.shape[0]), default=1)
+            rows = np.concatenate([p if p.shape[0] else np.zeros((0, dim), dtype=np.float32) for p in parts]) if parts else np.zeros((0, dim), np.float32)
+            lab = np.repeat(np.arange(len(parts)), [p.shape[0] for p in parts])
+            calculator = SimilarityCalculator(rows, lab, metric=calculator.metric)
         if nt == 0 or calculator._n < 2:
             return
         thr = self.threshold.astype(np.float64).reshape(-1)
@@ -385,7 +432,14 @@ class Report:
 def kfold_split(n, n_splits, seed=0):
     """The index sets of ``sklearn.model_selection.KFold(n_splits, shuffle=True, random_state=seed)
     .split(np.arange(n))`` (statistics.py:278-287) without the sklearn dependency: a
-    ``RandomState(seed)`` shuffle cut into folds, the first ``n % n_splits`` one longer."""
+    ``RandomState(seed)`` shuffle cut into folds, the first ``n % n_splits`` one longer.  Raises ``ValueError`` where
+    sklearn's KFold does (fewer than 2 splits, more splits than samples)."""
+    n_splits = int(n_splits)
+    if n_splits < 2:
+        raise ValueError('k-fold cross-validation requires at least one train/test split by setting n_splits=2 or more, '
+                         'got n_splits={0}.'.format(n_splits))
+    if n_splits > n:
+        raise ValueError('Cannot have number of splits n_splits={0} greater than the number of samples: n_samples={1}.'.format(n_splits, n))
     perm = np.arange(n)
     np.random.RandomState(seed).shuffle(perm)
     fold_sizes = np.full(n_splits, n // n_splits, dtype=np.int64)
@@ -403,6 +457,9 @@ class FaceToFaceValidation:
 
     def __init__(self, embeddings, labels, config):
         self.elapsed_time = time.monotonic()
+        # raw "dltensor" capsules (tf.experimental.dlpack.to_dlpack / torch.utils.dlpack.to_dlpack) are taken over per protocol
+        embeddings = _capi.from_dlpack(embeddings)
+        labels = _capi.from_dlpack(labels)
         self.embeddings = embeddings
         self.labels = labels
 
@@ -439,6 +496,8 @@ class FaceToFaceValidation:
         # subset of the one resident tensor (no D2H -> H2D round trip, facenet.py:184-201); ``config.normalize`` (not in
         # the reference's config) applies l2_normalize on load for raw network outputs
         gpu = _on_gpu(self.embeddings)
+        if isinstance(self.embeddings, _capi.DLPackTensor) and not gpu:
+            raise TypeError('host embeddings must be handed over as an array; the capsule path is for GPU tensors')
         embeddings = self.embeddings if gpu else np.asarray(self.embeddings)
         labels = _host_array(self.labels)
         normalize = bool(getattr(self.config, 'normalize', False))
@@ -505,11 +564,8 @@ class FaceToFaceValidation:
                 f.write(str(r))
 
     def write_h5file(self, h5file, tag=None):
-        # statistics.py:330-331 delegates to facenet.h5utils.write_dict (h5py); kept as a thin hook
-        try:
-            from facenet import h5utils
-        except ImportError as exc:
-            raise ImportError('write_h5file needs the reference package facenet.h5utils (h5py)') from exc
+        # statistics.py:330-331 -> h5utils.write_dict (h5utils.py:9-26): resizable gzip datasets, appended per call
+        from facenet_b200 import h5utils
         h5utils.write_dict(h5file, self.dict, group=tag)
 
 

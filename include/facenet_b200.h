@@ -9,7 +9,8 @@
  * Conventions
  *  - plain C: pointers, sizes and DLPack tensor structs only (no torch / numpy types);
  *  - tensors are BORROWED `DLTensor*` (the struct inside a DLPack capsule): kDLCPU data is
- *    staged through pinned memory, kDLCUDA data on the handle's device is used in place;
+ *    staged through a ring of pinned buffers (pageable memory) or copied in place (pinned memory),
+ *    kDLCUDA data on the handle's device is used in place;
  *  - embeddings: float32, C-contiguous [N, D], D a multiple of 64, 64 <= D <= 4096;
  *    labels: int32 or int64 [N];
  *  - every function returns FNB_OK (0) or an FNB_ERR_* code; fnb_last_error() gives the text;
@@ -154,6 +155,10 @@ typedef struct {
                               the arithmetic x a union bound over the pairs actually found in each similarity bin + the residual
                               of the bias correction); the contract needs <= eps.  AUTO re-runs in FP16X3 when FP16F8 exceeds it */
     int32_t  fallback;     /* 1: AUTO ran FP16F8, its error_bound exceeded eps and the launch was repeated in FP16X3 */
+    float    h2d_ms;       /* device time of the host -> device copy of a kDLCPU embedding tensor (0: device-resident input).
+                              Pageable memory goes through a ring of pinned slots filled by a pool of host threads while the
+                              previous slot is in flight (csrc/fnb_stage.cu); pinned memory is copied in place */
+    uint64_t h2d_bytes;    /* bytes copied host -> device by the call */
 } fnb_stats;
 
 /* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:

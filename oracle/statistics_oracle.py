@@ -470,13 +470,19 @@ def pair_histogram_window(embeddings, labels, thresholds, metric=0, eps=1.e-5, t
 
 def synthetic_embeddings(class_sizes, dim=512, sigma=1.1, seed=0, shuffle=True, label_values=None):
     """Clustered unit-norm fp32 embeddings: centre ~ N(0,I), sample = centre +
-    sigma*N(0,I), L2-normalised in fp32.  Returns (embeddings [N,dim] f32, labels [N] i64)."""
+    sigma*N(0,I), L2-normalised in fp32.  Returns (embeddings [N,dim] f32, labels [N] i64).
+    ``sigma`` may be a pair (lo, hi): every class draws its own sigma ~ U(lo, hi) -- tight and loose identities side by
+    side, which makes the same / different distance distributions overlap (AUC < 1; (1.5, 3.5) gives AUC ~ 0.97 at 512-d)."""
     rng = np.random.default_rng(seed)
     class_sizes = np.asarray(class_sizes, dtype=np.int64)
     nc = class_sizes.size
     centres = rng.standard_normal((nc, dim), dtype=np.float32)
     cls = np.repeat(np.arange(nc), class_sizes)
-    x = centres[cls] + np.float32(sigma) * rng.standard_normal((cls.size, dim), dtype=np.float32)
+    if np.ndim(sigma) == 0:
+        x = centres[cls] + np.float32(sigma) * rng.standard_normal((cls.size, dim), dtype=np.float32)
+    else:
+        per_class = rng.uniform(float(sigma[0]), float(sigma[1]), size=nc).astype(np.float32)
+        x = centres[cls] + per_class[cls][:, None] * rng.standard_normal((cls.size, dim), dtype=np.float32)
     x /= np.linalg.norm(x, axis=1, keepdims=True)
     values = np.arange(nc, dtype=np.int64) if label_values is None else np.asarray(label_values, dtype=np.int64)
     labels = values[cls]

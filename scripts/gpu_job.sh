@@ -37,6 +37,12 @@ ncu_full)   # --set full of one Gram launch of the bench command
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --no-e2e --no-strict "${@:2}" > $O/ncu_full_$1.log 2>&1
     tail -3 $O/ncu_full_$1.log
     ;;
+ncu_any)    # launch list (per-kernel durations) of any python command: name, then the command
+    name=$1; shift
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-600} --csv --log-file $O/launches_$name.csv \
+      python "$@" > $O/ncu_any_$name.log 2>&1
+    python scripts/ncu_launch_summary.py $O/launches_$name.csv | tee $O/launches_$name.txt
+    ;;
 py)         # any python script with arguments, log name first
     name=$1; shift
     timeout 1200 python "$@" > $O/$name.log 2>&1; echo "exit=$?" >> $O/$name.log

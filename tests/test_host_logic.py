@@ -293,3 +293,151 @@ def test_confidence_matrix_host_math_random_ragged_sets(emulated, seed):
             np.testing.assert_allclose(getattr(cm, name), getattr(ref, name), rtol=0, atol=1e-13, err_msg='%s seed %d' % (name, seed))
         for name in ('accuracy', 'precision', 'tp_rates', 'tn_rates', 'fp_rates', 'fn_rates'):
             np.testing.assert_allclose(getattr(cm, name), getattr(ref, name), rtol=0, atol=1e-12, err_msg=name)
+
+
+# ------------------------------------------------------------------------------ boundary hardening
+
+def test_raw_dlpack_capsule_is_consumed_per_protocol():
+    """A raw "dltensor" capsule (what tf.experimental.dlpack.to_dlpack / torch.utils.dlpack.to_dlpack return) is renamed
+    "used_dltensor" and its deleter is called exactly when the taken-over tensor is released (SURVEY.md section 8 b)."""
+    import gc
+    import sys
+    x = np.arange(12, dtype=np.float32).reshape(3, 4)
+    base = sys.getrefcount(x)
+    cap = x.__dlpack__()
+    assert sys.getrefcount(x) > base                                 # the managed tensor holds the array
+    t = _capi.from_dlpack(cap)
+    assert isinstance(t, _capi.DLPackTensor) and t.shape == (3, 4) and not t.is_cuda and t.__dlpack_device__()[0] == 1
+    assert _capi._pyapi.PyCapsule_IsValid(cap, b'used_dltensor') and not _capi._pyapi.PyCapsule_IsValid(cap, b'dltensor')
+    b = _capi.Borrowed(t)                                            # the C ABI sees the DLTensor in place
+    assert b.ptr.contents.data == x.ctypes.data and b.ptr.contents.ndim == 2
+    with pytest.raises(ValueError):
+        _capi.from_dlpack(cap)                                       # a consumed capsule cannot be taken twice
+    del b
+    t.release()
+    del cap
+    gc.collect()
+    assert sys.getrefcount(x) == base                                # deleter ran once: the array is free again
+    t.release()                                                      # idempotent
+    assert _capi.from_dlpack(x) is x                                 # everything else passes through
+
+
+def test_confidence_matrix_accepts_a_reference_style_calculator(emulated):
+    """ConfidenceMatrix needs only the reference's surface of its calculator (statistics.py:82-108: .embeddings list, .metric,
+    .nrof_classes): a foreign calculator gives the same matrix as the repo's own."""
+    x, labels = so.synthetic_embeddings([5, 1, 9, 2, 14], dim=64, sigma=1.2, seed=3)
+    thr = so.default_thresholds(0)
+
+    class ForeignCalculator:                                         # e.g. the reference's own class, or a user's
+        def __init__(self, embeddings, labels, metric=0):
+            self.metric = metric
+            self.embeddings = [embeddings[labels == v] for v in np.unique(labels)]
+
+        @property
+        def nrof_classes(self):
+            return len(self.embeddings)
+
+    own = fst.ConfidenceMatrix(fst.SimilarityCalculator(x, labels, 0), thr)
+    foreign = fst.ConfidenceMatrix(ForeignCalculator(x, labels), thr)
+    for name in ('tp', 'tn', 'fp', 'fn'):
+        np.testing.assert_array_equal(getattr(own, name), getattr(foreign, name))
+    ref = so.ConfidenceMatrix(so.SimilarityCalculator(x, labels, 0), thr)
+    np.testing.assert_allclose(foreign.tp, ref.tp, atol=1e-12)
+    np.testing.assert_allclose(foreign.fp, ref.fp, atol=1e-12)
+
+
+def test_validate_callback_shape_of_the_reference(emulated):
+    """facenet/callbacks.py:21-28 + facenet.py:184-201: model outputs per batch -> np.concatenate -> FaceToFaceValidation."""
+    from facenet_b200 import callbacks
+    x, labels = so.synthetic_embeddings([6] * 12 + [1] * 8, dim=64, sigma=1.5, seed=2)
+    batches = [(x[i:i + 16], labels[i:i + 16]) for i in range(0, x.shape[0], 16)]
+
+    class Validate:
+        metric, nrof_folds, far_target = 0, 4, 1.e-2
+
+    class Config:
+        validate = Validate
+
+    cb = callbacks.ValidateCallback(lambda images: images, batches, every_n_epochs=2, max_nrof_epochs=5, config=Config)
+    cb.on_epoch_end(0)
+    assert cb.validation is None                                     # epoch 1: not due
+    cb.on_epoch_end(1)
+    assert cb.validation is not None
+    direct = fst.FaceToFaceValidation(x, labels, Validate)
+    for a, b in zip(cb.validation.reports, direct.reports):
+        assert a.dict == b.dict
+    cb.validation = None
+    cb.on_epoch_end(4)                                               # last epoch always validates
+    assert cb.validation is not None
+    e, l = callbacks.evaluate_embeddings(lambda images: images, batches)
+    np.testing.assert_array_equal(e, x)
+    np.testing.assert_array_equal(l, labels)
+
+
+def test_kfold_split_rejects_what_sklearn_rejects():
+    with pytest.raises(ValueError, match='at least one train/test split'):
+        list(fst.kfold_split(10, 1))
+    with pytest.raises(ValueError, match='greater than the number of samples'):
+        list(fst.kfold_split(3, 4))
+    from sklearn.model_selection import KFold
+    for bad in ((10, 1), (3, 4)):
+        with pytest.raises(ValueError):
+            list(KFold(n_splits=bad[1], shuffle=True, random_state=0).split(np.arange(bad[0])))
+
+
+def test_write_dict_appends_resizable_gzip_datasets(monkeypatch, tmp_path):
+    """h5utils.write_dict (facenet/h5utils.py:9-26) against an in-memory stand-in for h5py (absent in this image): nested keys
+    become group paths, every dataset is 1-D, resizable and gzip-compressed, and a second write appends."""
+    import sys
+    import types
+
+    store = {}
+
+    class Dataset:
+        def __init__(self, data, maxshape, compression, dtype):
+            self.data = np.array(data, dtype=dtype)
+            self.maxshape, self.compression = maxshape, compression
+
+        @property
+        def shape(self):
+            return self.data.shape
+
+        def resize(self, size, axis=0):
+            assert self.maxshape == (None,) and axis == 0
+            self.data = np.concatenate([self.data, np.zeros(size - self.data.shape[0], dtype=self.data.dtype)])
+
+        def __setitem__(self, key, value):
+            self.data[key] = value
+
+    class File:
+        def __init__(self, name, mode='a'):
+            assert mode == 'a'
+            self.ds = store.setdefault(name, {})
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def __contains__(self, name):
+            return name in self.ds
+
+        def __getitem__(self, name):
+            return self.ds[name]
+
+        def create_dataset(self, name, data, maxshape, compression, dtype):
+            self.ds[name] = Dataset(data, maxshape, compression, dtype)
+
+    monkeypatch.setitem(sys.modules, 'h5py', types.SimpleNamespace(File=File))
+    from facenet_b200 import h5utils
+    f = tmp_path / 'report.h5'
+    h5utils.write_dict(f, {'MaximumAccuracy': {'auc': 0.97, 'eer': np.float64(0.08)}, 'elapsed': 1.5}, group='epoch')
+    h5utils.write_dict(f, {'MaximumAccuracy': {'auc': 0.98, 'eer': np.float64(0.07)}, 'elapsed': 1.25}, group='epoch')
+    ds = store[str(f)]
+    assert sorted(ds) == ['epoch/MaximumAccuracy/auc', 'epoch/MaximumAccuracy/eer', 'epoch/elapsed']
+    np.testing.assert_array_equal(ds['epoch/MaximumAccuracy/auc'].data, [0.97, 0.98])
+    np.testing.assert_array_equal(ds['epoch/elapsed'].data, [1.5, 1.25])
+    assert all(d.compression == 'gzip' and d.maxshape == (None,) and d.data.ndim == 1 for d in ds.values())
+    h5utils.write_dict(f, {'x': 1})                                  # no group: top level
+    assert 'x' in ds
