@@ -26,7 +26,7 @@ MAX_THRESHOLDS = 127
 EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info', 'fnb_set_stream',
            'fnb_pairwise', 'fnb_pair_histogram_bins', 'fnb_counts_from_bins', 'fnb_pair_histogram',
            'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine', 'fnb_mine_batched', 'fnb_mine_check',
-           'fnb_mine_select_kth', 'fnb_pair_cross_entropy', 'fnb_logits_cross_entropy')
+           'fnb_mine_select_kth', 'fnb_false_pairs', 'fnb_pair_cross_entropy', 'fnb_logits_cross_entropy')
 
 
 class DLDevice(ctypes.Structure):
@@ -117,6 +117,8 @@ def load_library():
                                          P(DLTensor), P(DLTensor), P(DLTensor), P(DLTensor), P(DLTensor), P(Stats)]
         lib.fnb_mine_check.argtypes = [c.c_void_p, P(c.c_int32), P(Stats)]
         lib.fnb_mine_select_kth.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(DLTensor), c.c_float, P(DLTensor)]
+        lib.fnb_false_pairs.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), c.c_double, P(Options), c.c_longlong, P(c.c_int32),
+                                        P(c.c_int32), P(c.c_float), P(c.c_uint64), P(Stats)]
         lib.fnb_pair_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, c.c_float, c.c_float, P(Options), P(c.c_double), P(Stats)]
         lib.fnb_logits_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, P(c.c_double)]
         for name in EXPORTS:
@@ -653,6 +655,31 @@ class Handle:
             self._raise(rc)
         out['stats'] = st.as_dict()
         return out
+
+    def false_pairs(self, embeddings, labels, threshold, metric=0, atol=1.e-5, capacity=1 << 20, raw_distance=False):
+        """Every same-identity pair with ``d > threshold`` and every different-identity pair with ``d < threshold``
+        (``fnb_false_pairs``): ``(rows, cols, dist, same)`` with original row indices; grows the buffer and repeats when the list
+        did not fit."""
+        embeddings = _as_f32_matrix(embeddings, 'embeddings')
+        labels = _as_labels(labels)
+        o, keep = self.options(metric=metric, atol=atol, raw_distance=raw_distance)
+        be, bl = self._borrow(embeddings), self._borrow(labels)
+        while True:
+            rows = np.empty(capacity, dtype=np.int32)
+            cols = np.empty(capacity, dtype=np.int32)
+            dist = np.empty(capacity, dtype=np.float32)
+            count = ctypes.c_uint64(0)
+            st = Stats()
+            rc = self.lib.fnb_false_pairs(self.h, be.ptr, bl.ptr, float(threshold), ctypes.byref(o), int(capacity),
+                                          rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                          dist.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.byref(count), ctypes.byref(st))
+            if rc != FNB_OK:
+                self._raise(rc)
+            if count.value <= capacity:
+                break
+            capacity = int(count.value) + 1024
+        k = int(count.value)
+        return rows[:k], cols[:k], dist[:k], st.as_dict()
 
     def mine_check(self):
         """Synchronise and raise what the last ``mine_batched`` call on device tensors could not report; returns

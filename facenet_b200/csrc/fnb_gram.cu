@@ -92,6 +92,10 @@ int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const Gram
         if (op.num_pass == 3 && !op.tf32) return launch_one<2, 3, false, EPI_HIST, 4>(h, max_ctas, op, p, smem);
         return h->fail(FNB_ERR_UNSUPPORTED, "cluster_pairs = 4 is built for the fp16f8 and fp16x3 modes");
     }
+    if (epi == EPI_FILTER) {
+        if (op.num_pass != 3 || op.tf32 || cta_group != 2) return h->fail(FNB_ERR_INVALID, "the false-pair filter runs in fp16x3 mode on CTA pairs");
+        return launch_one<2, 3, false, EPI_FILTER>(h, max_ctas, op, p, smem);
+    }
     if (epi == EPI_BCE) {
         // one batch of a few thousand rows: the strict fp32-equivalent split only (the loss feeds an optimiser)
         if (op.num_pass != 3 || op.tf32) return h->fail(FNB_ERR_INVALID, "the cross-entropy epilogue runs in fp16x3 mode");

@@ -35,7 +35,7 @@ constexpr int kSlotBytes    = 2 * kBoxBytes;       // {A part, B part}
 constexpr int kMaxSlots     = 8;
 constexpr int kHist8Row     = kEpiThreads;         // bytes per bin of the thread-private u8 counters
 
-enum EpiKind : int { EPI_HIST = 0, EPI_PAIRWISE = 1, EPI_ROWSTRIP = 2, EPI_BCE = 3 };
+enum EpiKind : int { EPI_HIST = 0, EPI_PAIRWISE = 1, EPI_ROWSTRIP = 2, EPI_BCE = 3, EPI_FILTER = 4 };
 
 struct RegionDev {
     int32_t row_begin, row_end, col_begin, col_end;
@@ -123,6 +123,17 @@ struct GramParams {
     const long long* mine_lab;
     unsigned long long* mine_pos_key;
     unsigned long long* mine_neg_key;
+    // FILTER epilogue (false pairs at one threshold, the commented FalseExamples search of facenet/statistics.py:334-387): every
+    // same-identity pair with d > threshold (a miss) and every different-identity pair with d < threshold (a false accept) is
+    // appended to a compact list -- (original row, original row, distance) -- through one atomic counter; the N x N matrix is
+    // never materialised.  Entries beyond filter_cap are counted but not stored.
+    float filter_threshold;
+    int* filter_rows;
+    int* filter_cols;
+    float* filter_dist;
+    unsigned long long* filter_count;
+    long long filter_cap;
+    const long long* filter_perm;   // permuted row -> original row (class-sorted order of the launch)
     // Cluster-progress window (off unless sync_window > 0).  The clusters walk a static schedule, and over a long launch
     // they drift apart by many column panels: each then streams its own column panel AND evicts the row panels the
     // others still need (measured at 1M rows: 824 GB of DRAM reads per launch).  Every cluster publishes the column
@@ -779,6 +790,41 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                     if (s <= misc->whi[ke] || s >= misc->wlo[ke]) ++eps_cnt;
                                     atomicAdd(&misc->cta_all[ke], 1u);
                                     if (misc->col_cls[acc][col - t.col0] == my_cls) atomicAdd(&misc->cta_same[ke], 1u);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (kEpi == EPI_FILTER) {
+                // ------------------- false pairs at one threshold: compact candidate list ----------
+                mbar_wait_relaxed(&misc->tfull[acc], acc_phase);
+                tc_fence_after();
+                const bool row_ok = row < t.row_end;
+                const int my_cls = row_ok ? __ldg(p.row_cls + row) : -1;
+                const float thr = p.filter_threshold;
+#pragma unroll 1
+                for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr0 + c * 32, r);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll 4
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = colw + c * 32 + j;
+                            if (col < t.col_end && (!t.tri || col > row)) {
+                                float s = __uint_as_float(r[j]) * scale;
+                                smin = fminf(smin, s); smax = fmaxf(smax, s);
+                                s = bias_correct(misc->beta[0], s);
+                                if (!p.raw) s = fminf(fmaxf(s, -1.0f), 1.0f);
+                                const float d = (p.metric == 0) ? __fmul_rn(2.0f, __fsub_rn(1.0f, s)) : acosf(s);
+                                const bool same = (__ldg(p.col_cls + col) == my_cls);
+                                if (same ? (d > thr) : (d < thr)) {
+                                    const unsigned long long idx = atomicAdd(p.filter_count, 1ull);
+                                    if ((long long)idx < p.filter_cap) {
+                                        p.filter_rows[idx] = (int)__ldg(p.filter_perm + row);
+                                        p.filter_cols[idx] = (int)__ldg(p.filter_perm + col);
+                                        p.filter_dist[idx] = d;
+                                    }
                                 }
                             }
                         }

@@ -470,3 +470,100 @@ extern "C" int fnb_mine(fnb_handle h, const DLTensor* emb, const DLTensor* label
     return fnb_mine_batched(h, emb, labels, 1, alpha, opt_in, kmax, &t_hp, &t_hn, kmax > 0 ? &t_pi : nullptr,
                             kmax > 0 ? &t_sh : nullptr, kmax > 0 ? &t_el : nullptr, nullptr, stats);
 }
+
+// False pairs at one threshold over a labelled set (FalseExamples, facenet/statistics.py:334-387): candidate list only; the greedy
+// per-class selection of the reference is host work on the (short) list.
+extern "C" int fnb_false_pairs(fnb_handle h, const DLTensor* emb, const DLTensor* labels, double threshold, const fnb_options* opt_in,
+                               long long capacity, int32_t* rows, int32_t* cols, float* dist, uint64_t* count, fnb_stats* stats)
+{
+    if (!h) return FNB_ERR_INVALID;
+    fnb_options opt; if (opt_in) opt = *opt_in; else fnb_default_options(&opt);
+    if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
+    if (!count || capacity < 0 || (capacity > 0 && (!rows || !cols || !dist))) return h->fail(FNB_ERR_INVALID, "NULL output");
+    CK(cudaSetDevice(h->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    *count = 0;
+    GramOperands op;
+    opt.mode = FNB_MODE_FP16X3;                          // materialised decisions: the strict split
+    DLView ve, vl;
+    int rc = dl_view(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
+    if ((rc = dl_check_embeddings(h, ve, "embeddings"))) return rc;
+    if ((rc = dl_view(h, labels, "labels", 1, 1, &vl))) return rc;
+    if (vl.code != kDLInt || (vl.bits != 32 && vl.bits != 64)) return h->fail(FNB_ERR_INVALID, "labels must be int32 or int64");
+    if (vl.rows != ve.rows) return h->fail(FNB_ERR_INVALID, "len(labels) != embeddings.shape[0]");
+    const long long n = ve.rows;
+    const int d = (int)ve.cols;
+    if (n < 2) return FNB_OK;
+    const void* de = nullptr; const void* dl = nullptr;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    h->last_h2d_bytes = 0; h->h2d_timed = false; h->h2d_timed_bytes = 0;
+    if ((rc = dl_to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
+    if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
+    if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    if ((rc = prepare_operand(h, opt.mode, (const float*)de, h->perm.as<long long>(), n, d, false, op, opt.normalize))) return rc;
+    if ((rc = self_b_maps(h, op, d))) return rc;
+    const int cg = 2, tile = kRowsPerCta * cg;
+    std::vector<RegionDev> regs;
+    {
+        const long long rr = std::max<long long>(tile, std::min<long long>(32768, ((n / 6) / tile) * tile));
+        for (long long r0 = 0; r0 < n; r0 += rr) {
+            const long long r1 = std::min(n, r0 + rr);
+            RegionDev a = {}; a.row_begin = a.col_begin = (int)r0; a.row_end = a.col_end = (int)r1; a.tri = 1; regs.push_back(a);
+            if (r1 < n) { RegionDev b = {}; b.row_begin = (int)r0; b.row_end = (int)r1; b.col_begin = (int)r1; b.col_end = (int)n; regs.push_back(b); }
+        }
+    }
+    finish_regions(regs, tile);
+    if ((rc = upload_regions(h, regs))) return rc;
+    if ((rc = reset_scalars(h))) return rc;
+    const size_t cap = (size_t)capacity;
+    CK(h->mine_out.ensure(cap * 12 + 64));
+    CK(h->mine_status.ensure(64));
+    CK(cudaMemsetAsync(h->mine_status.p, 0, 16, h->stream));
+    GramParams p = {};
+    p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
+    p.shard = ShardSpec{1, 0, 1, nullptr};
+    p.kblocks = d / (128 / op.elem_bytes);
+    p.acc_scale = gram_acc_scale(op);
+    p.operand_fmt = op.fmt;
+    DeviceScalars* sc = h->counters.as<DeviceScalars>();
+    p.counters = sc->counters; p.range_ord = sc->range_ord;
+    p.row_cls = h->cls.as<int32_t>(); p.col_cls = p.row_cls;
+    p.metric = opt.metric; p.raw = opt.raw_distance;
+    p.n_rows = (int)n; p.n_cols = (int)n;
+    p.filter_threshold = (float)threshold;
+    p.filter_rows = h->mine_out.as<int>(); p.filter_cols = p.filter_rows + cap; p.filter_dist = reinterpret_cast<float*>(p.filter_cols + cap);
+    p.filter_count = h->mine_status.as<unsigned long long>();
+    p.filter_cap = capacity; p.filter_perm = h->perm.as<long long>();
+    if ((rc = upload_bias(h, op.mode, d, opt.bias_correction < 0, &p.bias_beta))) return rc;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if ((rc = launch_gram(h, cg, EPI_FILTER, opt.max_ctas, op, p, 0))) return rc;
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(h->pinned.ensure(16384));
+    DeviceScalars hs;
+    CK(cudaMemcpyAsync(h->pinned.p, h->counters.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pinned.as<char>() + 1024, h->mine_status.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(&hs, h->pinned.p, sizeof(hs));
+    unsigned long long found = 0;
+    memcpy(&found, h->pinned.as<char>() + 1024, 8);
+    *count = found;
+    const float smin = ordered_to_float(hs.range_ord[0]), smax = ordered_to_float(hs.range_ord[1]);
+    if (stats) {
+        float ms = 0.f, pm = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&pm, h->ev[0], h->ev[1]);
+        stats->kernel_ms = ms; stats->prepare_ms = pm; stats->smin = smin; stats->smax = smax;
+        stats->n_pairs = (uint64_t)n * (uint64_t)(n - 1) / 2; stats->tiles = hs.counters[1];
+        stats->kernel_launches = 4; stats->grid_ctas = (uint32_t)h->last_grid; stats->mode_used = op.mode;
+    }
+    const double lim = 1.0 + (double)opt.atol;
+    if (!opt.raw_distance && ((double)smin < -lim || (double)smax > lim || smin != smin || smax != smax))
+        return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
+    const size_t take = (size_t)std::min<unsigned long long>(found, (unsigned long long)capacity);
+    if (take) {
+        CK(cudaMemcpy(rows, p.filter_rows, take * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cols, p.filter_cols, take * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(dist, p.filter_dist, take * 4, cudaMemcpyDeviceToHost));
+    }
+    return FNB_OK;
+}

@@ -75,48 +75,75 @@ __global__ void confidence_kernel(const unsigned long long* __restrict__ suffix,
     if (threadIdx.x < 4) rates[(size_t)threadIdx.x * T + n] = red[threadIdx.x][0];
 }
 
-// one thread: accuracy argmax (first maximum; NaN counts as maximum like np.argmax) and the FAR threshold.
+// one block of kMaxBins threads: thread n forms accuracy[n] and fp_rate[n]; accuracy argmax (FIRST maximum; NaN counts as
+// maximum like np.argmax) by a packed-key block reduction; the FAR threshold by thread 0 over the shared fp_rates:
+//   j = last sample (in threshold order) with fp_rate <= target, then the k = 1 B-spline weights of scipy 1.4.1's
+//   interp1d(kind='slinear') (statistics.py:299-302):  w = 1 / (x1 - x0);  thr[j] ((x1 - t) w) + thr[j+1] ((t - x0) w).
+// (When the left sample belongs to a RUN of equal fp_rates the reference's unstable argsort decides which tied threshold is
+// used: the Python host replays that case, facenet_b200/statistics.py:_slinear.)
 // sel[0] = argmax index; far[0] = far threshold (0 if max(fp_rates) < far_target; NaN if outside the range)
-__global__ void select_kernel(const double* __restrict__ rates, int T, const double* __restrict__ thr, double far_target,
-                              int* __restrict__ sel, double* __restrict__ far)
+__global__ void __launch_bounds__(kMaxBins)
+select_kernel(const double* __restrict__ rates, int T, const double* __restrict__ thr, double far_target,
+              int* __restrict__ sel, double* __restrict__ far)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ double s_fpr[kMaxBins];
+    __shared__ unsigned long long s_key[kMaxBins / 32];
+    __shared__ double s_max[kMaxBins / 32];
+    const int n = threadIdx.x;
     const double* tp = rates; const double* tn = rates + T; const double* fp = rates + 2 * T; const double* fn = rates + 3 * T;
-    int best = 0; double best_acc = 0; bool best_nan = false;
-    double fp_max = -INFINITY;
-    for (int n = 0; n < T; ++n) {
+    // key: larger accuracy wins, NaN beats everything, ties -> lowest index
+    unsigned long long key = 0ull;
+    double fpr = -INFINITY;
+    if (n < T) {
         const double num = __dadd_rn(tp[n], tn[n]);
         const double den = __dadd_rn(__dadd_rn(__dadd_rn(tp[n], fp[n]), tn[n]), fn[n]);
         const double acc = __ddiv_rn(num, den);
-        if (n == 0) { best_acc = acc; best_nan = (acc != acc); }
-        else if (!best_nan && (acc != acc || acc > best_acc)) { best = n; best_acc = acc; best_nan = (acc != acc); }
+        unsigned long long bits = (unsigned long long)__double_as_longlong(acc);
+        bits = (bits & 0x8000000000000000ull) ? ~bits : (bits | 0x8000000000000000ull);      // order-preserving for doubles
+        if (acc != acc) bits = ~0ull;
+        // 57 bits of order + 7 bits of (127 - n) would lose accuracy bits: reduce (value, index) pairs instead
+        key = bits;
         const double d = __dadd_rn(tn[n], fp[n]);
         const double tnr = d > 0 ? __ddiv_rn(tn[n], d) : 1.0;
-        const double fpr = __dsub_rn(1.0, tnr);
-        if (fpr > fp_max) fp_max = fpr;
+        fpr = __dsub_rn(1.0, tnr);
+        s_fpr[n] = fpr;
     }
-    sel[0] = best;
-    auto fpr_at = [&](int n) {
-        const double d = __dadd_rn(tn[n], fp[n]);
-        const double tnr = d > 0 ? __ddiv_rn(tn[n], d) : 1.0;
-        return __dsub_rn(1.0, tnr);
-    };
+    // block argmax of (key, lowest index) and max of fpr
+    int idx = (n < T) ? n : 0x7fffffff;
+    double mx = fpr;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        const double om = __shfl_xor_sync(0xffffffffu, mx, o);
+        if (oi != 0x7fffffff && (idx == 0x7fffffff || ok > key || (ok == key && oi < idx))) { key = ok; idx = oi; }
+        mx = fmax(mx, om);
+    }
+    __shared__ int s_idx[kMaxBins / 32];
+    if ((n & 31) == 0) { s_key[n >> 5] = key; s_idx[n >> 5] = idx; s_max[n >> 5] = mx; }
+    __syncthreads();
+    if (n != 0) return;
+    for (int w = 1; w < kMaxBins / 32; ++w) {
+        if (s_idx[w] != 0x7fffffff && (idx == 0x7fffffff || s_key[w] > key || (s_key[w] == key && s_idx[w] < idx))) { key = s_key[w]; idx = s_idx[w]; }
+        mx = fmax(mx, s_max[w]);
+    }
+    sel[0] = idx;
     double out = 0.0;
-    if (fp_max >= far_target) {
-        if (T < 2 || far_target < fpr_at(0) || far_target > fpr_at(T - 1)) {
+    if (mx >= far_target) {
+        if (T < 2 || far_target < s_fpr[0] || far_target > s_fpr[T - 1]) {
             out = __longlong_as_double(0x7ff8000000000000LL);
         } else {
             int lo = 0, hi = T;                       // np.searchsorted(x, xq, side='right')
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (fpr_at(mid) <= far_target) lo = mid + 1; else hi = mid;
+                if (s_fpr[mid] <= far_target) lo = mid + 1; else hi = mid;
             }
             int j = lo - 1;
             if (j < 0) j = 0;
             if (j > T - 2) j = T - 2;
-            const double x0 = fpr_at(j), x1 = fpr_at(j + 1);
-            if (x1 == x0) out = thr[j];
-            else out = __dadd_rn(thr[j], __dmul_rn(__ddiv_rn(__dsub_rn(far_target, x0), __dsub_rn(x1, x0)), __dsub_rn(thr[j + 1], thr[j])));
+            const double x0 = s_fpr[j], x1 = s_fpr[j + 1];
+            const double w = __ddiv_rn(1.0, __dsub_rn(x1, x0));
+            out = __dadd_rn(__dmul_rn(thr[j], __dmul_rn(__dsub_rn(x1, far_target), w)), __dmul_rn(thr[j + 1], __dmul_rn(__dsub_rn(far_target, x0), w)));
         }
     }
     far[0] = out;
@@ -174,7 +201,7 @@ extern "C" int fnb_confidence_from_last_bins(fnb_handle h, int nkeys, const doub
     CK(cudaGetLastError());
     confidence_kernel<<<T, 128, 0, h->stream>>>(h->scan.as<unsigned long long>(), nkeys, T, d_pos, d_in, d_in + nkeys, d_rates);
     CK(cudaGetLastError());
-    select_kernel<<<1, 32, 0, h->stream>>>(d_rates, T, d_in + 2 * nkeys, far_target, d_sel, d_far);
+    select_kernel<<<1, kMaxBins, 0, h->stream>>>(d_rates, T, d_in + 2 * nkeys, far_target, d_sel, d_far);
     CK(cudaGetLastError());
     char* hout = (char*)h->pinned.p + out_off;
     CK(cudaMemcpyAsync(hout, d_rates, out_bytes, cudaMemcpyDeviceToHost, h->stream));

@@ -30,7 +30,7 @@ import numpy as np
 from facenet_b200 import _capi
 
 __all__ = ['pairwise_similarities', 'split_embeddings', 'SimilarityCalculator', 'ConfidenceMatrix', 'Report',
-           'FaceToFaceValidation', 'pair_histogram', 'mean', 'std', 'set_default_mode', 'kfold_split']
+           'FaceToFaceValidation', 'FalseExamples', 'pair_histogram', 'mean', 'std', 'set_default_mode', 'kfold_split']
 
 _state = {'mode': 'fp16x3', 'device': 0, 'cta_group': 0}
 
@@ -362,19 +362,82 @@ class ConfidenceMatrix:
         return 1 - self.tp_rates
 
 
+def _argsort_numpy_scalar(v):
+    """The order ``np.argsort`` gives under the reference's pinned numpy 1.19.4 (requirements.txt:9): the scalar introsort --
+    median-of-3 quicksort down to 16 elements, then insertion sort -- which is NOT stable, so runs of equal keys come out
+    permuted (newer numpy sorts with SIMD kernels on AVX2 / AVX-512 hosts and orders ties differently: the result must not
+    depend on the host)."""
+    v = np.asarray(v, dtype=np.float64)
+    num = v.size
+    tosort = list(range(num))
+    SMALL = 15
+    def lt(a, b):      # npy DOUBLE_LT: a < b || (b != b && a == a)
+        return a < b or (b != b and a == a)
+    pl, pr = 0, num - 1
+    stack = []
+    depth_stack = []
+    cdepth = (num.bit_length() - 1) * 2 if num > 0 else 0
+    while True:
+        heap = False
+        if cdepth < 0:
+            # heapsort fallback (never reached for the short arrays this is used on)
+            sub = sorted(tosort[pl:pr + 1], key=lambda i: (v[i] != v[i], v[i]))
+            tosort[pl:pr + 1] = sub
+            heap = True
+        if not heap:
+            while (pr - pl) > SMALL:
+                pm = pl + ((pr - pl) >> 1)
+                if lt(v[tosort[pm]], v[tosort[pl]]): tosort[pm], tosort[pl] = tosort[pl], tosort[pm]
+                if lt(v[tosort[pr]], v[tosort[pm]]): tosort[pr], tosort[pm] = tosort[pm], tosort[pr]
+                if lt(v[tosort[pm]], v[tosort[pl]]): tosort[pm], tosort[pl] = tosort[pl], tosort[pm]
+                vp = v[tosort[pm]]
+                pi, pj = pl, pr - 1
+                tosort[pm], tosort[pj] = tosort[pj], tosort[pm]
+                while True:
+                    pi += 1
+                    while lt(v[tosort[pi]], vp): pi += 1
+                    pj -= 1
+                    while lt(vp, v[tosort[pj]]): pj -= 1
+                    if pi >= pj: break
+                    tosort[pi], tosort[pj] = tosort[pj], tosort[pi]
+                pk = pr - 1
+                tosort[pi], tosort[pk] = tosort[pk], tosort[pi]
+                if pi - pl < pr - pi:
+                    stack.append((pi + 1, pr)); pr = pi - 1
+                else:
+                    stack.append((pl, pi - 1)); pl = pi + 1
+                cdepth -= 1
+                depth_stack.append(cdepth)
+            for pi in range(pl + 1, pr + 1):
+                vi = tosort[pi]; vp = v[vi]; pj = pi
+                while pj > pl and lt(vp, v[tosort[pj - 1]]):
+                    tosort[pj] = tosort[pj - 1]; pj -= 1
+                tosort[pj] = vi
+        if not stack: break
+        pl, pr = stack.pop()
+        cdepth = depth_stack.pop()
+    return np.asarray(tosort, dtype=np.int64)
+
+
 def _slinear(x, y, xq):
-    """``scipy.interpolate.interp1d(x, y, kind='slinear')(xq)`` as the reference's pinned scipy 1.4.1
-    evaluated it (statistics.py:301-302): linear interpolation on the last interval whose left end is
-    <= xq.  (scipy >= 1.10 rejects the duplicate abscissae fp_rates always contains.)"""
+    """``scipy.interpolate.interp1d(x, y, kind='slinear')(xq)`` as the reference's pinned scipy 1.4.1 evaluated it
+    (statistics.py:301-302): samples sorted by ``np.argsort(x)`` (see ``_argsort_numpy_scalar``), a k = 1 B-spline on the knots
+    ``r_[x[0], x, x[-1]]``, evaluated on the last span whose left end is <= xq with de Boor's weights.  (scipy >= 1.10 rejects
+    the duplicate abscissae fp_rates always contains.)"""
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
-    if xq < x[0] or xq > x[-1]:
-        raise ValueError('A value in x_new is outside the interpolation range.')
-    j = int(np.searchsorted(x, xq, side='right')) - 1
-    j = min(max(j, 0), x.size - 2)
-    if x[j + 1] == x[j]:
-        return np.array(y[j])
-    return np.array(y[j] + (xq - x[j]) / (x[j + 1] - x[j]) * (y[j + 1] - y[j]))
+    ind = _argsort_numpy_scalar(x)
+    xs, ys = x[ind], y[ind]
+    if xq < xs[0]:
+        raise ValueError('A value in x_new is below the interpolation range.')
+    if xq > xs[-1]:
+        raise ValueError('A value in x_new is above the interpolation range.')
+    j = int(np.searchsorted(xs, xq, side='right')) - 1
+    j = min(max(j, 0), xs.size - 2)
+    xa, xb = xs[j], xs[j + 1]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        w = np.float64(1.0) / (xb - xa)
+        return np.array(ys[j] * ((xb - xq) * w) + ys[j + 1] * ((xq - xa) * w))
 
 
 class Report:
@@ -524,9 +587,17 @@ class FaceToFaceValidation:
                 accuracy_threshold = self.thresholds[matrix._argmax_accuracy]
                 far_threshold = matrix._far_threshold
                 if far_threshold != far_threshold:
-                    raise ValueError('A value in x_new is outside the interpolation range.')
+                    raise ValueError('A value in x_new is below the interpolation range.')
                 if far_threshold != 0:
-                    far_threshold = np.array(far_threshold)
+                    # The device interpolates on the bracketing samples in threshold order.  The reference sorts the samples
+                    # with an unstable argsort first (scipy 1.4.1 / numpy 1.19): when the target sits right behind a RUN of
+                    # equal fp_rates, the left sample is whichever tied one that sort puts last -- replayed on the host.
+                    fpr = matrix.fp_rates
+                    below = fpr[fpr <= self.config.far_target]
+                    if below.size and np.count_nonzero(fpr == below.max()) > 1:
+                        far_threshold = _slinear(fpr, self.thresholds, self.config.far_target)
+                    else:
+                        far_threshold = np.array(far_threshold)
                 else:
                     far_threshold = 0
             else:
@@ -567,6 +638,138 @@ class FaceToFaceValidation:
         # statistics.py:330-331 -> h5utils.write_dict (h5utils.py:9-26): resizable gzip datasets, appended per call
         from facenet_b200 import h5utils
         h5utils.write_dict(h5file, self.dict, group=tag)
+
+
+class FalseExamples:
+    """The hardest false pairs at a threshold -- the class the reference keeps commented out (statistics.py:334-421).
+
+    Reference algorithm (``write_false_pairs``, :341-387), per class ("folder") in ``np.unique(labels)`` order:
+      * within the class: up to ``nrof_fpos_images`` times, take the pair with the LARGEST distance; if it exceeds the threshold
+        it is a missed match: record it and retire both images (rows and columns of the class's matrix), else stop (:355-368);
+      * against every later class: up to ``nrof_fneg_images`` times, take the pair with the SMALLEST distance; if it is below
+        the threshold it is a false accept: record it and retire that row and that column, else stop (:371-386).
+    (The reference's directory names are crossed: missed matches go to ``fneg_dir``, false accepts to ``fpos_dir``; kept.)
+
+    Here the candidates come from ONE launch -- a filter epilogue of the Gram kernel appends every same-identity pair above and
+    every different-identity pair below the threshold to a compact list (``fnb_false_pairs``) -- and the greedy selection runs
+    on that short list.  ``embeddings [N, D]``, ``labels [N]``; ``files`` (optional, [N]) are the image paths the reference's
+    ``dbase`` supplies.  ``subtract_mean`` subtracts the mean embedding first, like :346-349 (distances are then those of
+    un-normalised vectors, exactly as the reference would compute them)."""
+
+    def __init__(self, embeddings, labels, threshold, metric=0, subtract_mean=False, files=None):
+        self.embeddings = np.ascontiguousarray(_host_array(embeddings), dtype=np.float32)
+        self.labels = _host_array(labels)
+        if self.embeddings.shape[0] != len(self.labels):
+            raise ValueError('embeddings and labels have different lengths')
+        if metric not in (0, 1):
+            raise ValueError('Undefined similarity metric {}'.format(metric))
+        self.threshold = threshold
+        self.metric = metric
+        self.subtract_mean = subtract_mean
+        self.files = files
+        self.stats = None
+
+    def false_pairs(self, nrof_fpos_images=10, nrof_fneg_images=2):
+        """``{'fneg': [(distance, a, b), ...], 'fpos': [...]}``: missed same-identity pairs and false accepts in the reference's
+        visiting order (class by class; within a class the greedy order), ``a``, ``b`` = row indices into ``embeddings``."""
+        x = self.embeddings
+        if self.subtract_mean:
+            x = x - np.mean(x, axis=0)
+        x = _pad64(np.ascontiguousarray(x, dtype=np.float32))
+        _, cls = np.unique(self.labels, return_inverse=True)
+        cls = np.asarray(cls).reshape(-1)
+        try:
+            rows, cols, dist, self.stats = _handle().false_pairs(x, self.labels, float(self.threshold), metric=self.metric)
+        except _capi.FnbError as err:
+            _raise_like_reference(err, self.metric)
+        # position of every row inside its class (files1[i] of dbase.extract_data: original order within the class)
+        order = np.argsort(cls, kind='stable')
+        start = np.concatenate([[0], np.cumsum(np.bincount(cls))])
+        local = np.empty(cls.size, dtype=np.int64)
+        local[order] = np.arange(cls.size) - start[cls[order]]
+        # orient every pair: a belongs to the earlier class (within a class: the earlier image)
+        swap = (cls[cols] < cls[rows]) | ((cls[cols] == cls[rows]) & (local[cols] < local[rows]))
+        a = np.where(swap, cols, rows).astype(np.int64)
+        b = np.where(swap, rows, cols).astype(np.int64)
+        same = cls[a] == cls[b]
+        out = {'fneg': [], 'fpos': []}
+        # missed matches: np.argmax over the class's symmetric matrix = largest distance, first in row-major order
+        idx = np.nonzero(same)[0]
+        key = np.lexsort((local[b[idx]], local[a[idx]], -dist[idx].astype(np.float64), cls[a[idx]]))
+        self._greedy(idx[key], cls[a], None, a, b, dist, nrof_fpos_images, out['fneg'], both=True)
+        # false accepts: np.argmin over the [n_1, n_2] block = smallest distance, first in row-major order
+        idx = np.nonzero(~same)[0]
+        key = np.lexsort((local[b[idx]], local[a[idx]], dist[idx].astype(np.float64), cls[b[idx]], cls[a[idx]]))
+        self._greedy(idx[key], cls[a], cls[b], a, b, dist, nrof_fneg_images, out['fpos'], both=False)
+        return out
+
+    @staticmethod
+    def _greedy(sorted_idx, g1, g2, a, b, dist, limit, sink, both):
+        """walk the candidates group by group (already sorted by group, then by the reference's pick order); a pick retires
+        its row and its column (``both``: either image in either role)"""
+        prev, used_a, used_b, taken = None, set(), set(), 0
+        for i in sorted_idx:
+            group = (g1[i],) if g2 is None else (g1[i], g2[i])
+            if group != prev:
+                prev, used_a, used_b, taken = group, set(), set(), 0
+            if taken >= limit:
+                continue
+            ia, ib = int(a[i]), int(b[i])
+            if both:
+                if ia in used_a or ib in used_a:
+                    continue
+                used_a.update((ia, ib))
+            else:
+                if ia in used_a or ib in used_b:
+                    continue
+                used_a.add(ia)
+                used_b.add(ib)
+            sink.append((float(dist[i]), ia, ib))
+            taken += 1
+
+    def generate_filename(self, dirname, distance, file1, file2):
+        # statistics.py:389-396
+        import os
+        dir1 = os.path.basename(os.path.dirname(file1))
+        name1 = os.path.splitext(os.path.basename(file1))[0]
+        dir2 = os.path.basename(os.path.dirname(file2))
+        name2 = os.path.splitext(os.path.basename(file2))[0]
+        return os.path.join(dirname, '{:2.3f} & {}|{} & {}|{}.png'.format(distance, dir1, name1, dir2, name2))
+
+    def generate_text(self, distance, file1, file2):
+        # statistics.py:398-403
+        import os
+
+        def text(file):
+            return os.path.join(os.path.basename(os.path.dirname(file)), os.path.splitext(os.path.basename(file))[0])
+
+        return '{} & {}\n{:2.3f}/{:2.3f}'.format(text(file1), text(file2), distance, self.threshold)
+
+    def write_false_pairs(self, fpos_dir, fneg_dir, nrof_fpos_images=10, nrof_fneg_images=2):
+        """The reference renders each pair side by side into a PNG (PIL, :405-421); here every directory receives
+        ``false_pairs.txt`` with one line per pair -- the file name the reference would have written and its caption -- and the
+        montage itself when PIL and the image files are available."""
+        pairs = self.false_pairs(nrof_fpos_images, nrof_fneg_images)
+        files = self.files if self.files is not None else ['{}/{}'.format(l, i) for i, l in enumerate(self.labels)]
+        for dirname, key in ((Path(fneg_dir).expanduser(), 'fneg'), (Path(fpos_dir).expanduser(), 'fpos')):
+            dirname.mkdir(parents=True, exist_ok=True)
+            with (dirname / 'false_pairs.txt').open('wt') as f:
+                for distance, ia, ib in pairs[key]:
+                    name = self.generate_filename(str(dirname), distance, str(files[ia]), str(files[ib]))
+                    f.write('{}\t{}\n'.format(name, self.generate_text(distance, str(files[ia]), str(files[ib])).replace('\n', ' ')))
+                    self._write_image(name, str(files[ia]), str(files[ib]))
+        return pairs
+
+    @staticmethod
+    def _write_image(fname, file1, file2):
+        try:
+            from PIL import Image
+            if not (Path(file1).is_file() and Path(file2).is_file()):
+                return
+            img = Image.fromarray(np.concatenate([np.asarray(Image.open(file1)), np.asarray(Image.open(file2))], axis=1))
+            img.save(fname)
+        except Exception:
+            pass
 
 
 def pair_histogram(embeddings, labels, thresholds, metric=0, mode='auto', **kw):

@@ -279,6 +279,16 @@ int fnb_mine_check(fnb_handle h, int32_t* status /* [4], may be NULL */, fnb_sta
 int fnb_mine_select_kth(fnb_handle h, const DLTensor* anchors, const DLTensor* positives, const DLTensor* kth,
                         float alpha, DLTensor* out);
 
+/* False pairs at one threshold (the hardest-pair search of the commented-out FalseExamples class, facenet/statistics.py:334-387):
+ * every same-identity pair with distance > threshold and every different-identity pair with distance < threshold, found by a
+ * filter epilogue of the Gram kernel (strict FP16X3 arithmetic) and appended to a compact list -- the N x N matrix is never
+ * materialised.  rows / cols: int32 [capacity] ORIGINAL row indices of the pair (row's class rank <= col's), dist: float32
+ * [capacity], all host; *count = number of pairs found (may exceed capacity: only the first `capacity` appended are stored, in
+ * no particular order -- call again with a larger capacity).  The reference's greedy per-class / per-class-pair top-k selection
+ * runs on this list on the host (facenet_b200/statistics.py: FalseExamples). */
+int fnb_false_pairs(fnb_handle h, const DLTensor* emb, const DLTensor* labels, double threshold, const fnb_options* opt,
+                    long long capacity, int32_t* rows, int32_t* cols, float* dist, uint64_t* count, fnb_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

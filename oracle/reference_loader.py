@@ -12,10 +12,11 @@ executed as-is.
 One shim: ``statistics.py:301`` calls
 ``scipy.interpolate.interp1d(fp_rates, thresholds, kind='slinear')`` which under
 this container's scipy (1.18) raises ``ValueError`` for duplicate abscissae
-(fp_rates always has repeated 0s/1s).  Under the pinned scipy 1.4.1 it built a
-k=1 B-spline == piecewise-linear interpolation on the bracketing interval.  The
-module attribute ``interpolate`` is replaced by a proxy that special-cases
-``kind='slinear'`` (see ``slinear_interp``); every other attribute is scipy's.
+(fp_rates always has repeated 0s/1s).  Under the pinned scipy 1.4.1 it sorted the
+samples with ``np.argsort`` (numpy 1.19: unstable scalar introsort, ties come out
+permuted) and built a k=1 B-spline.  The module attribute ``interpolate`` is replaced
+by a proxy that special-cases ``kind='slinear'`` with a step-by-step restatement of
+exactly that (see ``statistics_oracle.slinear_interp``); every other attribute is scipy's.
 """
 import importlib.util
 import sys
@@ -33,20 +34,10 @@ def reference_available():
 
 
 def slinear_interp(x, y, xq):
-    """Piecewise-linear interpolation as scipy 1.4.1's ``interp1d(kind='slinear')``
-    evaluated it for a non-decreasing ``x`` with duplicates: use the LAST interval
-    [x[j], x[j+1]] with x[j] <= xq (j clipped so j+1 is valid), slope form.
-    """
-    x = np.asarray(x, dtype=np.float64)
-    y = np.asarray(y, dtype=np.float64)
-    xq = float(xq)
-    if xq < x[0] or xq > x[-1]:
-        raise ValueError('A value in x_new is outside the interpolation range.')
-    j = int(np.searchsorted(x, xq, side='right')) - 1
-    j = min(max(j, 0), x.size - 2)
-    if x[j + 1] == x[j]:
-        return np.float64(y[j])
-    return np.float64(y[j] + (xq - x[j]) / (x[j + 1] - x[j]) * (y[j + 1] - y[j]))
+    """scipy 1.4.1's ``interp1d(kind='slinear')`` restated step by step, including the unstable ``np.argsort`` of numpy 1.19 that
+    permutes tied abscissae: ``oracle.statistics_oracle.slinear_interp``."""
+    from oracle import statistics_oracle as so
+    return so.slinear_interp(x, y, xq)
 
 
 class _InterpolateProxy:

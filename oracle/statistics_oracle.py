@@ -394,16 +394,87 @@ def kfold_split(n, n_splits, seed=0):
         start += size
 
 
+def argsort_numpy_scalar(v):
+    """``np.argsort(v)`` as NumPy's scalar introsort orders it (``aquicksort``, numpy/core/src/npysort/quicksort: median-of-3
+    partition down to 16 elements, then insertion sort) -- NOT stable: runs of equal keys come out permuted.  The reference's
+    pinned numpy 1.19.4 (requirements.txt:9) has only this path; numpy >= 1.25 dispatches to SIMD sorts on AVX2 / AVX-512
+    machines, which order ties differently.  Checked against this container's numpy with the SIMD dispatch disabled
+    (tests/test_oracle.py::test_argsort_restatement_matches_numpy_scalar_path)."""
+    v = np.asarray(v, dtype=np.float64)
+    num = v.size
+    tosort = list(range(num))
+    SMALL = 15
+    def lt(a, b):      # npy DOUBLE_LT: a < b || (b != b && a == a)
+        return a < b or (b != b and a == a)
+    pl, pr = 0, num - 1
+    stack = []
+    depth_stack = []
+    cdepth = (num.bit_length() - 1) * 2 if num > 0 else 0
+    while True:
+        heap = False
+        if cdepth < 0:
+            # heapsort fallback (never reached for the short arrays this is used on)
+            sub = sorted(tosort[pl:pr + 1], key=lambda i: (v[i] != v[i], v[i]))
+            tosort[pl:pr + 1] = sub
+            heap = True
+        if not heap:
+            while (pr - pl) > SMALL:
+                pm = pl + ((pr - pl) >> 1)
+                if lt(v[tosort[pm]], v[tosort[pl]]): tosort[pm], tosort[pl] = tosort[pl], tosort[pm]
+                if lt(v[tosort[pr]], v[tosort[pm]]): tosort[pr], tosort[pm] = tosort[pm], tosort[pr]
+                if lt(v[tosort[pm]], v[tosort[pl]]): tosort[pm], tosort[pl] = tosort[pl], tosort[pm]
+                vp = v[tosort[pm]]
+                pi, pj = pl, pr - 1
+                tosort[pm], tosort[pj] = tosort[pj], tosort[pm]
+                while True:
+                    pi += 1
+                    while lt(v[tosort[pi]], vp): pi += 1
+                    pj -= 1
+                    while lt(vp, v[tosort[pj]]): pj -= 1
+                    if pi >= pj: break
+                    tosort[pi], tosort[pj] = tosort[pj], tosort[pi]
+                pk = pr - 1
+                tosort[pi], tosort[pk] = tosort[pk], tosort[pi]
+                if pi - pl < pr - pi:
+                    stack.append((pi + 1, pr)); pr = pi - 1
+                else:
+                    stack.append((pl, pi - 1)); pl = pi + 1
+                cdepth -= 1
+                depth_stack.append(cdepth)
+            for pi in range(pl + 1, pr + 1):
+                vi = tosort[pi]; vp = v[vi]; pj = pi
+                while pj > pl and lt(vp, v[tosort[pj - 1]]):
+                    tosort[pj] = tosort[pj - 1]; pj -= 1
+                tosort[pj] = vi
+        if not stack: break
+        pl, pr = stack.pop()
+        cdepth = depth_stack.pop()
+    return np.asarray(tosort, dtype=np.int64)
+
+
 def slinear_interp(x, y, xq):
-    """The one restated library step (statistics.py:300-302 under scipy 1.4.1):
-    piecewise-linear interpolation on the last interval whose left end is <= xq."""
+    """``scipy.interpolate.interp1d(x, y, kind='slinear')(xq)`` as the reference's pinned scipy 1.4.1 evaluates it
+    (statistics.py:300-302; scipy >= 1.10 rejects the duplicate abscissae ``fp_rates`` always contains):
+      1. ``interp1d.__init__``: ``ind = np.argsort(x)`` (default kind: the unstable scalar introsort), ``x, y = x[ind], y[ind]``;
+      2. ``make_interp_spline(x, y, k=1)``: knots ``t = r_[x[0], x, x[-1]]``, coefficients ``y`` (no sortedness check on this path);
+      3. ``BSpline.__call__``: interval = the LAST knot span whose left end is <= xq, then de Boor for k = 1:
+         ``w = 1 / (xb - xa); y[j] * ((xb - xq) * w) + y[j + 1] * ((xq - xa) * w)``.
+    Where ``xq`` falls behind a run of tied abscissae the left end is whichever tied sample the unstable sort put last."""
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
-    j = int(np.searchsorted(x, xq, side='right')) - 1
-    j = min(max(j, 0), x.size - 2)
-    if x[j + 1] == x[j]:
-        return np.float64(y[j])
-    return np.float64(y[j] + (xq - x[j]) / (x[j + 1] - x[j]) * (y[j + 1] - y[j]))
+    xq = float(xq)
+    ind = argsort_numpy_scalar(x)
+    xs, ys = x[ind], y[ind]
+    if xq < xs[0]:
+        raise ValueError('A value in x_new is below the interpolation range.')
+    if xq > xs[-1]:
+        raise ValueError('A value in x_new is above the interpolation range.')
+    j = int(np.searchsorted(xs, xq, side='right')) - 1
+    j = min(max(j, 0), xs.size - 2)
+    xa, xb = xs[j], xs[j + 1]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        w = np.float64(1.0) / (xb - xa)
+        return np.float64(ys[j] * ((xb - xq) * w) + ys[j + 1] * ((xq - xa) * w))
 
 
 def report_dict(train, test):
@@ -456,6 +527,52 @@ def face_to_face_validation(embeddings, labels, metric=0, nrof_folds=10, far_tar
 
 # --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8 d)
+
+
+def false_examples(embeddings, labels, threshold, metric=0, subtract_mean=False, nrof_fpos_images=10, nrof_fneg_images=2):
+    """Literal NumPy statement of the search in the reference's COMMENTED-OUT ``FalseExamples.write_false_pairs``
+    (facenet/statistics.py:341-387; PARITY UNPINNED: the code is commented out upstream and needs its dbase / tfrecord objects,
+    so it cannot be executed -- the loops below follow it line by line): ``folder`` = class in ``np.unique(labels)`` order,
+    images of a class in original order.  Returns ``{'fneg': [(distance, a, b)], 'fpos': [...]}`` with row indices."""
+    x = np.ascontiguousarray(embeddings, dtype=np.float32)
+    labels = np.asarray(labels)
+    mean = np.mean(x, axis=0) if subtract_mean else 0                                  # :346-349
+    values = np.unique(labels)
+    members = [np.nonzero(labels == v)[0] for v in values]
+    out = {'fneg': [], 'fpos': []}
+    for f1 in range(len(values)):                                                      # :351
+        rows1 = members[f1]
+        e1 = (x[rows1] - mean).astype(np.float32)
+        n1 = rows1.size
+        sims = np.zeros((n1, n1), dtype=np.float32)                                    # squareform of the triangle, :358-359
+        if n1 > 1:
+            iu = np.triu_indices(n1, 1)
+            tri = pairwise_similarities(e1.copy(), None, metric)
+            sims[iu] = tri
+            sims[(iu[1], iu[0])] = tri
+        for _ in range(nrof_fpos_images):                                              # :361-368
+            if sims.size == 0:
+                break
+            i, k = np.unravel_index(np.argmax(sims), sims.shape)
+            if sims[i, k] > threshold:
+                out['fneg'].append((float(sims[i, k]), int(rows1[i]), int(rows1[k])))
+                sims[[i, k], :] = -1
+                sims[:, [i, k]] = -1
+            else:
+                break
+        for f2 in range(f1 + 1, len(values)):                                          # :371
+            rows2 = members[f2]
+            e2 = (x[rows2] - mean).astype(np.float32)
+            cross = pairwise_similarities(e1.copy(), e2.copy(), metric).astype(np.float32)
+            for _ in range(nrof_fneg_images):                                          # :376-386
+                i, k = np.unravel_index(np.argmin(cross), cross.shape)
+                if cross[i, k] < threshold:
+                    out['fpos'].append((float(cross[i, k]), int(rows1[i]), int(rows2[k])))
+                    cross[i, :] = np.inf
+                    cross[:, k] = np.inf
+                else:
+                    break
+    return out
 
 
 def pair_histogram_window(embeddings, labels, thresholds, metric=0, eps=1.e-5, threads=1):

@@ -71,7 +71,9 @@ def confidence_from_bins(bins, w_same, w_diff, thresholds, cuts, far_target):
             far = float('nan')
         else:
             j = min(max(int(np.searchsorted(fpr, far_target, side='right')) - 1, 0), thr.size - 2)
-            far = thr[j] if fpr[j + 1] == fpr[j] else thr[j] + (far_target - fpr[j]) / (fpr[j + 1] - fpr[j]) * (thr[j + 1] - thr[j])
+            with np.errstate(divide='ignore', invalid='ignore'):
+                w = np.float64(1.0) / (fpr[j + 1] - fpr[j])                     # the k = 1 B-spline weights (select_kernel)
+                far = thr[j] * ((fpr[j + 1] - far_target) * w) + thr[j + 1] * ((far_target - fpr[j]) * w)
     return {'tp': tp, 'tn': tn, 'fp': fp, 'fn': fn, 'argmax_accuracy': int(np.argmax(acc)), 'far_threshold': float(far)}
 
 

@@ -128,3 +128,48 @@ def test_pageable_and_pinned_host_inputs_agree(handle):
     page2, _ = handle.pair_histogram_bins(x[:33333], labels[:33333], thr, 0, mode='auto')
     dev2, _ = handle.pair_histogram_bins(torch.from_numpy(x[:33333]).cuda(), torch.from_numpy(labels[:33333]).cuda(), thr, 0, mode='auto')
     np.testing.assert_array_equal(page2, dev2)
+
+
+@pytest.mark.parametrize('metric,subtract_mean', [(0, False), (1, False), (0, True)])
+def test_false_examples_vs_oracle(fst, metric, subtract_mean):
+    """FalseExamples (the reference's commented-out class, statistics.py:334-387) through the filter epilogue: the same pairs in
+    the same order as the literal NumPy statement of its loops, distances within 1e-5; candidates within 1e-5 of the threshold
+    (or near-ties of the greedy pick) may differ."""
+    x, labels = so.synthetic_embeddings([6, 1, 9, 3, 12, 1, 30, 2], dim=128, sigma=(1.0, 2.5), seed=7)
+    thr = 1.7 if metric == 0 else 1.45
+    ref = so.false_examples(x, labels, thr, metric=metric, subtract_mean=subtract_mean)
+    got = fst.FalseExamples(x, labels, thr, metric=metric, subtract_mean=subtract_mean).false_pairs()
+    for key in ('fneg', 'fpos'):
+        assert len(ref[key]) > 0
+        r_pairs = [(a, b) for _, a, b in ref[key]]
+        g_pairs = [(a, b) for _, a, b in got[key]]
+        if r_pairs != g_pairs:
+            # only pairs at the edge of the threshold (or tied picks) may differ
+            only = set(r_pairs) ^ set(g_pairs)
+            d_of = {(a, b): d for d, a, b in ref[key] + got[key]}
+            assert all(abs(d_of[p] - thr) <= 2e-5 for p in only), (key, only)
+        for (dr, a, b), (dg, a2, b2) in zip(ref[key], got[key]):
+            if (a, b) == (a2, b2):
+                assert abs(dr - dg) <= 1e-5
+    ex = fst.FalseExamples(x, labels, thr, metric=metric, subtract_mean=subtract_mean)
+    assert ex.false_pairs(nrof_fpos_images=1, nrof_fneg_images=1)['fneg'] == [p for i, p in enumerate(got['fneg'])
+                                                                               if i == 0 or labels[p[1]] != labels[got['fneg'][i - 1][1]]]
+
+
+def test_false_examples_listing_and_capacity(fst, handle, tmp_path):
+    x, labels = so.synthetic_embeddings([8] * 10 + [1] * 5, dim=64, sigma=(1.0, 2.5), seed=9)
+    files = ['/data/id%03d/img%04d.png' % (l, i) for i, l in enumerate(labels)]
+    ex = fst.FalseExamples(x, labels, 1.75, files=files)
+    pairs = ex.write_false_pairs(tmp_path / 'fpos', tmp_path / 'fneg')
+    lines = (tmp_path / 'fneg' / 'false_pairs.txt').read_text().splitlines()
+    assert len(lines) == len(pairs['fneg']) > 0
+    d, a, b = pairs['fneg'][0]
+    assert lines[0].startswith(str(tmp_path / 'fneg' / ('%2.3f & id%03d|img%04d & id%03d|img%04d.png' % (d, labels[a], a, labels[b], b))))
+    assert '{:2.3f}/{:2.3f}'.format(d, 1.75) in lines[0]
+    # the candidate list outgrows a small buffer: the binding repeats the call with the reported size
+    r1, c1, d1, _ = handle.false_pairs(x, labels, 1.75, capacity=4)
+    r2, c2, d2, _ = handle.false_pairs(x, labels, 1.75)
+    assert r1.size == r2.size > 4
+    assert sorted(zip(r1.tolist(), c1.tolist())) == sorted(zip(r2.tolist(), c2.tolist()))
+    with pytest.raises(ValueError, match='normalized'):
+        fst.FalseExamples(x * 1.5, labels, 1.75).false_pairs()

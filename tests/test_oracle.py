@@ -6,6 +6,7 @@ import pytest
 
 from oracle import statistics_oracle as so
 from oracle import mining_oracle as mo
+from pathlib import Path
 
 
 def test_pairwise_golden(golden_dir):
@@ -214,3 +215,95 @@ def test_validation_edge_cases_golden(golden_dir):
                 np.testing.assert_allclose(got, g['%s_%s_vals' % (name, tag)], rtol=0, atol=1e-9, err_msg='%s %s' % (name, key))
             np.testing.assert_array_equal(out['_thresholds'][:, 0], g[name + '_acc_thr'])
             np.testing.assert_allclose(out['_thresholds'][:, 1], g[name + '_far_thr'], rtol=0, atol=1e-12)
+
+
+def test_false_examples_oracle_invariants():
+    """The restated search of statistics.py:341-387: missed matches are same-identity pairs above the threshold, at most
+    ``nrof_fpos_images`` per class, no image twice per class; false accepts are different-identity pairs below it, at most
+    ``nrof_fneg_images`` per class pair, no row / column twice; each is the extreme of what was left."""
+    x, labels = so.synthetic_embeddings([6, 1, 9, 3, 12, 1], dim=32, sigma=(1.0, 2.5), seed=1)
+    thr = 1.7
+    out = so.false_examples(x, labels, thr, nrof_fpos_images=3, nrof_fneg_images=2)
+    d = mo.distance_matrix(x)
+    assert out['fneg'] and out['fpos']
+    seen = {}
+    for dist, a, b in out['fneg']:
+        assert labels[a] == labels[b] and dist > thr and abs(dist - d[a, b]) < 1e-6
+        used = seen.setdefault(labels[a], set())
+        assert a not in used and b not in used
+        used.update((a, b))
+    assert all(len(v) <= 6 for v in seen.values())
+    first = {}
+    for dist, a, b in out['fneg']:
+        first.setdefault(labels[a], dist)
+    for lab, dist in first.items():
+        m = labels == lab
+        assert abs(dist - d[np.ix_(m, m)].max()) < 1e-6
+    per_pair = {}
+    for dist, a, b in out['fpos']:
+        assert labels[a] < labels[b] and dist < thr
+        rows, cols = per_pair.setdefault((labels[a], labels[b]), (set(), set()))
+        assert a not in rows and b not in cols
+        rows.add(a); cols.add(b)
+    assert all(len(r) <= 2 for r, _ in per_pair.values())
+
+
+def test_argsort_restatement_matches_numpy_scalar_path():
+    """``so.argsort_numpy_scalar`` (and the product's copy) against NumPy's own scalar introsort -- this container's numpy with
+    every SIMD sort dispatch disabled, the only path numpy 1.19.4 had -- on arrays with long runs of ties (what fp_rates is)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from oracle import statistics_oracle as so
+from facenet_b200 import statistics as fst
+rng = np.random.default_rng(0)
+for trial in range(200):
+    n = int(rng.integers(1, 300))
+    kind = trial %% 4
+    if kind == 0: x = rng.integers(0, 5, n).astype(float)
+    elif kind == 1: x = np.sort(rng.integers(0, 8, n).astype(float))
+    elif kind == 2:
+        z = int(rng.integers(0, n)); o = int(rng.integers(0, n - z + 1))
+        x = np.concatenate([np.zeros(z), np.sort(rng.random(n - z - o)), np.ones(o)])
+    else: x = rng.random(n)
+    ref = np.argsort(x)
+    assert np.array_equal(so.argsort_numpy_scalar(x), ref), (trial, n, kind)
+    assert np.array_equal(fst._argsort_numpy_scalar(x), ref), (trial, n, kind)
+x = np.concatenate([np.zeros(40), np.linspace(0.001, 0.9, 45), np.ones(15)])
+assert not np.array_equal(np.argsort(x), np.arange(100)), 'the scalar path permutes ties: SIMD dispatch still active?'
+print('ok')
+''' % str(Path(__file__).resolve().parent.parent)
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES='AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX2')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+    if 'SIMD dispatch still active' in out.stderr:
+        pytest.skip('cannot disable the SIMD sort dispatch of this numpy build')
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]
+
+
+def test_far_threshold_behind_a_run_of_tied_fp_rates():
+    """ADVICE round 1: under scipy 1.4.1 / numpy 1.19 interp1d(kind='slinear') sorts (fp_rates, thresholds) with an UNSTABLE
+    argsort; when far_target lies right behind a run of equal fp_rates the left sample is whichever tied threshold that sort
+    put last -- not the largest one.  Oracle, product host code and the stable formula on a hand-made case."""
+    from facenet_b200 import statistics as fst
+    thr = np.linspace(0, 4, 100)
+    fpr = np.concatenate([np.zeros(40), np.linspace(0.004, 0.9, 45), np.ones(15)])          # first non-zero rate above the target
+    far = 1.e-3
+    ind = so.argsort_numpy_scalar(fpr)
+    assert sorted(ind[:40].tolist()) == list(range(40)) and ind[39] != 39                     # the zeros come out permuted
+    j = int(ind[39])                                                                          # the tied sample the sort puts last
+    w = 1.0 / (fpr[40] - 0.0)
+    expect = thr[j] * ((fpr[40] - far) * w) + thr[40] * ((far - 0.0) * w)
+    got = so.slinear_interp(fpr, thr, far)
+    assert got == expect == float(fst._slinear(fpr, thr, far))
+    stable = thr[39] + far / fpr[40] * (thr[40] - thr[39])
+    assert abs(got - stable) > 0.1                                                            # the deviation the advisor flagged
+    # no tie at the bracket: the sorted order is irrelevant and the result is ordinary linear interpolation
+    far2 = 0.3
+    k = int(np.searchsorted(fpr, far2, side='right')) - 1
+    lin = thr[k] + (far2 - fpr[k]) / (fpr[k + 1] - fpr[k]) * (thr[k + 1] - thr[k])
+    assert abs(so.slinear_interp(fpr, thr, far2) - lin) < 1e-14
+    with pytest.raises(ValueError, match='above the interpolation range'):
+        so.slinear_interp(fpr[:50], thr[:50], 0.99)
