@@ -110,7 +110,7 @@ static float cut_for_threshold(double t, int metric) {
 }
 
 int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out,
-                     const float* beta_knots) {
+                     const float* beta_knots, const float* beta_knots_strict) {
     if (T < 1 || T >= kMaxBins) return -1;
     CutTables& c = *out;
     c.T = T;
@@ -151,6 +151,16 @@ int build_cut_tables(const double* thresholds, int T, int metric, double eps, co
         for (int j = 0; j < c.T_fin; ++j) dev = std::max(dev, std::fabs(raw[j] - (c.e0 + j * c.h)));
         c.dev = dev;
         if (c.h > 1e-4 && dev / c.h < 2e-4) c.uniform = 1;
+        // the same fit for the fp16x3 arithmetic of the strict tiles of an fp16f8 launch
+        c.e0x = c.e0; c.hx = c.h; c.devx = c.dev;
+        if (beta_knots_strict) {
+            for (int j = 0; j < c.T_fin; ++j) { const double cj = (double)c.cuts[j]; raw[j] = cj * (1.0 - beta_at(beta_knots_strict, cj)); }
+            c.e0x = raw[0];
+            c.hx = (raw[c.T_fin - 1] - raw[0]) / (c.T_fin - 1);
+            double devx = 0;
+            for (int j = 0; j < c.T_fin; ++j) devx = std::max(devx, std::fabs(raw[j] - (c.e0x + j * c.hx)));
+            c.devx = devx;
+        }
     }
     return 0;
 }
@@ -669,10 +679,11 @@ struct HistLaunch {
 static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, const std::vector<RegionDev>& regs, int cg,
                     int d, const int32_t* cls_dev, const double* thresholds, int T, HistLaunch& hl, int force_slow)
 {
-    float knots[kBiasStride];
+    float knots[kBiasStride], knots_x3[kBiasStride];
     bias_table(op.mode, d, knots);
+    bias_table(FNB_MODE_FP16X3, d, knots_x3);
     const bool bias_off = opt.bias_correction < 0;
-    if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &hl.ct, bias_off ? nullptr : knots))
+    if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &hl.ct, bias_off ? nullptr : knots, bias_off ? nullptr : knots_x3))
         return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
     int rc;
     if ((rc = upload_regions(h, regs))) return rc;
@@ -744,7 +755,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
         int F = 16;
         while (F > 4 && (double)(Q + 1) * (double)(1u << F) > 4194304.0) --F;
         const double R = (double)(1u << F);
-        const double need = (eps_s / hl.ct.h + 2.0 * hl.ct.dev / hl.ct.h) * R + 1.5;
+        const double need = (eps_s / hl.ct.h + 2.0 * std::max(hl.ct.dev, hl.ct.devx) / hl.ct.h) * R + 1.5;
         int W = 1;
         while ((double)(1u << (W - 1)) < need && W < 30) ++W;
         if (W > F - 2) {
@@ -766,6 +777,8 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
                 p.noclip = 1;
                 p.f_g1 = (float)((double)p.acc_scale / hl.ct.h * R);
                 p.f_g0 = (float)((-hl.ct.e0 / hl.ct.h + 1.0) * R + 12582912.0);
+                p.f_g1x = (float)((double)p.acc_scale / hl.ct.hx * R);           // strict (fp16x3) tiles of an fp16f8 launch
+                p.f_g0x = (float)((-hl.ct.e0x / hl.ct.hx + 1.0) * R + 12582912.0);
                 p.near_half = (unsigned)half;
             }
             h->last_eps_counted = (opt.metric == 0 ? 2.0 : 1.0) * half / R * hl.ct.h;

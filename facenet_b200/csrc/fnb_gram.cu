@@ -80,6 +80,8 @@ static int launch_mode(fnb_context* h, int max_ctas, const GramOperands& op, con
 
 int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const GramOperands& op, GramParams& p, size_t hist_bytes)
 {
+    // distance epilogues stage a 32 x 33 float tile per epilogue warp (the transpose in front of the coalesced stores)
+    if (epi == EPI_PAIRWISE || epi == EPI_ROWSTRIP) hist_bytes = (size_t)kEpiWarps * 32 * 33 * 4;
     p.num_slots = gram_pick_slots(hist_bytes);
     const size_t smem = gram_smem_bytes(p.num_slots, hist_bytes);
     if (smem > kSmemLimit) return h->fail(FNB_ERR_UNSUPPORTED, "shared memory budget exceeded (%zu bytes)", smem);

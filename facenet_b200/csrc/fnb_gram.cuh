@@ -92,6 +92,7 @@ struct GramParams {
     // near a threshold <=> ((word + near_half) & near_mask) == 0
     int noclip;
     float f_g1, f_g0;
+    float f_g1x, f_g0x;        // the same map for the strict (fp16x3) tiles of an fp16f8 launch
     unsigned int near_half;
     int nb8;                   // bins of the u8 counters (T_fin + 3)
     unsigned long long* bins;  // [nkeys][2][bins_stride]  (0: all pairs, 1: same-identity pairs)
@@ -419,7 +420,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         int last_gcp = -1;
         const bool sync_on = p.sync_window > 0 && cluster_rank == 0;
         bool sync_wait = true;        // cleared for good when a wait runs into kSyncSpinLimit
-        while (sched.next(t)) {
+        // the strict flag of tile i + 1 is fetched while tile i is processed: its global-load latency never sits in front of a tile
+        TileInfo t_next;
+        bool more = sched.next(t_next);
+        bool strict_next = more && strict_tile(t_next);
+        while (more) {
+            t = t_next;
+            const bool strict_now = strict_next;
+            more = sched.next(t_next);
+            strict_next = more && strict_tile(t_next);
             ++ntile;
             if (sync_on && t.gcp != last_gcp) {
                 // entering a new column panel: publish it, then wait for the stragglers (the slowest cluster never waits)
@@ -476,7 +485,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 __syncwarp();
                 if (++slot == num_slots) { slot = 0; phase ^= 1u; }
             };
-            if (kF8 && strict_tile(t)) {
+            if (kF8 && strict_now) {
                 // strict tile of an fp16f8 launch: the fp16x3 slots {hi, hi}, {l16, l16} per k-block (same slot count)
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     load_slot(&tm_a_hi, &tm_b_hi, kb * 64);
@@ -512,7 +521,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             TileInfo t;
             int slot = 0; uint32_t phase = 0;
             uint32_t it = 0;
-            while (sched.next(t)) {
+            TileInfo t_next;
+            bool more = sched.next(t_next);
+            bool strict_next = more && strict_tile(t_next);
+            while (more) {
+                t = t_next;
+                const bool strict_now = strict_next;
+                more = sched.next(t_next);
+                strict_next = more && strict_tile(t_next);      // consumed one tile later: the load overlaps this tile's MMAs
                 const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
                 mbar_wait(&misc->tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
@@ -551,7 +567,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         if (++slot == num_slots) { slot = 0; phase ^= 1u; }
                     }
                 };
-                if (kF8 && strict_tile(t)) {
+                if (kF8 && strict_now) {
                     x3_tile();
                 } else if constexpr (kF8) {
                     // kblocks e4m3 slots (K = 128 each: the cross terms), then kblocks fp16 slots (K = 64 each: hi*hi)
@@ -668,9 +684,15 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             tiles_since_global = 0;
         };
 
-        while (sched.next(t)) {
+        TileInfo t_next;
+        bool more = sched.next(t_next);
+        bool strict_next = more && strict_tile(t_next);
+        while (more) {
+            t = t_next;
+            const bool strict = strict_next;
+            more = sched.next(t_next);
+            strict_next = more && strict_tile(t_next);
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-            const TileInfo t_super = t;
             if constexpr (kPairs > 1) { t.row0 += (int)pair_row * kTile; t.col0 += (int)pair_col * kTile; }   // this pair's tile of the super-tile
             // a pair whose tile lies outside the region / below the diagonal still runs the pipeline (lockstep) and drops the result
             const bool null_tile = (kPairs > 1) && (t.col0 >= t.col_end || t.row0 >= t.row_end || (t.tri && t.col0 + kTile - 1 <= t.row0));
@@ -692,8 +714,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 // (a pair tile outside the region is dropped below: its corner rows may lie past the class array)
                 const bool lab = !null_tile && (__ldg(p.row_cls + t.row0) <= __ldg(p.col_cls + clast)) &&
                                  (__ldg(p.col_cls + t.col0) <= __ldg(p.row_cls + rlast));
-                const bool strict = strict_tile(t_super);
-                const bool slow = all_slow || edge || lab || strict;
+                // a strict tile without ragged edges or same-identity pairs still bins arithmetically, with the map fitted to the
+                // fp16x3 arithmetic it was computed in
+                const bool slow = all_slow || edge || lab || (strict && !p.noclip);
                 const float* beta = misc->beta[strict ? 1 : 0];
 
                 if ((p.debug & 1) || null_tile) {
@@ -718,7 +741,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     if (p.noclip) {
                         // the cuts span the whole similarity range (guard bins absorb |s| <= 1 + atol + mode error):
                         // one FMA takes the accumulator straight to the fixed-point bin word
-                        const float g1 = p.f_g1, g0 = p.f_g0;
+                        const float g1 = strict ? p.f_g1x : p.f_g1, g0 = strict ? p.f_g0x : p.f_g0;
                         const uint32_t half = p.near_half;
 #pragma unroll 1
                         for (int c = 0; c < kColsPerWarp / 32; ++c) {
@@ -885,34 +908,57 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const long long my_lab = (mining && row_ok) ? __ldg(p.mine_lab + row) : 0;
                 unsigned long long best_pos = 0ull, best_neg = ~0ull;
                 const int cbeg = (kEpi == EPI_ROWSTRIP) ? t.cbeg : 0;
+                // Distances leave through a 32 x 32 transpose in shared memory (one padded tile per warp): the accumulator hands
+                // every thread ONE ROW, so a direct store would scatter a warp's 32 words over 32 rows (32 sectors per store,
+                // 8 x the bytes at L2: the 1800 x 1800 mining strips ran at 0.4 TB/s); after the transpose a warp writes 128
+                // contiguous bytes of one row per store.
+                float* tile_s = reinterpret_cast<float*>(hist8) + (size_t)e * (32 * 33);
+                const int row_w0 = t.row0 + (int)cta_rank * kRowsPerCta + q * 32;       // first row of this warp
 #pragma unroll 1
                 for (int c = 0; c < kColsPerWarp / 32; ++c) {
                     uint32_t r[32];
                     tmem_ld32(taddr0 + c * 32, r);
                     tmem_ld_wait();
+                    const int col_c0 = colw + c * 32;
+                    const bool store = (kEpi == EPI_PAIRWISE) || (p.out != nullptr);
+                    __syncwarp();                                    // the previous chunk's tile has been read by every lane
                     if (row_ok) {
-                        long long base;
-                        if (p.tri_packed) base = (long long)row * p.n_rows - ((long long)row * (row + 1)) / 2 - row - 1;
-                        else base = (long long)row * p.out_ld - cbeg;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const int col = colw + c * 32 + j;
+                            const int col = col_c0 + j;
                             const bool ok = (col < t.col_end) && (!t.tri || col > row);
+                            float d = 0.f;
                             if (ok) {
                                 float s = __uint_as_float(r[j]) * scale;
                                 if (kEpi == EPI_PAIRWISE || col != row) { smin = fminf(smin, s); smax = fmaxf(smax, s); }
                                 s = bias_correct(misc->beta[0], s);
                                 if (!p.raw) s = fminf(fmaxf(s, -1.0f), 1.0f);
-                                float d;
                                 if (p.row_nrm != nullptr) d = classifier_distance(s, my_nrm, __ldg(p.col_nrm + col), p.theta);
                                 else if (p.metric == 0) d = __fmul_rn(2.0f, __fsub_rn(1.0f, s));
                                 else d = acosf(s);
-                                if (kEpi == EPI_PAIRWISE || p.out != nullptr) p.out[base + col] = d;
                                 if (kEpi == EPI_ROWSTRIP && mining && col != row) {
                                     const unsigned long long dk = (unsigned long long)__float_as_uint(d) << 32;
                                     const unsigned int ci = (unsigned int)(col - cbeg);
                                     if (__ldg(p.mine_lab + col) == my_lab) best_pos = max(best_pos, dk | (0xFFFFFFFFu - ci));
                                     else best_neg = min(best_neg, dk | ci);
+                                }
+                            }
+                            if (store) tile_s[lane * 33 + j] = d;
+                        }
+                    }
+                    if (store) {
+                        __syncwarp();
+                        const int col = col_c0 + lane;
+                        const int rows_here = min(32, t.row_end - row_w0);
+                        if (col < t.col_end) {
+#pragma unroll 4
+                            for (int rr = 0; rr < rows_here; ++rr) {
+                                const int rowg = row_w0 + rr;
+                                if (!t.tri || col > rowg) {
+                                    long long base;
+                                    if (p.tri_packed) base = (long long)rowg * p.n_rows - ((long long)rowg * (rowg + 1)) / 2 - rowg - 1;
+                                    else base = (long long)rowg * p.out_ld - cbeg;
+                                    p.out[base + col] = tile_s[rr * 33 + lane];
                                 }
                             }
                         }

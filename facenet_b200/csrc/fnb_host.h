@@ -52,7 +52,8 @@ struct CutTables {
     int order[kMaxBins];           // sorted position j -> threshold index
     int pos[kMaxBins];             // threshold n -> number of sorted cuts <= cut_n
     int uniform = 0;
-    double e0 = 0, h = 0, dev = 0; // arithmetic-progression fit of the finite cuts
+    double e0 = 0, h = 0, dev = 0; // arithmetic-progression fit of the finite cuts (raw similarity of the launch's arithmetic)
+    double e0x = 0, hx = 0, devx = 0;  // the same for the fp16x3 arithmetic of strict tiles
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -169,7 +170,7 @@ int reset_scalars(fnb_context* h);
 int mode_info(int mode, int* num_pass, bool* tf32, int* fmt, int* elem_bytes, float* prescale);
 inline float gram_acc_scale(const GramOperands& op) { return 1.0f / (op.prescale * op.prescale); }
 int build_cut_tables(const double* thresholds, int T, int metric, double eps, const float* cuts_override, CutTables* out,
-                     const float* beta_knots = nullptr);
+                     const float* beta_knots = nullptr, const float* beta_knots_strict = nullptr);
 void bias_table(int mode, int d, float* knots);
 double mode_sigma_s(int mode, int d, double abs_s, double peakedness);
 int upload_bias(fnb_context* h, int mode, int d, bool strict_x3, const float** dev);

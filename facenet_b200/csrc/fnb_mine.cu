@@ -76,6 +76,11 @@ __global__ void mine_decode_kernel(const unsigned long long* __restrict__ pos_ke
 }
 
 // One CTA per anchor (global row a of batch a / b; all indices written are local to the batch).
+// The row of the distance strip is staged in shared memory with every non-negative column (self, positives) set to +inf -- the
+// inner loop then needs no class test: fp32(inf - d(a,p)) < alpha is false.  Each warp takes kPosGroup positives at a time in
+// registers and walks the negatives once for all of them (one shared-memory load per negative and kPosGroup x 6 instructions).
+constexpr int kPosGroup = 5;
+
 __global__ void __launch_bounds__(kMineThreads)
 mine_rows_kernel(const float* __restrict__ dist, long long ld, const long long* __restrict__ labels, int b, float alpha, int kmax,
                  const unsigned long long* __restrict__ pos_key, const unsigned long long* __restrict__ neg_key,
@@ -84,10 +89,12 @@ mine_rows_kernel(const float* __restrict__ dist, long long ld, const long long* 
                  int* __restrict__ status)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* d_row = reinterpret_cast<float*>(smem_raw);                        // [b]
-    unsigned char* is_pos = reinterpret_cast<unsigned char*>(d_row + b);      // [b] 1 = positive, 0 = negative, 2 = self
-    int* pos_list = reinterpret_cast<int*>(is_pos + ((b + 15) / 16) * 16);    // [kmax]
+    float* d_neg = reinterpret_cast<float*>(smem_raw);                        // [b] distance of a negative, +inf for the rest
+    int* pos_list = reinterpret_cast<int*>(d_neg + b);                        // [kmax]
+    float* pos_d = reinterpret_cast<float*>(pos_list + kmax);                 // [kmax]
+    constexpr int kMaxIters = 8192 / 32 / (kMineThreads / 32);                // 32-column steps per warp at the largest batch
     __shared__ int warp_cnt[kMineThreads / 32];
+    __shared__ unsigned int same_mask[(kMineThreads / 32) * kMaxIters];
     __shared__ int s_npos;
 
     const long long ag = blockIdx.x;                        // global anchor row
@@ -97,32 +104,57 @@ mine_rows_kernel(const float* __restrict__ dist, long long ld, const long long* 
     const long long la = lab[a];
     const float* src = dist + ag * ld;
 
-    // ---- stage the row, classify the columns, ordered list of positives
-    int running = 0;                                        // positives found in earlier chunks
-    for (int c0 = 0; c0 < b; c0 += kMineThreads) {
-        const int n = c0 + tid;
-        int flag = 0;
-        if (n < b) {
-            d_row[n] = src[n];
-            const bool same = (lab[n] == la);
-            if (n == a) is_pos[n] = 2;
-            else if (same) { is_pos[n] = 1; flag = 1; }
-            else is_pos[n] = 0;
+    // ---- stage the row, classify the columns, ordered list of positives.  Every warp owns a contiguous range of columns and
+    //      keeps its loads in flight (no block barrier between them: a barrier per 256 columns made this latency-bound);
+    //      the same-label ballots are kept, one block barrier exchanges the warps' totals, and the positives are then
+    //      written in ascending order.
+    constexpr int kWarps = kMineThreads / 32;
+    const int span = (((b + kWarps - 1) / kWarps) + 31) & ~31;           // columns per warp, a multiple of 32
+    const int w_begin = warp * span;
+    const int iters = span / 32;                                          // <= kMaxIters (b <= 8192)
+    int mine = 0;                                                         // positives in this warp's range
+    for (int it0 = 0; it0 < iters; it0 += 8) {
+        float dv[8];
+        long long lv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int n = w_begin + (it0 + u) * 32 + lane;
+            const bool in = (it0 + u < iters) && (n < b);
+            dv[u] = in ? src[n] : 0.f;
+            lv[u] = in ? lab[n] : 0;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        int before = running;
-        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
-        int total = 0;
-        for (int w = 0; w < kMineThreads / 32; ++w) total += warp_cnt[w];
-        if (flag) {
-            const int j = before + __popc(m & ((1u << lane) - 1u));
-            if (j < kmax) pos_list[j] = n;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int n = w_begin + (it0 + u) * 32 + lane;
+            const bool in = (it0 + u < iters) && (n < b);
+            const bool same = in && (lv[u] == la);
+            if (in) d_neg[n] = dv[u];                                     // raw for now: the positives' distances are read back below
+            const unsigned m = __ballot_sync(0xffffffffu, same);
+            if (it0 + u < iters) {
+                if (lane == 0) same_mask[warp * kMaxIters + it0 + u] = m;
+                mine += __popc(m);
+            }
         }
-        running += total;
-        __syncthreads();
     }
+    // the anchor itself carries the label too: it is not a positive
+    const bool has_self = (a >= w_begin) && (a < w_begin + span);
+    if (lane == 0) warp_cnt[warp] = mine - (has_self ? 1 : 0);
+    __syncthreads();
+    int before = 0, running = 0;
+    for (int w = 0; w < kWarps; ++w) { if (w < warp) before += warp_cnt[w]; running += warp_cnt[w]; }
+    for (int it = 0; it < iters; ++it) {
+        const unsigned m = same_mask[warp * kMaxIters + it];
+        const int n = w_begin + it * 32 + lane;
+        if ((m >> lane) & 1u) {
+            int j = before + __popc(m & ((1u << lane) - 1u));
+            // the anchor's own bit, if it precedes this column in the warp's range, is not counted
+            if (has_self && a < n) --j;
+            if (n != a && j < kmax) { pos_list[j] = n; pos_d[j] = d_neg[n]; }
+            d_neg[n] = INFINITY;                                          // self and positives never act as negatives
+        }
+        before += __popc(m);
+    }
+    __syncthreads();
     if (tid == 0) {
         s_npos = running;
         // the arg-extrema were folded in the Gram epilogue
@@ -134,33 +166,86 @@ mine_rows_kernel(const float* __restrict__ dist, long long ld, const long long* 
     __syncthreads();
     const int npos = min(s_npos, kmax);
 
-    // ---- one warp per positive: eligible count and semi-hard argmin over the negatives
-    for (int j = warp; j < kmax; j += kMineThreads / 32) {
-        int p = -1, cnt = 0;
-        unsigned long long best = ~0ull;
-        if (j < npos) {
-            p = pos_list[j];
-            const float dp = d_row[p];
+    // ---- groups of kPosGroup positives, one warp per group: eligible counts and semi-hard argmins over the negatives.
+    // The hardest negative (d_min, n_min) of the anchor is already known from the Gram epilogue's running argmin: a positive
+    // that is closer than EVERY negative (d(a,p) < d_min, the usual case) has all negatives behind it, so its semi-hard
+    // negative is n_min itself (if it passes the margin test) and only the eligible count needs the scan -- one subtract, one
+    // compare and one predicated add per (negative, positive).  Positives at or beyond d_min take the full scan.
+    const unsigned long long nk = neg_key[ag];
+    const bool have_neg = (nk != ~0ull);
+    const float d_min = have_neg ? __uint_as_float((unsigned int)(nk >> 32)) : INFINITY;
+    const int n_min = have_neg ? (int)(nk & 0xFFFFFFFFull) : -1;
+    const int ngroups = (kmax + kPosGroup - 1) / kPosGroup;
+    for (int g = warp; g < ngroups; g += kMineThreads / 32) {
+        const int j0 = g * kPosGroup;
+        float dp[kPosGroup];
+        bool easy = true;
+#pragma unroll
+        for (int i = 0; i < kPosGroup; ++i) {
+            // a slot without a positive compares against -inf: nothing is eligible (inf - (-inf) and d - (-inf) are +inf)
+            dp[i] = (j0 + i < npos) ? pos_d[j0 + i] : -INFINITY;
+            easy = easy && (dp[i] < d_min);
+        }
+        int cnt[kPosGroup], semi[kPosGroup];
+        if (j0 >= npos) {
+#pragma unroll
+            for (int i = 0; i < kPosGroup; ++i) { cnt[i] = 0; semi[i] = -1; }
+        } else if (easy) {
+            float cf[kPosGroup];
+#pragma unroll
+            for (int i = 0; i < kPosGroup; ++i) cf[i] = 0.f;
             for (int n = lane; n < b; n += 32) {
-                if (is_pos[n] == 0) {
-                    const float dn = d_row[n];
-                    if (__fsub_rn(dn, dp) < alpha) {                     // fp32 subtraction, like the oracle
-                        ++cnt;
-                        if (dn > dp) best = min(best, min_key(dn, n));
-                    }
+                const float dn = d_neg[n];
+#pragma unroll
+                for (int i = 0; i < kPosGroup; ++i)
+                    if (__fsub_rn(dn, dp[i]) < alpha) cf[i] += 1.0f;     // exact: counts stay far below 2^24
+            }
+#pragma unroll
+            for (int i = 0; i < kPosGroup; ++i) {
+                int c = (int)cf[i];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                cnt[i] = c;
+                semi[i] = (have_neg && __fsub_rn(d_min, dp[i]) < alpha) ? n_min : -1;
+            }
+        } else {
+            float best_d[kPosGroup];
+            int best_i[kPosGroup];
+#pragma unroll
+            for (int i = 0; i < kPosGroup; ++i) { best_d[i] = INFINITY; best_i[i] = -1; cnt[i] = 0; }
+            for (int n = lane; n < b; n += 32) {
+                const float dn = d_neg[n];
+#pragma unroll
+                for (int i = 0; i < kPosGroup; ++i) {
+                    const bool el = __fsub_rn(dn, dp[i]) < alpha;        // fp32 subtraction, like the oracle
+                    cnt[i] += el ? 1 : 0;
+                    if (el && dn > dp[i] && dn < best_d[i]) { best_d[i] = dn; best_i[i] = n; }     // ascending n: ties keep the lowest index
                 }
             }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                best = min(best, shfl_xor_u64(best, o));
+            for (int i = 0; i < kPosGroup; ++i) {
+                unsigned long long key = (best_i[i] >= 0) ? min_key(best_d[i], best_i[i]) : ~0ull;
+                int c = cnt[i];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                    key = min(key, shfl_xor_u64(key, o));
+                }
+                cnt[i] = c;
+                semi[i] = (key != ~0ull) ? (int)(key & 0xFFFFFFFFull) : -1;
             }
         }
         if (lane == 0) {
-            const long long o = ag * kmax + j;
-            pos_index[o] = p;
-            semi_hard[o] = (best != ~0ull) ? (int)(best & 0xFFFFFFFFull) : -1;
-            eligible[o] = cnt;
+#pragma unroll
+            for (int i = 0; i < kPosGroup; ++i) {
+                const int j = j0 + i;
+                if (j < kmax) {
+                    const long long o = ag * kmax + j;
+                    pos_index[o] = (j < npos) ? pos_list[j] : -1;
+                    semi_hard[o] = (j < npos) ? semi[i] : -1;
+                    eligible[o] = (j < npos) ? cnt[i] : 0;
+                }
+            }
         }
     }
 }
@@ -295,7 +380,10 @@ extern "C" int fnb_mine_batched(fnb_handle h, const DLTensor* emb, const DLTenso
     }
 
     // stage 1: one region per batch -- B x B distances (every ordered pair, diagonal included) + running arg-extrema
-    const int cg = 1;                                   // 128 x 128 tiles: 225 tiles per 1800-row batch spread over the 148 SMs
+    // CTA pairs on 256 x 256 tiles for real batches: half the operand bytes per distance of 128 x 128 tiles (an 1800-row
+    // batch in fp16x3 is L2 -> SM bandwidth bound: 112 MB of operand boxes per batch at 128, 64 MB at 256); small batches keep
+    // the finer tiles
+    const int cg = (b >= 768) ? 2 : 1;
     const int tile = kRowsPerCta * cg;
     std::vector<RegionDev> regs((size_t)nbatches);
     for (int sb = 0; sb < nbatches; ++sb) {
@@ -333,7 +421,7 @@ extern "C" int fnb_mine_batched(fnb_handle h, const DLTensor* emb, const DLTenso
         dst[3] = dst[2] + (size_t)rows * kmax; dst[4] = dst[3] + (size_t)rows * kmax;
     }
     if (kmax > 0) {
-        const size_t smem = (size_t)b * 4 + ((b + 15) / 16) * 16 + (size_t)kmax * 4;
+        const size_t smem = (size_t)b * 4 + (size_t)kmax * 8;
         if (smem > 200 * 1024) return h->fail(FNB_ERR_UNSUPPORTED, "mining row does not fit shared memory");
         CK(cudaFuncSetAttribute(mine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mine_rows_kernel<<<(unsigned)rows, kMineThreads, smem, h->stream>>>(h->strip.as<float>(), ld, lab64, (int)b, alpha, kmax, pos_key, neg_key,
