@@ -51,7 +51,8 @@ class Options(ctypes.Structure):
                 ('cluster_pairs', ctypes.c_int32), ('normalize', ctypes.c_int32), ('theta', ctypes.c_float),
                 ('raw_distance', ctypes.c_int32), ('subset_rows', ctypes.c_int32), ('shard_mod', ctypes.c_int32),
                 ('shard_lo', ctypes.c_int32), ('shard_width', ctypes.c_int32), ('shard_slots', ctypes.POINTER(ctypes.c_int32)),
-                ('panel_window', ctypes.c_int32), ('strict_tiles', ctypes.c_int32), ('bias_correction', ctypes.c_int32)]
+                ('panel_window', ctypes.c_int32), ('strict_tiles', ctypes.c_int32), ('bias_correction', ctypes.c_int32),
+                ('streamed', ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -59,7 +60,8 @@ class Stats(ctypes.Structure):
                 ('smax', ctypes.c_float), ('max_abs', ctypes.c_float), ('kernel_ms', ctypes.c_float),
                 ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
                 ('eps_counted', ctypes.c_float), ('grid_ctas', ctypes.c_uint32), ('mode_used', ctypes.c_int32), ('peakedness', ctypes.c_float),
-                ('panel_window', ctypes.c_int32), ('error_bound', ctypes.c_float), ('fallback', ctypes.c_int32), ('h2d_ms', ctypes.c_float), ('h2d_bytes', ctypes.c_uint64)]
+                ('panel_window', ctypes.c_int32), ('error_bound', ctypes.c_float), ('fallback', ctypes.c_int32), ('h2d_ms', ctypes.c_float), ('h2d_bytes', ctypes.c_uint64),
+                ('streamed_chunks', ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
@@ -385,7 +387,7 @@ class Handle:
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
                 cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0, normalize=0, theta=0.0, raw_distance=False,
-                shard=None, subset_rows=0, panel_window=None, strict_tiles=None, bias_correction=None):
+                shard=None, subset_rows=0, panel_window=None, strict_tiles=None, bias_correction=None, streamed=None):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -408,6 +410,8 @@ class Handle:
         # measurement knobs (None: environment, else 0 = on, -1 = off)
         o.strict_tiles = int(os.environ.get('FNB_STRICT_TILES', '0')) if strict_tiles is None else int(strict_tiles)
         o.bias_correction = int(os.environ.get('FNB_BIAS_CORRECTION', '0')) if bias_correction is None else int(bias_correction)
+        # chunked upload under the launches for host rows in class order: 0 = auto, 1 = always, -1 = off (fnb_options.streamed)
+        o.streamed = int(os.environ.get('FNB_STREAMED', '0')) if streamed is None else int(streamed)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -450,7 +454,7 @@ class Handle:
     def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
                             rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy',
                             force_checked=False, cluster_pairs=0, normalize=0, shard=None, panel_window=None,
-                            strict_tiles=None, bias_correction=None):
+                            strict_tiles=None, bias_correction=None, streamed=None):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
@@ -459,7 +463,7 @@ class Handle:
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
                                region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked,
                                cluster_pairs=cluster_pairs, normalize=normalize, shard=shard, panel_window=panel_window,
-                               strict_tiles=strict_tiles, bias_correction=bias_correction)
+                               strict_tiles=strict_tiles, bias_correction=bias_correction, streamed=streamed)
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()

@@ -8,6 +8,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <limits>
 
 using namespace fnb;
@@ -412,6 +413,7 @@ extern "C" void fnb_destroy(fnb_handle h) {
                       &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io, &h->mine_lab, &h->mine_keys, &h->mine_status};
     for (DevBuf* b : bufs) b->release();
     h->pinned.release();
+    h->perm_host.release();
     if (h->copier) { destroy_copier(h->copier); h->copier = nullptr; }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     h->ring.release();
@@ -455,7 +457,7 @@ extern "C" int fnb_device_info(fnb_handle h, int* sm_count, int* cc_major, int* 
 // split/convert `x` ([n, d] fp32 on the device, optionally gathered through perm) into the operand arrays of one
 // side of the Gram product and encode their TMA maps into `op`
 int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
-                         bool side_b, GramOperands& op, int normalize) {
+                         bool side_b, GramOperands& op, int normalize, bool defer_split) {
     if (mode == FNB_MODE_AUTO) {
         // FP16F8 when the data satisfies its error model (see FNB_MODE_AUTO in the header), else FP16X3
         int rc = (d % 128 == 0) ? prepare_operand(h, FNB_MODE_FP16F8, x, perm, n, d, side_b, op, normalize) : FNB_OK;
@@ -500,8 +502,10 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
         nrm_out = nb.as<float>();
     }
     (side_b ? op.b_nrm : op.a_nrm) = nrm_out;
-    CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream,
-                         normalize, nrm_out, want_l16 ? l16.p : nullptr));
+    // defer_split (streamed launches): the arrays and maps are set up here, split_operand_rows fills them chunk by chunk
+    if (!defer_split)
+        CK(launch_split_rows(mode, x, perm, n, n_pad, d, hi.p, op.num_pass != 1 ? lo.p : nullptr, f8 ? h8.p : nullptr, norm, h->stream,
+                             normalize, nrm_out, want_l16 ? l16.p : nullptr));
     // an operand that two pairs of a cluster share is fetched as two 64-row halves (A: pairs 2 and 4, B: pairs 4)
     const int box_rows = (side_b ? op.pairs == 4 : op.pairs > 1) ? kRowsPerCta / 2 : kRowsPerCta;
     if (!side_b) { op.a_rows_pad = n_pad; h->last_rows = n; }
@@ -515,6 +519,18 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
     *m_l16 = *m_hi;
     if (!rc && want_l16) { rc = make_tmap(h, m_l16, l16.p, kFmtF16, n_pad, d, box_rows); if (!side_b) op.have_l16 = true; }
     return rc;
+}
+
+// rows [row_begin, row_end) of the A-side operand arrays that prepare_operand(defer_split) set up; row_end may reach the padded
+// row count (the zero rows behind n).  The row-norm / peakedness maxima accumulate over the chunks.
+int fnb::split_operand_rows(fnb_context* h, const GramOperands& op, const float* x, const long long* perm, long long n, int d,
+                            int normalize, long long row_begin, long long row_end) {
+    const bool f8 = (op.num_pass == 2);
+    unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;
+    CK(launch_split_rows(op.mode, x, perm, n, op.a_rows_pad, d, h->a_hi.p, op.num_pass != 1 ? h->a_lo.p : nullptr, f8 ? h->a_h8.p : nullptr,
+                         norm, h->stream, normalize, normalize ? h->a_nrm.as<float>() : nullptr, op.have_l16 ? h->a_l16.p : nullptr,
+                         row_begin, row_end));
+    return FNB_OK;
 }
 
 int fnb::self_b_maps(fnb_context* h, GramOperands& op, int d) {
@@ -673,6 +689,11 @@ struct HistLaunch {
     // the auto rule of fnb_options.panel_window applies (whole-set launches: every region is a super-row whose column panels
     // hold many tiles per cluster; keyed launches can have one-tile regions, where a progress window would serialise the clusters)
     bool auto_window = false;
+    // Streamed pass: the launch is cut into one launch per column chunk of the pair matrix (chunks[k] = the regions whose
+    // columns lie in chunk k, rows anywhere above); before_launch(k) queues whatever launch k waits for (the upload and the
+    // split of the chunk's rows).  The bins, counters and range words accumulate over the launches.
+    const std::vector<std::vector<RegionDev>>* chunks = nullptr;
+    std::function<int(int)> before_launch;
 };
 
 // uploads tables, zeroes bins, launches the HIST kernel over `regs`; leaves bins on the device
@@ -686,7 +707,9 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     if (build_cut_tables(thresholds, T, opt.metric, opt.eps, opt.cuts, &hl.ct, bias_off ? nullptr : knots, bias_off ? nullptr : knots_x3))
         return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
     int rc;
-    if ((rc = upload_regions(h, regs))) return rc;
+    std::vector<RegionDev> all_chunks;                   // streamed pass: every chunk's regions (each list ends with its sentinel)
+    if (hl.chunks) for (const auto& c : *hl.chunks) all_chunks.insert(all_chunks.end(), c.begin(), c.end());
+    if ((rc = upload_regions(h, hl.chunks ? all_chunks : regs))) return rc;
     if ((rc = reset_scalars(h))) return rc;
     const size_t tab_floats = kMaxBins + 2 * (kMaxBins + 4);
     CK(h->tables.ensure(tab_floats * 4));
@@ -700,7 +723,8 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     CK(cudaMemsetAsync(h->bins.p, 0, bins_bytes, h->stream));
 
     GramParams p = {};
-    p.regions = h->regions.as<RegionDev>(); p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin;
+    p.regions = h->regions.as<RegionDev>();
+    if (!hl.chunks) { p.nregions = (int)regs.size() - 1; p.total_tiles = regs.back().tile_begin; }     // streamed pass: set per launch below
     p.shard = h->last_shard;
     p.kblocks = d / (128 / op.elem_bytes);
     p.acc_scale = 1.0f / (op.prescale * op.prescale);
@@ -724,22 +748,25 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.debug = opt.debug & 3;
     // cluster-progress window (fnb_options.panel_window, GramParams::sync_window): auto = on for the launches long enough for the
     // clusters to drift apart (this rank's share of the pair matrix >= 5e10 pairs, the same launches pick_pairs calls long)
-    p.sync_window = opt.panel_window > 0 ? std::min(opt.panel_window, 7) : 0;
-    if (opt.panel_window == 0 && hl.auto_window) {
+    auto own_pairs_of = [](const std::vector<RegionDev>& rv) {
         double own_pairs = 0.0;
-        for (size_t i = 0; i + 1 < regs.size(); ++i) {
-            const RegionDev& r = regs[i];
+        for (size_t i = 0; i + 1 < rv.size(); ++i) {
+            const RegionDev& r = rv[i];
             const double area = (double)(r.row_end - r.row_begin) * (double)(r.col_end - r.col_begin) * (r.tri ? 0.5 : 1.0);
             if (r.nrb > 0) own_pairs += area * (double)r.own_cnt / (double)r.nrb;
         }
-        if (own_pairs >= 5.0e10) p.sync_window = 2;
-    }
+        return own_pairs;
+    };
+    auto window_of = [&](const std::vector<RegionDev>& rv) {
+        if (opt.panel_window > 0) return std::min(opt.panel_window, 7);
+        return (opt.panel_window == 0 && hl.auto_window && own_pairs_of(rv) >= 5.0e10) ? 2 : 0;
+    };
+    const int nlaunch = hl.chunks ? (int)hl.chunks->size() : 1;
+    p.sync_window = window_of(hl.chunks ? hl.chunks->back() : regs);
     h->last_window = p.sync_window;
-    if (p.sync_window) {
-        CK(h->progress.ensure(1024 * 4));
-        CK(cudaMemsetAsync(h->progress.p, 0, 1024 * 4, h->stream));
-        p.progress = h->progress.as<unsigned int>();
-    }
+    CK(h->progress.ensure((size_t)nlaunch * 1024 * 4));
+    CK(cudaMemsetAsync(h->progress.p, 0, (size_t)nlaunch * 1024 * 4, h->stream));
+    p.progress = h->progress.as<unsigned int>();
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
@@ -793,9 +820,33 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.counters = sc->counters; p.range_ord = sc->range_ord;
     p.metric = opt.metric;
     const size_t hist_bytes = (size_t)p.nb8 * kHist8Row;
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    if ((rc = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, p, hist_bytes))) return rc;
-    CK(cudaEventRecord(h->ev[2], h->stream));
+    h->chunk_launches = 0;
+    if (!hl.chunks) {
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        if ((rc = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, p, hist_bytes))) return rc;
+        CK(cudaEventRecord(h->ev[2], h->stream));
+    } else {
+        while (h->chunk_ev.size() < 2 * (size_t)nlaunch) {
+            cudaEvent_t e = nullptr;
+            CK(cudaEventCreate(&e));
+            h->chunk_ev.push_back(e);
+        }
+        size_t off = 0;
+        for (int k = 0; k < nlaunch; ++k) {
+            const std::vector<RegionDev>& rv = (*hl.chunks)[k];
+            if (hl.before_launch && (rc = hl.before_launch(k))) return rc;
+            p.regions = h->regions.as<RegionDev>() + off;
+            p.nregions = (int)rv.size() - 1;
+            p.total_tiles = rv.back().tile_begin;
+            p.sync_window = window_of(rv);
+            p.progress = h->progress.as<unsigned int>() + (size_t)k * 1024;
+            off += rv.size();
+            CK(cudaEventRecord(h->chunk_ev[2 * k], h->stream));
+            if (p.total_tiles > 0 && (rc = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, p, hist_bytes))) return rc;
+            CK(cudaEventRecord(h->chunk_ev[2 * k + 1], h->stream));
+        }
+        h->chunk_launches = nlaunch;
+    }
     h->last_nkeys = hl.nkeys; h->last_T = T;
     return FNB_OK;
 }
@@ -819,8 +870,14 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
     h->last_peak_mean = h->last_rows > 0 ? hs.peak_sum / (float)h->last_rows : 0.f;
     if (stats) {
         float ms = 0.f, pm = 0.f;
-        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
-        cudaEventElapsedTime(&pm, h->ev[0], h->ev[1]);
+        if (h->chunk_launches > 0) {
+            // streamed pass: the launches' own durations (the waits for the chunks in between are not kernel time)
+            for (int k = 0; k < h->chunk_launches; ++k) { float m1 = 0.f; cudaEventElapsedTime(&m1, h->chunk_ev[2 * k], h->chunk_ev[2 * k + 1]); ms += m1; }
+            cudaEventElapsedTime(&pm, h->ev[0], h->chunk_ev[0]);
+        } else {
+            cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
+            cudaEventElapsedTime(&pm, h->ev[0], h->ev[1]);
+        }
         stats->kernel_ms = ms;
         stats->prepare_ms = pm;
         stats->eps_window = hs.counters[0];
@@ -829,7 +886,7 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         stats->smax = smax;
         stats->max_abs = amax;
         stats->eps_counted = (float)h->last_eps_counted;
-        stats->kernel_launches += 1;
+        stats->kernel_launches += h->chunk_launches > 0 ? 2 * h->chunk_launches - 1 : 1;     // streamed: a split + a Gram launch per chunk
         stats->grid_ctas = (uint32_t)h->last_grid;
         stats->mode_used = h->last_mode;
         stats->panel_window = h->last_window;
@@ -937,7 +994,8 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     // labels first: the class sort (np.unique ranks, statistics.py:68-79) runs on the stream while the embeddings are staged
     if ((rc = dl_to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
-    if ((rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+    const bool host_emb = !ve.on_device;
+    if (!host_emb) de = ve.data;                         // host rows: uploaded below, in one piece or chunk by chunk (streamed pass)
     const int cg = pick_cta_group(&opt);
     const int tile = kRowsPerCta * cg;
     const int requested = opt.mode;
@@ -946,13 +1004,14 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
     h->last_shard = shard.spec;
     uint64_t host_bins[2 * (kMaxBins + 1)];
 
+    const long long* perm_dev = h->perm.as<long long>(); // class order of the rows at `de` (NULL once they are stored in class order)
     // one pass in `mode`: operands, schedule, launch, range check, bins to the host, error certificate
     auto pass = [&](int mode, double* bound) -> int {
         int rc2;
         op = GramOperands();
         op.pairs = pick_pairs(&opt, cg, n);
         op.want_l16 = opt.strict_tiles >= 0;
-        if ((rc2 = prepare_operand(h, mode, (const float*)de, h->perm.as<long long>(), n, d, false, op, opt.normalize))) return rc2;
+        if ((rc2 = prepare_operand(h, mode, (const float*)de, perm_dev, n, d, false, op, opt.normalize))) return rc2;
         if ((rc2 = self_b_maps(h, op, d))) return rc2;
         opt.mode = op.mode;                              // AUTO resolved
         h->last_mode = op.mode; h->last_peak = op.peakedness;
@@ -981,9 +1040,98 @@ extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const 
         return FNB_OK;
     };
 
+    // Streamed pass (host embeddings, fnb_options.streamed): the upload is cut into
+    // column chunks of the pair matrix, each a whole number of super-rows; launch k covers the pairs (row < chunk k's end,
+    // column in chunk k) and needs only the rows uploaded so far, so the H2D copy of chunk k + 1 runs under launch k.  Chunk sizes
+    // grow with the work already queued (1, 1, 1, 1, 2, 3, 4, 6, 9 ... super-rows): the first launch starts after ~1/30 of the
+    // upload and only that first chunk's copy is exposed.  The integer bins do not depend on the chunking (512-aligned
+    // regions, same strict-tile rule).
+    auto labels_in_class_order = [&]() -> bool {
+        if (vl.on_device) return false;
+        if (vl.bits == 64) { const long long* l = (const long long*)vl.data; for (long long i = 1; i < n; ++i) if (l[i] < l[i - 1]) return false; }
+        else { const int* l = (const int*)vl.data; for (long long i = 1; i < n; ++i) if (l[i] < l[i - 1]) return false; }
+        return true;
+    };
+    // rows out of class order: the host threads that fill the pinned ring GATHER them in class order (they copy the bytes anyway),
+    // with the permutation the device sort produced -- the only extra cost is its 8 n byte copy back
+    const long long* perm_h = nullptr;
+    auto pass_streamed = [&](int mode, double* bound) -> int {
+        int rc2;
+        op = GramOperands();
+        op.pairs = pick_pairs(&opt, cg, n);
+        op.want_l16 = opt.strict_tiles >= 0;
+        CK(h->stage_a.ensure((size_t)n * d * 4));
+        if ((rc2 = prepare_operand(h, mode, h->stage_a.as<float>(), nullptr, n, d, false, op, opt.normalize, /*defer_split=*/true))) return rc2;
+        if ((rc2 = self_b_maps(h, op, d))) return rc2;
+        opt.mode = op.mode;
+        h->last_mode = op.mode; h->last_peak = 0.f;
+        const int cl_size = cg * op.pairs;
+        const int clusters = h->hist_grid[op.pairs] > 0 ? h->hist_grid[op.pairs] / cl_size
+                                                        : (op.pairs == 1 ? h->sm_count / cl_size : op.pairs == 2 ? h->sm_count / cl_size - 4 : 15);
+        const long long rr = pick_region_rows(&opt, 512, n, d, clusters, tile * (op.pairs == 4 ? 2 : 1));
+        const long long nsr = (n + rr - 1) / rr;
+        std::vector<long long> bounds = {0};             // chunk boundaries in rows
+        for (long long b = 0; b < nsr;) { b = std::min(nsr, b + std::max<long long>(1, b / 2)); bounds.push_back(std::min<long long>(n, b * rr)); }
+        const int nchunks = (int)bounds.size() - 1;
+        std::vector<std::vector<RegionDev>> chunks((size_t)nchunks);
+        for (int k = 0; k < nchunks; ++k) {
+            const long long c0 = bounds[k], c1 = bounds[k + 1];
+            for (long long r0 = 0; r0 < c1; r0 += rr) {
+                const long long r1 = std::min<long long>(n, r0 + rr);
+                RegionDev g = {};
+                g.row_begin = (int)r0; g.row_end = (int)r1; g.key = 0;
+                if (r1 <= c0) { g.col_begin = (int)c0; g.col_end = (int)c1; chunks[k].push_back(g); continue; }
+                g.col_begin = (int)r0; g.col_end = (int)r1; g.tri = 1;
+                chunks[k].push_back(g);
+                if (r1 < c1) { g.tri = 0; g.col_begin = (int)r1; g.col_end = (int)c1; chunks[k].push_back(g); }
+            }
+            finish_regions(chunks[k], tile, op.pairs, &shard);
+        }
+        HistLaunch hl; hl.auto_window = true; hl.chunks = &chunks;
+        const char* src = (const char*)ve.data;
+        const size_t row_bytes_f32 = (size_t)d * 4;
+        hl.before_launch = [&](int k) -> int {
+            const long long c0 = bounds[k], c1 = bounds[k + 1];
+            int r = stage_chunk(h, h->stage_a.as<char>() + (size_t)c0 * row_bytes_f32, perm_h ? src : src + (size_t)c0 * row_bytes_f32,
+                                (size_t)(c1 - c0) * row_bytes_f32, k == 0, perm_h ? perm_h + c0 : nullptr, row_bytes_f32);
+            if (r) return r;
+            // the staged rows are in class order: no permutation (the last chunk also zeroes the padding rows)
+            return split_operand_rows(h, op, h->stage_a.as<float>(), nullptr, n, d, opt.normalize, c0, k + 1 == nchunks ? op.a_rows_pad : c1);
+        };
+        std::vector<RegionDev> none;
+        if ((rc2 = run_hist(h, opt, op, none, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc2;
+        de = h->stage_a.p; perm_dev = nullptr;           // the rows are resident now, in class order: a fallback pass re-reads them from here
+        float smin, smax; bool violated = false;
+        if ((rc2 = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc2;
+        if (violated) return pass(mode, bound);          // the one-launch pass re-runs checked and reports the exact range
+        op.peakedness = h->last_peak;
+        CK(cudaMemcpyAsync(h->pinned.as<char>() + 4096, h->bins.p, 2 * (size_t)hl.stride * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const uint64_t* pb = reinterpret_cast<const uint64_t*>(h->pinned.as<char>() + 4096);
+        for (int r = 0; r < 2; ++r) memcpy(host_bins + (size_t)r * (T + 1), pb + (size_t)r * hl.stride, row_bytes);
+        *bound = error_certificate(opt, op.mode, h->last_strict != 0, d, h->last_peak_mean, h->last_peak, n, hl.ct, host_bins, host_bins + (T + 1), T);
+        return FNB_OK;
+    };
+
     double bound = 0.0;
     int fallback = 0;
-    if ((rc = pass(requested, &bound))) return rc;
+    const bool want_stream = host_emb && opt.streamed >= 0 && (opt.streamed > 0 || (size_t)n * d * 4 >= ((size_t)64 << 20));
+    if (want_stream) {
+        if (!labels_in_class_order()) {
+            CK(h->perm_host.ensure((size_t)n * 8));
+            CK(cudaMemcpyAsync(h->perm_host.p, h->perm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            perm_h = h->perm_host.as<long long>();
+        }
+        // AUTO starts optimistically in FP16F8; the peakedness gate is evaluated when every chunk has been split
+        const int first = (requested == FNB_MODE_AUTO) ? (d % 128 == 0 ? FNB_MODE_FP16F8 : FNB_MODE_FP16X3) : requested;
+        if ((rc = pass_streamed(first, &bound))) return rc;
+        if (requested == FNB_MODE_AUTO && op.mode == FNB_MODE_FP16F8 && !(h->last_peak <= kAutoPeakLimit)) bound = INFINITY;
+        if (stats) stats->streamed_chunks = h->chunk_launches;
+    } else {
+        if (host_emb && (rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
+        if ((rc = pass(requested, &bound))) return rc;
+    }
     // (every rank of a sharded job evaluates the same model on its share scaled to the whole; the shares are interleaved
     // row blocks, so the ranks agree except at the very edge of the bound)
     if (requested == FNB_MODE_AUTO && op.mode == FNB_MODE_FP16F8 && bound > (double)opt.eps) {

@@ -72,6 +72,8 @@ struct fnb_context {
     cudaStream_t stream = nullptr;       // stream in use
     cudaStream_t own_stream = nullptr;   // created by fnb_create
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> chunk_ev;   // streamed histogram launches: one (start, end) pair per launch
+    int chunk_launches = 0;              // launches of the last streamed pass (0: one launch timed by ev[1] .. ev[2])
     fnb::PFN_tmapEncodeTiled encode = nullptr;
     std::string err;
 
@@ -90,12 +92,14 @@ struct fnb_context {
     long long mine_rows = 0, mine_b = 0, mine_ld = 0; // geometry of the last mining call (its strips stay in `strip`)
     int mine_kmax = 0; float mine_atol = 0.f; bool mine_has_strip = false;
     fnb::HostBuf pinned;
+    fnb::HostBuf perm_host;              // class-order permutation on the host (streamed upload of rows that are not in class order)
     // pipelined staging of pageable host tensors (fnb_stage.cu)
     cudaStream_t copy_stream = nullptr;
     fnb::HostBuf ring;
     cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};
     fnb::HostCopier* copier = nullptr;
+    int ring_next = 0;                   // next ring slot of a chunked upload (stage_chunk)
     size_t last_h2d_bytes = 0;           // host -> device bytes of the call in progress
     size_t h2d_timed_bytes = 0;          // size of the copy those events bracket
     bool h2d_timed = false;              // copy_ev[1] .. copy_ev[2] bracket a staged copy of the call in progress
@@ -148,9 +152,15 @@ struct DeviceScalars {      // layout of fnb_context::counters
 int dl_view(fnb_context* h, const DLTensor* t, const char* name, int want_ndim_min, int want_ndim_max, DLView* v);
 int dl_to_device(fnb_context* h, const DLView& v, size_t bytes, DevBuf& stage, const void** out);
 int stage_to_device(fnb_context* h, void* dst, const void* src, size_t bytes);   // fnb_stage.cu
+// one chunk of a streamed upload on the copy stream (the handle's stream waits for it; `first` orders the copy stream after
+// the work already queued on the handle's stream and starts the h2d timing)
+// perm != NULL: a gather -- dst row i <- src + perm[i] * row_bytes (src is then the BASE of the host array, dst the chunk's place)
+int stage_chunk(fnb_context* h, void* dst, const void* src, size_t bytes, bool first, const long long* perm = nullptr, size_t row_bytes = 0);
 int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
-                    bool side_b, GramOperands& op, int normalize = 0);
+                    bool side_b, GramOperands& op, int normalize = 0, bool defer_split = false);
+int split_operand_rows(fnb_context* h, const GramOperands& op, const float* x, const long long* perm, long long n, int d,
+                       int normalize, long long row_begin, long long row_end);
 // host view of a rank's share: the residues it owns (ascending) and the device spec
 struct ShardHost {
     ShardSpec spec = ShardSpec{1, 0, 1, nullptr};
@@ -178,7 +188,8 @@ int upload_bias(fnb_context* h, int mode, int d, bool strict_x3, const float** d
 // fnb_prepare.cu
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
                               void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s,   // norm_max_ord[1] = peakedness
-                              int normalize = 0, float* row_nrm = nullptr, void* l16 = nullptr);
+                              int normalize = 0, float* row_nrm = nullptr, void* l16 = nullptr,
+                              long long row_begin = 0, long long row_end = -1);     // rows of [0, n_pad) to write (-1: n_pad)
 cudaError_t launch_strict_blocks(const int32_t* cls, int n, int tile, int nb, unsigned int* bits, cudaStream_t s);
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
 

@@ -20,14 +20,15 @@ template <int kMode>
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ perm, long long n, long long n_pad, int d,
                   void* __restrict__ hi, void* __restrict__ lo, void* __restrict__ h8, unsigned int* __restrict__ norm_max_ord,
-                  int normalize, float* __restrict__ row_nrm, void* __restrict__ l16)
+                  int normalize, float* __restrict__ row_nrm, void* __restrict__ l16, long long row_begin, long long row_end)
 {
     const int vec_per_row = d >> 3;
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     float norm_max = 0.f, peak_max = 0.f, peak_sum = 0.f;
-    for (long long row = warp0; row < n_pad; row += nwarps) {
+    // rows [row_begin, row_end) of the padded operand arrays (a chunk of a streamed launch, or all of [0, n_pad))
+    for (long long row = row_begin + warp0; row < row_end; row += nwarps) {
         const long long src = (row < n) ? (perm ? perm[row] : row) : 0;
         // normalise-on-load (fnb_options.normalize): a first pass over the row forms |x|; the second pass below re-reads
         // the row (L1/L2 hit) and scales every element before the split.
@@ -138,19 +139,20 @@ split_rows_kernel(const float* __restrict__ x, const long long* __restrict__ per
 
 cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, long long n, long long n_pad, int d,
                               void* hi, void* lo, void* h8, unsigned int* norm_max_ord, cudaStream_t s,
-                              int normalize, float* row_nrm, void* l16)
+                              int normalize, float* row_nrm, void* l16, long long row_begin, long long row_end)
 {
-    if (n_pad == 0) return cudaSuccess;
+    if (row_end < 0) row_end = n_pad;
+    if (row_end <= row_begin) return cudaSuccess;
     const int threads = 256;
-    long long blocks = (n_pad + 7) / 8;                  // 8 warps (rows) per block
+    long long blocks = (row_end - row_begin + 7) / 8;    // 8 warps (rows) per block
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     switch (mode) {
-        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
-        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
-        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
-        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
-        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
-        case FNB_MODE_FP16F8: split_rows_kernel<FNB_MODE_FP16F8><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16); break;
+        case FNB_MODE_FP16X3: split_rows_kernel<FNB_MODE_FP16X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16, row_begin, row_end); break;
+        case FNB_MODE_TF32X3: split_rows_kernel<FNB_MODE_TF32X3><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16, row_begin, row_end); break;
+        case FNB_MODE_TF32:   split_rows_kernel<FNB_MODE_TF32><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16, row_begin, row_end); break;
+        case FNB_MODE_BF16:   split_rows_kernel<FNB_MODE_BF16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16, row_begin, row_end); break;
+        case FNB_MODE_FP16:   split_rows_kernel<FNB_MODE_FP16><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16, row_begin, row_end); break;
+        case FNB_MODE_FP16F8: split_rows_kernel<FNB_MODE_FP16F8><<<(unsigned)blocks, threads, 0, s>>>(x, perm, n, n_pad, d, hi, lo, h8, norm_max_ord, normalize, row_nrm, l16, row_begin, row_end); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -23,7 +23,12 @@ constexpr size_t kStageSlotBytes = (size_t)16 << 20;
 constexpr int kRingSlots = 4;
 
 struct HostCopier {
-    struct Part { char* dst; const char* src; size_t bytes; };
+    // a contiguous range, or (perm != NULL) a gather of `rows` rows of row_bytes each: dst row i <- src + perm[i] * row_bytes
+    struct Part { char* dst; const char* src; size_t bytes; const long long* perm = nullptr; size_t row_bytes = 0; size_t rows = 0; };
+    static void run_part(const Part& p) {
+        if (!p.perm) { memcpy(p.dst, p.src, p.bytes); return; }
+        for (size_t i = 0; i < p.rows; ++i) memcpy(p.dst + i * p.row_bytes, p.src + (size_t)p.perm[i] * p.row_bytes, p.row_bytes);
+    }
     std::vector<std::thread> workers;
     std::mutex m;
     std::condition_variable cv_work, cv_done;
@@ -48,7 +53,7 @@ struct HostCopier {
             const Part p = parts[next++];
             ++busy;
             g.unlock();
-            memcpy(p.dst, p.src, p.bytes);
+            run_part(p);
             g.lock();
             if (--busy == 0 && next >= parts.size()) cv_done.notify_all();
         }
@@ -58,15 +63,32 @@ struct HostCopier {
         const size_t nparts = workers.size() + 1;
         const size_t chunk = ((bytes / nparts + 4095) / 4096) * 4096;
         if (workers.empty() || bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
-        std::vector<Part> mine;
         {
             std::lock_guard<std::mutex> g(m);
             parts.clear(); next = 0;
             for (size_t off = 0; off < bytes; off += chunk)
                 parts.push_back(Part{(char*)dst + off, (const char*)src + off, std::min(chunk, bytes - off)});
         }
+        drain();
+    }
+    // dst row i <- src_base + perm[i] * row_bytes, i < rows (the class-order gather of a streamed upload)
+    void gather(void* dst, const void* src_base, const long long* perm, size_t rows, size_t row_bytes) {
+        const size_t nparts = 4 * (workers.size() + 1);
+        const size_t per = std::max<size_t>(1, (rows + nparts - 1) / nparts);
+        {
+            std::lock_guard<std::mutex> g(m);
+            parts.clear(); next = 0;
+            for (size_t r = 0; r < rows; r += per) {
+                Part p{(char*)dst + r * row_bytes, (const char*)src_base, 0};
+                p.perm = perm + r; p.row_bytes = row_bytes; p.rows = std::min(per, rows - r);
+                parts.push_back(p);
+            }
+        }
+        drain();
+    }
+    // the caller works too, then waits for the pool
+    void drain() {
         cv_work.notify_all();
-        // the caller works too
         for (;;) {
             Part p;
             {
@@ -75,7 +97,7 @@ struct HostCopier {
                 p = parts[next++];
                 ++busy;
             }
-            memcpy(p.dst, p.src, p.bytes);
+            run_part(p);
             std::lock_guard<std::mutex> g(m);
             --busy;
         }
@@ -88,13 +110,20 @@ void destroy_copier(HostCopier* c) { delete c; }
 
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return h->fail(FNB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
-static int ensure_staging(fnb_context* h) {
+static int ensure_copy_stream(fnb_context* h) {
     if (h->copy_stream) return FNB_OK;
     CKS(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    return FNB_OK;
+}
+
+static int ensure_staging(fnb_context* h) {
+    int rc = ensure_copy_stream(h);
+    if (rc) return rc;
+    if (h->copier) return FNB_OK;
     CKS(h->ring.ensure(kRingSlots * kStageSlotBytes));
     for (int i = 0; i < kRingSlots; ++i) CKS(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     unsigned hw = std::thread::hardware_concurrency();
-    int n = (int)std::min(3u, hw > 2 ? hw / 2 - 1 : 0u);          // 3 workers + the caller; fewer on small hosts
+    int n = (int)std::min(7u, hw > 2 ? hw / 2 - 1 : 0u);          // up to 7 workers + the caller; fewer on small hosts
     const char* env = getenv("FNB_COPY_THREADS");
     if (env) n = std::max(0, atoi(env) - 1);
     h->copier = new HostCopier(n);
@@ -138,6 +167,48 @@ int stage_to_device(fnb_context* h, void* dst, const void* src, size_t bytes) {
     CKS(cudaStreamWaitEvent(h->stream, timed ? h->copy_ev[2] : h->copy_ev[0], 0));
     h->last_h2d_bytes += bytes;
     if (timed) { h->h2d_timed = true; h->h2d_timed_bytes = bytes; }
+    return FNB_OK;
+}
+
+// One chunk of a streamed upload (fnb_pair_histogram_bins over host rows): the bytes travel on the copy stream -- from the
+// caller's buffer when it is pinned, through the ring otherwise -- and the handle's stream waits for them, so the split and the
+// Gram launch queued next start when the chunk has landed while the launches queued EARLIER keep the GPU busy.
+int stage_chunk(fnb_context* h, void* dst, const void* src, size_t bytes, bool first, const long long* perm, size_t row_bytes) {
+    if (bytes == 0) return FNB_OK;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, src);
+    // a gather (perm != NULL: dst row i <- src row perm[i]) always goes through the ring: the host threads collect the rows
+    const bool pinned = !perm && (e == cudaSuccess) && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    if (e != cudaSuccess) cudaGetLastError();
+    int rc = pinned ? ensure_copy_stream(h) : ensure_staging(h);
+    if (rc) return rc;
+    if (first) {
+        // dst may still be read by work queued earlier on the handle's stream
+        CKS(cudaEventRecord(h->copy_ev[0], h->stream));
+        CKS(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[0], 0));
+        CKS(cudaEventRecord(h->copy_ev[1], h->copy_stream));
+        h->h2d_timed = true; h->h2d_timed_bytes = 0;
+    }
+    if (pinned) {
+        CKS(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    } else {
+        char* ring = h->ring.as<char>();
+        int slot = h->ring_next;
+        const size_t step = perm ? (kStageSlotBytes / row_bytes) * row_bytes : kStageSlotBytes;
+        for (size_t off = 0; off < bytes; off += step, slot = (slot + 1) % kRingSlots) {
+            const size_t len = std::min(step, bytes - off);
+            CKS(cudaEventSynchronize(h->ring_ev[slot]));                 // the DMA that last used this slot has finished
+            if (perm) h->copier->gather(ring + (size_t)slot * kStageSlotBytes, src, perm + off / row_bytes, len / row_bytes, row_bytes);
+            else h->copier->copy(ring + (size_t)slot * kStageSlotBytes, (const char*)src + off, len);
+            CKS(cudaMemcpyAsync((char*)dst + off, ring + (size_t)slot * kStageSlotBytes, len, cudaMemcpyHostToDevice, h->copy_stream));
+            CKS(cudaEventRecord(h->ring_ev[slot], h->copy_stream));
+        }
+        h->ring_next = slot;
+    }
+    CKS(cudaEventRecord(h->copy_ev[2], h->copy_stream));
+    CKS(cudaStreamWaitEvent(h->stream, h->copy_ev[2], 0));
+    h->last_h2d_bytes += bytes;
+    h->h2d_timed_bytes += bytes;
     return FNB_OK;
 }
 

@@ -132,6 +132,11 @@ typedef struct {
                               error model.  0 = on (default), -1 = off (measurement knob) */
     int32_t bias_correction; /* the calibrated correction of the tensor core's accumulation bias (fnb_stats.error_bound, DESIGN.md
                               section 2): 0 = on (default), -1 = off (measurement knob: scripts/probe_bias.py) */
+    int32_t streamed;      /* fnb_pair_histogram[_bins] over HOST embeddings whose labels are non-decreasing (rows already in class
+                              order -- what np.concatenate over the classes gives, facenet/facenet.py:184-201): the upload is cut
+                              into column chunks of the pair matrix and launch k (pairs whose column lies in chunk k) runs while
+                              chunk k + 1 is copied, so only the first chunk's copy is exposed.  0 = auto (inputs >= 64 MiB),
+                              1 = always, -1 = off (one copy, one launch).  The integer bins do not depend on it. */
 } fnb_options;
 
 typedef struct {
@@ -159,6 +164,8 @@ typedef struct {
                               Pageable memory goes through a ring of pinned slots filled by a pool of host threads while the
                               previous slot is in flight (csrc/fnb_stage.cu); pinned memory is copied in place */
     uint64_t h2d_bytes;    /* bytes copied host -> device by the call */
+    int32_t  streamed_chunks; /* launches of a streamed pass (fnb_options.streamed; 0: one upload, one launch); kernel_ms is then
+                              the sum of the launches' durations */
 } fnb_stats;
 
 /* One rectangle of the pair matrix (rows/cols index the PERMUTED embedding order).  tri != 0:

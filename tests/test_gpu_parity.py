@@ -411,6 +411,64 @@ def test_histogram_panel_window_identical_bins(handle):
     np.testing.assert_array_equal(acc, whole)
 
 
+def test_histogram_streamed_upload_identical_bins(handle):
+    """fnb_options.streamed: host rows in class order are uploaded chunk by chunk under the launches that already have their
+    rows (one launch per column chunk of the pair matrix).  Timing only: integer bins identical to the one-copy, one-launch
+    pass for every mode, for pageable and pinned memory, for shards, for ragged last chunks, and for AUTO (optimistic fp16f8,
+    peakedness gate at the end -> strict pass over the resident rows), and for rows out of class order (gathered on the host)."""
+    import torch
+    from facenet_b200 import _capi
+    thr = so.default_thresholds(0)
+    x, labels = so.synthetic_embeddings([23] * 150 + [1] * 77 + [9] * 40, dim=512, sigma=0.9, seed=21, shuffle=False)     # 3887 rows in class order
+    assert np.all(np.diff(labels) >= 0)
+    for mode in ('fp16x3', 'fp16f8', 'auto', 'tf32'):
+        whole, st0 = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode, streamed=-1, region_rows=512)
+        assert st0['streamed_chunks'] == 0
+        for rr in (512, 1024):
+            got, st = handle.pair_histogram_bins(x, labels, thr, 0, mode=mode, streamed=1, region_rows=rr)
+            assert st['streamed_chunks'] >= 3 and st['h2d_bytes'] >= x.nbytes
+            assert st['mode_used'] == st0['mode_used'] and st['n_pairs'] == st0['n_pairs']
+            np.testing.assert_array_equal(got, whole)
+    # pinned host memory (DMA straight from the caller's buffer on the copy stream)
+    xp = torch.from_numpy(x).pin_memory()
+    whole, _ = handle.pair_histogram_bins(x, labels, thr, 0, streamed=-1)
+    got, st = handle.pair_histogram_bins(xp.numpy(), labels, thr, 0, streamed=1, region_rows=512, cluster_pairs=2)
+    assert st['streamed_chunks'] >= 3
+    np.testing.assert_array_equal(got, whole)
+    # row-block shards of a streamed pass sum to the whole
+    acc = np.zeros_like(whole)
+    for rank in range(3):
+        part, _ = handle.pair_histogram_bins(x, labels, thr, 0, rank=rank, world=3, streamed=1, region_rows=768)
+        acc += part
+    np.testing.assert_array_equal(acc, whole)
+    # AUTO on peaky rows: streamed optimistically in fp16f8, then repeated strictly
+    rng = np.random.default_rng(5)
+    xs = np.zeros((1500, 512), dtype=np.float32)
+    for r in range(xs.shape[0]):
+        xs[r, rng.choice(512, 6, replace=False)] = rng.standard_normal(6)
+    xs /= np.linalg.norm(xs, axis=1, keepdims=True)
+    ls = np.repeat(np.arange(150), 10)
+    ref, st0 = handle.pair_histogram_bins(xs, ls, thr, 0, mode='auto', streamed=-1)
+    got, st = handle.pair_histogram_bins(xs, ls, thr, 0, mode='auto', streamed=1, region_rows=512)
+    assert _capi.MODE_NAMES[st['mode_used']] == 'fp16x3' and st['fallback'] == 1
+    np.testing.assert_array_equal(got, ref)
+    # un-normalised rows still raise the reference's error
+    bad = x.copy(); bad[3000] = bad[3001] * 1.01          # s(3000, 3001) = 1.01 > 1 + atol
+    with pytest.raises(ValueError, match='normalized'):
+        handle.pair_histogram_bins(bad, labels, thr, 0, streamed=1, region_rows=512)
+    # rows out of class order: the host threads gather them in class order while they fill the pinned ring (pageable and pinned)
+    perm = np.random.default_rng(1).permutation(x.shape[0])
+    xs_, ls_ = np.ascontiguousarray(x[perm]), np.ascontiguousarray(labels[perm])
+    for src in (xs_, torch.from_numpy(xs_).pin_memory().numpy()):
+        for mode in ('fp16x3', 'auto'):
+            ref, _ = handle.pair_histogram_bins(xs_, ls_, thr, 0, mode=mode, streamed=-1)
+            got, st = handle.pair_histogram_bins(src, ls_, thr, 0, mode=mode, streamed=1, region_rows=512)
+            assert st['streamed_chunks'] >= 3
+            np.testing.assert_array_equal(got, ref)
+    got, st = handle.pair_histogram_bins(xs_, ls_.astype(np.int32), thr, 0, streamed=1, region_rows=1024)
+    np.testing.assert_array_equal(got, whole)
+
+
 def test_histogram_fp16f8_mode(handle):
     """fp16f8 (hi*hi in fp16 + e4m3 cross terms): distances within the 1e-5 tolerance of the oracle on dense
     embeddings, histogram disagreements bounded by the counted eps-window pairs."""
