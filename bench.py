@@ -348,6 +348,10 @@ def run_allpairs(args):
         _, st = handle.pair_histogram_bins(emb, labels, thresholds_, metric, rank=rank_, world=world_, bins_out=bins_out,
                                            mode=run_mode[0], cta_group=args.cta_group, shard=kw.get('shard'),
                                            panel_window=args.panel_window, region_rows=args.region_rows)
+        record(st)
+        return st
+
+    def record(st):
         acc['kernel_ms'].append(st['kernel_ms'])
         acc['prepare_ms'].append(st['prepare_ms'])
         acc['launches'] += st['kernel_launches']
@@ -356,17 +360,28 @@ def run_allpairs(args):
         acc['windows'].add(st['panel_window'])
         acc['bounds'].append(st['error_bound'])
         acc['fallbacks'] += st['fallback']
-        return st
+        acc.setdefault('gather_ms', []).append(st.get('gather_ms', 0.0))
+        acc.setdefault('chunks', set()).add(st.get('streamed_chunks', 0))
 
     def reset_acc():
-        acc.update(kernel_ms=[], prepare_ms=[], launches=0, bounds=[], fallbacks=0)
+        acc.update(kernel_ms=[], prepare_ms=[], launches=0, bounds=[], fallbacks=0, gather_ms=[])
 
     # equal shares by default; --adaptive-shares lets the shares follow the measured speed of each GPU (measured on two
     # 8-GPU boxes: the per-rank kernel times level out, but the step is no shorter -- profiles/r01c_multi_gpu.md)
     balancer = fd.default_balancer(world) if (world > 1 and args.adaptive_shares) else None
 
+    def sharded(xs_, ls_):
+        # N > 1: the exchange (labels, then rows by ncclBroadcast chunk by chunk under the launches) and the ncclAllReduce of
+        # the bins run inside the library (fnb_pair_histogram_sharded); N = 1: the plain call
+        if world > 1:
+            b, st = fd.pair_histogram_sharded(xs_, ls_, thr, 0, balancer=balancer, mode=run_mode[0], cta_group=args.cta_group,
+                                              panel_window=args.panel_window, region_rows=args.region_rows)
+            record(st)
+            return b, st
+        return fd.pair_histogram_sharded(xs_, ls_, thr, 0, hist_fn=hist_fn, balancer=balancer)
+
     def step_device():
-        bins, st = fd.pair_histogram_sharded(x_shard, labels_shard, thr, 0, hist_fn=hist_fn, balancer=balancer)
+        bins, st = sharded(x_shard, labels_shard)
         return bins.cpu() if rank == 0 else bins      # final histogram on the host (rank 0)
 
     def barrier():
@@ -405,11 +420,14 @@ def run_allpairs(args):
         allk = [torch.zeros_like(kt) for _ in range(world)]
         dist.all_gather(allk, kt)
         k_ranks = [float(t.item()) for t in allk]
-    # where the rest of the step goes (not part of `value`): the all-gather alone, timed the same way
-    gather_ms = 0.0
+    # the row exchange (fnb_stats.gather_ms: first to last piece on the copy stream; all but the first chunk of it runs UNDER the
+    # Gram launches) and, for reference, a plain torch all-gather of the same shards timed alone
+    gather_ms = float(np.mean(acc['gather_ms'])) if world > 1 and acc.get('gather_ms') else 0.0
+    plain_gather_ms = 0.0
+    chunks_used = sorted(acc.get('chunks', {0}))
     if world > 1:
         g_total, _, _, _ = timed(lambda: fd.gather_shards(x_shard, labels_shard), args.steps)
-        gather_ms = g_total / args.steps
+        plain_gather_ms = g_total / args.steps
     timed_launches = acc['launches']
     value = pairs * args.steps / (total_ms * 1e-3) / 1e9
     mode_used = sorted(acc['modes'])[0] if len(acc['modes']) == 1 else args.mode      # what 'auto' resolved to
@@ -540,16 +558,12 @@ def run_allpairs(args):
                     h2d.append(out_['stats']['h2d_ms'])
                     return out_
             else:
-                xd = torch.empty_like(x_shard); ld = torch.empty_like(labels_shard)
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-
                 def step_e2e():
-                    ev[0].record(stream)
-                    xd.copy_(xh_t, non_blocking=True); ld.copy_(lh_t, non_blocking=True)
-                    ev[1].record(stream)
-                    b, _ = fd.pair_histogram_sharded(xd, ld, thr, 0, hist_fn=hist_fn, balancer=balancer)
+                    # host shards straight into the library: each rank uploads its rows piece by piece (pinned ring) and
+                    # broadcasts them from the GPU, under the launches
+                    b, st_ = sharded(xh_np, lh_np)
                     r = b.cpu()
-                    h2d.append(ev[0].elapsed_time(ev[1]))
+                    h2d.append(st_.get('gather_ms', 0.0))
                     return r
             for _ in range(max(1, min(args.warmup, 2))):
                 step_e2e()
@@ -560,13 +574,14 @@ def run_allpairs(args):
                     'd2h_ms': None, 'steps': steps}
 
         e2e = leg(x_host.numpy(), l_host.numpy(), x_host, l_host, args.steps)
-        e2e['host_memory'] = 'pinned (torch pin_memory viewed as NumPy): copied in place, one cudaMemcpyAsync'
+        e2e['host_memory'] = ('pinned (torch pin_memory viewed as NumPy): streamed chunk by chunk under the Gram launches (rows out of class order are '
+                              'gathered by the copy threads through the pinned ring); h2d_ms = first to last chunk on the copy stream')
         # what the reference's caller really hands over: pageable np.concatenate output (facenet.py:184-201)
         x_page, l_page = np.array(x_host.numpy()), np.array(l_host.numpy())
         steps_p = max(1, min(args.steps, 3))
         e2e_pageable = leg(x_page, l_page, torch.from_numpy(x_page), torch.from_numpy(l_page), steps_p)
         e2e_pageable['host_memory'] = ('pageable NumPy arrays: staged through a ring of pinned slots filled by a pool of host threads '
-                                       '(csrc/fnb_stage.cu)' if world == 1 else 'pageable NumPy arrays through torch copy_')
+                                       '(csrc/fnb_stage.cu), chunk by chunk under the Gram launches')
         e2e_pageable['e2e_over_value'] = e2e_pageable['value'] / value
         e2e['e2e_over_value'] = e2e['value'] / value
 
@@ -624,8 +639,8 @@ def run_allpairs(args):
         v, ms, sample, cores = cpu_arm(args.cpu_sample_rows, ids, n, 2, 1)
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
 
-    rest = total_ms / args.steps - gather_ms - p_ms - k_ms
-    parts = {'all_gather': gather_ms, 'sort_split': p_ms, 'rest (all-reduce, D2H of the bins, host)': rest}
+    rest = total_ms / args.steps - k_ms
+    parts = {'everything outside the Gram launches (label exchange + sorts, first chunk of the row exchange, splits, all-reduce, D2H, host)': rest}
     limiter = max(parts, key=parts.get)
     line = {'metric': METRIC, 'value': value, 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
@@ -640,9 +655,12 @@ def run_allpairs(args):
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
                        'pairs_per_step': pairs, 'region_rows': args.region_rows,
                        'grid_ctas': grids, 'panel_window': windows, 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},
-            'breakdown_ms': {'all_gather': gather_ms, 'sort_split': p_ms, 'gram_kernel': k_ms, 'gram_kernel_per_rank': k_ranks,
-                             'rest (all-reduce, D2H of the bins, host)': rest,
-                             'limiter_outside_the_kernel': limiter},
+            'breakdown_ms': {'row_exchange_first_to_last_piece': gather_ms, 'row_exchange_chunks': chunks_used,
+                             'plain_torch_all_gather_alone': plain_gather_ms, 'sort_split_until_first_launch': p_ms,
+                             'gram_kernel': k_ms, 'gram_kernel_per_rank': k_ranks,
+                             'step_minus_gram_kernel': rest,
+                             'note': 'N > 1: labels first, then the fp32 rows by ncclBroadcast from their owner, chunk by chunk on a copy '
+                                     'stream under the Gram launches (fnb_pair_histogram_sharded); ncclAllReduce of the integer bins'},
             'clocks': clocks, 'e2e': e2e, 'e2e_pageable': e2e_pageable, 'gpu_launches': timed_launches, 'roofline': roofline,
             'cpu_baseline': cpu, 'parity': parity, 'strict': strict,
             'pct_tf32_peak': 100.0 * value * 1e9 * FLOP_PER_PAIR / 1e12 / (tf32_peak * world)}

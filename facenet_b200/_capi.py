@@ -26,7 +26,8 @@ MAX_THRESHOLDS = 127
 EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'fnb_last_error', 'fnb_device_info', 'fnb_set_stream',
            'fnb_pairwise', 'fnb_pair_histogram_bins', 'fnb_counts_from_bins', 'fnb_pair_histogram',
            'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine', 'fnb_mine_batched', 'fnb_mine_check',
-           'fnb_mine_select_kth', 'fnb_false_pairs', 'fnb_pair_cross_entropy', 'fnb_logits_cross_entropy')
+           'fnb_mine_select_kth', 'fnb_false_pairs', 'fnb_pair_cross_entropy', 'fnb_logits_cross_entropy',
+           'fnb_comm_unique_id', 'fnb_comm_init', 'fnb_comm_destroy', 'fnb_comm_info', 'fnb_comm_last_error', 'fnb_pair_histogram_sharded')
 
 
 class DLDevice(ctypes.Structure):
@@ -61,7 +62,7 @@ class Stats(ctypes.Structure):
                 ('prepare_ms', ctypes.c_float), ('tiles', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint32),
                 ('eps_counted', ctypes.c_float), ('grid_ctas', ctypes.c_uint32), ('mode_used', ctypes.c_int32), ('peakedness', ctypes.c_float),
                 ('panel_window', ctypes.c_int32), ('error_bound', ctypes.c_float), ('fallback', ctypes.c_int32), ('h2d_ms', ctypes.c_float), ('h2d_bytes', ctypes.c_uint64),
-                ('streamed_chunks', ctypes.c_int32)]
+                ('gather_ms', ctypes.c_float), ('streamed_chunks', ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
@@ -123,6 +124,14 @@ def load_library():
                                         P(c.c_int32), P(c.c_float), P(c.c_uint64), P(Stats)]
         lib.fnb_pair_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, c.c_float, c.c_float, P(Options), P(c.c_double), P(Stats)]
         lib.fnb_logits_cross_entropy.argtypes = [c.c_void_p, P(DLTensor), c.c_int, P(c.c_double)]
+        lib.fnb_comm_unique_id.argtypes = [c.c_void_p]
+        lib.fnb_comm_init.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int]
+        lib.fnb_comm_destroy.argtypes = [c.c_void_p]
+        lib.fnb_comm_info.argtypes = [c.c_void_p, P(c.c_int), P(c.c_int), P(c.c_int)]
+        lib.fnb_comm_last_error.argtypes = []
+        lib.fnb_comm_last_error.restype = c.c_char_p
+        lib.fnb_pair_histogram_sharded.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(c.c_double), c.c_int, P(Options),
+                                                   P(DLTensor), P(Stats)]
         for name in EXPORTS:
             fn = getattr(lib, name)
             if fn.restype is c.c_int and name not in ('fnb_version',):
@@ -470,6 +479,63 @@ class Handle:
         be, bl, bb = self._borrow(embeddings), self._borrow(labels), self._borrow(bins_out)
         rc = self.lib.fnb_pair_histogram_bins(self.h, be.ptr, bl.ptr, thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                               thr.size, ctypes.byref(o), bb.ptr, ctypes.byref(st))
+        if rc != FNB_OK:
+            self._raise(rc)
+        return bins_out, st.as_dict()
+
+    # ---- multi-GPU inside the library (NCCL behind the C ABI)
+    def comm_unique_id(self):
+        """128 bytes (an ncclUniqueId) made on rank 0; ship them to the other ranks and call ``comm_init`` everywhere."""
+        buf = ctypes.create_string_buffer(128)
+        rc = self.lib.fnb_comm_unique_id(buf)
+        if rc != FNB_OK:
+            raise FnbError(rc, self.lib.fnb_comm_last_error().decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        rc = self.lib.fnb_comm_init(self.h, ctypes.c_char_p(bytes(unique_id)), int(rank), int(world))
+        if rc != FNB_OK:
+            self._raise(rc)
+        self.comm = (int(rank), int(world))
+
+    def comm_init_from_torch(self, group=None):
+        """Communicator over the ranks of a ``torch.distributed`` group: rank 0's id travels through the group's own
+        broadcast (any backend); the communicator itself is NCCL's, inside the library."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(box[0], rank, world)
+
+    def comm_destroy(self):
+        if getattr(self, 'comm', None) is not None:
+            self.lib.fnb_comm_destroy(self.h)
+            self.comm = None
+
+    def comm_info(self):
+        r, w, v = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.lib.fnb_comm_info(self.h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(v))
+        return {'rank': r.value, 'world': w.value, 'nccl_version': v.value}
+
+    def pair_histogram_sharded(self, emb_shard, labels_shard, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='auto',
+                               cta_group=0, region_rows=0, bins_out=None, cuts='numpy', cluster_pairs=0, normalize=0, shard=None,
+                               panel_window=None, strict_tiles=None, bias_correction=None, streamed=None):
+        """Collective over the handle's communicator: every rank passes its rows, every rank gets the bins of the whole set
+        (``fnb_pair_histogram_sharded``)."""
+        emb_shard = _as_f32_matrix(emb_shard, 'embeddings')
+        labels_shard = _as_labels(labels_shard)
+        thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
+        if isinstance(cuts, str) and cuts == 'numpy':
+            cuts = numpy_cuts(thr, metric)
+        o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, cta_group=cta_group, region_rows=region_rows, cuts=cuts,
+                               cluster_pairs=cluster_pairs, normalize=normalize, shard=shard, panel_window=panel_window,
+                               strict_tiles=strict_tiles, bias_correction=bias_correction, streamed=streamed)
+        if bins_out is None:
+            bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
+        st = Stats()
+        be, bl, bb = self._borrow(emb_shard), self._borrow(labels_shard), self._borrow(bins_out)
+        rc = self.lib.fnb_pair_histogram_sharded(self.h, be.ptr, bl.ptr, thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                 thr.size, ctypes.byref(o), bb.ptr, ctypes.byref(st))
         if rc != FNB_OK:
             self._raise(rc)
         return bins_out, st.as_dict()

@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / 'csrc'
 OUT_DIR = PKG / '_lib'
 LIB = OUT_DIR / 'libfacenet_b200.so'
-SOURCES = ['fnb_api.cu', 'fnb_gram.cu', 'fnb_prepare.cu', 'fnb_select.cu', 'fnb_mine.cu', 'fnb_bce.cu', 'fnb_stage.cu']
+SOURCES = ['fnb_api.cu', 'fnb_gram.cu', 'fnb_prepare.cu', 'fnb_select.cu', 'fnb_mine.cu', 'fnb_bce.cu', 'fnb_stage.cu', 'fnb_comm.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
 

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -414,6 +415,8 @@ extern "C" void fnb_destroy(fnb_handle h) {
     for (DevBuf* b : bufs) b->release();
     h->pinned.release();
     h->perm_host.release();
+    comm_release(h);
+    h->comm_buf.release(); h->lab_all.release(); h->local_perm.release();
     if (h->copier) { destroy_copier(h->copier); h->copier = nullptr; }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     h->ring.release();
@@ -757,9 +760,15 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
         }
         return own_pairs;
     };
+    // streamed pass: the job as a whole decides (its launches are as long, in sum, as the one launch they replace); launches
+    // of less than 1e9 pairs have nothing to drift over
+    double job_pairs = 0.0;
+    if (hl.chunks) for (const auto& c : *hl.chunks) job_pairs += own_pairs_of(c);
     auto window_of = [&](const std::vector<RegionDev>& rv) {
         if (opt.panel_window > 0) return std::min(opt.panel_window, 7);
-        return (opt.panel_window == 0 && hl.auto_window && own_pairs_of(rv) >= 5.0e10) ? 2 : 0;
+        if (opt.panel_window != 0 || !hl.auto_window) return 0;
+        const double own = own_pairs_of(rv);
+        return (own >= 5.0e10 || (job_pairs >= 5.0e10 && own >= 1.0e9)) ? 2 : 0;
     };
     const int nlaunch = hl.chunks ? (int)hl.chunks->size() : 1;
     p.sync_window = window_of(hl.chunks ? hl.chunks->back() : regs);
@@ -873,6 +882,23 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         if (h->chunk_launches > 0) {
             // streamed pass: the launches' own durations (the waits for the chunks in between are not kernel time)
             for (int k = 0; k < h->chunk_launches; ++k) { float m1 = 0.f; cudaEventElapsedTime(&m1, h->chunk_ev[2 * k], h->chunk_ev[2 * k + 1]); ms += m1; }
+            if (getenv("FNB_TRACE")) {
+                // timeline of the launches on the handle's stream, ms since the start of the call: start, end of every launch
+                fprintf(stderr, "[fnb trace] rank %d:", h->last_shard.lo);
+                for (int k = 0; k < h->chunk_launches; ++k) {
+                    float t0 = 0.f, t1 = 0.f;
+                    cudaEventElapsedTime(&t0, h->ev[0], h->chunk_ev[2 * k]); cudaEventElapsedTime(&t1, h->ev[0], h->chunk_ev[2 * k + 1]);
+                    fprintf(stderr, " [%.2f %.2f]", t0, t1);
+                }
+                fprintf(stderr, "\n[fnb trace] rank %d exchange (start, own rows in place, broadcast done):", h->last_shard.lo);
+                for (size_t k = 0; 3 * k + 2 < h->xchg_ev.size() && (int)k < h->chunk_launches; ++k) {
+                    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+                    if (cudaEventElapsedTime(&t0, h->ev[0], h->xchg_ev[3 * k]) != cudaSuccess) { cudaGetLastError(); break; }
+                    cudaEventElapsedTime(&t1, h->ev[0], h->xchg_ev[3 * k + 1]); cudaEventElapsedTime(&t2, h->ev[0], h->xchg_ev[3 * k + 2]);
+                    fprintf(stderr, " [%.2f %.2f %.2f]", t0, t1, t2);
+                }
+                fprintf(stderr, "\n");
+            }
             cudaEventElapsedTime(&pm, h->ev[0], h->chunk_ev[0]);
         } else {
             cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]);
@@ -906,6 +932,22 @@ static double mode_slack(int mode) {
         case FNB_MODE_FP16F8: return 2.0e-5;
         default: return 0.0;
     }
+}
+
+// the range check of finish_hist, on the device: *flag = 1 when this rank's checked tiles saw a similarity outside
+// [-(1 + atol + slack), 1 + atol + slack] (NaN included).  Sharded jobs carry the flag through the all-reduce of the bins.
+__global__ void range_violation_kernel(const unsigned int* __restrict__ range_ord, double lim, int raw, unsigned long long* flag) {
+    const unsigned int mn = range_ord[0], mx = range_ord[1];
+    const bool have = mn != 0xFFFFFFFFu;
+    const double smin = (double)ordered_to_float(mn), smax = (double)ordered_to_float(mx);
+    *flag = (!raw && have && !(smin >= -lim && smax <= lim)) ? 1ull : 0ull;
+}
+
+static int flag_range_violation(fnb_context* h, const fnb_options& opt, unsigned long long* flag) {
+    const double lim = 1.0 + (double)opt.atol + mode_slack(opt.mode);
+    range_violation_kernel<<<1, 1, 0, h->stream>>>(h->counters.as<DeviceScalars>()->range_ord, lim, opt.raw_distance, flag);
+    CK(cudaGetLastError());
+    return FNB_OK;
 }
 
 static uint64_t sum_bins(const uint64_t* b, int n) { uint64_t s = 0; for (int i = 0; i < n; ++i) s += b[i]; return s; }
@@ -949,212 +991,545 @@ static double error_certificate(const fnb_options& opt, int mode, bool strict_ti
     return worst;
 }
 
+// ---------------------------------------------------------------------------------------
+// whole-set histogram: one job object shared by fnb_pair_histogram_bins (one GPU, or a caller that shards by itself through
+// fnb_options.rank / world) and fnb_pair_histogram_sharded (NCCL inside the library)
+
+namespace {
+
+struct WholeSetJob {
+    fnb_context* h;
+    fnb_options opt;
+    fnb_stats* stats;
+    const double* thresholds;
+    int T;
+    long long n = 0;
+    int d = 0;
+    int cg = 2, tile = 256;
+    int requested = FNB_MODE_FP16X3;
+    ShardHost shard;
+    GramOperands op;
+    const void* de = nullptr;               // fp32 rows on the device
+    const long long* perm_dev = nullptr;    // class order of the rows at `de` (NULL: they are stored in class order)
+    const long long* stream_perm = nullptr; // streamed pass: class position -> row of h->stage_a (NULL: the pieces are fed in class order)
+    bool reduce = false;                    // all-reduce the bins (and the range-violation flag) over the handle's communicator
+    uint64_t host_bins[2 * (kMaxBins + 1)];
+    size_t row_bytes = 0;
+
+    long long super_rows() {
+        const int cl_size = cg * op.pairs;
+        const int clusters = h->hist_grid[op.pairs] > 0 ? h->hist_grid[op.pairs] / cl_size
+                                                        : (op.pairs == 1 ? h->sm_count / cl_size : op.pairs == 2 ? h->sm_count / cl_size - 4 : 15);
+        // 512-aligned regions (see strict_tile in the kernel), super-row height matched to the cluster count of the launch
+        return pick_region_rows(&opt, 512, n, d, clusters, tile * (op.pairs == 4 ? 2 : 1));
+    }
+
+    // after the launches of a pass: (sharded) sum the bins over the ranks, then scalars + bins to the host
+    int collect(HistLaunch& hl, double* bound, bool* violated, float* smin, float* smax) {
+        if (reduce) {
+            // slot [0][kMaxBins] of the bins (never a bin: T < kMaxBins) carries the ranks' range violations through the all-reduce
+            int rc = flag_range_violation(h, opt, h->bins.as<unsigned long long>() + kMaxBins);
+            if (rc) return rc;
+            if ((rc = comm_all_reduce_u64(h, h->bins.p, 2 * (size_t)hl.stride, false, h->stream))) return rc;
+        }
+        CK(cudaMemcpyAsync(h->pinned.as<char>() + 4096, h->bins.p, 2 * (size_t)hl.stride * 8, cudaMemcpyDeviceToHost, h->stream));
+        int rc = finish_hist(h, opt, stats, smin, smax, violated);          // synchronises
+        if (rc) return rc;
+        const uint64_t* pb = reinterpret_cast<const uint64_t*>(h->pinned.as<char>() + 4096);
+        if (reduce && pb[kMaxBins] != 0) *violated = true;
+        for (int r = 0; r < 2; ++r) memcpy(host_bins + (size_t)r * (T + 1), pb + (size_t)r * hl.stride, (size_t)(T + 1) * 8);
+        if (!*violated) {
+            fnb_options o = opt;
+            if (reduce) o.world = 1;                     // the bins are the whole job's
+            *bound = error_certificate(o, op.mode, h->last_strict != 0, d, h->last_peak_mean, h->last_peak, n, hl.ct, host_bins, host_bins + (T + 1), T);
+        }
+        return FNB_OK;
+    }
+
+    int not_normalized(HistLaunch& hl, const std::vector<RegionDev>& regs) {
+        // re-run with every tile on the checked path to report the exact similarity range (of this rank's tiles)
+        int rc;
+        float smin, smax; bool violated = false;
+        if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 1))) return rc;
+        if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
+        if (smin == smin) return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
+        return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1 (similarity out of range on another rank)");
+    }
+
+    // one pass in `mode` over the resident rows: operands, schedule, launch, range check, bins to the host, error certificate
+    int pass(int mode, double* bound) {
+        int rc;
+        op = GramOperands();
+        op.pairs = pick_pairs(&opt, cg, n);
+        op.want_l16 = opt.strict_tiles >= 0;
+        if ((rc = prepare_operand(h, mode, (const float*)de, perm_dev, n, d, false, op, opt.normalize))) return rc;
+        if ((rc = self_b_maps(h, op, d))) return rc;
+        opt.mode = op.mode;                              // AUTO resolved
+        h->last_mode = op.mode; h->last_peak = op.peakedness;
+        std::vector<RegionDev> regs;
+        triangle_regions(n, (int)super_rows(), 0, regs);
+        finish_regions(regs, tile, op.pairs, &shard);
+        HistLaunch hl; hl.auto_window = true;
+        if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
+        float smin, smax; bool violated = false;
+        if ((rc = collect(hl, bound, &violated, &smin, &smax))) return rc;
+        if (violated) return not_normalized(hl, regs);
+        return FNB_OK;
+    }
+
+    // Streamed pass: the rows arrive in class order, piece by piece (`feed(k, c0, c1)` makes rows [c0, c1) of h->stage_a ready on
+    // the handle's stream -- an upload from the host, or a broadcast from the rank that holds them).  The pair matrix is cut into
+    // column chunks at `bounds`; launch k covers the pairs (row < column, column in chunk k) and needs only the rows fed so far,
+    // so the transfer of chunk k + 1 runs under launch k and only the first chunk's transfer is exposed.  The integer bins do
+    // not depend on the chunking (512-aligned regions, same strict-tile rule).
+    int pass_streamed(int mode, double* bound, const std::vector<long long>& bounds,
+                      const std::function<int(int, long long, long long)>& feed) {
+        int rc;
+        op = GramOperands();
+        op.pairs = pick_pairs(&opt, cg, n);
+        op.want_l16 = opt.strict_tiles >= 0;
+        if ((rc = prepare_operand(h, mode, h->stage_a.as<float>(), nullptr, n, d, false, op, opt.normalize, /*defer_split=*/true))) return rc;
+        if ((rc = self_b_maps(h, op, d))) return rc;
+        opt.mode = op.mode;
+        h->last_mode = op.mode; h->last_peak = 0.f;
+        const long long rr = super_rows();
+        const int nchunks = (int)bounds.size() - 1;
+        std::vector<std::vector<RegionDev>> chunks((size_t)nchunks);
+        for (int k = 0; k < nchunks; ++k) {
+            // pairs (row < col) with col in [c0, c1): per super-row [r0, r1) of the tile order -- columns inside the super-row's own
+            // span [a, b) see the rows [r0, a) above them (a rectangle) and each other (a triangle); columns to its right see all
+            // of its rows (a rectangle)
+            const long long c0 = bounds[k], c1 = bounds[k + 1];
+            for (long long r0 = 0; r0 < c1; r0 += rr) {
+                const long long r1 = std::min<long long>(n, r0 + rr);
+                const long long a = std::max(c0, r0), b = std::min(c1, r1);
+                RegionDev g = {};
+                g.key = 0;
+                if (a < b) {
+                    if (a > r0) { g.row_begin = (int)r0; g.row_end = (int)a; g.col_begin = (int)a; g.col_end = (int)b; g.tri = 0; chunks[k].push_back(g); }
+                    g.row_begin = (int)a; g.row_end = (int)b; g.col_begin = (int)a; g.col_end = (int)b; g.tri = 1; chunks[k].push_back(g);
+                }
+                const long long right = std::max(c0, r1);
+                if (right < c1) { g.row_begin = (int)r0; g.row_end = (int)r1; g.col_begin = (int)right; g.col_end = (int)c1; g.tri = 0; chunks[k].push_back(g); }
+            }
+            finish_regions(chunks[k], tile, op.pairs, &shard);
+        }
+        HistLaunch hl; hl.auto_window = true; hl.chunks = &chunks;
+        hl.before_launch = [&](int k) -> int {
+            const long long c0 = bounds[k], c1 = bounds[k + 1];
+            int r = feed(k, c0, c1);
+            if (r) return r;
+            // (the last chunk also zeroes the padding rows)
+            return split_operand_rows(h, op, h->stage_a.as<float>(), stream_perm, n, d, opt.normalize, c0, k + 1 == nchunks ? op.a_rows_pad : c1);
+        };
+        std::vector<RegionDev> none;
+        if ((rc = run_hist(h, opt, op, none, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
+        de = h->stage_a.p; perm_dev = stream_perm;       // the rows are resident now: a later pass re-reads them from here
+        const int launches = h->chunk_launches;
+        float smin, smax; bool violated = false;
+        if ((rc = collect(hl, bound, &violated, &smin, &smax))) return rc;
+        if (stats) stats->streamed_chunks = launches;
+        if (violated) {
+            std::vector<RegionDev> regs;
+            triangle_regions(n, (int)rr, 0, regs);
+            finish_regions(regs, tile, op.pairs, &shard);
+            HistLaunch whole; whole.auto_window = true;
+            return not_normalized(whole, regs);
+        }
+        op.peakedness = h->last_peak;
+        return FNB_OK;
+    }
+
+    // column-chunk boundaries of a streamed pass: multiples of a granule of about one super-row, growing with the work already
+    // queued (1, 1, 1, 1, 2, 3, 4, 6, 9 ... granules): launch k is then at least as long as the transfer of chunk k + 1
+    std::vector<long long> chunk_bounds() {
+        op.pairs = pick_pairs(&opt, cg, n);
+        long long g = super_rows();
+        while (g > 49152) g /= 2;
+        g = std::max<long long>(512, g / 512 * 512);
+        std::vector<long long> bounds = {0};
+        for (long long pos = 0; pos < n;) {
+            pos = std::min(n, pos + std::max(g, (pos / 2) / g * g));
+            bounds.push_back(pos);
+        }
+        return bounds;
+    }
+
+    // AUTO: FP16F8 when the a-priori gate and the a-posteriori certificate hold, else the strict pass over the resident rows.
+    // `streamed_first` ran the first pass already (optimistically in FP16F8) and left the bound.
+    int finish_auto(double bound, int* fallback) {
+        bool again = requested == FNB_MODE_AUTO && op.mode == FNB_MODE_FP16F8 && (bound > (double)opt.eps || !(h->last_peak <= kAutoPeakLimit));
+        if (reduce && requested == FNB_MODE_AUTO) {
+            // the ranks must take the same branch (their certificates can differ in the last bits: float atomics): any rank's yes wins
+            unsigned long long* flag = h->bins.as<unsigned long long>() + kMaxBins;
+            const unsigned long long v = again ? 1ull : 0ull;
+            CK(cudaMemcpyAsync(flag, &v, 8, cudaMemcpyHostToDevice, h->stream));
+            int rc = comm_all_reduce_u64(h, flag, 1, true, h->stream);
+            if (rc) return rc;
+            unsigned long long got = 0;
+            CK(cudaMemcpyAsync(&got, flag, 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            again = got != 0;
+        }
+        if (again) {
+            // the fast contraction cannot vouch for this data (e.g. many different-identity pairs at high similarity): strict pass
+            int rc = pass(FNB_MODE_FP16X3, &bound);
+            if (rc) return rc;
+            if (stats) stats->kernel_launches += 1;      // the second split_rows
+            *fallback = 1;
+        }
+        if (stats) {
+            stats->kernel_launches += 3;      // labels_to_keys, boundary_flags, split_rows (+ the Gram kernel counted above)
+            stats->n_pairs = sum_bins(host_bins, T + 1);
+            stats->error_bound = (float)bound;
+            stats->fallback = *fallback;
+        }
+        return FNB_OK;
+    }
+
+    int write_bins(const DLView& vb) {
+        const size_t rb = (size_t)(T + 1) * 8;
+        if (vb.on_device) {
+            for (int r = 0; r < 2; ++r)
+                CK(cudaMemcpyAsync((char*)vb.data + r * rb, h->bins.as<unsigned long long>() + (size_t)r * (kMaxBins + 1), rb, cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+            memcpy(vb.data, host_bins, 2 * rb);
+        }
+        return FNB_OK;
+    }
+};
+
+static bool labels_in_class_order(const DLView& vl, long long n) {
+    if (vl.on_device) return false;
+    if (vl.bits == 64) { const long long* l = (const long long*)vl.data; for (long long i = 1; i < n; ++i) if (l[i] < l[i - 1]) return false; }
+    else { const int* l = (const int*)vl.data; for (long long i = 1; i < n; ++i) if (l[i] < l[i - 1]) return false; }
+    return true;
+}
+
+static int check_hist_args(fnb_context* h, const fnb_options& opt, const DLTensor* emb, const DLTensor* labels, const double* thresholds, int T,
+                           DLTensor* bins_out, DLView* ve, DLView* vl, DLView* vb)
+{
+    if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
+    if (!thresholds || T < 1 || T >= kMaxBins) return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
+    int np; bool tf; int fmt, eb; float ps;
+    if (mode_info(opt.mode, &np, &tf, &fmt, &eb, &ps)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
+    int rc = dl_view(h, emb, "embeddings", 2, 2, ve); if (rc) return rc;
+    if ((rc = dl_check_embeddings(h, *ve, "embeddings"))) return rc;
+    if ((rc = dl_view(h, labels, "labels", 1, 1, vl))) return rc;
+    if (vl->code != kDLInt || (vl->bits != 32 && vl->bits != 64)) return h->fail(FNB_ERR_INVALID, "labels must be int32 or int64");
+    if (vl->rows != ve->rows) return h->fail(FNB_ERR_INVALID, "len(labels) != embeddings.shape[0]");
+    if ((rc = dl_view(h, bins_out, "bins_out", 2, 2, vb))) return rc;
+    if (vb->bits != 64 || vb->rows != 2 || vb->cols != T + 1) return h->fail(FNB_ERR_INVALID, "bins_out must be a 64-bit integer [2, T+1] tensor");
+    return FNB_OK;
+}
+
+}  // namespace
+
 extern "C" int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const DLTensor* labels,
                                        const double* thresholds, int T, const fnb_options* opt_in,
                                        DLTensor* bins_out, fnb_stats* stats)
 {
     if (!h) return FNB_ERR_INVALID;
-    fnb_options opt; if (opt_in) opt = *opt_in; else fnb_default_options(&opt);
-    if (opt.metric != 0 && opt.metric != 1) return h->fail(FNB_ERR_BAD_METRIC, "Undefined similarity metric %d", opt.metric);
-    if (!thresholds || T < 1 || T >= kMaxBins) return h->fail(FNB_ERR_INVALID, "number of thresholds must be in [1, %d]", kMaxBins - 1);
+    WholeSetJob job;
+    job.h = h; job.stats = stats; job.thresholds = thresholds; job.T = T;
+    if (opt_in) job.opt = *opt_in; else fnb_default_options(&job.opt);
+    fnb_options& opt = job.opt;
     if (opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) return h->fail(FNB_ERR_INVALID, "bad rank/world %d/%d", opt.rank, opt.world);
     CK(cudaSetDevice(h->device));
     if (stats) memset(stats, 0, sizeof(*stats));
-    GramOperands op;
-    if (mode_info(opt.mode, &op.num_pass, &op.tf32, &op.fmt, &op.elem_bytes, &op.prescale)) return h->fail(FNB_ERR_INVALID, "bad mode %d", opt.mode);
     DLView ve, vl, vb;
-    int rc = dl_view(h, emb, "embeddings", 2, 2, &ve); if (rc) return rc;
-    if ((rc = dl_check_embeddings(h, ve, "embeddings"))) return rc;
-    if ((rc = dl_view(h, labels, "labels", 1, 1, &vl))) return rc;
-    if (vl.code != kDLInt || (vl.bits != 32 && vl.bits != 64)) return h->fail(FNB_ERR_INVALID, "labels must be int32 or int64");
-    if (vl.rows != ve.rows) return h->fail(FNB_ERR_INVALID, "len(labels) != embeddings.shape[0]");
-    if ((rc = dl_view(h, bins_out, "bins_out", 2, 2, &vb))) return rc;
-    if (vb.bits != 64 || vb.rows != 2 || vb.cols != T + 1) return h->fail(FNB_ERR_INVALID, "bins_out must be a 64-bit integer [2, T+1] tensor");
+    int rc = check_hist_args(h, opt, emb, labels, thresholds, T, bins_out, &ve, &vl, &vb);
+    if (rc) return rc;
     const long long n = ve.rows;
     const int d = (int)ve.cols;
+    job.n = n; job.d = d; job.row_bytes = (size_t)d * 4;
 
-    const size_t row_bytes = (size_t)(T + 1) * 8;
-    auto write_bins = [&](const unsigned long long* dev_bins, int stride) -> int {
-        for (int r = 0; r < 2; ++r) {
-            CK(cudaMemcpyAsync((char*)vb.data + r * row_bytes, dev_bins + (size_t)r * stride, row_bytes,
-                               vb.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-        }
-        CK(cudaStreamSynchronize(h->stream));
-        return FNB_OK;
-    };
     if (n < 2) {
         CK(h->bins.ensure(2 * (kMaxBins + 1) * 8));
         CK(cudaMemsetAsync(h->bins.p, 0, 2 * (kMaxBins + 1) * 8, h->stream));
-        return write_bins(h->bins.as<unsigned long long>(), kMaxBins + 1);
+        memset(job.host_bins, 0, sizeof(job.host_bins));
+        if ((rc = job.write_bins(vb))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        return FNB_OK;
     }
 
-    const void* de = nullptr; const void* dl = nullptr;
+    const void* dl = nullptr;
     CK(cudaEventRecord(h->ev[0], h->stream));
     h->last_h2d_bytes = 0; h->h2d_timed = false; h->h2d_timed_bytes = 0;
     // labels first: the class sort (np.unique ranks, statistics.py:68-79) runs on the stream while the embeddings are staged
     if ((rc = dl_to_device(h, vl, (size_t)n * (vl.bits / 8), h->stage_lab, &dl))) return rc;
     if ((rc = sort_labels(h, dl, vl.bits, n))) return rc;
     const bool host_emb = !ve.on_device;
-    if (!host_emb) de = ve.data;                         // host rows: uploaded below, in one piece or chunk by chunk (streamed pass)
-    const int cg = pick_cta_group(&opt);
-    const int tile = kRowsPerCta * cg;
-    const int requested = opt.mode;
-    ShardHost shard;
-    if ((rc = shard_from_options(h, opt, &shard))) return rc;
-    h->last_shard = shard.spec;
-    uint64_t host_bins[2 * (kMaxBins + 1)];
-
-    const long long* perm_dev = h->perm.as<long long>(); // class order of the rows at `de` (NULL once they are stored in class order)
-    // one pass in `mode`: operands, schedule, launch, range check, bins to the host, error certificate
-    auto pass = [&](int mode, double* bound) -> int {
-        int rc2;
-        op = GramOperands();
-        op.pairs = pick_pairs(&opt, cg, n);
-        op.want_l16 = opt.strict_tiles >= 0;
-        if ((rc2 = prepare_operand(h, mode, (const float*)de, perm_dev, n, d, false, op, opt.normalize))) return rc2;
-        if ((rc2 = self_b_maps(h, op, d))) return rc2;
-        opt.mode = op.mode;                              // AUTO resolved
-        h->last_mode = op.mode; h->last_peak = op.peakedness;
-        std::vector<RegionDev> regs;
-        // 512-aligned regions (see strict_tile in the kernel), super-row height matched to the cluster count of the launch
-        const int cl_size = cg * op.pairs;
-        const int clusters = h->hist_grid[op.pairs] > 0 ? h->hist_grid[op.pairs] / cl_size
-                                                        : (op.pairs == 1 ? h->sm_count / cl_size : op.pairs == 2 ? h->sm_count / cl_size - 4 : 15);
-        triangle_regions(n, pick_region_rows(&opt, 512, n, d, clusters, tile * (op.pairs == 4 ? 2 : 1)), 0, regs);
-        finish_regions(regs, tile, op.pairs, &shard);
-        HistLaunch hl; hl.auto_window = true;
-        if ((rc2 = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc2;
-        float smin, smax; bool violated = false;
-        if ((rc2 = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc2;
-        if (violated) {
-            // re-run with every tile on the checked path to report the exact similarity range
-            if ((rc2 = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 1))) return rc2;
-            if ((rc2 = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc2;
-            return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
-        }
-        CK(cudaMemcpyAsync(h->pinned.as<char>() + 4096, h->bins.p, 2 * (size_t)hl.stride * 8, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        const uint64_t* pb = reinterpret_cast<const uint64_t*>(h->pinned.as<char>() + 4096);
-        for (int r = 0; r < 2; ++r) memcpy(host_bins + (size_t)r * (T + 1), pb + (size_t)r * hl.stride, row_bytes);
-        *bound = error_certificate(opt, op.mode, h->last_strict != 0, d, h->last_peak_mean, h->last_peak, n, hl.ct, host_bins, host_bins + (T + 1), T);
-        return FNB_OK;
-    };
-
-    // Streamed pass (host embeddings, fnb_options.streamed): the upload is cut into
-    // column chunks of the pair matrix, each a whole number of super-rows; launch k covers the pairs (row < chunk k's end,
-    // column in chunk k) and needs only the rows uploaded so far, so the H2D copy of chunk k + 1 runs under launch k.  Chunk sizes
-    // grow with the work already queued (1, 1, 1, 1, 2, 3, 4, 6, 9 ... super-rows): the first launch starts after ~1/30 of the
-    // upload and only that first chunk's copy is exposed.  The integer bins do not depend on the chunking (512-aligned
-    // regions, same strict-tile rule).
-    auto labels_in_class_order = [&]() -> bool {
-        if (vl.on_device) return false;
-        if (vl.bits == 64) { const long long* l = (const long long*)vl.data; for (long long i = 1; i < n; ++i) if (l[i] < l[i - 1]) return false; }
-        else { const int* l = (const int*)vl.data; for (long long i = 1; i < n; ++i) if (l[i] < l[i - 1]) return false; }
-        return true;
-    };
-    // rows out of class order: the host threads that fill the pinned ring GATHER them in class order (they copy the bytes anyway),
-    // with the permutation the device sort produced -- the only extra cost is its 8 n byte copy back
-    const long long* perm_h = nullptr;
-    auto pass_streamed = [&](int mode, double* bound) -> int {
-        int rc2;
-        op = GramOperands();
-        op.pairs = pick_pairs(&opt, cg, n);
-        op.want_l16 = opt.strict_tiles >= 0;
-        CK(h->stage_a.ensure((size_t)n * d * 4));
-        if ((rc2 = prepare_operand(h, mode, h->stage_a.as<float>(), nullptr, n, d, false, op, opt.normalize, /*defer_split=*/true))) return rc2;
-        if ((rc2 = self_b_maps(h, op, d))) return rc2;
-        opt.mode = op.mode;
-        h->last_mode = op.mode; h->last_peak = 0.f;
-        const int cl_size = cg * op.pairs;
-        const int clusters = h->hist_grid[op.pairs] > 0 ? h->hist_grid[op.pairs] / cl_size
-                                                        : (op.pairs == 1 ? h->sm_count / cl_size : op.pairs == 2 ? h->sm_count / cl_size - 4 : 15);
-        const long long rr = pick_region_rows(&opt, 512, n, d, clusters, tile * (op.pairs == 4 ? 2 : 1));
-        const long long nsr = (n + rr - 1) / rr;
-        std::vector<long long> bounds = {0};             // chunk boundaries in rows
-        for (long long b = 0; b < nsr;) { b = std::min(nsr, b + std::max<long long>(1, b / 2)); bounds.push_back(std::min<long long>(n, b * rr)); }
-        const int nchunks = (int)bounds.size() - 1;
-        std::vector<std::vector<RegionDev>> chunks((size_t)nchunks);
-        for (int k = 0; k < nchunks; ++k) {
-            const long long c0 = bounds[k], c1 = bounds[k + 1];
-            for (long long r0 = 0; r0 < c1; r0 += rr) {
-                const long long r1 = std::min<long long>(n, r0 + rr);
-                RegionDev g = {};
-                g.row_begin = (int)r0; g.row_end = (int)r1; g.key = 0;
-                if (r1 <= c0) { g.col_begin = (int)c0; g.col_end = (int)c1; chunks[k].push_back(g); continue; }
-                g.col_begin = (int)r0; g.col_end = (int)r1; g.tri = 1;
-                chunks[k].push_back(g);
-                if (r1 < c1) { g.tri = 0; g.col_begin = (int)r1; g.col_end = (int)c1; chunks[k].push_back(g); }
-            }
-            finish_regions(chunks[k], tile, op.pairs, &shard);
-        }
-        HistLaunch hl; hl.auto_window = true; hl.chunks = &chunks;
-        const char* src = (const char*)ve.data;
-        const size_t row_bytes_f32 = (size_t)d * 4;
-        hl.before_launch = [&](int k) -> int {
-            const long long c0 = bounds[k], c1 = bounds[k + 1];
-            int r = stage_chunk(h, h->stage_a.as<char>() + (size_t)c0 * row_bytes_f32, perm_h ? src : src + (size_t)c0 * row_bytes_f32,
-                                (size_t)(c1 - c0) * row_bytes_f32, k == 0, perm_h ? perm_h + c0 : nullptr, row_bytes_f32);
-            if (r) return r;
-            // the staged rows are in class order: no permutation (the last chunk also zeroes the padding rows)
-            return split_operand_rows(h, op, h->stage_a.as<float>(), nullptr, n, d, opt.normalize, c0, k + 1 == nchunks ? op.a_rows_pad : c1);
-        };
-        std::vector<RegionDev> none;
-        if ((rc2 = run_hist(h, opt, op, none, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc2;
-        de = h->stage_a.p; perm_dev = nullptr;           // the rows are resident now, in class order: a fallback pass re-reads them from here
-        float smin, smax; bool violated = false;
-        if ((rc2 = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc2;
-        if (violated) return pass(mode, bound);          // the one-launch pass re-runs checked and reports the exact range
-        op.peakedness = h->last_peak;
-        CK(cudaMemcpyAsync(h->pinned.as<char>() + 4096, h->bins.p, 2 * (size_t)hl.stride * 8, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        const uint64_t* pb = reinterpret_cast<const uint64_t*>(h->pinned.as<char>() + 4096);
-        for (int r = 0; r < 2; ++r) memcpy(host_bins + (size_t)r * (T + 1), pb + (size_t)r * hl.stride, row_bytes);
-        *bound = error_certificate(opt, op.mode, h->last_strict != 0, d, h->last_peak_mean, h->last_peak, n, hl.ct, host_bins, host_bins + (T + 1), T);
-        return FNB_OK;
-    };
+    if (!host_emb) job.de = ve.data;                     // host rows: uploaded below, in one piece or chunk by chunk (streamed pass)
+    job.perm_dev = h->perm.as<long long>();
+    job.cg = pick_cta_group(&opt);
+    job.tile = kRowsPerCta * job.cg;
+    job.requested = opt.mode;
+    if ((rc = shard_from_options(h, opt, &job.shard))) return rc;
+    h->last_shard = job.shard.spec;
 
     double bound = 0.0;
     int fallback = 0;
+    // Streamed pass (host embeddings, fnb_options.streamed): the upload is cut into column chunks of the pair matrix and the copy
+    // of chunk k + 1 runs under launch k.  Rows out of class order: the host threads that fill the pinned ring GATHER them in
+    // class order (they copy the bytes anyway), with the permutation the device sort produced -- the extra cost is its 8 n
+    // byte copy back.
     const bool want_stream = host_emb && opt.streamed >= 0 && (opt.streamed > 0 || (size_t)n * d * 4 >= ((size_t)64 << 20));
     if (want_stream) {
-        if (!labels_in_class_order()) {
+        const long long* perm_h = nullptr;
+        if (!labels_in_class_order(vl, n)) {
             CK(h->perm_host.ensure((size_t)n * 8));
             CK(cudaMemcpyAsync(h->perm_host.p, h->perm.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             perm_h = h->perm_host.as<long long>();
         }
-        // AUTO starts optimistically in FP16F8; the peakedness gate is evaluated when every chunk has been split
-        const int first = (requested == FNB_MODE_AUTO) ? (d % 128 == 0 ? FNB_MODE_FP16F8 : FNB_MODE_FP16X3) : requested;
-        if ((rc = pass_streamed(first, &bound))) return rc;
-        if (requested == FNB_MODE_AUTO && op.mode == FNB_MODE_FP16F8 && !(h->last_peak <= kAutoPeakLimit)) bound = INFINITY;
-        if (stats) stats->streamed_chunks = h->chunk_launches;
+        CK(h->stage_a.ensure((size_t)n * d * 4));
+        const char* src = (const char*)ve.data;
+        const size_t rb = job.row_bytes;
+        auto feed = [&](int k, long long c0, long long c1) -> int {
+            return stage_chunk(h, h->stage_a.as<char>() + (size_t)c0 * rb, perm_h ? src : src + (size_t)c0 * rb, (size_t)(c1 - c0) * rb, k == 0,
+                               perm_h ? perm_h + c0 : nullptr, rb);
+        };
+        // AUTO starts optimistically in FP16F8; the peakedness gate is evaluated when every chunk has been split (finish_auto)
+        const int first = (job.requested == FNB_MODE_AUTO) ? (d % 128 == 0 ? FNB_MODE_FP16F8 : FNB_MODE_FP16X3) : job.requested;
+        if ((rc = job.pass_streamed(first, &bound, job.chunk_bounds(), feed))) return rc;
     } else {
-        if (host_emb && (rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &de))) return rc;
-        if ((rc = pass(requested, &bound))) return rc;
+        if (host_emb && (rc = dl_to_device(h, ve, (size_t)n * d * 4, h->stage_a, &job.de))) return rc;
+        if ((rc = job.pass(job.requested, &bound))) return rc;
     }
-    // (every rank of a sharded job evaluates the same model on its share scaled to the whole; the shares are interleaved
-    // row blocks, so the ranks agree except at the very edge of the bound)
-    if (requested == FNB_MODE_AUTO && op.mode == FNB_MODE_FP16F8 && bound > (double)opt.eps) {
-        // the fast contraction cannot vouch for this data (e.g. many different-identity pairs at high similarity): strict pass
-        if ((rc = pass(FNB_MODE_FP16X3, &bound))) return rc;
-        if (stats) stats->kernel_launches += 1;          // the second split_rows
-        fallback = 1;
-    }
+    // (a caller that shards by itself: every rank evaluates the same model on its share scaled to the whole; the shares are
+    // interleaved row blocks, so the ranks agree except at the very edge of the bound)
+    if ((rc = job.finish_auto(bound, &fallback))) return rc;
     // the bins are already on the host; hand them over (device output: one small copy on the stream)
-    if (vb.on_device) {
-        for (int r = 0; r < 2; ++r)
-            CK(cudaMemcpyAsync((char*)vb.data + r * row_bytes, h->bins.as<unsigned long long>() + (size_t)r * (kMaxBins + 1), row_bytes,
-                               cudaMemcpyDeviceToDevice, h->stream));
+    return job.write_bins(vb);
+}
+
+
+// cnt[k * world + r] = number of class positions j in chunk k (bounds[k] <= j < bounds[k + 1]) whose row perm[j] belongs to rank r
+// (off[r] <= perm[j] < off[r + 1]); block-private counters in shared memory, one flush per block
+__global__ void run_counts_kernel(const long long* __restrict__ perm, long long n, const long long* __restrict__ off, int world,
+                                  const long long* __restrict__ bounds, int nchunks, unsigned int* __restrict__ cnt)
+{
+    extern __shared__ unsigned int s_cnt[];
+    const int total = nchunks * world;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        const long long g = perm[j];
+        int r = 0;
+        while (r + 1 < world && g >= off[r + 1]) ++r;
+        int k = 0;
+        while (k + 1 < nchunks && j >= bounds[k + 1]) ++k;
+        atomicAdd(&s_cnt[k * world + r], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) if (s_cnt[i]) atomicAdd(cnt + i, s_cnt[i]);
+}
+
+// dst row i <- src row perm[i], i < rows (one warp per row; d is a multiple of 64 floats)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ perm, long long rows, int d, float* __restrict__ dst)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int vec = d >> 2;
+    for (long long i = warp0; i < rows; i += nwarps) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + perm[i] * d);
+        float4* d4 = reinterpret_cast<float4*>(dst + i * d);
+        for (int c = lane; c < vec; c += 32) d4[c] = __ldg(s4 + c);
+    }
+}
+
+extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shard, const DLTensor* labels_shard,
+                                          const double* thresholds, int T, const fnb_options* opt_in,
+                                          DLTensor* bins_out, fnb_stats* stats)
+{
+    if (!h) return FNB_ERR_INVALID;
+    if (!h->comm) return h->fail(FNB_ERR_INVALID, "fnb_pair_histogram_sharded needs a communicator (fnb_comm_init)");
+    WholeSetJob job;
+    job.h = h; job.stats = stats; job.thresholds = thresholds; job.T = T;
+    if (opt_in) job.opt = *opt_in; else fnb_default_options(&job.opt);
+    fnb_options& opt = job.opt;
+    const int world = comm_world(h), rank = comm_rank(h);
+    opt.rank = rank; opt.world = world;
+    CK(cudaSetDevice(h->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    DLView ve, vl, vb;
+    int rc = check_hist_args(h, opt, emb_shard, labels_shard, thresholds, T, bins_out, &ve, &vl, &vb);
+    if (rc) return rc;
+    const long long n_local = ve.rows;
+    const int d = (int)ve.cols;
+    const size_t rb = (size_t)d * 4;
+    job.d = d; job.row_bytes = rb; job.reduce = world > 1;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    h->last_h2d_bytes = 0; h->h2d_timed = false; h->h2d_timed_bytes = 0;
+    float gather_ms = 0.f;
+
+    // ---- 1. row counts of the ranks (shards may be ragged) and the dimension check
+    std::vector<long long> off((size_t)world + 1, 0);
+    {
+        CK(h->comm_buf.ensure((size_t)(world + 1) * 16));
+        long long mine[2] = {n_local, (long long)d};
+        long long* dev = h->comm_buf.as<long long>();
+        CK(cudaMemcpyAsync(dev + 2 * world, mine, 16, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = comm_all_gather(h, dev + 2 * world, dev, 16, h->stream))) return rc;
+        std::vector<long long> all((size_t)2 * world);
+        CK(cudaMemcpyAsync(all.data(), dev, (size_t)world * 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < world; ++r) {
+            if (all[2 * r + 1] != d) return h->fail(FNB_ERR_INVALID, "rank %d has embedding dimension %lld, this rank %d", r, all[2 * r + 1], d);
+            off[r + 1] = off[r] + all[2 * r];
+        }
+    }
+    const long long n = off[world];
+    job.n = n;
+    if (n > (1LL << 30)) return h->fail(FNB_ERR_INVALID, "too many rows");
+    if (n < 2) {
+        CK(h->bins.ensure(2 * (kMaxBins + 1) * 8));
+        CK(cudaMemsetAsync(h->bins.p, 0, 2 * (kMaxBins + 1) * 8, h->stream));
+        memset(job.host_bins, 0, sizeof(job.host_bins));
+        if ((rc = job.write_bins(vb))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        return FNB_OK;
+    }
+
+    // ---- 2. labels.  Every rank first puts ITS rows in class order (a local sort: the rows of a rank then form a sorted run),
+    //         the sorted label runs are exchanged (8 n bytes), and every rank sorts the concatenation of the runs itself.  The global
+    //         class order is then a MERGE of the ranks' runs: any range of it takes a CONTIGUOUS range of every run -- which is
+    //         what lets the row exchange below be cut into column chunks whatever order the caller's rows came in.
+    CK(h->lab_all.ensure((size_t)n * 8));
+    long long* lab_all = h->lab_all.as<long long>();
+    CK(h->local_perm.ensure((size_t)std::max<long long>(n_local, 1) * 8));
+    if (n_local > 0) {
+        const void* dl = nullptr;
+        if ((rc = dl_to_device(h, vl, (size_t)n_local * (vl.bits / 8), h->stage_lab, &dl))) return rc;
+        if ((rc = sort_labels(h, dl, vl.bits, n_local))) return rc;         // h->perm: local class order, h->keys_out: sorted labels
+        CK(cudaMemcpyAsync(h->local_perm.p, h->perm.p, (size_t)n_local * 8, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(lab_all + off[rank], h->keys_out.p, (size_t)n_local * 8, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (world > 1) {
+        if ((rc = comm_group_start(h))) return rc;
+        for (int r = 0; r < world; ++r)
+            if (off[r + 1] > off[r] && (rc = comm_broadcast(h, lab_all + off[r], lab_all + off[r], (size_t)(off[r + 1] - off[r]) * 8, r, h->stream))) return rc;
+        if ((rc = comm_group_end(h))) return rc;
+    }
+    if ((rc = sort_labels(h, lab_all, 64, n))) return rc;                   // h->perm: class position -> row of the concatenated runs
+
+    job.cg = pick_cta_group(&opt);
+    job.tile = kRowsPerCta * job.cg;
+    job.requested = opt.mode;
+    if ((rc = shard_from_options(h, opt, &job.shard))) return rc;
+    h->last_shard = job.shard.spec;
+
+    // column chunks of the pair matrix (class positions) and, per chunk, how many rows of every rank's run it takes
+    const bool want_stream = opt.streamed >= 0 && world > 1;
+    std::vector<long long> bounds = want_stream ? job.chunk_bounds() : std::vector<long long>{0, n};
+    const int nchunks = (int)bounds.size() - 1;
+    std::vector<long long> run_pos((size_t)(nchunks + 1) * world, 0);      // run_pos[k * world + r]: rows of run r in front of chunk k
+    {
+        std::vector<long long> meta(off.begin(), off.end());
+        meta.insert(meta.end(), bounds.begin(), bounds.end());
+        const size_t cnt_bytes = (size_t)nchunks * world * 4;
+        CK(h->comm_buf.ensure(meta.size() * 8 + cnt_bytes + 64));
+        long long* meta_dev = h->comm_buf.as<long long>();
+        unsigned int* cnt_dev = reinterpret_cast<unsigned int*>(meta_dev + meta.size());
+        CK(cudaMemcpyAsync(meta_dev, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(cnt_dev, 0, cnt_bytes, h->stream));
+        run_counts_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148LL * 8), 256, cnt_bytes, h->stream>>>(
+            h->perm.as<long long>(), n, meta_dev, world, meta_dev + world + 1, nchunks, cnt_dev);
+        CK(cudaGetLastError());
+        std::vector<unsigned int> cnt((size_t)nchunks * world);
+        CK(cudaMemcpyAsync(cnt.data(), cnt_dev, cnt_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (!ve.on_device && n_local > 0) {
+            // host rows: the copy threads gather this rank's run while they fill the pinned ring (fnb_stage.cu)
+            CK(h->perm_host.ensure((size_t)n_local * 8));
+            CK(cudaMemcpyAsync(h->perm_host.p, h->local_perm.p, (size_t)n_local * 8, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));              // meta and cnt are local vectors: consumed here
+        for (int k = 0; k < nchunks; ++k)
+            for (int r = 0; r < world; ++r) run_pos[(size_t)(k + 1) * world + r] = run_pos[(size_t)k * world + r] + cnt[(size_t)k * world + r];
+    }
+
+    // ---- 3. the rows.  Every rank needs all of them (the columns of its tiles); they travel as fp32 (4 bytes per element; the
+    //         split operands would be 6) on the copy stream, run by run: rank r's part of a chunk is gathered out of r's tensor in
+    //         class order (device rows: a gather kernel; host rows: the copy threads + the pinned ring) straight into its place
+    //         in the array of concatenated runs, and broadcast in place from there.
+    CK(h->stage_a.ensure((size_t)n * rb));
+    char* runs = h->stage_a.as<char>();
+    const char* local = (const char*)ve.data;
+    bool first_chunk = true;
+    // every run's part of chunk k: this rank's part is gathered into place, then all parts are broadcast in place by their owners
+    // (one NCCL group: the broadcasts of a chunk run side by side); the handle's stream waits for the chunk
+    auto move_chunk = [&](int k) -> int {
+        int r2;
+        if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (first_chunk) {
+            // the array may still be read by work queued earlier on the handle's stream; the local permutation is ready there too
+            CK(cudaEventRecord(h->copy_ev[0], h->stream));
+            CK(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[0], 0));
+            CK(cudaEventRecord(h->copy_ev[1], h->copy_stream));
+            h->h2d_timed = true;
+            first_chunk = false;
+        } else if (k >= 1 && (size_t)(2 * k - 1) < h->chunk_ev.size()) {
+            // Chunk k travels while launch k - 1 runs -- and not earlier: it starts when launch k - 1 is about to start (the event
+            // in front of it).  The Gram kernel is persistent with a static tile schedule: a broadcast or gather kernel that holds
+            // SMs at the moment a launch starts keeps some of its clusters from becoming resident, and the launch then ends late by
+            // their whole share (measured at 2 GPUs with the exchange running ahead: one rank's launches 17 % longer).  Started
+            // behind the launch, the exchange only ever gets the 16 SMs a 132-CTA grid leaves free.
+            CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[2 * (k - 1)], 0));
+        }
+        const bool trace = getenv("FNB_TRACE") != nullptr;
+        if (trace) {
+            while (h->xchg_ev.size() < 3 * (size_t)(k + 1)) { cudaEvent_t e = nullptr; CK(cudaEventCreate(&e)); h->xchg_ev.push_back(e); }
+            CK(cudaEventRecord(h->xchg_ev[3 * k], h->copy_stream));
+        }
+        const long long s0 = run_pos[(size_t)k * world + rank], s1 = run_pos[(size_t)(k + 1) * world + rank];
+        if (s1 > s0) {
+            char* dst = runs + (size_t)(off[rank] + s0) * rb;
+            if (ve.on_device) {
+                gather_rows_kernel<<<(unsigned)std::min<long long>((s1 - s0 + 7) / 8, 148LL * 8), 256, 0, h->copy_stream>>>(
+                    (const float*)local, h->local_perm.as<long long>() + s0, s1 - s0, d, (float*)dst);
+                CK(cudaGetLastError());
+            } else if ((r2 = stage_chunk(h, dst, local, (size_t)(s1 - s0) * rb, false, h->perm_host.as<long long>() + s0, rb))) return r2;
+        }
+        if (trace) CK(cudaEventRecord(h->xchg_ev[3 * k + 1], h->copy_stream));
+        if (world > 1) {
+            if ((r2 = comm_group_start(h))) return r2;
+            for (int r = 0; r < world; ++r) {
+                const long long a = run_pos[(size_t)k * world + r], b = run_pos[(size_t)(k + 1) * world + r];
+                char* dst = runs + (size_t)(off[r] + a) * rb;
+                if (b > a && (r2 = comm_broadcast(h, dst, dst, (size_t)(b - a) * rb, r, h->copy_stream))) return r2;
+            }
+            if ((r2 = comm_group_end(h))) return r2;
+        }
+        if (trace) CK(cudaEventRecord(h->xchg_ev[3 * k + 2], h->copy_stream));
+        CK(cudaEventRecord(h->copy_ev[2], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->copy_ev[2], 0));
+        return FNB_OK;
+    };
+
+    double bound = 0.0;
+    int fallback = 0;
+    job.stream_perm = h->perm.as<long long>();
+    if (want_stream) {
+        // chunk k + 1 travels on the copy stream while launch k runs
+        auto feed = [&](int k, long long, long long) -> int { return move_chunk(k); };
+        const int first = (job.requested == FNB_MODE_AUTO) ? (d % 128 == 0 ? FNB_MODE_FP16F8 : FNB_MODE_FP16X3) : job.requested;
+        if ((rc = job.pass_streamed(first, &bound, bounds, feed))) return rc;
     } else {
-        memcpy(vb.data, host_bins, 2 * row_bytes);
+        // streaming switched off (or one rank): everything first, then one launch
+        if ((rc = move_chunk(0))) return rc;
+        job.de = runs;
+        job.perm_dev = h->perm.as<long long>();
+        if ((rc = job.pass(job.requested, &bound))) return rc;
     }
+    if ((rc = job.finish_auto(bound, &fallback))) return rc;
     if (stats) {
-        stats->kernel_launches += 3;      // labels_to_keys, boundary_flags, split_rows (+ the Gram kernel counted above)
-        stats->n_pairs = sum_bins(host_bins, T + 1);
-        stats->error_bound = (float)bound;
-        stats->fallback = fallback;
+        if (cudaEventElapsedTime(&gather_ms, h->copy_ev[1], h->copy_ev[2]) == cudaSuccess) stats->gather_ms = gather_ms;
+        stats->h2d_ms = 0.f;
     }
-    return FNB_OK;
+    return job.write_bins(vb);
 }
 
 extern "C" int fnb_counts_from_bins(const double* thresholds, int T, const fnb_options* opt_in, const uint64_t* bins,

@@ -62,7 +62,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 }  // namespace fnb
 
-namespace fnb { struct HostCopier; void destroy_copier(HostCopier*); }
+namespace fnb { struct HostCopier; void destroy_copier(HostCopier*); struct Comm; }
 
 struct fnb_context {
     int device = 0;
@@ -73,6 +73,7 @@ struct fnb_context {
     cudaStream_t own_stream = nullptr;   // created by fnb_create
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> chunk_ev;   // streamed histogram launches: one (start, end) pair per launch
+    std::vector<cudaEvent_t> xchg_ev;    // FNB_TRACE: three events per chunk of a sharded row exchange
     int chunk_launches = 0;              // launches of the last streamed pass (0: one launch timed by ev[1] .. ev[2])
     fnb::PFN_tmapEncodeTiled encode = nullptr;
     std::string err;
@@ -99,6 +100,8 @@ struct fnb_context {
     cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};
     fnb::HostCopier* copier = nullptr;
+    fnb::Comm* comm = nullptr;           // NCCL communicator of a sharded job (fnb_comm_init, fnb_comm.cu)
+    fnb::DevBuf comm_buf, lab_all, local_perm;   // sharded jobs: row counts of the ranks / chunk metadata, all labels as int64, class order of this rank's rows
     int ring_next = 0;                   // next ring slot of a chunked upload (stage_chunk)
     size_t last_h2d_bytes = 0;           // host -> device bytes of the call in progress
     size_t h2d_timed_bytes = 0;          // size of the copy those events bracket
@@ -192,6 +195,16 @@ cudaError_t launch_split_rows(int mode, const float* x, const long long* perm, l
                               long long row_begin = 0, long long row_end = -1);     // rows of [0, n_pad) to write (-1: n_pad)
 cudaError_t launch_strict_blocks(const int32_t* cls, int n, int tile, int nb, unsigned int* bits, cudaStream_t s);
 int sort_labels(fnb_context* h, const void* labels_dev, int label_bits, long long n);   // fills h->perm (i64), h->cls (i32)
+
+// fnb_comm.cu (NCCL, resolved at run time)
+int comm_world(const fnb_context* h);
+int comm_rank(const fnb_context* h);
+int comm_all_gather(fnb_context* h, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
+int comm_broadcast(fnb_context* h, const void* send, void* recv, size_t bytes, int root, cudaStream_t s);
+int comm_group_start(fnb_context* h);
+int comm_group_end(fnb_context* h);
+int comm_all_reduce_u64(fnb_context* h, void* buf, size_t count, bool max_op, cudaStream_t s);
+void comm_release(fnb_context* h);
 
 // fnb_gram.cu
 int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const GramOperands& op, GramParams& p, size_t hist_bytes);

@@ -9,8 +9,10 @@ triangle regardless of N (no triangle imbalance).  Exchange steps:
   2. all-reduce (sum) of the [2, T+1] int64 histogram bins -- integer, so the result is identical for
      every world size.
 
-``hist_fn`` is the per-rank compute call; the default is the CUDA library.  The CPU tests (gloo,
-world_size 2) inject the NumPy stand-in to exercise this plumbing without a GPU.
+Both steps run inside the library (``fnb_comm_init`` / ``fnb_pair_histogram_sharded``, NCCL behind the C ABI) -- a host
+without torch can shard too; ``torch.distributed`` only carries the 128-byte communicator id here.  ``hist_fn`` replaces the
+per-rank compute call: the CPU tests (gloo, world_size 2) inject a NumPy stand-in and ``torch.distributed`` then does the
+all-gather and the all-reduce around it.
 """
 import numpy as np
 
@@ -110,35 +112,94 @@ def gather_shards(emb_shard, labels_shard, group=None):
     return emb, labels
 
 
+_native = {}
+
+
+def native_handle(device_index, group=None):
+    """The library handle of this process's GPU with an NCCL communicator over ``group`` (made on first use: rank 0's
+    ``ncclUniqueId`` travels through the group's own broadcast; the communicator itself lives behind the C ABI)."""
+    import torch.distributed as dist
+    from facenet_b200 import _capi
+    key = (int(device_index), id(group) if group is not None else None)
+    h = _native.get(key)
+    if h is None:
+        h = _capi.default_handle(int(device_index))
+        if getattr(h, 'comm', None) is None or h.comm[1] != dist.get_world_size(group):
+            h.comm_init_from_torch(group)
+        _native[key] = h
+    return h
+
+
 def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=None, hist_fn=None, balancer=None, **kw):
-    """Every rank passes its shard (torch tensors on its device, equal row counts); returns on every
-    rank ``(bins [2, T+1] int64 torch tensor summed over ranks, stats of this rank)``.
+    """Every rank passes its shard (torch tensors on its device, or host arrays); returns on every rank
+    ``(bins [2, T+1] int64 torch tensor summed over ranks, stats of this rank)``.
+
+    Default (``hist_fn=None``, an initialised process group, a GPU): the exchange and the reduction run INSIDE the library
+    (``fnb_pair_histogram_sharded``: labels first, rows by ncclBroadcast from their owner on a side stream -- chunk by chunk
+    under the Gram launches when the shards are in class order -- and an ncclAllReduce of the integer bins).
+    ``hist_fn`` given (the CPU tests inject a NumPy stand-in): ``torch.distributed`` does the all-gather and the all-reduce
+    around it.  An error on one rank (embeddings not normalised, ...) is raised on EVERY rank -- never a hang in the all-reduce.
 
     ``balancer`` (a ``ShardBalancer``, e.g. ``default_balancer(world)``): split the work by measured GPU speed and keep
     adapting; ``None`` = equal shares."""
     import torch
     import torch.distributed as dist
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
-    emb, labels = gather_shards(emb_shard, labels_shard, group)
     thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
-    bins = torch.zeros((2, thr.size + 1), dtype=torch.int64, device=emb.device)
-    if hist_fn is None:
-        hist_fn = _default_hist_fn(emb.device.index or 0)
     if balancer is not None and world > 1:
         if balancer._pending is not None:
             # times of the previous step: that all-reduce finished long ago, reading it now does not stall the GPU
             balancer.update(balancer._pending.tolist())
             balancer._pending = None
         kw = dict(kw, shard=balancer.spec(rank))
-    stats = hist_fn(emb, labels, thr, metric, rank, world, bins, **kw)
+    if hist_fn is None and world > 1 and torch.cuda.is_available():
+        dev = emb_shard.device if getattr(emb_shard, 'is_cuda', False) else torch.device('cuda', torch.cuda.current_device())
+        handle = native_handle(dev.index or 0, group)
+        bins = torch.zeros((2, thr.size + 1), dtype=torch.int64, device=dev)
+        from facenet_b200 import _capi
+        try:
+            _, stats = handle.pair_histogram_sharded(emb_shard, labels_shard, thr, metric, bins_out=bins, **kw)
+        except _capi.FnbError as e:
+            if e.code == _capi.FNB_ERR_NOT_NORMALIZED:       # the reference's exception (statistics.py:40-42), on every rank
+                raise ValueError(str(e)) from None
+            raise
+        _exchange_times(balancer, stats, rank, world, dev, group)
+        return bins, stats
+    emb, labels = gather_shards(emb_shard, labels_shard, group)
+    # one spare slot per row carries the ranks' error flags through the same all-reduce as the bins
+    buf = torch.zeros((2, thr.size + 2), dtype=torch.int64, device=emb.device)
+    bins = buf[:, :thr.size + 1]
+    if hist_fn is None:
+        hist_fn = _default_hist_fn(emb.device.index or 0)
+    stats, err = None, None
+    try:
+        local = torch.zeros((2, thr.size + 1), dtype=torch.int64, device=emb.device)
+        stats = hist_fn(emb, labels, thr, metric, rank, world, local, **kw)
+        bins.copy_(local)
+    except Exception as e:          # raised below, on every rank
+        err = e
+        buf[0 if isinstance(e, ValueError) else 1, thr.size + 1] = 1
     if world > 1:
-        dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
-        if balancer is not None and isinstance(stats, dict) and 'kernel_ms' in stats:
-            times = torch.zeros(world, dtype=torch.float64, device=emb.device)
-            times[rank] = float(stats['kernel_ms'])
-            dist.all_reduce(times, op=dist.ReduceOp.SUM, group=group)
-            balancer._pending = times
-    return bins, stats
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    flags = buf[:, thr.size + 1].tolist() if (world > 1 or err is not None) else (0, 0)
+    if err is not None:
+        raise err
+    if flags[0]:
+        raise ValueError('embeddings must be normalized to 1 (reported by another rank)')
+    if flags[1]:
+        raise RuntimeError('pair_histogram_sharded failed on another rank')
+    _exchange_times(balancer, stats, rank, world, emb.device, group)
+    return bins.contiguous(), stats
+
+
+def _exchange_times(balancer, stats, rank, world, device, group):
+    import torch
+    import torch.distributed as dist
+    if world > 1 and balancer is not None and isinstance(stats, dict) and 'kernel_ms' in stats:
+        times = torch.zeros(world, dtype=torch.float64, device=device)
+        times[rank] = float(stats['kernel_ms'])
+        dist.all_reduce(times, op=dist.ReduceOp.SUM, group=group)
+        balancer._pending = times
 
 
 def counts_from_bins(bins, thresholds, metric=0):

@@ -164,6 +164,8 @@ typedef struct {
                               Pageable memory goes through a ring of pinned slots filled by a pool of host threads while the
                               previous slot is in flight (csrc/fnb_stage.cu); pinned memory is copied in place */
     uint64_t h2d_bytes;    /* bytes copied host -> device by the call */
+    float    gather_ms;    /* fnb_pair_histogram_sharded: device time from the first to the last piece of the row exchange on the copy
+                              stream (uploads of this rank's rows + broadcasts); all but the first chunk of it runs under the launches */
     int32_t  streamed_chunks; /* launches of a streamed pass (fnb_options.streamed; 0: one upload, one launch); kernel_ms is then
                               the sum of the launches' durations */
 } fnb_stats;
@@ -207,6 +209,35 @@ int fnb_pairwise(fnb_handle h, const DLTensor* xa, const DLTensor* xb, const fnb
 int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const DLTensor* labels,
                             const double* thresholds, int T, const fnb_options* opt,
                             DLTensor* bins_out, fnb_stats* stats);
+
+/* ---- multi-GPU inside the library: one process per GPU, one handle per process, NCCL over NVLink / NVSwitch -----------------
+ * (north_star: "each GPU takes row blocks of the pair matrix, the small embedding matrix is all-gathered over NVLink with NCCL, and
+ * the per-threshold count histograms are all-reduced".)  NCCL is resolved at run time: the libnccl.so.2 already loaded into the
+ * process (torch's), else the system's, else the path in FNB_NCCL_LIB.
+ *   fnb_comm_unique_id: rank 0 fills 128 bytes (an ncclUniqueId) and ships them to the other processes by any means;
+ *   fnb_comm_init:      every process, same id; collective (returns when the communicator is up);
+ *   fnb_comm_destroy:   releases it (fnb_destroy does too);  fnb_comm_info: rank / world / NCCL version in use.
+ * fnb_comm_last_error: text of a failed fnb_comm_unique_id (which has no handle). */
+int fnb_comm_unique_id(void* id128);
+int fnb_comm_init(fnb_handle h, const void* id128, int rank, int world);
+int fnb_comm_destroy(fnb_handle h);
+int fnb_comm_info(fnb_handle h, int* rank, int* world, int* nccl_version);
+const char* fnb_comm_last_error(void);
+
+/* fnb_pair_histogram_bins over a set that is spread over the ranks of the handle's communicator: every rank passes ITS rows
+ * (emb_shard [n_r, D], labels_shard [n_r]; host or device; the shards may differ in size; the set is their concatenation in
+ * rank order) and receives the bins of the WHOLE set (already summed: ncclAllReduce of the [2, T+1] integer bins), identical
+ * on every rank and identical to the one-GPU result.  Collective: every rank must call it with the same thresholds / options.
+ *   exchange: 8 N bytes of labels first (every rank sorts the classes itself), then the fp32 rows by ncclBroadcast from their
+ *   owner straight into place.  When the concatenation is already in class order (labels non-decreasing across the ranks) the
+ *   exchange is cut into column chunks of the pair matrix and chunk k + 1 travels on the copy stream while launch k runs
+ *   (fnb_options.streamed; fnb_stats.streamed_chunks, gather_ms): only the first chunk's transfer is exposed.  Otherwise all
+ *   rows are gathered first.  opt->rank / world are taken from the communicator; shard_* (unequal shares) are honoured.
+ *   A similarity out of range on ANY rank fails the call on EVERY rank (FNB_ERR_NOT_NORMALIZED), and AUTO's choice between
+ *   FP16F8 and the strict pass is agreed between the ranks. */
+int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shard, const DLTensor* labels_shard,
+                               const double* thresholds, int T, const fnb_options* opt,
+                               DLTensor* bins_out, fnb_stats* stats);
 
 /* Host-side conversion of (summed) bins into per-threshold counts:
  *   same_lt[n] = #{same-identity pairs with d < thresholds[n]}, diff_lt[n] likewise (strict <,

@@ -48,6 +48,11 @@ py)         # any python script with arguments, log name first
     timeout 1200 python "$@" > $O/$name.log 2>&1; echo "exit=$?" >> $O/$name.log
     tail -${TAIL:-60} $O/$name.log
     ;;
+torchrun)   # N ranks of any script: name, N, then the script and its arguments
+    name=$1; n=$2; shift 2
+    timeout ${TORCHRUN_TIMEOUT:-900} python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 "$@" > $O/$name.log 2>&1; echo "exit=$?" >> $O/$name.log
+    grep -v "^\[W\|^W[0-9]\|OMP_NUM_THREADS\|^\*\*\*" $O/$name.log | tail -${TAIL:-80} | cut -c1-${CUT:-600}
+    ;;
 multi)      # several jobs in one session:  multi "job1 args" "job2 args" ...
     for j in "$@"; do echo "=== $j"; bash scripts/gpu_job.sh $j; done
     ;;

@@ -73,6 +73,21 @@ def _worker(rank, world, port, x, labels, result):
         gathered = [torch.zeros_like(bins) for _ in range(world)]
         dist.all_gather(gathered, bins)
         assert all(torch.equal(g, bins) for g in gathered)
+
+        # an error on ONE rank is raised on EVERY rank (no rank is left waiting in the all-reduce), and the next call works
+        def failing(emb, lab, thresholds, metric, rank_, world_, bins_out, **kw):
+            if rank_ == 1:
+                raise ValueError('embeddings must be normalized to 1, range -1 1.5')
+            return _emulated_hist(emb, lab, thresholds, metric, rank_, world_, bins_out, **kw)
+        try:
+            fd.pair_histogram_sharded(xs, ls, thr, 0, hist_fn=failing)
+            raised = None
+        except ValueError as e:
+            raised = str(e)
+        assert raised is not None and 'normalized' in raised
+        result['raised_%d' % rank] = raised
+        again, _ = fd.pair_histogram_sharded(xs, ls, thr, 0, hist_fn=_emulated_hist)
+        assert torch.equal(again, bins)
     finally:
         dist.destroy_process_group()
 
@@ -86,6 +101,7 @@ def test_two_rank_histogram_equals_single_process():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, x, labels, result), nprocs=2, join=True)
     assert result['n'] == (ref['n_same'], ref['n_diff'])
+    assert 'another rank' in result['raised_0'] and 'range' in result['raised_1']
     assert np.abs(result['same'] - ref['same']).sum() + np.abs(result['diff'] - ref['diff']).sum() <= 2
 
 

@@ -454,7 +454,7 @@ def test_histogram_streamed_upload_identical_bins(handle):
     np.testing.assert_array_equal(got, ref)
     # un-normalised rows still raise the reference's error
     bad = x.copy(); bad[3000] = bad[3001] * 1.01          # s(3000, 3001) = 1.01 > 1 + atol
-    with pytest.raises(ValueError, match='normalized'):
+    with pytest.raises(_capi.FnbError, match='normalized'):
         handle.pair_histogram_bins(bad, labels, thr, 0, streamed=1, region_rows=512)
     # rows out of class order: the host threads gather them in class order while they fill the pinned ring (pageable and pinned)
     perm = np.random.default_rng(1).permutation(x.shape[0])
