@@ -53,7 +53,7 @@ class Options(ctypes.Structure):
                 ('raw_distance', ctypes.c_int32), ('subset_rows', ctypes.c_int32), ('shard_mod', ctypes.c_int32),
                 ('shard_lo', ctypes.c_int32), ('shard_width', ctypes.c_int32), ('shard_slots', ctypes.POINTER(ctypes.c_int32)),
                 ('panel_window', ctypes.c_int32), ('strict_tiles', ctypes.c_int32), ('bias_correction', ctypes.c_int32),
-                ('streamed', ctypes.c_int32)]
+                ('streamed', ctypes.c_int32), ('tile_queue', ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -396,7 +396,7 @@ class Handle:
 
     def options(self, mode='fp16x3', metric=0, atol=1.e-5, eps=1.e-5, rank=0, world=1, cta_group=0, region_rows=0,
                 cuts=None, max_ctas=0, force_checked=False, cluster_pairs=0, normalize=0, theta=0.0, raw_distance=False,
-                shard=None, subset_rows=0, panel_window=None, strict_tiles=None, bias_correction=None, streamed=None):
+                shard=None, subset_rows=0, panel_window=None, strict_tiles=None, bias_correction=None, streamed=None, tile_queue=None):
         o = Options()
         self.lib.fnb_default_options(ctypes.byref(o))
         o.mode = MODES[mode] if isinstance(mode, str) else int(mode)
@@ -421,6 +421,8 @@ class Handle:
         o.bias_correction = int(os.environ.get('FNB_BIAS_CORRECTION', '0')) if bias_correction is None else int(bias_correction)
         # chunked upload under the launches for host rows in class order: 0 = auto, 1 = always, -1 = off (fnb_options.streamed)
         o.streamed = int(os.environ.get('FNB_STREAMED', '0')) if streamed is None else int(streamed)
+        # tile queue of the histogram launches: 0 = on (+ the second launch on the free SMs), 2 = queue only, -1 = static schedule
+        o.tile_queue = int(os.environ.get('FNB_TILE_QUEUE', '0')) if tile_queue is None else int(tile_queue)
         keep = None
         if cuts is not None:
             keep = np.ascontiguousarray(cuts, dtype=np.float32)
@@ -463,7 +465,7 @@ class Handle:
     def pair_histogram_bins(self, embeddings, labels, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='fp16x3',
                             rank=0, world=1, cta_group=0, region_rows=0, bins_out=None, max_ctas=0, cuts='numpy',
                             force_checked=False, cluster_pairs=0, normalize=0, shard=None, panel_window=None,
-                            strict_tiles=None, bias_correction=None, streamed=None):
+                            strict_tiles=None, bias_correction=None, streamed=None, tile_queue=None):
         embeddings = _as_f32_matrix(embeddings, 'embeddings')
         labels = _as_labels(labels)
         thr = np.ascontiguousarray(np.atleast_1d(thresholds), dtype=np.float64)
@@ -472,7 +474,7 @@ class Handle:
         o, keep = self.options(mode=mode, metric=metric, atol=atol, eps=eps, rank=rank, world=world, cta_group=cta_group,
                                region_rows=region_rows, cuts=cuts, max_ctas=max_ctas, force_checked=force_checked,
                                cluster_pairs=cluster_pairs, normalize=normalize, shard=shard, panel_window=panel_window,
-                               strict_tiles=strict_tiles, bias_correction=bias_correction, streamed=streamed)
+                               strict_tiles=strict_tiles, bias_correction=bias_correction, streamed=streamed, tile_queue=tile_queue)
         if bins_out is None:
             bins_out = np.zeros((2, thr.size + 1), dtype=np.uint64)
         st = Stats()

@@ -409,6 +409,9 @@ extern "C" void fnb_destroy(fnb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
+    for (int i = 0; i < 2; ++i) if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
+    h->tile_counter.release();
     DevBuf* bufs[] = {&h->stage_a, &h->stage_b, &h->stage_lab, &h->a_hi, &h->a_lo, &h->b_hi, &h->b_lo, &h->a_h8, &h->b_h8, &h->a_l16, &h->b_l16, &h->bias_tab, &h->strict_bits, &h->a_nrm, &h->b_nrm, &h->shard_slots, &h->progress, &h->perm, &h->cls,
                       &h->keys_in, &h->keys_out, &h->vals_in, &h->flags, &h->cub_tmp, &h->regions, &h->tables, &h->bins,
                       &h->counters, &h->out, &h->strip, &h->mine_out, &h->scan, &h->select_io, &h->mine_lab, &h->mine_keys, &h->mine_status};
@@ -776,6 +779,37 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     CK(h->progress.ensure((size_t)nlaunch * 1024 * 4));
     CK(cudaMemsetAsync(h->progress.p, 0, (size_t)nlaunch * 1024 * 4, h->stream));
     p.progress = h->progress.as<unsigned int>();
+    // tile queue (fnb_options.tile_queue): on for every histogram launch; the auxiliary launch on the free SMs only for one-GPU
+    // jobs (a sharded job's row exchange runs there) and never under the profiling knobs
+    const bool use_queue = opt.tile_queue >= 0 && opt.panel_window <= 0;     // (an explicit progress window asks for the static schedule)
+    const bool use_aux = use_queue && opt.tile_queue != 2 && opt.world == 1 && opt.max_ctas == 0 && op.pairs == 2;
+    if (use_queue) {
+        CK(h->tile_counter.ensure((size_t)nlaunch * 8));
+        CK(cudaMemsetAsync(h->tile_counter.p, 0, (size_t)nlaunch * 8, h->stream));
+        p.tile_counter = h->tile_counter.as<unsigned long long>();
+        p.sync_window = 0;
+        h->last_window = 0;
+    }
+    if (use_aux && !h->aux_stream) {
+        CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->aux_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->aux_ev[1], cudaEventDisableTiming));
+    }
+    auto hist_bytes_of = [](const GramParams& pl) { return (size_t)pl.nb8 * kHist8Row; };
+    // main launch, then (behind it) the pairs on the SMs it leaves free; the handle's stream continues after both
+    auto launch_both = [&](GramParams& pl) -> int {
+        int r2;
+        // the auxiliary launch starts BEHIND the main one (the event in front of it): the main grid takes its SMs first
+        if (use_aux) CK(cudaEventRecord(h->aux_ev[0], h->stream));
+        if ((r2 = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, pl, hist_bytes_of(pl)))) return r2;
+        if (use_aux) {
+            CK(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
+            if ((r2 = launch_gram_aux(h, op, pl, hist_bytes_of(pl)))) return r2;
+            CK(cudaEventRecord(h->aux_ev[1], h->aux_stream));
+            CK(cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0));
+        }
+        return FNB_OK;
+    };
     p.row_cls = cls_dev; p.col_cls = cls_dev;
     p.cuts = h->tables.as<float>(); p.wlo = p.cuts + kMaxBins; p.whi = p.wlo + kMaxBins + 4;
     p.T = T; p.T_fin = hl.ct.T_fin; p.uniform = hl.ct.uniform;
@@ -828,11 +862,10 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     DeviceScalars* sc = h->counters.as<DeviceScalars>();
     p.counters = sc->counters; p.range_ord = sc->range_ord;
     p.metric = opt.metric;
-    const size_t hist_bytes = (size_t)p.nb8 * kHist8Row;
     h->chunk_launches = 0;
     if (!hl.chunks) {
         CK(cudaEventRecord(h->ev[1], h->stream));
-        if ((rc = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, p, hist_bytes))) return rc;
+        if ((rc = launch_both(p))) return rc;
         CK(cudaEventRecord(h->ev[2], h->stream));
     } else {
         while (h->chunk_ev.size() < 2 * (size_t)nlaunch) {
@@ -847,11 +880,12 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
             p.regions = h->regions.as<RegionDev>() + off;
             p.nregions = (int)rv.size() - 1;
             p.total_tiles = rv.back().tile_begin;
-            p.sync_window = window_of(rv);
+            p.sync_window = use_queue ? 0 : window_of(rv);
             p.progress = h->progress.as<unsigned int>() + (size_t)k * 1024;
+            if (use_queue) p.tile_counter = h->tile_counter.as<unsigned long long>() + k;
             off += rv.size();
             CK(cudaEventRecord(h->chunk_ev[2 * k], h->stream));
-            if (p.total_tiles > 0 && (rc = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, p, hist_bytes))) return rc;
+            if (p.total_tiles > 0 && (rc = launch_both(p))) return rc;
             CK(cudaEventRecord(h->chunk_ev[2 * k + 1], h->stream));
         }
         h->chunk_launches = nlaunch;

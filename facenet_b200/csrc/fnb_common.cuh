@@ -125,6 +125,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Cluster-scope forms for barriers that guard GENERIC-proxy data written by another CTA (the tile-queue ring): the writer
+// stores with st.shared::cluster and arrives with release.cluster, the reader waits with acquire.cluster.
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+
+__device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" :: "r"(cluster_addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000u) : "memory");
+        if (ok) return;
+        if (spins > FNB_SPIN_LIMIT) __trap();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // TMA (bulk tensor copy global -> shared, completion on an mbarrier)
 

@@ -21,7 +21,7 @@ template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi, int kPairs = 1>
 static int launch_one(fnb_context* h, int max_ctas, const GramOperands& op, const GramParams& p, size_t smem)
 {
     constexpr int kCluster = kCtaGroup * kPairs;
-    auto kern = gram_kernel<kCtaGroup, kNumPass, kTf32, kEpi, kPairs>;
+    auto kern = gram_kernel<kCtaGroup, kNumPass, kTf32, kEpi, kPairs, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
     cudaLaunchConfig_t cfg = {};
@@ -76,6 +76,47 @@ static int launch_mode(fnb_context* h, int max_ctas, const GramOperands& op, con
     if (op.num_pass == 1 && !op.tf32) return launch_one<kCtaGroup, 1, false, kEpi>(h, max_ctas, op, p, smem);
     if (op.num_pass == 1 && op.tf32)  return launch_one<kCtaGroup, 1, true, kEpi>(h, max_ctas, op, p, smem);
     return h->fail(FNB_ERR_INVALID, "no kernel for num_pass=%d tf32=%d", op.num_pass, (int)op.tf32);
+}
+
+// The SMs a grid of two-pair clusters leaves free (16 of 148: four-CTA clusters do not tile the GPCs) run plain CTA pairs on the
+// SAME tile queue: a second launch on the handle's auxiliary stream, started behind the main launch (an event in front of
+// it), that walks the main launch's 256 x 512 super-tiles two tiles at a time.  Self Gram products only (the full-height
+// B-side maps serve as A maps too).  The caller orders the handle's stream after it (aux_done).
+template <int kNumPass>
+static int launch_aux_pairs(fnb_context* h, int ctas, const GramOperands& op, const GramParams& p, size_t smem)
+{
+    auto kern = gram_kernel<2, kNumPass, false, EPI_HIST, 1, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kGramThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->aux_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, op.b_hi, op.b_lo, op.b_hi, op.b_lo, op.b_h8, op.b_h8, op.b_l16, op.b_l16, p);
+    if (e != cudaSuccess) return h->fail(FNB_ERR_CUDA, "gram kernel launch (auxiliary pairs): %s", cudaGetErrorString(e));
+    return FNB_OK;
+}
+
+int launch_gram_aux(fnb_context* h, const GramOperands& op, const GramParams& p_main, size_t hist_bytes)
+{
+    const int ctas = (h->sm_count - h->last_grid) & ~1;
+    if (ctas < 2 || op.pairs != 2 || op.tf32 || (op.num_pass != 2 && op.num_pass != 3) || p_main.tile_counter == nullptr) return FNB_OK;
+    GramParams p = p_main;
+    p.sync_window = 0;
+    const size_t smem = gram_smem_bytes(p.num_slots, hist_bytes);
+    if (!h->aux_stream) return h->fail(FNB_ERR_INVALID, "auxiliary stream missing");
+    int rc = op.num_pass == 2 ? launch_aux_pairs<2>(h, ctas, op, p, smem) : launch_aux_pairs<3>(h, ctas, op, p, smem);
+    if (rc) return rc;
+    h->last_grid += ctas;
+    return FNB_OK;
 }
 
 int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const GramOperands& op, GramParams& p, size_t hist_bytes)

@@ -160,7 +160,18 @@ struct GramParams {
     int strict_tiles;
     const unsigned int* strict_bits;   // strict_tiles == 1: bit (R / 512) * strict_nb + C / 512 of the block at (R, C)
     int strict_nb;
+    // Tile queue (HIST launches; NULL: every cluster walks its static share, tile = cluster_id + i * num_clusters).  One 64-bit
+    // counter, zeroed before the launch; a cluster takes its next super-tile with one atomicAdd (warp 3 of the cluster's first
+    // CTA fetches a few tiles ahead and hands the index to every role of every CTA of the cluster through a small ring in
+    // shared memory).  Tiles leave in schedule order -- row blocks fastest inside a column panel -- so at any time all clusters
+    // work inside the same one or two column panels (no drift, no progress window), a cluster that starts late or runs on a
+    // slower SM simply takes fewer tiles, and a SECOND launch of another cluster shape can drain the same queue (the 16 SMs a
+    // grid of 4-CTA clusters cannot use run CTA pairs on it: fnb_gram.cu).  The integer bins do not depend on who took which tile.
+    unsigned long long* tile_counter;
 };
+
+constexpr int kSchedDepth = 4;                     // raw tile indices in flight per cluster (fetch warp -> decode warps)
+constexpr int kTileRing = 8;                       // decoded tiles per CTA (the producer runs two tiles ahead of the epilogue, and every role looks one tile ahead)
 
 constexpr int kBiasKnots  = 41;                    // |s| = 0, 0.025, ..., 1
 constexpr int kBiasStride = 44;
@@ -188,7 +199,10 @@ struct TileInfo {
     int row0, col0, row_end, col_end, tri, key;
     int gcp;                   // launch-wide index of the tile's column panel (non-decreasing along a cluster's tile sequence)
     int cbeg;                  // first column of the tile's region (ROWSTRIP writes region-local column indices)
+    int strictq;               // tile queue: the strict flag of the tile, decided by the CTA's decode warp (-1: static schedule)
 };
+
+constexpr int kTileWords = 12;                     // one decoded queue entry: the nine ints of TileInfo, padded to three 16-byte words
 
 // One scheduler step hands a cluster a SUPER-TILE of (kPR * kTile) rows x (kPC * kTile) columns; the CTA pair at
 // (pair_row, pair_col) of the cluster's kPR x kPC pair grid owns the tile at [row0 + pair_row * kTile, col0 + pair_col *
@@ -196,11 +210,13 @@ struct TileInfo {
 template <int kPairs> struct Sched_PR { static constexpr int value = (kPairs == 4) ? 2 : 1; };
 template <int kPairs> struct Sched_PC { static constexpr int value = (kPairs == 1) ? 1 : 2; };
 
-template <int kCtaGroup, int kPairs = 1>
+// kSub > 1 (kPairs == 1 only): the scheduler step is kSub tiles wide and the pair works through them one after the other --
+// a launch of plain CTA pairs walking the schedule of a launch of two-pair clusters (same super-tiles, same tile queue).
+template <int kCtaGroup, int kPairs = 1, int kSub = 1>
 struct TileScheduler {
     static constexpr int kTile = kRowsPerCta * kCtaGroup;
     static constexpr int kSuperRows = kTile * Sched_PR<kPairs>::value;
-    static constexpr int kSuperCols = kTile * Sched_PC<kPairs>::value;
+    static constexpr int kSuperCols = kTile * Sched_PC<kPairs>::value * kSub;
     const RegionDev* regions;
     long long pos, stride, total;
     int cur;
@@ -209,12 +225,62 @@ struct TileScheduler {
     RegionDev r;
     int cb, j;                 // column panel; index among this rank's row blocks of the region
     bool fresh;                // (cb, j) must be recomputed from pos (first call, or a new region)
+    // tile queue (GramParams::tile_counter): the roles read DECODED tiles from a ring in shared memory that the CTA's decode
+    // warp fills -- no division, no global load and no remote traffic on the roles' side
+    const int* qtiles;         // [kTileRing][kTileWords]
+    uint64_t* qfull;           // [kTileRing] entry written (one arrive: the decode warp)
+    uint64_t* qempty;          // [kTileRing] entry read by every role of this CTA
+    int qslot; uint32_t qphase;
+    long long next_begin;      // locate(): first tile of the next region
 
     __device__ TileScheduler(const GramParams& p, int cluster_id, int num_clusters)
         : regions(p.regions), pos(cluster_id), stride(num_clusters), total(p.total_tiles), cur(0), shard(p.shard),
-          cb(0), j(0), fresh(true) {}
+          cb(0), j(0), fresh(true), qtiles(nullptr), qfull(nullptr), qempty(nullptr), qslot(0), qphase(0), next_begin(0) {}
 
+    __device__ void use_queue(const int* tiles_, uint64_t* full_, uint64_t* empty_) { qtiles = tiles_; qfull = full_; qempty = empty_; }
+
+    __device__ void fill(TileInfo& t, int rb) const {
+        t.row0 = r.row_begin + rb * kSuperRows;
+        t.col0 = r.col_begin + cb * kSuperCols;
+        t.row_end = r.row_end;
+        t.col_end = r.col_end;
+        t.tri = r.tri;
+        t.key = r.key;
+        t.gcp = r.cp_begin + cb;
+        t.cbeg = r.col_begin;
+        t.strictq = -1;
+    }
+
+    // decode warp: tile index (indices only grow) -> tile; false when the tile lies entirely on / below the diagonal
+    __device__ bool locate(long long id, TileInfo& t) {
+        if (fresh || id >= next_begin) {
+            while (id >= regions[cur + 1].tile_begin) ++cur;
+            r = regions[cur];                                   // one global load per REGION, not per tile
+            next_begin = regions[cur + 1].tile_begin;
+            fresh = false;
+        }
+        const int li = (int)(id - r.tile_begin);
+        cb = li / r.own_cnt;
+        j = li - cb * r.own_cnt;
+        const int rb = (shard.width == 1 && shard.slots == nullptr) ? j * shard.mod + shard.lo : shard.block(j);
+        fill(t, rb);
+        return !(r.tri && t.col0 + kSuperCols - 1 <= t.row0);
+    }
+
+    // every lane of the calling warp runs this (warp-uniform)
     __device__ bool next(TileInfo& t) {
+        if (qtiles != nullptr) {
+            mbar_wait(&qfull[qslot], qphase);
+            const int4* e = reinterpret_cast<const int4*>(qtiles + qslot * kTileWords);
+            const int4 a = e[0], b = e[1], c = e[2];
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&qempty[qslot]);
+            if (++qslot == kTileRing) { qslot = 0; qphase ^= 1u; }
+            if (a.x < 0) return false;                          // the queue is empty
+            t.row0 = a.x; t.col0 = a.y; t.row_end = a.z; t.col_end = a.w;
+            t.tri = b.x; t.key = b.y; t.gcp = b.z; t.cbeg = b.w; t.strictq = c.x;
+            return true;
+        }
         while (pos < total) {
             if (fresh || pos >= regions[cur + 1].tile_begin) {
                 while (pos >= regions[cur + 1].tile_begin) ++cur;
@@ -225,14 +291,7 @@ struct TileScheduler {
                 fresh = false;
             }
             const int rb = (shard.width == 1 && shard.slots == nullptr) ? j * shard.mod + shard.lo : shard.block(j);
-            t.row0 = r.row_begin + rb * kSuperRows;
-            t.col0 = r.col_begin + cb * kSuperCols;
-            t.row_end = r.row_end;
-            t.col_end = r.col_end;
-            t.tri = r.tri;
-            t.key = r.key;
-            t.gcp = r.cp_begin + cb;
-            t.cbeg = r.col_begin;
+            fill(t, rb);
             // advance by `stride` tiles inside the region (row blocks fastest)
             pos += stride;
             j += (int)stride;
@@ -251,6 +310,12 @@ struct __align__(16) GramSmemMisc {
     uint64_t tempty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
+    uint64_t ring_full[kSchedDepth];    // tile queue, raw indices: "written" (this CTA's copy, signalled by the cluster's fetch warp)
+    uint64_t ring_empty[kSchedDepth];   // "read by the decode warp of every CTA" (the first CTA's copy is the one in use)
+    uint64_t tile_full[kTileRing];      // decoded tiles of this CTA: "written" (its decode warp)
+    uint64_t tile_empty[kTileRing];     // "read by every role of this CTA"
+    int32_t ring[kSchedDepth];
+    __align__(16) int32_t tiles[kTileRing][kTileWords];
     float cuts[kMaxBins];
     float wlo[kMaxBins + 4];
     float whi[kMaxBins + 4];
@@ -317,7 +382,9 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
 // the A rows, so every A box is read from L2 ONCE and multicast to the matching CTA of both pairs (each of the two
 // CTAs issues one 64-row half of it).  L2 -> SM operand traffic drops to 3/4; the two pairs run in lockstep
 // (a slot is refilled only after BOTH pairs' MMAs have consumed it).
-template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi, int kPairs = 1>
+// kSub == 2 (kPairs == 1, HIST only): a launch of plain CTA pairs that walks the 256 x 512 super-tiles of a two-pair-cluster
+// launch, two tiles one after the other (GramParams::tile_counter).
+template <int kCtaGroup, int kNumPass, bool kTf32, int kEpi, int kPairs = 1, int kSub = 1>
 __global__ void __launch_bounds__(kGramThreads, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -326,12 +393,13 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             const GramParams p)
 {
     static_assert(kPairs == 1 || ((kPairs == 2 || kPairs == 4) && kCtaGroup == 2 && kEpi == EPI_HIST), "multicast clusters: CTA pairs, HIST only");
+    static_assert(kSub == 1 || (kPairs == 1 && kEpi == EPI_HIST), "sub-tiles: plain pairs on the histogram schedule of a wider cluster");
     constexpr int kPR = Sched_PR<kPairs>::value;           // pair grid of the cluster: kPR x kPC pairs (1x1, 1x2, 2x2)
     constexpr int kPC = Sched_PC<kPairs>::value;
     constexpr int kTile   = kRowsPerCta * kCtaGroup;       // tile rows == tile cols
     constexpr int kUmmaN  = kTile;                         // accumulator columns per stage
     constexpr int kClusterCtas = kCtaGroup * kPairs;
-    using Sched = TileScheduler<kCtaGroup, kPairs>;
+    using Sched = TileScheduler<kCtaGroup, kPairs, kSub>;
     // kNumPass: 1 = one MMA per k-step; 3 = split operands x = hi + lo, hi*hi + hi*lo + lo*hi in the operand type;
     //           2 = hi*hi in fp16 plus the two cross terms in fp8 (e4m3) at twice the MMA rate (kSchemeF8)
     constexpr bool kF8    = (kNumPass == 2);
@@ -369,6 +437,11 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int i = 0; i < num_slots; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], kPairs); }
         for (int i = 0; i < 2; ++i) { mbar_init(&misc->tfull[i], 1); mbar_init(&misc->tempty[i], kEpiWarps * kCtaGroup); }
+        // tile queue: an entry is consumed by the producer warp and the epilogue warps of every CTA and by the MMA warp of every leader
+        // tile queue: a raw index is read by the decode warp of every CTA; a decoded tile by the producer warp, the epilogue warps
+        // and (leader CTAs) the MMA warp of this CTA
+        for (int i = 0; i < kSchedDepth; ++i) { mbar_init(&misc->ring_full[i], 1); mbar_init(&misc->ring_empty[i], kClusterCtas); }
+        for (int i = 0; i < kTileRing; ++i) { mbar_init(&misc->tile_full[i], 1); mbar_init(&misc->tile_empty[i], 1 + kEpiWarps + (is_leader ? 1 : 0)); }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
@@ -403,22 +476,84 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // the integer bins of an fp16f8 launch stay identical across all of them (regions are 512-aligned, fnb_api.cu).
     auto strict_tile = [&](const TileInfo& t) -> bool {
         if (!kF8 || !p.strict_tiles) return false;
+        if (t.strictq >= 0) return t.strictq != 0;               // decided by the decode warp (tile queue)
         if (p.strict_tiles == 2) return true;
         const unsigned int idx = (unsigned int)(t.row0 >> 9) * (unsigned int)p.strict_nb + (unsigned int)(t.col0 >> 9);
         return (__ldg(p.strict_bits + (idx >> 5)) >> (idx & 31u)) & 1u;          // one bit per 512 x 512 block (strict_blocks_kernel)
     };
 
+    const bool use_queue = (kEpi == EPI_HIST) && (p.tile_counter != nullptr);
+    // kSub > 1: sub-tile `sub` of the super-tile lies outside the region or on / below the diagonal (same test in every role)
+    auto sub_null = [&](const TileInfo& t, int sub) -> bool {
+        if (kSub == 1) return false;
+        const int c0 = t.col0 + sub * kTile;
+        return c0 >= t.col_end || (t.tri && c0 + kTile - 1 <= t.row0);
+    };
+
     // =====================================================================================
-    if (warp == 0) {
+    if (warp == 3) {
+        // ------------------------------ tile queue: fetch + decode warp ------------------
+        // First CTA of the cluster: one atomicAdd per super-tile, the raw index written into the ring of EVERY CTA of the cluster
+        // (st.shared::cluster) and announced on their ring_full barriers (release.cluster); -1 ends the launch.  Every CTA: the
+        // raw index is decoded here (region search, one division, the strict flag's global load) and published as a complete
+        // TileInfo in the CTA's own ring, so the roles pay one local barrier wait and three shared-memory loads per tile.
+        if (use_queue) {
+            Sched loc(p, 0, 1);
+            int rslot = 0; uint32_t rphase = 0;
+            int qslot = 0; uint32_t qphase = 0;
+            for (;;) {
+                if (cluster_rank == 0) {
+                    mbar_wait_relaxed(&misc->ring_empty[rslot], rphase ^ 1u);
+                    int got_id = 0;
+                    if (lane == 0) {
+                        const unsigned long long got = atomicAdd(p.tile_counter, 1ull);
+                        got_id = got < (unsigned long long)p.total_tiles ? (int)got : -1;
+                    }
+                    got_id = __shfl_sync(0xffffffffu, got_id, 0);
+                    if (lane < kClusterCtas) {
+                        st_cluster_s32(mapa_u32(smem_u32(&misc->ring[rslot]), (uint32_t)lane), got_id);
+                        mbar_arrive_cluster_addr(mapa_u32(smem_u32(&misc->ring_full[rslot]), (uint32_t)lane));
+                    }
+                    __syncwarp();
+                }
+                // CTA-scope acquire: the index arrives by st.shared::cluster + an arrive with release.cluster and is read from
+                // this CTA's own shared memory (no cache in between); a cluster-scope acquire would make ptxas invalidate the L1
+                mbar_wait(&misc->ring_full[rslot], rphase);
+                const int id = *reinterpret_cast<const volatile int*>(&misc->ring[rslot]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_addr(mapa_u32(smem_u32(&misc->ring_empty[rslot]), 0u));
+                if (++rslot == kSchedDepth) { rslot = 0; rphase ^= 1u; }
+                TileInfo t;
+                t.row0 = -1; t.col0 = 0; t.row_end = 0; t.col_end = 0; t.tri = 0; t.key = 0; t.gcp = 0; t.cbeg = 0; t.strictq = 0;
+                if (id >= 0) {
+                    if (!loc.locate(id, t)) continue;            // entirely on / below the diagonal: nothing to hand out
+                    t.strictq = -1;
+                    t.strictq = strict_tile(t) ? 1 : 0;
+                }
+                mbar_wait_relaxed(&misc->tile_empty[qslot], qphase ^ 1u);
+                if (lane == 0) {
+                    int4* e = reinterpret_cast<int4*>(&misc->tiles[qslot][0]);
+                    e[0] = make_int4(t.row0, t.col0, t.row_end, t.col_end);
+                    e[1] = make_int4(t.tri, t.key, t.gcp, t.cbeg);
+                    e[2] = make_int4(t.strictq, 0, 0, 0);
+                    mbar_arrive(&misc->tile_full[qslot]);        // release (CTA scope): the stores above are visible to the waiters
+                }
+                __syncwarp();
+                if (++qslot == kTileRing) { qslot = 0; qphase ^= 1u; }
+                if (id < 0) break;
+            }
+        }
+    } else if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------------
         // The whole warp walks the schedule and polls the barriers (warp-uniform control flow, so the compiler keeps
         // addresses and descriptors in uniform registers); one elected lane issues the copies.
         Sched sched(p, cluster_id, num_clusters);
+        if (use_queue) sched.use_queue(&misc->tiles[0][0], misc->tile_full, misc->tile_empty);
         TileInfo t;
         int slot = 0; uint32_t phase = 0;
         int ntile = -1;
         int last_gcp = -1;
-        const bool sync_on = p.sync_window > 0 && cluster_rank == 0;
+        const bool sync_on = p.sync_window > 0 && cluster_rank == 0 && !use_queue;
         bool sync_wait = true;        // cleared for good when a wait runs into kSyncSpinLimit
         // the strict flag of tile i + 1 is fetched while tile i is processed: its global-load latency never sits in front of a tile
         TileInfo t_next;
@@ -447,8 +582,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     __nanosleep(400);
                 }
             }
+            for (int sub = 0; sub < kSub; ++sub) {
+            if (sub_null(t, sub)) continue;
             const int arow = t.row0 + (int)pair_row * kTile + (int)cta_rank * kRowsPerCta;
-            const int brow = t.col0 + (int)pair_col * kTile + (int)cta_rank * kRowsPerCta;
+            const int brow = t.col0 + ((int)pair_col * kSub + sub) * kTile + (int)cta_rank * kRowsPerCta;
             auto load_slot = [&](const CUtensorMap* ma, const CUtensorMap* mb, int kcol) {
                 mbar_wait_relaxed(&misc->empty[slot], phase ^ 1u);
                 if (elect_one()) {
@@ -507,6 +644,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     if (kParts == 2) load_slot(&tm_a_lo, &tm_b_lo, kb * kElemsPerBox);
                 }
             }
+            }   // sub
         }
         if (sync_on && lane == 0) {
             volatile unsigned int* prog = p.progress;
@@ -518,6 +656,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         // tcgen05.commit (the commits track the MMAs of the issuing thread: elect.sync picks the same lane each time).
         if (is_leader) {
             Sched sched(p, cluster_id, num_clusters);
+            if (use_queue) sched.use_queue(&misc->tiles[0][0], misc->tile_full, misc->tile_empty);
             TileInfo t;
             int slot = 0; uint32_t phase = 0;
             uint32_t it = 0;
@@ -529,6 +668,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const bool strict_now = strict_next;
                 more = sched.next(t_next);
                 strict_next = more && strict_tile(t_next);      // consumed one tile later: the load overlaps this tile's MMAs
+                for (int sub = 0; sub < kSub; ++sub) {
+                if (sub_null(t, sub)) continue;
                 const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
                 mbar_wait(&misc->tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
@@ -620,6 +761,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (elect_one()) umma_commit<kCtaGroup>(&misc->tfull[acc], pair_mask);
                 __syncwarp();
                 ++it;
+                }   // sub
             }
         }
     } else if (warp >= kFirstEpiWarp) {
@@ -633,7 +775,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         const float scale = p.acc_scale;
 
         Sched sched(p, cluster_id, num_clusters);
-        TileInfo t;
+        if (use_queue) sched.use_queue(&misc->tiles[0][0], misc->tile_full, misc->tile_empty);
+        TileInfo tq;
         uint32_t it = 0;
 
         float smin = INFINITY, smax = -INFINITY;
@@ -688,10 +831,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         bool more = sched.next(t_next);
         bool strict_next = more && strict_tile(t_next);
         while (more) {
-            t = t_next;
+            tq = t_next;
             const bool strict = strict_next;
             more = sched.next(t_next);
             strict_next = more && strict_tile(t_next);
+            for (int sub = 0; sub < kSub; ++sub) {
+            if (sub_null(tq, sub)) continue;
+            TileInfo t = tq;
+            if constexpr (kSub > 1) t.col0 += sub * kTile;
             const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
             if constexpr (kPairs > 1) { t.row0 += (int)pair_row * kTile; t.col0 += (int)pair_col * kTile; }   // this pair's tile of the super-tile
             // a pair whose tile lies outside the region / below the diagonal still runs the pipeline (lockstep) and drops the result
@@ -978,6 +1125,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 else mbar_arrive(&misc->tempty[acc]);
             }
             ++it; ++tiles_done;
+            }   // sub
         }
 
         if constexpr (kEpi == EPI_HIST) {

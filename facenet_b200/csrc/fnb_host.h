@@ -83,6 +83,9 @@ struct fnb_context {
     fnb::DevBuf a_l16, b_l16;                         // fp16f8 mode: fp16 low parts (strict tiles)
     fnb::DevBuf a_nrm, b_nrm;                         // row norms before normalise-on-load (fnb_options.normalize)
     fnb::DevBuf shard_slots;                          // residues of fnb_options.shard_slots on the device
+    fnb::DevBuf tile_counter;                         // one 64-bit tile-queue counter per launch of a pass (GramParams::tile_counter)
+    cudaStream_t aux_stream = nullptr;                // second Gram launch on the SMs the main grid leaves free (launch_gram_aux)
+    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     fnb::DevBuf progress;                             // per-cluster column-panel progress (GramParams::sync_window)
     fnb::DevBuf perm, cls, keys_in, keys_out, vals_in, flags, cub_tmp;
     fnb::DevBuf regions, tables, bins, counters, out, strip, mine_out, scan, select_io;
@@ -208,6 +211,7 @@ void comm_release(fnb_context* h);
 
 // fnb_gram.cu
 int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const GramOperands& op, GramParams& p, size_t hist_bytes);
+int launch_gram_aux(fnb_context* h, const GramOperands& op, const GramParams& p_main, size_t hist_bytes);   // on h->aux_stream
 size_t gram_smem_bytes(int num_slots, size_t hist_bytes);
 int gram_pick_slots(size_t hist_bytes);
 

@@ -137,6 +137,13 @@ typedef struct {
                               into column chunks of the pair matrix and launch k (pairs whose column lies in chunk k) runs while
                               chunk k + 1 is copied, so only the first chunk's copy is exposed.  0 = auto (inputs >= 64 MiB),
                               1 = always, -1 = off (one copy, one launch).  The integer bins do not depend on it. */
+    int32_t tile_queue;    /* histogram launches: the clusters of the persistent Gram kernel take their tiles from ONE queue (an atomic
+                              counter; tiles leave in schedule order, so all clusters stay inside the same column panels -- no
+                              progress window needed -- and a cluster that starts late or runs slower takes fewer tiles), and on one
+                              GPU a second launch of plain CTA pairs drains the same queue on the 16 SMs that a grid of 4-CTA
+                              clusters cannot use (148 of 148 SMs busy).  0 = on (default), 2 = queue without the second launch,
+                              -1 = off: static interleaved schedule (+ panel_window).  An explicit panel_window > 0 also selects
+                              the static schedule.  Timing only: the integer bins do not depend on it. */
 } fnb_options;
 
 typedef struct {

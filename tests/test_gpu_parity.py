@@ -465,8 +465,50 @@ def test_histogram_streamed_upload_identical_bins(handle):
             got, st = handle.pair_histogram_bins(src, ls_, thr, 0, mode=mode, streamed=1, region_rows=512)
             assert st['streamed_chunks'] >= 3
             np.testing.assert_array_equal(got, ref)
+    ref, _ = handle.pair_histogram_bins(xs_, ls_, thr, 0, streamed=-1)
     got, st = handle.pair_histogram_bins(xs_, ls_.astype(np.int32), thr, 0, streamed=1, region_rows=1024)
+    np.testing.assert_array_equal(got, ref)
+    # (against the class-ordered copy of the same set only the pairs inside the eps window may move: which row of a pair is
+    # the MMA's A operand depends on the order of the rows within their class, and the split contraction adds the two cross
+    # terms in that order)
+    assert np.abs(got.astype(np.int64) - whole.astype(np.int64)).sum() <= 2 * st['eps_window']
+
+
+def test_histogram_tile_queue_identical_bins(handle):
+    """fnb_options.tile_queue: the clusters take their tiles from one atomic queue instead of a static interleaved share, and a
+    second launch of plain CTA pairs drains the same queue on the SMs a grid of 4-CTA clusters leaves free.  Timing only: the
+    integer bins equal those of the static schedule for every cluster shape, super-row height, mode, shard and for streamed
+    uploads; the stats report 148 CTAs when the second launch ran."""
+    x, labels = ragged(12, n_classes=300, d=128, max_size=40)
+    x5, l5 = so.synthetic_embeddings([31] * 120 + [1] * 99 + [6] * 50, dim=512, sigma=0.9, seed=8)
+    thr = so.default_thresholds(0)
+    for (xx, ll, modes) in ((x, labels, ('fp16x3', 'tf32', 'fp16f8')), (x5, l5, ('fp16x3', 'auto'))):
+        for mode in modes:
+            static, st = handle.pair_histogram_bins(xx, ll, thr, 0, mode=mode, tile_queue=-1)
+            for pairs, rr in ((0, 0), (1, 512), (2, 0), (2, 1024), (4, 1024)):
+                if pairs == 4 and mode not in ('fp16x3', 'fp16f8', 'auto'):
+                    continue
+                for q in (0, 2):
+                    got, st = handle.pair_histogram_bins(xx, ll, thr, 0, mode=mode, tile_queue=q, cluster_pairs=pairs, region_rows=rr)
+                    np.testing.assert_array_equal(got, static)
+                    if pairs == 2 and q == 0 and mode != 'tf32':
+                        assert st['grid_ctas'] == handle.device_info()['sm_count']       # both launches ran
+                    if pairs == 2 and q == 2:
+                        assert st['grid_ctas'] < handle.device_info()['sm_count']
+    # row-block shards on the queue sum to the whole; a streamed upload on the queue
+    whole, _ = handle.pair_histogram_bins(x5, l5, thr, 0, tile_queue=-1)
+    acc = np.zeros_like(whole)
+    for rank in range(3):
+        part, _ = handle.pair_histogram_bins(x5, l5, thr, 0, rank=rank, world=3, cluster_pairs=2, region_rows=768)
+        acc += part
+    np.testing.assert_array_equal(acc, whole)
+    got, st = handle.pair_histogram_bins(x5, l5, thr, 0, streamed=1, region_rows=512, cluster_pairs=2)
+    assert st['streamed_chunks'] >= 3
     np.testing.assert_array_equal(got, whole)
+    # the queue under repeated launches (counter reset per launch)
+    for _ in range(5):
+        got, _ = handle.pair_histogram_bins(x5, l5, thr, 0, cluster_pairs=2)
+        np.testing.assert_array_equal(got, whole)
 
 
 def test_histogram_fp16f8_mode(handle):
