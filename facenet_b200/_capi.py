@@ -27,7 +27,8 @@ EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'f
            'fnb_pairwise', 'fnb_pair_histogram_bins', 'fnb_counts_from_bins', 'fnb_pair_histogram',
            'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine', 'fnb_mine_batched', 'fnb_mine_check',
            'fnb_mine_select_kth', 'fnb_false_pairs', 'fnb_pair_cross_entropy', 'fnb_logits_cross_entropy',
-           'fnb_comm_unique_id', 'fnb_comm_init', 'fnb_comm_destroy', 'fnb_comm_info', 'fnb_comm_last_error', 'fnb_pair_histogram_sharded')
+           'fnb_comm_unique_id', 'fnb_comm_init', 'fnb_comm_destroy', 'fnb_comm_info', 'fnb_comm_shared_queue', 'fnb_comm_last_error',
+           'fnb_pair_histogram_sharded')
 
 
 class DLDevice(ctypes.Structure):
@@ -129,6 +130,7 @@ def load_library():
         lib.fnb_comm_destroy.argtypes = [c.c_void_p]
         lib.fnb_comm_info.argtypes = [c.c_void_p, P(c.c_int), P(c.c_int), P(c.c_int)]
         lib.fnb_comm_last_error.argtypes = []
+        lib.fnb_comm_shared_queue.argtypes = [c.c_void_p]
         lib.fnb_comm_last_error.restype = c.c_char_p
         lib.fnb_pair_histogram_sharded.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(c.c_double), c.c_int, P(Options),
                                                    P(DLTensor), P(Stats)]
@@ -517,7 +519,7 @@ class Handle:
     def comm_info(self):
         r, w, v = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self.lib.fnb_comm_info(self.h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(v))
-        return {'rank': r.value, 'world': w.value, 'nccl_version': v.value}
+        return {'rank': r.value, 'world': w.value, 'nccl_version': v.value, 'shared_queue': bool(self.lib.fnb_comm_shared_queue(self.h))}
 
     def pair_histogram_sharded(self, emb_shard, labels_shard, thresholds, metric=0, atol=1.e-5, eps=1.e-5, mode='auto',
                                cta_group=0, region_rows=0, bins_out=None, cuts='numpy', cluster_pairs=0, normalize=0, shard=None,

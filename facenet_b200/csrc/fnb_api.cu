@@ -264,7 +264,7 @@ int fnb::shard_from_options(fnb_context* h, const fnb_options& opt, ShardHost* o
     return FNB_OK;
 }
 
-void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, const ShardHost* shard) {
+void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, const ShardHost* shard, bool pad_equal) {
     const ShardHost whole;
     if (!shard) shard = &whole;
     int cp = 0;
@@ -276,6 +276,9 @@ void fnb::finish_regions(std::vector<RegionDev>& regs, int tile, int pairs, cons
         r.nrb = (r.row_end - r.row_begin + super_rows - 1) / super_rows;
         r.ncb = (r.col_end - r.col_begin + super_cols - 1) / super_cols;
         r.own_cnt = shard->spec.width > 0 ? shard->owned(r.nrb) : 0;
+        // ranks that share their tile queues walk schedules of identical shape: everybody ceil(nrb / world) row blocks (the kernel skips
+        // the blocks past the region's end)
+        if (pad_equal && shard->spec.mod > 1) r.own_cnt = (r.nrb + shard->spec.mod - 1) / shard->spec.mod;
         r.cp_begin = cp;
         cp += r.ncb;
         r.tile_begin = t;
@@ -530,11 +533,11 @@ int fnb::prepare_operand(fnb_context* h, int mode, const float* x, const long lo
 // rows [row_begin, row_end) of the A-side operand arrays that prepare_operand(defer_split) set up; row_end may reach the padded
 // row count (the zero rows behind n).  The row-norm / peakedness maxima accumulate over the chunks.
 int fnb::split_operand_rows(fnb_context* h, const GramOperands& op, const float* x, const long long* perm, long long n, int d,
-                            int normalize, long long row_begin, long long row_end) {
+                            int normalize, long long row_begin, long long row_end, cudaStream_t stream) {
     const bool f8 = (op.num_pass == 2);
     unsigned int* norm = &h->counters.as<DeviceScalars>()->norm_max_ord;
     CK(launch_split_rows(op.mode, x, perm, n, op.a_rows_pad, d, h->a_hi.p, op.num_pass != 1 ? h->a_lo.p : nullptr, f8 ? h->a_h8.p : nullptr,
-                         norm, h->stream, normalize, normalize ? h->a_nrm.as<float>() : nullptr, op.have_l16 ? h->a_l16.p : nullptr,
+                         norm, stream ? stream : h->stream, normalize, normalize ? h->a_nrm.as<float>() : nullptr, op.have_l16 ? h->a_l16.p : nullptr,
                          row_begin, row_end));
     return FNB_OK;
 }
@@ -700,6 +703,11 @@ struct HistLaunch {
     // split of the chunk's rows).  The bins, counters and range words accumulate over the launches.
     const std::vector<std::vector<RegionDev>>* chunks = nullptr;
     std::function<int(int)> before_launch;
+    // sharded job (fnb_pair_histogram_sharded): SMs are kept free for the row exchange; steal_world > 1: the ranks can take tiles
+    // from each other's queues (every rank's counters are mapped into every rank and zeroed by their owner before the label exchange)
+    bool sharded = false;
+    int steal_world = 0, steal_rank = 0;
+    unsigned long long* steal_ctr[8] = {};          // rank v's counters for this pass (steal_ctr[steal_rank] = this rank's own)
 };
 
 // uploads tables, zeroes bins, launches the HIST kernel over `regs`; leaves bins on the device
@@ -782,11 +790,21 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     // tile queue (fnb_options.tile_queue): on for every histogram launch; the auxiliary launch on the free SMs only for one-GPU
     // jobs (a sharded job's row exchange runs there) and never under the profiling knobs
     const bool use_queue = opt.tile_queue >= 0 && opt.panel_window <= 0;     // (an explicit progress window asks for the static schedule)
-    const bool use_aux = use_queue && opt.tile_queue != 2 && opt.world == 1 && opt.max_ctas == 0 && op.pairs == 2;
+    // (a sharded job keeps kAuxReserve of the free SMs for its row exchange -- gather kernels and NCCL's CTAs run there under the launches)
+    const bool use_aux = use_queue && opt.tile_queue != 2 && opt.max_ctas == 0 && op.pairs == 2;
+    const int aux_reserve = hl.sharded ? kAuxReserveSms : 0;
+    unsigned long long* counters = nullptr;
     if (use_queue) {
-        CK(h->tile_counter.ensure((size_t)nlaunch * 8));
-        CK(cudaMemsetAsync(h->tile_counter.p, 0, (size_t)nlaunch * 8, h->stream));
-        p.tile_counter = h->tile_counter.as<unsigned long long>();
+        if (hl.steal_world > 1) {
+            counters = hl.steal_ctr[hl.steal_rank];          // zeroed by its owner at the start of the call
+            p.steal_world = hl.steal_world; p.steal_rank = hl.steal_rank;
+            for (int v = 0; v < hl.steal_world; ++v) p.steal_counter[v] = hl.steal_ctr[v];
+        } else {
+            CK(h->tile_counter.ensure((size_t)nlaunch * 8));
+            CK(cudaMemsetAsync(h->tile_counter.p, 0, (size_t)nlaunch * 8, h->stream));
+            counters = h->tile_counter.as<unsigned long long>();
+        }
+        p.tile_counter = counters;
         p.sync_window = 0;
         h->last_window = 0;
     }
@@ -804,7 +822,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
         if ((r2 = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, pl, hist_bytes_of(pl)))) return r2;
         if (use_aux) {
             CK(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
-            if ((r2 = launch_gram_aux(h, op, pl, hist_bytes_of(pl)))) return r2;
+            if ((r2 = launch_gram_aux(h, op, pl, hist_bytes_of(pl), aux_reserve))) return r2;
             CK(cudaEventRecord(h->aux_ev[1], h->aux_stream));
             CK(cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0));
         }
@@ -882,7 +900,8 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
             p.total_tiles = rv.back().tile_begin;
             p.sync_window = use_queue ? 0 : window_of(rv);
             p.progress = h->progress.as<unsigned int>() + (size_t)k * 1024;
-            if (use_queue) p.tile_counter = h->tile_counter.as<unsigned long long>() + k;
+            if (use_queue) p.tile_counter = counters + k;
+            if (use_queue && hl.steal_world > 1) for (int v = 0; v < hl.steal_world; ++v) p.steal_counter[v] = hl.steal_ctr[v] + k;
             off += rv.size();
             CK(cudaEventRecord(h->chunk_ev[2 * k], h->stream));
             if (p.total_tiles > 0 && (rc = launch_both(p))) return rc;
@@ -1047,6 +1066,16 @@ struct WholeSetJob {
     const long long* perm_dev = nullptr;    // class order of the rows at `de` (NULL: they are stored in class order)
     const long long* stream_perm = nullptr; // streamed pass: class position -> row of h->stage_a (NULL: the pieces are fed in class order)
     bool reduce = false;                    // all-reduce the bins (and the range-violation flag) over the handle's communicator
+    bool sharded = false;                   // fnb_pair_histogram_sharded (row exchange under the launches)
+    int steal_world = 0, steal_rank = 0;    // > 1: the ranks share their tile queues (counters mapped through CUDA IPC)
+    unsigned long long* steal_ctr[8] = {};
+    int pass_index = 0;                     // every pass of a call takes its own 64 counters
+    void arm(HistLaunch& hl) {
+        hl.sharded = sharded;
+        hl.steal_world = steal_world; hl.steal_rank = steal_rank;
+        const int base = 64 * std::min(pass_index++, 3);
+        for (int v = 0; v < steal_world && v < 8; ++v) hl.steal_ctr[v] = steal_ctr[v] + base;
+    }
     uint64_t host_bins[2 * (kMaxBins + 1)];
     size_t row_bytes = 0;
 
@@ -1084,6 +1113,7 @@ struct WholeSetJob {
         // re-run with every tile on the checked path to report the exact similarity range (of this rank's tiles)
         int rc;
         float smin, smax; bool violated = false;
+        arm(hl);
         if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 1))) return rc;
         if ((rc = finish_hist(h, opt, stats, &smin, &smax, &violated))) return rc;
         if (smin == smin) return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
@@ -1102,8 +1132,9 @@ struct WholeSetJob {
         h->last_mode = op.mode; h->last_peak = op.peakedness;
         std::vector<RegionDev> regs;
         triangle_regions(n, (int)super_rows(), 0, regs);
-        finish_regions(regs, tile, op.pairs, &shard);
+        finish_regions(regs, tile, op.pairs, &shard, steal_world > 1);
         HistLaunch hl; hl.auto_window = true;
+        arm(hl);
         if ((rc = run_hist(h, opt, op, regs, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
         float smin, smax; bool violated = false;
         if ((rc = collect(hl, bound, &violated, &smin, &smax))) return rc;
@@ -1146,15 +1177,25 @@ struct WholeSetJob {
                 const long long right = std::max(c0, r1);
                 if (right < c1) { g.row_begin = (int)r0; g.row_end = (int)r1; g.col_begin = (int)right; g.col_end = (int)c1; g.tri = 0; chunks[k].push_back(g); }
             }
-            finish_regions(chunks[k], tile, op.pairs, &shard);
+            finish_regions(chunks[k], tile, op.pairs, &shard, steal_world > 1);
         }
         HistLaunch hl; hl.auto_window = true; hl.chunks = &chunks;
+        arm(hl);
         hl.before_launch = [&](int k) -> int {
             const long long c0 = bounds[k], c1 = bounds[k + 1];
             int r = feed(k, c0, c1);
             if (r) return r;
-            // (the last chunk also zeroes the padding rows)
-            return split_operand_rows(h, op, h->stage_a.as<float>(), stream_perm, n, d, opt.normalize, c0, k + 1 == nchunks ? op.a_rows_pad : c1);
+            // Sharded jobs: the split follows the transfer on the COPY stream -- it runs on the SMs the launch in progress leaves
+            // free (kAuxReserveSms) instead of sitting between two launches on the handle's stream.  One GPU: every SM is busy
+            // under a launch, and a split parked on the copy stream would only hold back the next chunk's upload behind it.
+            // (The last chunk also zeroes the padding rows.)
+            cudaStream_t ss = (sharded && h->copy_stream) ? h->copy_stream : h->stream;
+            if ((r = split_operand_rows(h, op, h->stage_a.as<float>(), stream_perm, n, d, opt.normalize, c0, k + 1 == nchunks ? op.a_rows_pad : c1, ss))) return r;
+            if (ss != h->stream) {
+                CK(cudaEventRecord(h->copy_ev[2], ss));
+                CK(cudaStreamWaitEvent(h->stream, h->copy_ev[2], 0));
+            }
+            return FNB_OK;
         };
         std::vector<RegionDev> none;
         if ((rc = run_hist(h, opt, op, none, cg, d, h->cls.as<int32_t>(), thresholds, T, hl, 0))) return rc;
@@ -1166,7 +1207,7 @@ struct WholeSetJob {
         if (violated) {
             std::vector<RegionDev> regs;
             triangle_regions(n, (int)rr, 0, regs);
-            finish_regions(regs, tile, op.pairs, &shard);
+            finish_regions(regs, tile, op.pairs, &shard, steal_world > 1);
             HistLaunch whole; whole.auto_window = true;
             return not_normalized(whole, regs);
         }
@@ -1428,6 +1469,20 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
         return FNB_OK;
     }
 
+    // ---- tile queues shared by the ranks (fnb_comm_init mapped every rank's counters into every rank): a rank drains its own queue,
+    //      then helps the others (GramParams::steal_counter), so nobody waits in the all-reduce for the GPU that runs slowest
+    //      under the power limit.  Every rank zeroes ITS counters here, in front of the label exchange -- no launch of any rank
+    //      can start before every rank has contributed to that exchange.
+    job.sharded = true;
+    {
+        int cap = 0;
+        if (comm_shared_counters(h, rank, &cap) && world > 1 && world <= 8 && opt.tile_queue >= 0 && opt.shard_mod == 0 && opt.panel_window <= 0 && cap >= 256) {
+            job.steal_world = world; job.steal_rank = rank;
+            for (int v = 0; v < world; ++v) job.steal_ctr[v] = comm_shared_counters(h, v, nullptr);
+            CK(cudaMemsetAsync(job.steal_ctr[rank], 0, (size_t)cap * 8, h->stream));
+        }
+    }
+
     // ---- 2. labels.  Every rank first puts ITS rows in class order (a local sort: the rows of a rank then form a sorted run),
     //         the sorted label runs are exchanged (8 n bytes), and every rank sorts the concatenation of the runs itself.  The global
     //         class order is then a MERGE of the ranks' runs: any range of it takes a CONTIGUOUS range of every run -- which is
@@ -1505,13 +1560,6 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
             CK(cudaEventRecord(h->copy_ev[1], h->copy_stream));
             h->h2d_timed = true;
             first_chunk = false;
-        } else if (k >= 1 && (size_t)(2 * k - 1) < h->chunk_ev.size()) {
-            // Chunk k travels while launch k - 1 runs -- and not earlier: it starts when launch k - 1 is about to start (the event
-            // in front of it).  The Gram kernel is persistent with a static tile schedule: a broadcast or gather kernel that holds
-            // SMs at the moment a launch starts keeps some of its clusters from becoming resident, and the launch then ends late by
-            // their whole share (measured at 2 GPUs with the exchange running ahead: one rank's launches 17 % longer).  Started
-            // behind the launch, the exchange only ever gets the 16 SMs a 132-CTA grid leaves free.
-            CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[2 * (k - 1)], 0));
         }
         const bool trace = getenv("FNB_TRACE") != nullptr;
         if (trace) {
@@ -1519,13 +1567,21 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
             CK(cudaEventRecord(h->xchg_ev[3 * k], h->copy_stream));
         }
         const long long s0 = run_pos[(size_t)k * world + rank], s1 = run_pos[(size_t)(k + 1) * world + rank];
-        if (s1 > s0) {
-            char* dst = runs + (size_t)(off[rank] + s0) * rb;
-            if (ve.on_device) {
-                gather_rows_kernel<<<(unsigned)std::min<long long>((s1 - s0 + 7) / 8, 148LL * 8), 256, 0, h->copy_stream>>>(
-                    (const float*)local, h->local_perm.as<long long>() + s0, s1 - s0, d, (float*)dst);
-                CK(cudaGetLastError());
-            } else if ((r2 = stage_chunk(h, dst, local, (size_t)(s1 - s0) * rb, false, h->perm_host.as<long long>() + s0, rb))) return r2;
+        char* own_dst = runs + (size_t)(off[rank] + s0) * rb;
+        // host rows: the upload (copy engine, no SM) starts as soon as the copy stream gets to it
+        if (s1 > s0 && !ve.on_device && (r2 = stage_chunk(h, own_dst, local, (size_t)(s1 - s0) * rb, false, h->perm_host.as<long long>() + s0, rb))) return r2;
+        if (k >= 1 && (size_t)(2 * k - 1) < h->chunk_ev.size()) {
+            // The KERNELS of chunk k's exchange run while launch k - 1 runs -- and not earlier: they start when launch k - 1 is
+            // about to start (the event in front of it).  A broadcast or gather kernel that holds SMs at the moment a launch starts
+            // keeps some of its clusters from becoming resident (measured at 2 GPUs with the exchange running ahead of a static
+            // schedule: one rank's launches 17 % longer).  Started behind the launch, the exchange only ever gets the SMs the
+            // launch leaves free.
+            CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[2 * (k - 1)], 0));
+        }
+        if (s1 > s0 && ve.on_device) {
+            gather_rows_kernel<<<(unsigned)std::min<long long>((s1 - s0 + 7) / 8, 148LL * 8), 256, 0, h->copy_stream>>>(
+                (const float*)local, h->local_perm.as<long long>() + s0, s1 - s0, d, (float*)own_dst);
+            CK(cudaGetLastError());
         }
         if (trace) CK(cudaEventRecord(h->xchg_ev[3 * k + 1], h->copy_stream));
         if (world > 1) {

@@ -64,9 +64,18 @@ static const NcclApi* nccl_api() {
     return &g_nccl;
 }
 
+constexpr int kSharedCounters = 256;
+constexpr int kMaxStealWorld = 8;
+
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // Tile-queue counters of every rank, mapped into every rank through CUDA IPC (peer access over NVLink): ctr[r] is rank r's
+    // array (ctr[rank] is this rank's own allocation).  A rank drains its OWN queue with local atomics and, when that is empty,
+    // takes tiles from the other ranks' queues (GramParams::steal_counter) -- a GPU that runs slower under the power limit is
+    // helped out by the others instead of holding up the all-reduce.
+    unsigned long long* ctr[kMaxStealWorld] = {};
+    bool shared = false;
 };
 
 #define NCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) \
@@ -96,7 +105,69 @@ int comm_all_reduce_u64(fnb_context* h, void* buf, size_t count, bool max_op, cu
     return FNB_OK;
 }
 
+// rank r's counters as mapped into this process (NULL: the ranks do not share their queues)
+unsigned long long* comm_shared_counters(const fnb_context* h, int r, int* count) {
+    if (count) *count = kSharedCounters;
+    return (h->comm && h->comm->shared && r >= 0 && r < h->comm->world) ? h->comm->ctr[r] : nullptr;
+}
+
+static void drop_shared_counters(Comm* c) {
+    for (int r = 0; r < kMaxStealWorld; ++r) {
+        if (!c->ctr[r]) continue;
+        if (r == c->rank) cudaFree(c->ctr[r]); else cudaIpcCloseMemHandle(c->ctr[r]);
+        c->ctr[r] = nullptr;
+    }
+    c->shared = false;
+    cudaGetLastError();
+}
+
+// every rank allocates its counters, the IPC handles travel by ncclAllGather, every rank maps the others'; the ranks then agree
+// (all-reduce of a flag) on whether everybody succeeded -- if not, nobody shares
+static void setup_shared_counters(fnb_context* h) {
+    Comm* c = h->comm;
+    if (c->world < 2 || c->world > kMaxStealWorld || getenv("FNB_NO_SHARED_QUEUE")) return;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    unsigned long long ok = 1;
+    unsigned char* tmp = nullptr;
+    if (cudaMalloc(&tmp, hb * (c->world + 1) + 8) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&c->ctr[c->rank], kSharedCounters * 8) != cudaSuccess || cudaMemset(c->ctr[c->rank], 0, kSharedCounters * 8) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, c->ctr[c->rank]) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
+    cudaMemcpyAsync(tmp + hb * c->world, &mine, hb, cudaMemcpyHostToDevice, h->stream);
+    const bool nccl_ok = g_nccl.AllGather(tmp + hb * c->world, tmp, hb, ncclUint8, c->comm, h->stream) == ncclSuccess;
+    cudaMemcpyAsync(all.data(), tmp, hb * c->world, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    unsigned long long* flag = (unsigned long long*)(tmp + hb * (c->world + 1));
+    if (!nccl_ok) ok = 0;
+    // every rank must have allocated before anybody maps: first round of agreement
+    cudaMemcpyAsync(flag, &ok, 8, cudaMemcpyHostToDevice, h->stream);
+    if (g_nccl.AllReduce(flag, flag, 1, ncclUint64, ncclMin, c->comm, h->stream) != ncclSuccess) ok = 0;
+    unsigned long long all_ok = 0;
+    cudaMemcpyAsync(&all_ok, flag, 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (ok && all_ok) {
+        for (int r = 0; r < c->world; ++r) {
+            if (r == c->rank) continue;
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            c->ctr[r] = (unsigned long long*)p;
+        }
+    } else {
+        ok = 0;
+    }
+    cudaMemcpyAsync(flag, &ok, 8, cudaMemcpyHostToDevice, h->stream);
+    if (g_nccl.AllReduce(flag, flag, 1, ncclUint64, ncclMin, c->comm, h->stream) != ncclSuccess) ok = 0;
+    cudaMemcpyAsync(&all_ok, flag, 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    c->shared = ok && all_ok;
+    if (!c->shared) drop_shared_counters(c);
+}
+
 void comm_release(fnb_context* h) {
+    if (h->comm) drop_shared_counters(h->comm);
     if (h->comm) {
         if (h->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm->comm);
         delete h->comm;
@@ -136,14 +207,15 @@ extern "C" int fnb_comm_init(fnb_handle h, const void* id128, int rank, int worl
     memcpy(&id, id128, sizeof(id));
     Comm* c = new Comm();
     c->rank = rank; c->world = world;
-    // The row exchange runs UNDER the persistent Gram kernel, which holds one CTA per SM on 132 of the 148 SMs (two-pair
-    // clusters): NCCL's CTAs have the 16 SMs left.  More CTAs than that would sit in the launch queue until a Gram launch
-    // ends -- with the ranks' collectives waiting on each other meanwhile -- so the communicator is capped (FNB_NCCL_MAX_CTAS).
+    // The row exchange runs UNDER the persistent Gram kernels, which hold one CTA per SM on all but kAuxReserveSms of the SMs
+    // (132 in two-pair clusters + plain pairs on the rest): NCCL's CTAs have those SMs.  More CTAs than that would sit in the
+    // launch queue until a Gram launch ends -- with the ranks' collectives waiting on each other meanwhile -- so the
+    // communicator is capped (FNB_NCCL_MAX_CTAS).
     ncclResult_t r;
     if (api->CommInitRankConfig) {
         ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
         const char* env = getenv("FNB_NCCL_MAX_CTAS");
-        cfg.maxCTAs = env ? atoi(env) : 12;
+        cfg.maxCTAs = env ? atoi(env) : kAuxReserveSms;
         if (cfg.maxCTAs <= 0) cfg.maxCTAs = NCCL_CONFIG_UNDEF_INT;
         // ... and those 16 SMs are the leftovers of the GPCs (two per GPC: the Gram clusters take four SMs each), so NCCL's own
         // default of 4-CTA clusters (CGA) could not be placed on them at all: measured at 2 GPUs, every broadcast then finished
@@ -156,6 +228,7 @@ extern "C" int fnb_comm_init(fnb_handle h, const void* id128, int rank, int worl
     }
     if (r != ncclSuccess) { delete c; return h->fail(FNB_ERR_CUDA, "ncclCommInitRank: %s", api->GetErrorString(r)); }
     h->comm = c;
+    setup_shared_counters(h);
     return FNB_OK;
 }
 
@@ -167,6 +240,8 @@ extern "C" int fnb_comm_destroy(fnb_handle h) {
     comm_release(h);
     return FNB_OK;
 }
+
+extern "C" int fnb_comm_shared_queue(fnb_handle h) { return (h && h->comm && h->comm->shared) ? 1 : 0; }
 
 extern "C" int fnb_comm_info(fnb_handle h, int* rank, int* world, int* nccl_version) {
     if (!h) return FNB_ERR_INVALID;

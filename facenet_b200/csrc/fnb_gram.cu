@@ -105,9 +105,9 @@ static int launch_aux_pairs(fnb_context* h, int ctas, const GramOperands& op, co
     return FNB_OK;
 }
 
-int launch_gram_aux(fnb_context* h, const GramOperands& op, const GramParams& p_main, size_t hist_bytes)
+int launch_gram_aux(fnb_context* h, const GramOperands& op, const GramParams& p_main, size_t hist_bytes, int reserve_sms)
 {
-    const int ctas = (h->sm_count - h->last_grid) & ~1;
+    const int ctas = std::max(0, h->sm_count - h->last_grid - reserve_sms) & ~1;
     if (ctas < 2 || op.pairs != 2 || op.tf32 || (op.num_pass != 2 && op.num_pass != 3) || p_main.tile_counter == nullptr) return FNB_OK;
     GramParams p = p_main;
     p.sync_window = 0;

@@ -168,7 +168,17 @@ struct GramParams {
     // slower SM simply takes fewer tiles, and a SECOND launch of another cluster shape can drain the same queue (the 16 SMs a
     // grid of 4-CTA clusters cannot use run CTA pairs on it: fnb_gram.cu).  The integer bins do not depend on who took which tile.
     unsigned long long* tile_counter;
+    // Sharded jobs whose ranks share their queues (fnb_comm_init mapped every rank's counters into every rank, CUDA IPC over
+    // NVLink): steal_counter[v] is rank v's counter of THIS launch (steal_counter[steal_rank] == tile_counter).  All ranks walk
+    // schedules of identical shape (every rank ceil(nrb / world) row blocks per region, rank v's j-th block = j * world + v; blocks
+    // past the region's end are skipped), so a tile index taken from rank v's queue decodes with v in place of this rank.  A
+    // cluster takes from its own queue while it has tiles -- local atomics, and its own row panels stay in its L2 -- then from the
+    // other ranks' queues in cyclic order: whoever finishes early helps the GPUs that run slower under the power limit.
+    unsigned long long* steal_counter[8];
+    int steal_world, steal_rank;
 };
+
+constexpr int kStealShift = 27;                    // raw queue entry = tile index | owner rank << 27
 
 constexpr int kSchedDepth = 4;                     // raw tile indices in flight per cluster (fetch warp -> decode warps)
 constexpr int kTileRing = 8;                       // decoded tiles per CTA (the producer runs two tiles ahead of the epilogue, and every role looks one tile ahead)
@@ -252,7 +262,8 @@ struct TileScheduler {
     }
 
     // decode warp: tile index (indices only grow) -> tile; false when the tile lies entirely on / below the diagonal
-    __device__ bool locate(long long id, TileInfo& t) {
+    __device__ bool locate(long long id, TileInfo& t, int owner = -1) {
+        if (!fresh && id < r.tile_begin) { cur = 0; fresh = true; }     // another rank's queue (stealing): its position may lie behind ours
         if (fresh || id >= next_begin) {
             while (id >= regions[cur + 1].tile_begin) ++cur;
             r = regions[cur];                                   // one global load per REGION, not per tile
@@ -262,7 +273,9 @@ struct TileScheduler {
         const int li = (int)(id - r.tile_begin);
         cb = li / r.own_cnt;
         j = li - cb * r.own_cnt;
-        const int rb = (shard.width == 1 && shard.slots == nullptr) ? j * shard.mod + shard.lo : shard.block(j);
+        const int rb = (owner >= 0) ? j * shard.mod + owner
+                     : (shard.width == 1 && shard.slots == nullptr) ? j * shard.mod + shard.lo : shard.block(j);
+        if (rb >= r.nrb) return false;                          // padded share (ranks that share their queues): no such row block
         fill(t, rb);
         return !(r.tri && t.col0 + kSuperCols - 1 <= t.row0);
     }
@@ -501,13 +514,25 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             Sched loc(p, 0, 1);
             int rslot = 0; uint32_t rphase = 0;
             int qslot = 0; uint32_t qphase = 0;
+            int victim = p.steal_rank, victim_tried = 0;             // (lane 0 of the fetch warp)
             for (;;) {
                 if (cluster_rank == 0) {
                     mbar_wait_relaxed(&misc->ring_empty[rslot], rphase ^ 1u);
                     int got_id = 0;
                     if (lane == 0) {
-                        const unsigned long long got = atomicAdd(p.tile_counter, 1ull);
-                        got_id = got < (unsigned long long)p.total_tiles ? (int)got : -1;
+                        got_id = -1;
+                        if (p.steal_world > 1) {
+                            // own queue first, then the other ranks' (system-scope atomics: those counters live on peer GPUs)
+                            while (victim_tried < p.steal_world) {
+                                const unsigned long long got = atomicAdd_system(p.steal_counter[victim], 1ull);
+                                if (got < (unsigned long long)p.total_tiles) { got_id = (int)got | (victim << kStealShift); break; }
+                                ++victim_tried;
+                                victim = (victim + 1 == p.steal_world) ? 0 : victim + 1;
+                            }
+                        } else {
+                            const unsigned long long got = atomicAdd(p.tile_counter, 1ull);
+                            if (got < (unsigned long long)p.total_tiles) got_id = (int)got;
+                        }
                     }
                     got_id = __shfl_sync(0xffffffffu, got_id, 0);
                     if (lane < kClusterCtas) {
@@ -526,7 +551,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 TileInfo t;
                 t.row0 = -1; t.col0 = 0; t.row_end = 0; t.col_end = 0; t.tri = 0; t.key = 0; t.gcp = 0; t.cbeg = 0; t.strictq = 0;
                 if (id >= 0) {
-                    if (!loc.locate(id, t)) continue;            // entirely on / below the diagonal: nothing to hand out
+                    const int owner = (p.steal_world > 1) ? (id >> kStealShift) : -1;
+                    if (!loc.locate(id & ((1 << kStealShift) - 1), t, owner)) continue;   // below the diagonal / padding: nothing to hand out
                     t.strictq = -1;
                     t.strictq = strict_tile(t) ? 1 : 0;
                 }

@@ -166,7 +166,7 @@ int dl_check_embeddings(fnb_context* h, const DLView& v, const char* name);
 int prepare_operand(fnb_context* h, int mode, const float* x, const long long* perm, long long n, int d,
                     bool side_b, GramOperands& op, int normalize = 0, bool defer_split = false);
 int split_operand_rows(fnb_context* h, const GramOperands& op, const float* x, const long long* perm, long long n, int d,
-                       int normalize, long long row_begin, long long row_end);
+                       int normalize, long long row_begin, long long row_end, cudaStream_t stream = nullptr);
 // host view of a rank's share: the residues it owns (ascending) and the device spec
 struct ShardHost {
     ShardSpec spec = ShardSpec{1, 0, 1, nullptr};
@@ -178,7 +178,7 @@ struct ShardHost {
         return c;
     }
 };
-void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1, const ShardHost* shard = nullptr);
+void finish_regions(std::vector<RegionDev>& regs, int tile, int pairs = 1, const ShardHost* shard = nullptr, bool pad_equal = false);
 int shard_from_options(fnb_context* h, const fnb_options& opt, ShardHost* out);
 int self_b_maps(fnb_context* h, GramOperands& op, int d);   // B side = the prepared A side (Gram of a set with itself)
 int upload_regions(fnb_context* h, const std::vector<RegionDev>& regs);
@@ -208,10 +208,13 @@ int comm_group_start(fnb_context* h);
 int comm_group_end(fnb_context* h);
 int comm_all_reduce_u64(fnb_context* h, void* buf, size_t count, bool max_op, cudaStream_t s);
 void comm_release(fnb_context* h);
+unsigned long long* comm_shared_counters(const fnb_context* h, int r, int* count);   // rank r's counters; NULL: the ranks do not share their queues
 
 // fnb_gram.cu
 int launch_gram(fnb_context* h, int cta_group, int epi, int max_ctas, const GramOperands& op, GramParams& p, size_t hist_bytes);
-int launch_gram_aux(fnb_context* h, const GramOperands& op, const GramParams& p_main, size_t hist_bytes);   // on h->aux_stream
+// on h->aux_stream; reserve_sms of the free SMs are left alone
+int launch_gram_aux(fnb_context* h, const GramOperands& op, const GramParams& p_main, size_t hist_bytes, int reserve_sms = 0);
+constexpr int kAuxReserveSms = 8;    // SMs a sharded job keeps free for its row exchange (= the CTA cap of its NCCL communicator)
 size_t gram_smem_bytes(int num_slots, size_t hist_bytes);
 int gram_pick_slots(size_t hist_bytes);
 

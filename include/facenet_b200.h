@@ -224,11 +224,16 @@ int fnb_pair_histogram_bins(fnb_handle h, const DLTensor* emb, const DLTensor* l
  *   fnb_comm_unique_id: rank 0 fills 128 bytes (an ncclUniqueId) and ships them to the other processes by any means;
  *   fnb_comm_init:      every process, same id; collective (returns when the communicator is up);
  *   fnb_comm_destroy:   releases it (fnb_destroy does too);  fnb_comm_info: rank / world / NCCL version in use.
+ * fnb_comm_init also maps every rank's tile-queue counters into every rank through CUDA IPC (peer access over NVLink): in a sharded
+ * job a rank drains its own queue (the row blocks rb % world == rank) and then takes tiles from the other ranks' queues, so a GPU
+ * that runs slower under the power limit is helped out instead of holding up the all-reduce (fnb_comm_shared_queue tells whether
+ * the mapping worked; without it every rank computes exactly its own row blocks).
  * fnb_comm_last_error: text of a failed fnb_comm_unique_id (which has no handle). */
 int fnb_comm_unique_id(void* id128);
 int fnb_comm_init(fnb_handle h, const void* id128, int rank, int world);
 int fnb_comm_destroy(fnb_handle h);
 int fnb_comm_info(fnb_handle h, int* rank, int* world, int* nccl_version);
+int fnb_comm_shared_queue(fnb_handle h);   /* 1: the ranks can take tiles from each other's queues (counters mapped through CUDA IPC) */
 const char* fnb_comm_last_error(void);
 
 /* fnb_pair_histogram_bins over a set that is spread over the ranks of the handle's communicator: every rank passes ITS rows
