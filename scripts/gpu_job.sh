@@ -33,7 +33,7 @@ ncu_list)   # launch list of one bench command
     tail -3 $O/ncu_list_$1.log
     ;;
 ncu_full)   # --set full of one Gram launch of the bench command
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -s 1 -c 1 -o $O/prof_$1 -f \
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -s ${NCU_SKIP:-2} -c 1 -o $O/prof_$1 -f \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --no-e2e --no-strict "${@:2}" > $O/ncu_full_$1.log 2>&1
     tail -3 $O/ncu_full_$1.log
     ;;
