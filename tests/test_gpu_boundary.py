@@ -173,3 +173,35 @@ def test_false_examples_listing_and_capacity(fst, handle, tmp_path):
     assert sorted(zip(r1.tolist(), c1.tolist())) == sorted(zip(r2.tolist(), c2.tolist()))
     with pytest.raises(ValueError, match='normalized'):
         fst.FalseExamples(x * 1.5, labels, 1.75).false_pairs()
+
+
+def test_sharded_entry_point_on_one_rank():
+    """fnb_comm_init / fnb_pair_histogram_sharded with a communicator of ONE rank (NCCL resolved at run time, behind the C ABI):
+    the collective entry point equals the plain one, for host and device rows in any order, and a second handle on the same
+    device is unaffected.  (The N > 1 forms are checked by scripts/check_multi_gpu.py under torchrun: profiles/r02n_check_n*.log.)"""
+    import torch
+    from facenet_b200 import _capi
+    h = _capi.Handle(0)
+    try:
+        uid = h.comm_unique_id()
+        assert len(uid) == 128
+        h.comm_init(uid, 0, 1)
+        info = h.comm_info()
+        assert info['rank'] == 0 and info['world'] == 1 and info['nccl_version'] >= 22000
+        x, labels = so.synthetic_embeddings([33] * 70 + [1] * 41, dim=512, sigma=0.8, seed=23)      # shuffled rows
+        thr = so.default_thresholds(0)
+        for mode in ('fp16x3', 'auto'):
+            ref, st0 = h.pair_histogram_bins(x, labels, thr, 0, mode=mode)
+            got, st = h.pair_histogram_sharded(x, labels, thr, 0, mode=mode)
+            np.testing.assert_array_equal(got, ref)
+            assert st['n_pairs'] == st0['n_pairs'] and st['mode_used'] == st0['mode_used']
+            got, _ = h.pair_histogram_sharded(torch.from_numpy(x).cuda(), torch.from_numpy(labels).cuda(), thr, 0, mode=mode)
+            np.testing.assert_array_equal(got, ref)
+        bad = x.copy(); bad[7] = bad[8] * 1.01
+        with pytest.raises(_capi.FnbError, match='normalized'):
+            h.pair_histogram_sharded(bad, labels, thr, 0)
+        h.comm_destroy()
+        with pytest.raises(_capi.FnbError, match='communicator'):
+            h.pair_histogram_sharded(x, labels, thr, 0)
+    finally:
+        h.close()
