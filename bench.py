@@ -625,7 +625,8 @@ def run_allpairs(args):
     if strict is not None:
         s_ach = (pairs / world) * FLOP_PER_PAIR / (strict['kernel_ms'] * 1e-3) / 1e12
         strict['roofline'] = {'achieved': s_ach, 'peak': tf32_peak, 'frac': s_ach / tf32_peak, 'unit': 'TFLOP/s',
-                              'note': 'fp16x3 executes 3 fp16 MMAs per algorithmic MMA = 1.5 TF32-pass equivalents: ceiling 0.667'}
+                              'note': 'fp16x3 executes 3 fp16 MMAs per algorithmic MMA = 1.5 TF32-pass equivalents: 0.667 of the fp16 pipe at best; the '
+                                              'denominator is cuBLAS\'s measured sustained rate / 2, which this MMA stream can exceed under the same power limit'}
 
     burst, sustained, reps = tf32_live(torch, dev)
     if burst:

@@ -822,7 +822,9 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
         if ((r2 = launch_gram(h, cg, EPI_HIST, opt.max_ctas, op, pl, hist_bytes_of(pl)))) return r2;
         if (use_aux) {
             CK(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
+            const int grid_before = h->last_grid;
             if ((r2 = launch_gram_aux(h, op, pl, hist_bytes_of(pl), aux_reserve))) return r2;
+            if (h->last_grid > grid_before) ++h->aux_launches;
             CK(cudaEventRecord(h->aux_ev[1], h->aux_stream));
             CK(cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0));
         }
@@ -881,6 +883,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.counters = sc->counters; p.range_ord = sc->range_ord;
     p.metric = opt.metric;
     h->chunk_launches = 0;
+    h->aux_launches = 0;
     if (!hl.chunks) {
         CK(cudaEventRecord(h->ev[1], h->stream));
         if ((rc = launch_both(p))) return rc;
@@ -965,7 +968,7 @@ static int finish_hist(fnb_context* h, const fnb_options& opt, fnb_stats* stats,
         stats->smax = smax;
         stats->max_abs = amax;
         stats->eps_counted = (float)h->last_eps_counted;
-        stats->kernel_launches += h->chunk_launches > 0 ? 2 * h->chunk_launches - 1 : 1;     // streamed: a split + a Gram launch per chunk
+        stats->kernel_launches += (h->chunk_launches > 0 ? 2 * h->chunk_launches - 1 : 1) + h->aux_launches;     // streamed: a split + a Gram launch per chunk; + the launches of CTA pairs on the free SMs
         stats->grid_ctas = (uint32_t)h->last_grid;
         stats->mode_used = h->last_mode;
         stats->panel_window = h->last_window;

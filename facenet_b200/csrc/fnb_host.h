@@ -74,6 +74,7 @@ struct fnb_context {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> chunk_ev;   // streamed histogram launches: one (start, end) pair per launch
     std::vector<cudaEvent_t> xchg_ev;    // FNB_TRACE: three events per chunk of a sharded row exchange
+    int aux_launches = 0;                // auxiliary Gram launches (launch_gram_aux) of the last pass
     int chunk_launches = 0;              // launches of the last streamed pass (0: one launch timed by ev[1] .. ev[2])
     fnb::PFN_tmapEncodeTiled encode = nullptr;
     std::string err;

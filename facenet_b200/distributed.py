@@ -121,13 +121,17 @@ def native_handle(device_index, group=None):
     import torch.distributed as dist
     from facenet_b200 import _capi
     key = (int(device_index), id(group) if group is not None else None)
-    h = _native.get(key)
-    if h is None:
+    if key not in _native:
         h = _capi.default_handle(int(device_index))
-        if getattr(h, 'comm', None) is None or h.comm[1] != dist.get_world_size(group):
-            h.comm_init_from_torch(group)
+        try:
+            if getattr(h, 'comm', None) is None or h.comm[1] != dist.get_world_size(group):
+                h.comm_init_from_torch(group)
+        except Exception as exc:      # NCCL not loadable / communicator refused: the same on every rank (same process image)
+            import warnings
+            warnings.warn('facenet_b200: no NCCL communicator inside the library (%s); torch.distributed does the exchange' % exc)
+            h = None
         _native[key] = h
-    return h
+    return _native[key]
 
 
 def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=None, hist_fn=None, balancer=None, **kw):
@@ -155,6 +159,9 @@ def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=
     if hist_fn is None and world > 1 and torch.cuda.is_available():
         dev = emb_shard.device if getattr(emb_shard, 'is_cuda', False) else torch.device('cuda', torch.cuda.current_device())
         handle = native_handle(dev.index or 0, group)
+    else:
+        handle = None
+    if handle is not None:
         bins = torch.zeros((2, thr.size + 1), dtype=torch.int64, device=dev)
         from facenet_b200 import _capi
         try:
@@ -165,6 +172,8 @@ def pair_histogram_sharded(emb_shard, labels_shard, thresholds, metric=0, group=
             raise
         _exchange_times(balancer, stats, rank, world, dev, group)
         return bins, stats
+    if isinstance(emb_shard, np.ndarray) and hist_fn is None and torch.cuda.is_available():      # (the library path takes host rows as they are)
+        emb_shard, labels_shard = torch.from_numpy(emb_shard).cuda(), torch.from_numpy(np.asarray(labels_shard)).cuda()
     emb, labels = gather_shards(emb_shard, labels_shard, group)
     # one spare slot per row carries the ranks' error flags through the same all-reduce as the bins
     buf = torch.zeros((2, thr.size + 2), dtype=torch.int64, device=emb.device)
