@@ -1551,6 +1551,18 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
     char* runs = h->stage_a.as<char>();
     const char* local = (const char*)ve.data;
     bool first_chunk = true;
+    // Option (fnb_options.streamed == 3), PINNED host rows only: the whole shard is copied as it lies by the DMA engine alone (one
+    // stream-ordered copy on the copy stream, no host thread touches the bytes) and the class-order gather runs on the device like
+    // for device-resident rows.  Not the default: the whole shard then sits in front of the FIRST launch (2 GPUs, 1 GB per rank:
+    // e2e 1,192 against 1,236 G pairs/s with the chunk-wise host gather); it is meant for hosts with very few cores per GPU.
+    bool bulk_upload = false;
+    if (!ve.on_device && n_local > 0) {
+        cudaPointerAttributes attr;
+        const cudaError_t pe = cudaPointerGetAttributes(&attr, ve.data);
+        if (pe != cudaSuccess) cudaGetLastError();
+        bulk_upload = (pe == cudaSuccess) && attr.type == cudaMemoryTypeHost && opt.streamed == 3;
+        if (bulk_upload) CK(h->stage_b.ensure((size_t)n_local * rb));
+    }
     // every run's part of chunk k: this rank's part is gathered into place, then all parts are broadcast in place by their owners
     // (one NCCL group: the broadcasts of a chunk run side by side); the handle's stream waits for the chunk
     auto move_chunk = [&](int k) -> int {
@@ -1563,7 +1575,13 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
             CK(cudaEventRecord(h->copy_ev[1], h->copy_stream));
             h->h2d_timed = true;
             first_chunk = false;
+            if (bulk_upload) {
+                CK(cudaMemcpyAsync(h->stage_b.p, ve.data, (size_t)n_local * rb, cudaMemcpyHostToDevice, h->copy_stream));
+                h->last_h2d_bytes += (size_t)n_local * rb;
+                local = h->stage_b.as<char>();
+            }
         }
+        const bool rows_on_device = ve.on_device || bulk_upload;
         const bool trace = getenv("FNB_TRACE") != nullptr;
         if (trace) {
             while (h->xchg_ev.size() < 3 * (size_t)(k + 1)) { cudaEvent_t e = nullptr; CK(cudaEventCreate(&e)); h->xchg_ev.push_back(e); }
@@ -1572,7 +1590,7 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
         const long long s0 = run_pos[(size_t)k * world + rank], s1 = run_pos[(size_t)(k + 1) * world + rank];
         char* own_dst = runs + (size_t)(off[rank] + s0) * rb;
         // host rows: the upload (copy engine, no SM) starts as soon as the copy stream gets to it
-        if (s1 > s0 && !ve.on_device && (r2 = stage_chunk(h, own_dst, local, (size_t)(s1 - s0) * rb, false, h->perm_host.as<long long>() + s0, rb))) return r2;
+        if (s1 > s0 && !rows_on_device && (r2 = stage_chunk(h, own_dst, local, (size_t)(s1 - s0) * rb, false, h->perm_host.as<long long>() + s0, rb))) return r2;
         if (k >= 1 && (size_t)(2 * k - 1) < h->chunk_ev.size()) {
             // The KERNELS of chunk k's exchange run while launch k - 1 runs -- and not earlier: they start when launch k - 1 is
             // about to start (the event in front of it).  A broadcast or gather kernel that holds SMs at the moment a launch starts
@@ -1581,7 +1599,7 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
             // launch leaves free.
             CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[2 * (k - 1)], 0));
         }
-        if (s1 > s0 && ve.on_device) {
+        if (s1 > s0 && rows_on_device) {
             gather_rows_kernel<<<(unsigned)std::min<long long>((s1 - s0 + 7) / 8, 148LL * 8), 256, 0, h->copy_stream>>>(
                 (const float*)local, h->local_perm.as<long long>() + s0, s1 - s0, d, (float*)own_dst);
             CK(cudaGetLastError());

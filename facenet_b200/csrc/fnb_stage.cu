@@ -124,6 +124,9 @@ static int ensure_staging(fnb_context* h) {
     for (int i = 0; i < kRingSlots; ++i) CKS(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     unsigned hw = std::thread::hardware_concurrency();
     int n = (int)std::min(7u, hw > 2 ? hw / 2 - 1 : 0u);          // up to 7 workers + the caller; fewer on small hosts
+    // a sharded job runs one process per GPU on the same host: the ranks share its cores
+    const int world = comm_world(h);
+    if (world > 1) n = std::max(1, std::min(n, (int)(hw / (2 * (unsigned)world))));
     const char* env = getenv("FNB_COPY_THREADS");
     if (env) n = std::max(0, atoi(env) - 1);
     h->copier = new HostCopier(n);

@@ -136,7 +136,9 @@ typedef struct {
                               order -- what np.concatenate over the classes gives, facenet/facenet.py:184-201): the upload is cut
                               into column chunks of the pair matrix and launch k (pairs whose column lies in chunk k) runs while
                               chunk k + 1 is copied, so only the first chunk's copy is exposed.  0 = auto (inputs >= 64 MiB),
-                              1 = always, -1 = off (one copy, one launch).  The integer bins do not depend on it. */
+                              1 = always, -1 = off (one copy, one launch); 3 (fnb_pair_histogram_sharded, pinned host rows): one DMA of the
+                              whole shard + class-order gather on the device instead of the chunk-wise gather by the copy threads.
+                              The integer bins do not depend on it. */
     int32_t tile_queue;    /* histogram launches: the clusters of the persistent Gram kernel take their tiles from ONE queue (an atomic
                               counter; tiles leave in schedule order, so all clusters stay inside the same column panels -- no
                               progress window needed -- and a cluster that starts late or runs slower takes fewer tiles), and on one

@@ -511,6 +511,37 @@ def test_histogram_tile_queue_identical_bins(handle):
         np.testing.assert_array_equal(got, whole)
 
 
+def test_bf16_mode_disagreement_report(handle):
+    """BASELINE config 5 at small N ("BF16 mode ... reporting eps-window disagreements versus TF32"): the single-pass bf16
+    histogram against the fp32-equivalent one of the same set.  Every pair that lands in another bin lies within the bf16 mode's
+    own distance error of a threshold (the report bench.py --workload c5 prints), the totals agree exactly, and the count of
+    moved pairs is bounded by the pairs the strict distances put within that error of a threshold."""
+    x, labels = so.synthetic_embeddings([20] * 30 + [3] * 20, dim=512, sigma=1.1, seed=31)
+    thr = so.default_thresholds(0)
+    lo = handle.pair_histogram(x, labels, thr, 0, mode='bf16')
+    hi = handle.pair_histogram(x, labels, thr, 0, mode='fp16x3')
+    assert lo['n_same'] == hi['n_same'] and lo['n_diff'] == hi['n_diff']
+    d_lo = handle.pairwise(x, None, 0, mode='bf16')
+    d_hi = handle.pairwise(x, None, 0, mode='fp16x3')
+    bound = float(np.abs(d_lo - d_hi).max())
+    assert 1.e-4 < bound < 4.e-3                                     # bf16: 8 significand bits per operand
+    thr32 = thr.astype(np.float32)
+    b_lo, b_hi = np.searchsorted(thr32, d_lo, side='right'), np.searchsorted(thr32, d_hi, side='right')
+    moved = b_lo != b_hi
+    assert moved.any()
+    gap = np.abs(d_hi[moved][:, None].astype(np.float64) - thr[None, :]).min(axis=1)
+    assert np.all(gap <= bound)                                      # every disagreement sits inside the mode's error of a threshold
+    within = (np.abs(d_hi[:, None].astype(np.float64) - thr[None, :]).min(axis=1) <= bound).sum()
+    # per threshold, the cumulative counts differ by no more than the pairs the strict pass has within the bound of THAT threshold
+    iu = np.triu_indices(x.shape[0], 1)
+    same = labels[iu[0]] == labels[iu[1]]
+    for cnt_lo, cnt_hi, sel in ((lo['same'], hi['same'], same), (lo['diff'], hi['diff'], ~same)):
+        near = (np.abs(d_hi[sel][:, None].astype(np.float64) - thr[None, :]) <= bound).sum(axis=0)
+        assert np.all(np.abs(cnt_lo - cnt_hi) <= near)
+    assert int(moved.sum()) <= int(within)
+    assert lo['stats']['error_bound'] > 1.e-5                        # the certificate says what it is: not a tolerance-claiming mode
+
+
 def test_histogram_fp16f8_mode(handle):
     """fp16f8 (hi*hi in fp16 + e4m3 cross terms): distances within the 1e-5 tolerance of the oracle on dense
     embeddings, histogram disagreements bounded by the counted eps-window pairs."""
