@@ -327,8 +327,13 @@ static int pick_pairs(const fnb_options* o, int cta_group, long long n = 0) {
 static int pick_region_rows(const fnb_options* o, int tile, long long n = 0, int d = 512, int clusters = 0, int row_block = 0) {
     long long rr = o->region_rows;
     const int world = std::max(1, o->world);
+    // Tile queue (the default): a row block is read by whichever cluster asks for the tile, i.e. from both dies, and is then cached
+    // in both L2 partitions -- the row panels get HALF the budget (32 MiB: 16,384 rows at d = 512; measured at 1M, queue + auxiliary
+    // pairs: 8,192 ... 25,344 rows 653-666 G pairs/s, 33,792 rows 633-642, 50,688 rows 585; profiles/r02q_queue_region_rows.log),
+    // and nothing ties row blocks to clusters, so the cluster alignment below does not apply.
+    const bool queue = o->tile_queue >= 0 && o->panel_window <= 0;
     if (rr <= 0) {
-        rr = (64ll << 20) / (4ll * std::max(d, 1)) * world;
+        rr = ((queue ? 32ll : 64ll) << 20) / (4ll * std::max(d, 1)) * world;
         if (n > 0) rr = std::min(rr, std::max<long long>(n / 6, 8ll * tile));
         // row blocks per super-row divisible by world: rank r then owns the SAME row blocks (r, r + world, ...) in every
         // column panel, i.e. 1/world of the row panels; otherwise its rows drift from column to column and it ends up
@@ -338,7 +343,7 @@ static int pick_region_rows(const fnb_options* o, int tile, long long n = 0, int
         // number of tiles in every column panel -- no cluster waits at the progress window for one that has an extra tile, and
         // each cluster re-reads the same row panels (measured at 1M, 33 clusters of two pairs: 132 row blocks per super-row
         // 849-854 ms and 64-66 GB of DRAM reads, 96 row blocks 890-894 ms and 78-85 GB; profiles/r02b_rr_window_dram.log)
-        if (clusters > 0 && row_block > 0) {
+        if (clusters > 0 && row_block > 0 && !queue) {
             long long unit = (long long)clusters * row_block * (o->shard_mod > 0 ? o->shard_mod : world);
             while (unit % tile) unit *= 2;
             if (rr >= unit) q = unit;
@@ -1556,6 +1561,7 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
     // for device-resident rows.  Not the default: the whole shard then sits in front of the FIRST launch (2 GPUs, 1 GB per rank:
     // e2e 1,192 against 1,236 G pairs/s with the chunk-wise host gather); it is meant for hosts with very few cores per GPU.
     bool bulk_upload = false;
+    const bool local_in_order = !ve.on_device && labels_in_class_order(vl, n_local);
     if (!ve.on_device && n_local > 0) {
         cudaPointerAttributes attr;
         const cudaError_t pe = cudaPointerGetAttributes(&attr, ve.data);
@@ -1590,7 +1596,12 @@ extern "C" int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shar
         const long long s0 = run_pos[(size_t)k * world + rank], s1 = run_pos[(size_t)(k + 1) * world + rank];
         char* own_dst = runs + (size_t)(off[rank] + s0) * rb;
         // host rows: the upload (copy engine, no SM) starts as soon as the copy stream gets to it
-        if (s1 > s0 && !rows_on_device && (r2 = stage_chunk(h, own_dst, local, (size_t)(s1 - s0) * rb, false, h->perm_host.as<long long>() + s0, rb))) return r2;
+        if (s1 > s0 && !rows_on_device) {
+            // rows already in class order (labels non-decreasing): the run IS the shard -- no gather; pinned memory then goes by DMA alone
+            r2 = local_in_order ? stage_chunk(h, own_dst, local + (size_t)s0 * rb, (size_t)(s1 - s0) * rb, false)
+                                : stage_chunk(h, own_dst, local, (size_t)(s1 - s0) * rb, false, h->perm_host.as<long long>() + s0, rb);
+            if (r2) return r2;
+        }
         if (k >= 1 && (size_t)(2 * k - 1) < h->chunk_ev.size()) {
             // The KERNELS of chunk k's exchange run while launch k - 1 runs -- and not earlier: they start when launch k - 1 is
             // about to start (the event in front of it).  A broadcast or gather kernel that holds SMs at the moment a launch starts
