@@ -797,7 +797,9 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     const bool use_queue = opt.tile_queue >= 0 && opt.panel_window <= 0;     // (an explicit progress window asks for the static schedule)
     // (a sharded job keeps kAuxReserve of the free SMs for its row exchange -- gather kernels and NCCL's CTAs run there under the launches)
     const bool use_aux = use_queue && opt.tile_queue != 2 && opt.max_ctas == 0 && op.pairs == 2;
-    const int aux_reserve = hl.sharded ? kAuxReserveSms : 0;
+    // ... while an exchange is still to come: nothing travels under the LAST launch of a pass (or under the one launch of a pass
+    // whose rows were gathered up front), which therefore takes every free SM
+    int aux_reserve = (hl.sharded && hl.chunks && hl.chunks->size() > 1) ? kAuxReserveSms : 0;
     unsigned long long* counters = nullptr;
     if (use_queue) {
         if (hl.steal_world > 1) {
@@ -910,6 +912,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
             p.progress = h->progress.as<unsigned int>() + (size_t)k * 1024;
             if (use_queue) p.tile_counter = counters + k;
             if (use_queue && hl.steal_world > 1) for (int v = 0; v < hl.steal_world; ++v) p.steal_counter[v] = hl.steal_ctr[v] + k;
+            if (k + 1 == nlaunch) aux_reserve = 0;
             off += rv.size();
             CK(cudaEventRecord(h->chunk_ev[2 * k], h->stream));
             if (p.total_tiles > 0 && (rc = launch_both(p))) return rc;
