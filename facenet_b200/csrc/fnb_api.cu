@@ -794,7 +794,10 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     p.progress = h->progress.as<unsigned int>();
     // tile queue (fnb_options.tile_queue): on for every histogram launch; the auxiliary launch on the free SMs only for one-GPU
     // jobs (a sharded job's row exchange runs there) and never under the profiling knobs
-    const bool use_queue = opt.tile_queue >= 0 && opt.panel_window <= 0;     // (an explicit progress window asks for the static schedule)
+    long long most_tiles = hl.chunks ? 0 : regs.back().tile_begin;
+    if (hl.chunks) for (const auto& c : *hl.chunks) most_tiles = std::max(most_tiles, c.back().tile_begin);
+    // (an explicit progress window asks for the static schedule; queue entries are 32-bit tile indices)
+    const bool use_queue = opt.tile_queue >= 0 && opt.panel_window <= 0 && most_tiles < 0x7fffffffll;
     // (a sharded job keeps kAuxReserve of the free SMs for its row exchange -- gather kernels and NCCL's CTAs run there under the launches)
     const bool use_aux = use_queue && opt.tile_queue != 2 && opt.max_ctas == 0 && op.pairs == 2;
     // ... while an exchange is still to come: nothing travels under the LAST launch of a pass (or under the one launch of a pass
@@ -802,10 +805,14 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
     int aux_reserve = (hl.sharded && hl.chunks && hl.chunks->size() > 1) ? kAuxReserveSms : 0;
     unsigned long long* counters = nullptr;
     if (use_queue) {
-        if (hl.steal_world > 1) {
+        // (a stolen tile travels as index | owner << kStealShift in one int: jobs with more tiles per rank than that keep to their own
+        // queues -- the same decision on every rank, their schedules have identical shape)
+        if (hl.steal_world > 1 && most_tiles < (1ll << kStealShift)) {
             counters = hl.steal_ctr[hl.steal_rank];          // zeroed by its owner at the start of the call
             p.steal_world = hl.steal_world; p.steal_rank = hl.steal_rank;
             for (int v = 0; v < hl.steal_world; ++v) p.steal_counter[v] = hl.steal_ctr[v];
+        } else if (hl.steal_world > 1) {
+            counters = hl.steal_ctr[hl.steal_rank];          // own queue only
         } else {
             CK(h->tile_counter.ensure((size_t)nlaunch * 8));
             CK(cudaMemsetAsync(h->tile_counter.p, 0, (size_t)nlaunch * 8, h->stream));
@@ -911,7 +918,7 @@ static int run_hist(fnb_context* h, const fnb_options& opt, GramOperands& op, co
             p.sync_window = use_queue ? 0 : window_of(rv);
             p.progress = h->progress.as<unsigned int>() + (size_t)k * 1024;
             if (use_queue) p.tile_counter = counters + k;
-            if (use_queue && hl.steal_world > 1) for (int v = 0; v < hl.steal_world; ++v) p.steal_counter[v] = hl.steal_ctr[v] + k;
+            if (use_queue && p.steal_world > 1) for (int v = 0; v < hl.steal_world; ++v) p.steal_counter[v] = hl.steal_ctr[v] + k;
             if (k + 1 == nlaunch) aux_reserve = 0;
             off += rv.size();
             CK(cudaEventRecord(h->chunk_ev[2 * k], h->stream));

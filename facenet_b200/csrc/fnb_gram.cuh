@@ -309,6 +309,7 @@ struct TileScheduler {
             pos += stride;
             j += (int)stride;
             while (j >= r.own_cnt) { j -= r.own_cnt; ++cb; }
+            if (rb >= r.nrb) continue;                                  // padded share (see locate)
             if (r.tri && t.col0 + kSuperCols - 1 <= t.row0) continue;   // entirely on/below the diagonal
             return true;
         }
