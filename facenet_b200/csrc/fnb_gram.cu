@@ -108,12 +108,13 @@ static int launch_aux_pairs(fnb_context* h, int ctas, const GramOperands& op, co
 int launch_gram_aux(fnb_context* h, const GramOperands& op, const GramParams& p_main, size_t hist_bytes, int reserve_sms)
 {
     const int ctas = std::max(0, h->sm_count - h->last_grid - reserve_sms) & ~1;
-    if (ctas < 2 || op.pairs != 2 || op.tf32 || (op.num_pass != 2 && op.num_pass != 3) || p_main.tile_counter == nullptr) return FNB_OK;
+    if (ctas < 2 || op.pairs != 2 || op.tf32 || p_main.tile_counter == nullptr) return FNB_OK;     // (the tf32 kinds keep to the main grid)
     GramParams p = p_main;
     p.sync_window = 0;
     const size_t smem = gram_smem_bytes(p.num_slots, hist_bytes);
     if (!h->aux_stream) return h->fail(FNB_ERR_INVALID, "auxiliary stream missing");
-    int rc = op.num_pass == 2 ? launch_aux_pairs<2>(h, ctas, op, p, smem) : launch_aux_pairs<3>(h, ctas, op, p, smem);
+    int rc = op.num_pass == 2 ? launch_aux_pairs<2>(h, ctas, op, p, smem)
+           : op.num_pass == 3 ? launch_aux_pairs<3>(h, ctas, op, p, smem) : launch_aux_pairs<1>(h, ctas, op, p, smem);   // 1: fp16 / bf16 single pass
     if (rc) return rc;
     h->last_grid += ctas;
     return FNB_OK;

@@ -482,7 +482,7 @@ def test_histogram_tile_queue_identical_bins(handle):
     x, labels = ragged(12, n_classes=300, d=128, max_size=40)
     x5, l5 = so.synthetic_embeddings([31] * 120 + [1] * 99 + [6] * 50, dim=512, sigma=0.9, seed=8)
     thr = so.default_thresholds(0)
-    for (xx, ll, modes) in ((x, labels, ('fp16x3', 'tf32', 'fp16f8')), (x5, l5, ('fp16x3', 'auto'))):
+    for (xx, ll, modes) in ((x, labels, ('fp16x3', 'tf32', 'fp16f8', 'bf16')), (x5, l5, ('fp16x3', 'auto'))):
         for mode in modes:
             static, st = handle.pair_histogram_bins(xx, ll, thr, 0, mode=mode, tile_queue=-1)
             for pairs, rr in ((0, 0), (1, 512), (2, 0), (2, 1024), (4, 1024)):
