@@ -28,7 +28,7 @@ EXPORTS = ('fnb_version', 'fnb_default_options', 'fnb_create', 'fnb_destroy', 'f
            'fnb_region_histogram_bins', 'fnb_confidence_from_last_bins', 'fnb_mine', 'fnb_mine_batched', 'fnb_mine_check',
            'fnb_mine_select_kth', 'fnb_false_pairs', 'fnb_pair_cross_entropy', 'fnb_logits_cross_entropy',
            'fnb_comm_unique_id', 'fnb_comm_init', 'fnb_comm_destroy', 'fnb_comm_info', 'fnb_comm_shared_queue', 'fnb_comm_last_error',
-           'fnb_pair_histogram_sharded')
+           'fnb_pair_histogram_sharded', 'fnb_debug_chunk_plan')
 
 
 class DLDevice(ctypes.Structure):
@@ -130,6 +130,7 @@ def load_library():
         lib.fnb_comm_destroy.argtypes = [c.c_void_p]
         lib.fnb_comm_info.argtypes = [c.c_void_p, P(c.c_int), P(c.c_int), P(c.c_int)]
         lib.fnb_comm_last_error.argtypes = []
+        lib.fnb_debug_chunk_plan.argtypes = [c.c_longlong, c.c_longlong, c.c_longlong, c.c_int, P(c.c_int), P(c.c_int)]
         lib.fnb_comm_shared_queue.argtypes = [c.c_void_p]
         lib.fnb_comm_last_error.restype = c.c_char_p
         lib.fnb_pair_histogram_sharded.argtypes = [c.c_void_p, P(DLTensor), P(DLTensor), P(c.c_double), c.c_int, P(Options),

@@ -1062,6 +1062,57 @@ static double error_certificate(const fnb_options& opt, int mode, bool strict_ti
     return worst;
 }
 
+// Regions of one column chunk of a streamed pass: the pairs (row < col) with col in [c0, c1), per super-row [r0, r1) of the tile
+// order -- columns inside the super-row's own span [a, b) see the rows [r0, a) above them (a rectangle) and each other (a
+// triangle); columns to its right see all of its rows (a rectangle).  Over the chunks of a partition of [0, n) every pair is
+// covered exactly once (tests/test_host_logic.py::test_chunk_plan_covers_every_pair_once through fnb_debug_chunk_plan).
+static void chunk_regions(long long n, long long rr, long long c0, long long c1, std::vector<RegionDev>& out) {
+    for (long long r0 = 0; r0 < c1; r0 += rr) {
+        const long long r1 = std::min<long long>(n, r0 + rr);
+        const long long a = std::max(c0, r0), b = std::min(c1, r1);
+        RegionDev g = {};
+        g.key = 0;
+        if (a < b) {
+            if (a > r0) { g.row_begin = (int)r0; g.row_end = (int)a; g.col_begin = (int)a; g.col_end = (int)b; g.tri = 0; out.push_back(g); }
+            g.row_begin = (int)a; g.row_end = (int)b; g.col_begin = (int)a; g.col_end = (int)b; g.tri = 1; out.push_back(g);
+        }
+        const long long right = std::max(c0, r1);
+        if (right < c1) { g.row_begin = (int)r0; g.row_end = (int)r1; g.col_begin = (int)right; g.col_end = (int)c1; g.tri = 0; out.push_back(g); }
+    }
+}
+
+// chunk boundaries of a streamed pass: multiples of `g` rows growing with the work already queued (1, 1, 1, 1, 2, 3, 4, 6, 9 ...
+// granules): launch k is then at least as long as the transfer of chunk k + 1
+static std::vector<long long> chunk_schedule(long long n, long long g) {
+    std::vector<long long> bounds = {0};
+    for (long long pos = 0; pos < n;) {
+        pos = std::min(n, pos + std::max(g, (pos / 2) / g * g));
+        bounds.push_back(pos);
+    }
+    return bounds;
+}
+
+// Test hook (host only, no GPU): the chunk plan of a streamed pass over n rows with super-rows of rr rows and a granule of g rows.
+// regions: up to cap entries {chunk, row_begin, row_end, col_begin, col_end, tri}; returns the number of regions (or -needed).
+extern "C" int fnb_debug_chunk_plan(long long n, long long rr, long long g, int cap, int* regions /* [cap][6] */, int* nchunks) {
+    if (n < 1 || rr < 1 || g < 1) return 0;
+    const std::vector<long long> bounds = chunk_schedule(n, g);
+    int count = 0;
+    for (size_t k = 0; k + 1 < bounds.size(); ++k) {
+        std::vector<RegionDev> regs;
+        chunk_regions(n, rr, bounds[k], bounds[k + 1], regs);
+        for (const RegionDev& r : regs) {
+            if (count < cap && regions) {
+                int* o = regions + (size_t)count * 6;
+                o[0] = (int)k; o[1] = r.row_begin; o[2] = r.row_end; o[3] = r.col_begin; o[4] = r.col_end; o[5] = r.tri;
+            }
+            ++count;
+        }
+    }
+    if (nchunks) *nchunks = (int)bounds.size() - 1;
+    return count <= cap ? count : -count;
+}
+
 // ---------------------------------------------------------------------------------------
 // whole-set histogram: one job object shared by fnb_pair_histogram_bins (one GPU, or a caller that shards by itself through
 // fnb_options.rank / world) and fnb_pair_histogram_sharded (NCCL inside the library)
@@ -1179,22 +1230,7 @@ struct WholeSetJob {
         const int nchunks = (int)bounds.size() - 1;
         std::vector<std::vector<RegionDev>> chunks((size_t)nchunks);
         for (int k = 0; k < nchunks; ++k) {
-            // pairs (row < col) with col in [c0, c1): per super-row [r0, r1) of the tile order -- columns inside the super-row's own
-            // span [a, b) see the rows [r0, a) above them (a rectangle) and each other (a triangle); columns to its right see all
-            // of its rows (a rectangle)
-            const long long c0 = bounds[k], c1 = bounds[k + 1];
-            for (long long r0 = 0; r0 < c1; r0 += rr) {
-                const long long r1 = std::min<long long>(n, r0 + rr);
-                const long long a = std::max(c0, r0), b = std::min(c1, r1);
-                RegionDev g = {};
-                g.key = 0;
-                if (a < b) {
-                    if (a > r0) { g.row_begin = (int)r0; g.row_end = (int)a; g.col_begin = (int)a; g.col_end = (int)b; g.tri = 0; chunks[k].push_back(g); }
-                    g.row_begin = (int)a; g.row_end = (int)b; g.col_begin = (int)a; g.col_end = (int)b; g.tri = 1; chunks[k].push_back(g);
-                }
-                const long long right = std::max(c0, r1);
-                if (right < c1) { g.row_begin = (int)r0; g.row_end = (int)r1; g.col_begin = (int)right; g.col_end = (int)c1; g.tri = 0; chunks[k].push_back(g); }
-            }
+            chunk_regions(n, rr, bounds[k], bounds[k + 1], chunks[k]);
             finish_regions(chunks[k], tile, op.pairs, &shard, steal_world > 1);
         }
         HistLaunch hl; hl.auto_window = true; hl.chunks = &chunks;
@@ -1240,11 +1276,7 @@ struct WholeSetJob {
         long long g = super_rows();
         while (g > 49152) g /= 2;
         g = std::max<long long>(512, g / 512 * 512);
-        std::vector<long long> bounds = {0};
-        for (long long pos = 0; pos < n;) {
-            pos = std::min(n, pos + std::max(g, (pos / 2) / g * g));
-            bounds.push_back(pos);
-        }
+        std::vector<long long> bounds = chunk_schedule(n, g);
         return bounds;
     }
 

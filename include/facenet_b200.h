@@ -253,6 +253,11 @@ int fnb_pair_histogram_sharded(fnb_handle h, const DLTensor* emb_shard, const DL
                                const double* thresholds, int T, const fnb_options* opt,
                                DLTensor* bins_out, fnb_stats* stats);
 
+/* Test hook, host only (no GPU needed): the column-chunk plan of a streamed pass (fnb_options.streamed, fnb_pair_histogram_sharded)
+ * over n rows with super-rows of rr rows and chunk granule g -- regions [cap][6] = {chunk, row_begin, row_end, col_begin, col_end,
+ * tri}; returns the number of regions (negative: cap too small).  Every pair (row < col) lies in exactly one region. */
+int fnb_debug_chunk_plan(long long n, long long rr, long long g, int cap, int* regions, int* nchunks);
+
 /* Host-side conversion of (summed) bins into per-threshold counts:
  *   same_lt[n] = #{same-identity pairs with d < thresholds[n]}, diff_lt[n] likewise (strict <,
  *   float64 compare against the fp32 distance, statistics.py:131). */

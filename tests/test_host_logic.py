@@ -441,3 +441,42 @@ def test_write_dict_appends_resizable_gzip_datasets(monkeypatch, tmp_path):
     assert all(d.compression == 'gzip' and d.maxshape == (None,) and d.data.ndim == 1 for d in ds.values())
     h5utils.write_dict(f, {'x': 1})                                  # no group: top level
     assert 'x' in ds
+
+
+def test_chunk_plan_covers_every_pair_once():
+    """The column-chunk plan of a streamed pass (host rows uploaded / shards broadcast chunk by chunk under the Gram launches):
+    over all chunks, every pair (row < col) of the set lies in exactly one region, the regions of chunk k only touch rows and
+    columns below chunk k's end (the rows fed so far), and the chunks grow with the work already queued.  Pure host logic of
+    the library (fnb_debug_chunk_plan): runs without a GPU."""
+    import ctypes
+    from facenet_b200 import _capi
+    lib = _capi.load_library()
+    rng = np.random.default_rng(0)
+    cases = [(1, 4, 2), (2, 1, 1), (37, 8, 8), (64, 16, 8), (100, 16, 24), (257, 32, 16), (300, 64, 32), (301, 50, 7)]
+    cases += [(int(rng.integers(2, 400)), int(rng.integers(1, 90)), int(rng.integers(1, 90))) for _ in range(12)]
+    for n, rr, g in cases:
+        cap = 4096
+        buf = (ctypes.c_int * (cap * 6))()
+        nch = ctypes.c_int()
+        cnt = lib.fnb_debug_chunk_plan(n, rr, g, cap, buf, ctypes.byref(nch))
+        assert 0 <= cnt <= cap
+        regs = np.frombuffer(buf, dtype=np.int32)[:cnt * 6].reshape(cnt, 6)
+        cover = np.zeros((n, n), dtype=np.int32)
+        ends = {}
+        for k, r0, r1, c0, c1, tri in regs:
+            assert 0 <= r0 < r1 <= n and 0 <= c0 < c1 <= n
+            blk = np.ones((r1 - r0, c1 - c0), dtype=np.int32)
+            if tri:
+                assert (r0, r1) == (c0, c1)
+                blk = np.triu(blk, 1)
+            cover[r0:r1, c0:c1] += blk
+            ends[k] = max(ends.get(k, 0), c1)
+            assert r1 <= ends[k] or r1 <= c1                  # rows of a region lie at or above its chunk's last column
+        want = np.triu(np.ones((n, n), dtype=np.int32), 1)
+        np.testing.assert_array_equal(cover, want)
+        assert sorted(ends) == list(range(nch.value)) or n == 1
+        e = [ends[k] for k in sorted(ends)]
+        assert e == sorted(e) and (not e or e[-1] == n)
+        # chunk k needs only rows < its own end: no region of chunk k reaches past ends[k]
+        for k, r0, r1, c0, c1, tri in regs:
+            assert r1 <= ends[k] and c1 <= ends[k]
