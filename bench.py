@@ -652,11 +652,12 @@ def run_allpairs(args):
                       'fp16f8': 'f16 hi*hi + e4m3 cross terms, f32 accumulate; strict f16x3 tiles for same-identity pairs'}[mode_used],
             'data': 'synthetic',
             'config': {'workload': wl['name'], 'mode': args.mode, 'mode_used': mode_used,
-                       'parallelism': ('row blocks split over %d ranks' % world) +
+                       'parallelism': ('row blocks rb %% world == rank over %d ranks, a rank that drains its queue takes tiles from the others (NVLink peer atomics)' % world if world > 1 else 'one GPU') +
                                       (', shares adapted to per-GPU kernel time: %s / %d' % (balancer.widths, balancer.mod) if balancer else ', equal shares'),
                        'l2': 'inputs (%.0f MB fp32 + split operands) larger than L2; no flush' % (n * DIM * 4 / 1e6),
                        'pairs_per_step': pairs, 'region_rows': args.region_rows,
-                       'grid_ctas': grids, 'panel_window': windows, 'cluster': 'CTA pairs (cta_group::2); 132-CTA grids are clusters of two pairs with the A operand multicast'},
+                       'grid_ctas': grids, 'panel_window': windows, 'cluster': 'CTA pairs (cta_group::2) on one tile queue: 132 CTAs in clusters of two pairs with the A operand multicast + plain pairs on the SMs '
+                                  'those clusters cannot use (N > 1: all but 8 of them, kept for the row exchange, except under the last launch)'},
             'breakdown_ms': {'row_exchange_first_to_last_piece': gather_ms, 'row_exchange_chunks': chunks_used,
                              'plain_torch_all_gather_alone': plain_gather_ms, 'sort_split_until_first_launch': p_ms,
                              'gram_kernel': k_ms, 'gram_kernel_per_rank': k_ranks,
