@@ -649,9 +649,11 @@ extern "C" int fnb_false_pairs(fnb_handle h, const DLTensor* emb, const DLTensor
         return h->fail(FNB_ERR_NOT_NORMALIZED, "embeddings must be normalized to 1, range %.9g %.9g", smin, smax);
     const size_t take = (size_t)std::min<unsigned long long>(found, (unsigned long long)capacity);
     if (take) {
-        CK(cudaMemcpy(rows, p.filter_rows, take * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(cols, p.filter_cols, take * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(dist, p.filter_dist, take * 4, cudaMemcpyDeviceToHost));
+        // on the handle's stream (never the null stream): the list was written by the launch queued there
+        CK(cudaMemcpyAsync(rows, p.filter_rows, take * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(cols, p.filter_cols, take * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(dist, p.filter_dist, take * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
     }
     return FNB_OK;
 }
