@@ -28,23 +28,24 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header(tmp_path):
-    """sizeof/offsetof of the ctypes mirrors equal what a C compiler sees in the header."""
+    """sizeof and the offset of EVERY field of the ctypes mirrors equal what a C compiler sees in the header (a field added in
+    the middle of fnb_options / fnb_stats on one side only would shift every option behind it silently)."""
     import subprocess
+    structs = (('fnb_options', _capi.Options), ('fnb_stats', _capi.Stats), ('fnb_region', _capi.Region), ('DLTensor', _capi.DLTensor))
+    lines = []
+    for cname, cls in structs:
+        lines.append('printf("%%zu\\n", sizeof(%s));' % cname)
+        for fname, _ in cls._fields_:
+            lines.append('printf("%%zu\\n", offsetof(%s, %s));' % (cname, fname))
     src = tmp_path / 'sizes.c'
-    src.write_text("""
-#include <stdio.h>
-#include <stddef.h>
-#include "facenet_b200.h"
-int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(DLTensor), sizeof(fnb_region), sizeof(fnb_options), sizeof(fnb_stats),
-         offsetof(fnb_options, cuts), offsetof(fnb_options, max_ctas), offsetof(fnb_stats, tiles), offsetof(fnb_stats, kernel_ms));
-  return 0; }
-""")
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "facenet_b200.h"\nint main(void) {\n' + '\n'.join(lines) + '\nreturn 0; }\n')
     exe = tmp_path / 'sizes'
     subprocess.run(['gcc', '-I', str(ROOT / 'include'), str(src), '-o', str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [ctypes.sizeof(_capi.DLTensor), ctypes.sizeof(_capi.Region), ctypes.sizeof(_capi.Options), ctypes.sizeof(_capi.Stats),
-            _capi.Options.cuts.offset, _capi.Options.max_ctas.offset, _capi.Stats.tiles.offset, _capi.Stats.kernel_ms.offset]
+    want = []
+    for _, cls in structs:
+        want.append(ctypes.sizeof(cls))
+        want += [getattr(cls, fname).offset for fname, _ in cls._fields_]
     assert got == want
     assert _capi.REGION_DTYPE.itemsize == ctypes.sizeof(_capi.Region)
 
